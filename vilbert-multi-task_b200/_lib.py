@@ -1,0 +1,69 @@
+"""ctypes binding of libvilbert_b200.so (C ABI: include/vilbert_b200.h).
+
+The library is the product; there is NO fallback. If the shared object is missing or a call
+returns a non-zero status this module raises — nothing here ever routes to a CPU/PyTorch path.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvilbert_b200.so")
+
+VB_ACT_NONE, VB_ACT_GELU, VB_ACT_RELU, VB_ACT_DGELU = 0, 1, 2, 3
+
+
+class VBError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    """Mirror of ``struct vb_gemm_args`` (include/vilbert_b200.h)."""
+
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int32),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("b_mn_major", C.c_int32),
+        ("alpha", C.c_float),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ld_res", C.c_int64),
+        ("aux", C.c_void_p), ("ld_aux", C.c_int64),
+        ("act", C.c_int32),
+        ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int64),
+        ("out_bf16", C.c_void_p), ("ld_out_bf16", C.c_int64),
+        ("out_pre", C.c_void_p), ("ld_out_pre", C.c_int64),
+        ("atomic_out", C.c_int32), ("split_k", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
+        ("dbg_lbo_a", C.c_uint32), ("dbg_sbo_a", C.c_uint32), ("dbg_lbo_b", C.c_uint32), ("dbg_sbo_b", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library once; raises VBError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VBError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for the ViLBERT B200 kernels)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.vb_last_error.restype = C.c_char_p
+        _lib.vb_version.restype = C.c_int
+    return _lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib().vb_last_error().decode("utf-8", "replace")
+        raise VBError(f"{what or 'libvilbert_b200'} failed with status {status}: {msg}")
+
+
+def exported_symbols():
+    """Names declared in include/vilbert_b200.h (parsed), used by the ABI test."""
+    import re
+    hdr = os.path.join(_HERE, "..", "include", "vilbert_b200.h")
+    with open(hdr) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vb_[a-z0-9_]+)\s*\(", text)))

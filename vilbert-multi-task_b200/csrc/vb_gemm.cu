@@ -1,0 +1,472 @@
+// vb_gemm.cu — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = alpha * A[M,K] . B[N,K]^T  (bf16 operands, fp32 accumulation in TMEM) + fused epilogue.
+//
+// Replaces the aten addmm behind every nn.Linear on the ViLBERT hot path and its autograd
+// (reference: vilbert/vilbert.py:410-412,466,492,509,553-555,625,653,670,716-725,830,837,865-869 and
+// SURVEY.md appendix A). Design:
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D boxes (64 x rows, 128B swizzle) into a
+//               NUM_STAGES-deep smem ring, completion on mbarriers (complete_tx);
+//   warp 1      single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1), accumulators
+//               double-buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the
+//               main loop of tile i+1; tcgen05.commit releases smem stages / publishes accumulators;
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> padded smem transpose -> row-wise,
+//               128-bit coalesced pass doing bias / erf-GELU / GELU' / residual / bf16 conversion.
+// Operands may be K-major (nn.Linear forward) or MN-major (dgrad / wgrad operands read in place, no
+// transposed copies); both use the canonical SWIZZLE_128B UMMA layouts written directly by TMA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vb_internal.h"
+#include "vb_ptx.cuh"
+
+namespace vb {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // one 128-byte swizzle span of bf16
+constexpr int UK = 16;           // UMMA K for 16-bit inputs
+constexpr int GEMM_THREADS = 192;
+constexpr int STAGE_PAD = 33;    // fp32 staging row stride (conflict-free transpose)
+constexpr int STAGING_BYTES_PER_WARP = 32 * STAGE_PAD * 4;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NUM_STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES =
+      1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + 4 * STAGING_BYTES_PER_WARP + 256 /*barriers*/;
+};
+
+struct GemmKernelParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int split_k, k_blocks_per_split;
+  float alpha;
+  const float* bias;
+  const float* residual;
+  long long ld_res;
+  const __nv_bfloat16* aux;
+  long long ld_aux;
+  int act;
+  float* out_f32;
+  long long ld_of;
+  __nv_bfloat16* out_bf16;
+  long long ld_ob;
+  __nv_bfloat16* out_pre;
+  long long ld_op;
+  int atomic_out;
+  int vec_f32, vec_bf16, vec_pre, vec_res, vec_aux;  // 128/64-bit access legal for that buffer
+  uint64_t desc_base_a, desc_base_b;                 // smem descriptor without the address field
+  uint32_t kadv_a, kadv_b;                           // descriptor address advance per UMMA_K (bytes)
+  uint32_t idesc;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int NUM_STAGES = Cfg::NUM_STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_tiles = smem;
+  float* staging = reinterpret_cast<float*>(smem + NUM_STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * Cfg::STAGE_BYTES + 4 * STAGING_BYTES_PER_WARP);
+  uint64_t* full_bar = bars;                       // [NUM_STAGES]
+  uint64_t* empty_bar = bars + NUM_STAGES;         // [NUM_STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * NUM_STAGES; // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tmem_full_bar[s]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+  const int total_tiles = tiles_mn * p.split_k;
+
+  if (warp_idx == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile % p.split_k;
+        const int t2 = tile / p.split_k;
+        const int m_blk = t2 % p.num_m_blocks;
+        const int n_blk = t2 / p.num_m_blocks;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, fb);
+          } else {
+            tma_load_2d(sa, &tmap_a, kb * BK, m_blk * BM, fb);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BK * 128), &tmap_b, n_blk * BN + j * 64, kb * BK, fb);
+          } else {
+            tma_load_2d(sb, &tmap_b, kb * BK, n_blk * BN, fb);
+          }
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int split = tile % p.split_k;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = umma_desc_at(p.desc_base_a, sa + k * p.kadv_a);
+            const uint64_t db = umma_desc_at(p.desc_base_b, sb + k * p.kadv_b);
+            umma_bf16(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));  // smem slot free once these MMAs retire
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 2..5)
+    const int lane_grp = warp_idx & 3;  // TMEM lanes [32*lane_grp, +32) are visible to this warp
+    float* stg = staging + (warp_idx - 2) * (32 * STAGE_PAD);
+    const int rr = lane >> 3;           // row within a 4-row group of the coalesced pass
+    const int cc = (lane & 7) * 4;      // first of 4 columns handled by this lane
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int t2 = tile / p.split_k;
+      const int m_blk = t2 % p.num_m_blocks;
+      const int n_blk = t2 / p.num_m_blocks;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+      tc_fence_after();
+      const int m_base = m_blk * BM + lane_grp * 32;
+      const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n_chunk = n_blk * BN + c * 32;
+        uint32_t r[32];
+        if (n_chunk < p.N) {  // warp-uniform
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+        }
+        if (c == BN / 32 - 1) {
+          // every TMEM read of this accumulator stage has landed in registers
+          tc_fence_before();
+          mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        }
+        if (n_chunk >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * STAGE_PAD + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int n = n_chunk + cc;
+#pragma unroll 2
+        for (int ps = 0; ps < 8; ++ps) {
+          const int row = ps * 4 + rr;
+          const long long m = m_base + row;
+          if (m >= p.M || n >= p.N) continue;
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = stg[row * STAGE_PAD + cc + j] * p.alpha;
+          const bool full4 = (n + 3 < p.N);
+          const int nv = full4 ? 4 : (p.N - n);
+          if (p.bias) {
+            if (full4) {
+              // bias base is 16B aligned (checked on host) and n % 4 == 0
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n);
+              v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+            } else {
+              for (int j = 0; j < nv; ++j) v[j] += p.bias[n + j];
+            }
+          }
+          if (p.act == VB_ACT_GELU) {
+            if (p.out_pre) {
+              __nv_bfloat16* dst = p.out_pre + m * p.ld_op + n;
+              if (full4 && p.vec_pre) {
+                uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                *reinterpret_cast<uint2*>(dst) = pk;
+              } else {
+                for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16(v[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == VB_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == VB_ACT_DGELU) {
+            const __nv_bfloat16* src = p.aux + m * p.ld_aux + n;
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full4 && p.vec_aux) {
+              const uint2 pk = *reinterpret_cast<const uint2*>(src);
+              const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
+              const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+              x[0] = __low2float(lo); x[1] = __high2float(lo);
+              x[2] = __low2float(hi); x[3] = __high2float(hi);
+            } else {
+              for (int j = 0; j < nv; ++j) x[j] = __bfloat162float(src[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(x[j]);
+          }
+          if (p.residual) {
+            const float* src = p.residual + m * p.ld_res + n;
+            if (full4 && p.vec_res) {
+              const float4 r4 = *reinterpret_cast<const float4*>(src);
+              v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+            } else {
+              for (int j = 0; j < nv; ++j) v[j] += src[j];
+            }
+          }
+          if (p.out_f32) {
+            float* dst = p.out_f32 + m * p.ld_of + n;
+            if (p.atomic_out) {
+              for (int j = 0; j < nv; ++j) atomicAdd(dst + j, v[j]);
+            } else if (full4 && p.vec_f32) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+              for (int j = 0; j < nv; ++j) dst[j] = v[j];
+            }
+          }
+          if (p.out_bf16) {
+            __nv_bfloat16* dst = p.out_bf16 + m * p.ld_ob + n;
+            if (full4 && p.vec_bf16) {
+              uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+              *reinterpret_cast<uint2*>(dst) = pk;
+            } else {
+              for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 2D bf16 tensor map: inner extent `inner` (contiguous), outer extent `outer` with row pitch ld elements.
+static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error(VB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return VB_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
+                       cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+  return VB_OK;
+}
+
+static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace vb
+
+extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
+  using namespace vb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: null args");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: empty problem %dx%dx%d", a->M, a->N, a->K);
+  if (!a->A || !a->B) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: null operand");
+  if ((a->lda % 8) || (a->ldb % 8) || !aligned(a->A, 16) || !aligned(a->B, 16))
+    return set_error(VB_ERR_INVALID, "vb_gemm_bf16: operands need ld %% 8 == 0 and 16-byte aligned bases (lda=%lld ldb=%lld)",
+                     (long long)a->lda, (long long)a->ldb);
+  if (!a->out_f32 && !a->out_bf16) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: no output");
+  if (a->act == VB_ACT_DGELU && !a->aux) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: DGELU needs aux");
+  if (a->bias && !aligned(a->bias, 16)) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: bias must be 16-byte aligned");
+  if (a->atomic_out && (!a->out_f32 || a->out_bf16 || a->out_pre))
+    return set_error(VB_ERR_INVALID, "vb_gemm_bf16: atomic_out supports only out_f32");
+  int dev_sms = 0, cc = 0;
+  if (int s = vb_device_info(&dev_sms, &cc)) return s;
+  if (cc / 10 != 10) return set_error(VB_ERR_UNSUPPORTED, "vb_gemm_bf16: needs an sm_100 device (found sm_%d)", cc);
+
+  const int num_m = (a->M + BM - 1) / BM;
+  const int num_k = (a->K + BK - 1) / BK;
+  int max_ctas = a->max_ctas > 0 ? a->max_ctas : dev_sms;
+
+  // tile width: minimise (waves x tile width); ties go to the wider tile (less smem traffic per flop)
+  int bn = a->block_n;
+  if (bn == 0) {
+    auto cost = [&](int w) {
+      long long tiles = (long long)num_m * ((a->N + w - 1) / w);
+      long long waves = (tiles + max_ctas - 1) / max_ctas;
+      return waves * w;
+    };
+    bn = (a->N > 128 && cost(256) <= cost(128)) ? 256 : 128;
+  }
+  if (bn != 128 && bn != 256) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: block_n must be 0, 128 or 256");
+  const int num_n = (a->N + bn - 1) / bn;
+
+  int split_k = a->split_k;
+  if (split_k <= 0) {
+    split_k = 1;
+    if (a->atomic_out) {
+      const int tiles = num_m * num_n;
+      if (tiles * 2 <= max_ctas) split_k = max_ctas / tiles;
+      if (split_k > num_k) split_k = num_k;
+      if (split_k < 1) split_k = 1;
+    }
+  }
+  if (split_k > 1 && (!a->atomic_out || a->act != VB_ACT_NONE || a->bias || a->residual))
+    return set_error(VB_ERR_INVALID, "vb_gemm_bf16: split_k > 1 needs atomic_out and a plain epilogue");
+  int kps = (num_k + split_k - 1) / split_k;
+  split_k = (num_k + kps - 1) / kps;  // no empty splits
+
+  GemmKernelParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.num_m_blocks = num_m; p.num_n_blocks = num_n; p.num_k_blocks = num_k;
+  p.split_k = split_k; p.k_blocks_per_split = kps;
+  p.alpha = a->alpha;
+  p.bias = a->bias;
+  p.residual = a->residual; p.ld_res = a->ld_res;
+  p.aux = static_cast<const __nv_bfloat16*>(a->aux); p.ld_aux = a->ld_aux;
+  p.act = a->act;
+  p.out_f32 = a->out_f32; p.ld_of = a->ld_out_f32;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); p.ld_ob = a->ld_out_bf16;
+  p.out_pre = static_cast<__nv_bfloat16*>(a->out_pre); p.ld_op = a->ld_out_pre;
+  p.atomic_out = a->atomic_out;
+  p.vec_f32 = a->out_f32 && aligned(a->out_f32, 16) && (a->ld_out_f32 % 4 == 0);
+  p.vec_bf16 = a->out_bf16 && aligned(a->out_bf16, 8) && (a->ld_out_bf16 % 4 == 0);
+  p.vec_pre = a->out_pre && aligned(a->out_pre, 8) && (a->ld_out_pre % 4 == 0);
+  p.vec_res = a->residual && aligned(a->residual, 16) && (a->ld_res % 4 == 0);
+  p.vec_aux = a->aux && aligned(a->aux, 8) && (a->ld_aux % 4 == 0);
+
+  // smem matrix descriptors (see vb_ptx.cuh). K-major: rows of 128 B, 8-row groups 1024 B apart (SBO),
+  // K advance of 16 elements = 32 B inside the swizzle span. MN-major: 64-element (128 B) rows indexed
+  // by k, 8-k groups 1024 B apart (SBO), next 64 MN elements BK*128 B further (LBO); K advance of 16 = 2 groups.
+  const uint32_t lbo_a = a->dbg_lbo_a ? a->dbg_lbo_a : (a->a_mn_major ? BK * 128 : 16);
+  const uint32_t sbo_a = a->dbg_sbo_a ? a->dbg_sbo_a : 1024;
+  const uint32_t lbo_b = a->dbg_lbo_b ? a->dbg_lbo_b : (a->b_mn_major ? BK * 128 : 16);
+  const uint32_t sbo_b = a->dbg_sbo_b ? a->dbg_sbo_b : 1024;
+  p.desc_base_a = umma_desc_base(lbo_a, sbo_a);
+  p.desc_base_b = umma_desc_base(lbo_b, sbo_b);
+  p.kadv_a = a->a_mn_major ? 2 * 1024 : UK * 2;
+  p.kadv_b = a->b_mn_major ? 2 * 1024 : UK * 2;
+  p.idesc = umma_idesc_bf16(BM, bn, a->a_mn_major ? 1 : 0, a->b_mn_major ? 1 : 0);
+
+  CUtensorMap ta, tb;
+  int st;
+  if (a->a_mn_major) st = make_tmap(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
+  else               st = make_tmap(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
+  if (st) return st;
+  if (a->b_mn_major) st = make_tmap(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
+  else               st = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)bn);
+  if (st) return st;
+
+  const long long total_tiles = (long long)num_m * num_n * split_k;
+  const int grid = (int)(total_tiles < max_ctas ? total_tiles : max_ctas);
+
+#define VB_LAUNCH(BN_, AM_, BM_) return launch_gemm<BN_, AM_, BM_>(ta, tb, p, grid, stream)
+  if (bn == 256) {
+    if (!a->a_mn_major && !a->b_mn_major) VB_LAUNCH(256, false, false);
+    if (!a->a_mn_major && a->b_mn_major) VB_LAUNCH(256, false, true);
+    if (a->a_mn_major && !a->b_mn_major) VB_LAUNCH(256, true, false);
+    VB_LAUNCH(256, true, true);
+  } else {
+    if (!a->a_mn_major && !a->b_mn_major) VB_LAUNCH(128, false, false);
+    if (!a->a_mn_major && a->b_mn_major) VB_LAUNCH(128, false, true);
+    if (a->a_mn_major && !a->b_mn_major) VB_LAUNCH(128, true, false);
+    VB_LAUNCH(128, true, true);
+  }
+#undef VB_LAUNCH
+}
