@@ -1,0 +1,169 @@
+"""ORACLE — TEST INFRASTRUCTURE. Pins oracle/vilbert_oracle.py against the real reference and writes
+the golden fixtures of tests/golden/. Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+For every case it (1) builds the reference VILBertForVLTasks (or BertForMultiModalPreTraining) from a
+config, loads oracle.synth_params into it with load_state_dict, (2) runs reference and oracle on the
+same synthetic inputs in fp32 eval mode, forward and backward, (3) asserts they agree to 1e-5 relative
+(max-abs / max-abs), and (4) stores summaries (and full tensors for the tiny case) that
+tests/test_oracle_golden.py re-checks without the reference.
+"""
+import json
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_loader, vilbert_oracle as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+TOL = 1e-5
+
+TINY = dict(vocab_size=120, hidden_size=64, num_hidden_layers=3, num_attention_heads=4, intermediate_size=128,
+            max_position_embeddings=40, type_vocab_size=2, v_feature_size=48, v_target_size=21, v_hidden_size=96,
+            v_num_hidden_layers=2, v_num_attention_heads=3, v_intermediate_size=80, bi_hidden_size=64,
+            bi_num_attention_heads=2, v_biattention_id=[0, 1], t_biattention_id=[1, 2],
+            hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, v_hidden_dropout_prob=0.1,
+            v_attention_probs_dropout_prob=0.1)
+
+
+def ref_config_json(name):
+    with open(os.path.join(ref_loader.REFERENCE_ROOT, "config", name)) as f:
+        return json.load(f)
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def summary(t):
+    t = t.detach().double().flatten()
+    n = t.numel(); k = min(16, n)
+    idx = (torch.arange(k, dtype=torch.int64) * (n - 1)) // max(k - 1, 1)
+    return dict(shape=None, mean=t.mean().item(), absmax=t.abs().max().item(), l2=t.norm().item(),
+                samples=t[idx].tolist(), sample_idx=idx.tolist())
+
+
+def run_case(ref, name, cfg_json, B, Nv, Nt, task_tokens=False, qk_scale=1.0, full=False, grads=True, seed=0):
+    cfgj = dict(cfg_json)
+    if task_tokens:
+        cfgj["task_specific_tokens"] = True
+    cfg = O.make_config(cfgj)
+    rcfg = ref.BertConfig.from_dict(cfgj)
+    torch.manual_seed(0)
+    model = ref.VILBertForVLTasks(rcfg, num_labels=1, default_gpu=False)
+    P = O.synth_params(cfg, seed=seed, qk_scale=qk_scale)
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    assert all("decoder.weight" in m for m in missing), missing
+    model.tie_weights()
+    model.eval()
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=1234 + seed)
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+            inp["image_attention_mask"], inp["co_attention_mask"], inp["task_ids"])
+    # ---- reference
+    ref_heads = model(*args)[:9]
+    ref_bert = model.bert(*args)[:4]
+    # ---- oracle
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, *args)
+    errs = {}
+    for n, a, b in zip(O.BERT_OUT_NAMES, bert_o, ref_bert):
+        errs[n] = rel(a, b)
+    for n, a, b in zip(O.HEAD_NAMES, heads_o, ref_heads):
+        errs[n] = rel(a, b)
+    grad_errs = {}
+    gold = dict(name=name, config=cfgj, B=B, Nv=Nv, Nt=Nt, task_tokens=task_tokens, qk_scale=qk_scale, seed=seed,
+                outputs={}, grads={})
+    for n, a in list(zip(O.BERT_OUT_NAMES, bert_o)) + list(zip(O.HEAD_NAMES, heads_o)):
+        s = summary(a); s["shape"] = list(a.shape); gold["outputs"][n] = s
+    if grads:
+        tgt = O.synth_vqa_target(B, 3129)
+        # a loss touching every head so that every parameter with a grad path is exercised
+        def total_loss(heads, bert):
+            l = O.vqa_loss(heads[0], tgt)
+            for h in heads[1:]:
+                l = l + 0.1 * h.float().clamp(-50, 50).pow(2).mean()
+            return l
+        lo = total_loss(heads_o, bert_o)
+        lo.backward()
+        model.zero_grad()
+        lr = total_loss(ref_heads, ref_bert)
+        lr.backward()
+        errs["loss"] = abs(lo.item() - lr.item()) / abs(lr.item())
+        gold["loss"] = lr.item()
+        ref_named = dict(model.named_parameters())
+        for k, v in Pg.items():
+            if k == "cls.predictions.decoder.weight":
+                continue
+            rg = ref_named[k].grad
+            if rg is None:
+                assert v.grad is None or v.grad.abs().max() == 0, k
+                continue
+            grad_errs[k] = rel(v.grad, rg)
+            s = summary(v.grad); s["shape"] = list(v.grad.shape); gold["grads"][k] = s
+    worst = max(list(errs.values()) + list(grad_errs.values()))
+    print(f"{name:28s} outputs worst {max(errs.values()):.2e}  grads worst {max(grad_errs.values()) if grad_errs else 0:.2e}")
+    assert worst < TOL, (name, {k: v for k, v in {**errs, **grad_errs}.items() if v >= TOL})
+    gold["pin"] = dict(worst_output_rel=max(errs.values()), worst_grad_rel=max(grad_errs.values()) if grad_errs else 0.0,
+                       tolerance=TOL, reference="facebookresearch/vilbert-multi-task@f22b84a vilbert/vilbert.py")
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump(gold, f)
+    if full:
+        torch.save(dict(inputs={k: v for k, v in inp.items() if v is not None},
+                        bert={n: a.detach() for n, a in zip(O.BERT_OUT_NAMES, ref_bert)},
+                        heads={n: a.detach() for n, a in zip(O.HEAD_NAMES, ref_heads)},
+                        grads={k: ref_named[k].grad.clone() for k in grad_errs}),
+                   os.path.join(GOLD, name + ".pt"))
+
+
+def run_pretraining_case(ref, name, cfg_json, B, Nv, Nt):
+    cfg = O.make_config(cfg_json)
+    rcfg = ref.BertConfig.from_dict(dict(cfg_json))
+    model = ref.BertForMultiModalPreTraining(rcfg)
+    P = O.synth_params(cfg, seed=3, with_task_heads=False)
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    model.tie_weights(); model.eval()
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=77)
+    g = torch.Generator().manual_seed(5)
+    lm = torch.full((B, Nt), -1, dtype=torch.long)
+    sel = torch.rand(B, Nt, generator=g) < 0.15; sel[:, 1] = True
+    lm[sel] = torch.randint(0, cfg["vocab_size"], (int(sel.sum()),), generator=g)
+    il = torch.full((B, Nv - 1), -1, dtype=torch.long); il[torch.rand(B, Nv - 1, generator=g) < 0.15] = 1; il[:, 0] = 1
+    it = torch.softmax(torch.randn(B, Nv - 1, cfg["v_target_size"], generator=g), -1)
+    ns = torch.randint(0, 2, (B,), generator=g)
+    a = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+         inp["image_attention_mask"], lm, il, it, ns)
+    lr = model(*a)
+    lo = O.pretraining_losses(P, cfg, *a)
+    errs = [abs(x.item() - y.item()) / abs(y.item()) for x, y in zip(lo, lr)]
+    print(f"{name:28s} losses rel err {max(errs):.2e}  ({[round(float(x), 5) for x in lr]})")
+    assert max(errs) < TOL
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump(dict(name=name, config=cfg_json, B=B, Nv=Nv, Nt=Nt, losses=[float(x) for x in lr],
+                       pin=dict(worst=max(errs), tolerance=TOL)), f)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref = ref_loader.load()
+    torch.set_num_threads(8)
+    run_case(ref, "tiny_b4", TINY, B=4, Nv=11, Nt=9, full=True)
+    run_case(ref, "tiny_tasktok_odd_b3", TINY, B=3, Nv=7, Nt=12, task_tokens=True, full=True, seed=1)
+    run_case(ref, "tiny_peaked_b2", TINY, B=2, Nv=37, Nt=21, qk_scale=8.0, full=True, seed=2)
+    base22 = ref_config_json("bert_base_2layer_2conect.json")
+    run_case(ref, "base_2layer_2conect_cfg1", base22, B=2, Nv=36, Nt=20, seed=0)           # BASELINE.json configs[0]
+    base66 = ref_config_json("bert_base_6layer_6conect.json")
+    run_case(ref, "base_6layer_6conect_b4", base66, B=4, Nv=100, Nt=36, seed=0)           # configs[1] shape, small B
+    run_case(ref, "base_6layer_6conect_tasktok", base66, B=2, Nv=101, Nt=23, task_tokens=True, grads=False, seed=1)
+    run_pretraining_case(ref, "tiny_pretraining_losses", TINY, B=4, Nv=9, Nt=8)
+    print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

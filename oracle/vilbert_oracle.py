@@ -1,0 +1,380 @@
+"""ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+fp32 restatement (plain torch, device-agnostic, autograd-capable) of the ViLBERT two-stream hot path
+of facebookresearch/vilbert-multi-task @ f22b84a, function by function, keyed on the reference's own
+state_dict names. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+leg may import this module; the product (vilbert-multi-task_b200/) never does.
+
+Pinning: the reference ships no golden vectors or model tests for this path, so
+this restatement is pinned against the reference ITSELF: oracle/make_golden.py imports
+/root/reference/vilbert/vilbert.py in the build container, checks that every output and gradient of
+this file equals the reference's (fp32, max-abs-diff <= 1e-5 relative) on every config of
+tests/golden/, and writes the fixtures that tests/test_oracle_golden.py re-checks everywhere
+(including the GPU box, where /root/reference does not exist).
+
+Each function cites the reference lines (vilbert/vilbert.py unless noted) it follows.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------- config defaults
+# BertConfig.__init__ defaults (vilbert.py:145-185); from_dict starts from these (:263-268).
+CONFIG_DEFAULTS = dict(
+    vocab_size=-1, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+    hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, max_position_embeddings=512,
+    type_vocab_size=2, initializer_range=0.02, v_feature_size=2048, v_target_size=1601, v_hidden_size=768,
+    v_num_hidden_layers=3, v_num_attention_heads=12, v_intermediate_size=3072, bi_hidden_size=1024,
+    bi_num_attention_heads=16, v_attention_probs_dropout_prob=0.1, v_hidden_act="gelu", v_hidden_dropout_prob=0.1,
+    v_initializer_range=0.2, v_biattention_id=[0, 1], t_biattention_id=[10, 11], visual_target=0, fast_mode=False,
+    fixed_v_layer=0, fixed_t_layer=0, in_batch_pairs=False, fusion_method="mul", dynamic_attention=False,
+    with_coattention=True, objective=0, num_negative=128, model="bert", task_specific_tokens=False,
+    visualization=False,
+)
+
+
+def make_config(json_dict):
+    cfg = dict(CONFIG_DEFAULTS)
+    cfg.update(json_dict)
+    return cfg
+
+
+# --------------------------------------------------------------------------- primitives
+def gelu(x):
+    """vilbert.py:111-117 — exact erf GELU."""
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def layer_norm(x, w, b, eps=1e-12):
+    """vilbert.py:304-317 — biased variance, eps inside the sqrt, affine after."""
+    u = x.mean(-1, keepdim=True)
+    s = (x - u).pow(2).mean(-1, keepdim=True)
+    return w * ((x - u) / torch.sqrt(s + eps)) + b
+
+
+def linear(P, name, x):
+    return F.linear(x, P[name + ".weight"], P.get(name + ".bias"))
+
+
+def _heads(x, n_heads):
+    """transpose_for_scores, vilbert.py:416-422 / :732-739."""
+    B, N, H = x.shape
+    return x.view(B, N, n_heads, H // n_heads).permute(0, 2, 1, 3)
+
+
+def attention(q, k, v, add_mask, n_heads):
+    """QK^T / sqrt(d) + mask -> softmax -> PV -> merge heads (vilbert.py:434-449, :593-608, :771-809).
+    add_mask is the additive [B,1,1,Nk] mask (0 / -10000). Dropout on the probabilities is identity
+    here (eval mode / p=0: the parity protocol of SURVEY.md §8c)."""
+    q, k, v = _heads(q, n_heads), _heads(k, n_heads), _heads(v, n_heads)
+    s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
+    s = s + add_mask
+    p = torch.softmax(s, dim=-1)
+    ctx = torch.matmul(p, v).permute(0, 2, 1, 3).contiguous()
+    return ctx.view(ctx.shape[0], ctx.shape[1], -1)
+
+
+# --------------------------------------------------------------------------- encoder blocks
+def text_layer(P, pre, cfg, h, mask):
+    """BertLayer.forward, vilbert.py:527-533 (= BertSelfAttention :424-460, BertSelfOutput :470-474,
+    BertIntermediate :500-503, BertOutput :513-517)."""
+    a = pre + ".attention"
+    ctx = attention(linear(P, a + ".self.query", h), linear(P, a + ".self.key", h), linear(P, a + ".self.value", h),
+                    mask, cfg["num_attention_heads"])
+    h1 = layer_norm(linear(P, a + ".output.dense", ctx) + h, P[a + ".output.LayerNorm.weight"], P[a + ".output.LayerNorm.bias"])
+    f = gelu(linear(P, pre + ".intermediate.dense", h1))
+    return layer_norm(linear(P, pre + ".output.dense", f) + h1, P[pre + ".output.LayerNorm.weight"], P[pre + ".output.LayerNorm.bias"])
+
+
+def image_layer(P, pre, cfg, h, mask):
+    """BertImageLayer.forward, vilbert.py:688-694 (self-attn :571-619 with dynamic_attention off,
+    :629-633, :661-664, :674-678). Same block on the visual stream."""
+    a = pre + ".attention"
+    ctx = attention(linear(P, a + ".self.query", h), linear(P, a + ".self.key", h), linear(P, a + ".self.value", h),
+                    mask, cfg["v_num_attention_heads"])
+    h1 = layer_norm(linear(P, a + ".output.dense", ctx) + h, P[a + ".output.LayerNorm.weight"], P[a + ".output.LayerNorm.bias"])
+    f = gelu(linear(P, pre + ".intermediate.dense", h1))
+    return layer_norm(linear(P, pre + ".output.dense", f) + h1, P[pre + ".output.LayerNorm.weight"], P[pre + ".output.LayerNorm.bias"])
+
+
+def connection_layer(P, pre, cfg, v, mask_v, t, mask_t):
+    """BertConnectionLayer.forward, vilbert.py:871-900. Subscript 1 = vision, 2 = text.
+    BertBiAttention :738-823: ctx1 = text queries over vision keys/values, ctx2 = vision queries over
+    text keys/values; BertBiOutput :844-855 with the argument swap of :890-892 (ctx2 -> vision stream
+    via dense1/LayerNorm1, ctx1 -> text stream via dense2/LayerNorm2); q_dense1/2 are never called."""
+    b = pre + ".biattention"
+    nh = cfg["bi_num_attention_heads"]
+    q1, k1, v1 = linear(P, b + ".query1", v), linear(P, b + ".key1", v), linear(P, b + ".value1", v)
+    q2, k2, v2 = linear(P, b + ".query2", t), linear(P, b + ".key2", t), linear(P, b + ".value2", t)
+    ctx1 = attention(q2, k1, v1, mask_v, nh)   # [B,Nt,Hb]
+    ctx2 = attention(q1, k2, v2, mask_t, nh)   # [B,Nv,Hb]
+    o = pre + ".biOutput"
+    v1_ = layer_norm(linear(P, o + ".dense1", ctx2) + v, P[o + ".LayerNorm1.weight"], P[o + ".LayerNorm1.bias"])
+    t1_ = layer_norm(linear(P, o + ".dense2", ctx1) + t, P[o + ".LayerNorm2.weight"], P[o + ".LayerNorm2.bias"])
+    fv = gelu(linear(P, pre + ".v_intermediate.dense", v1_))
+    v2_ = layer_norm(linear(P, pre + ".v_output.dense", fv) + v1_, P[pre + ".v_output.LayerNorm.weight"], P[pre + ".v_output.LayerNorm.bias"])
+    ft = gelu(linear(P, pre + ".t_intermediate.dense", t1_))
+    t2_ = layer_norm(linear(P, pre + ".t_output.dense", ft) + t1_, P[pre + ".t_output.LayerNorm.weight"], P[pre + ".t_output.LayerNorm.bias"])
+    return v2_, t2_
+
+
+def encoder(P, pre, cfg, t, v, mask_t, mask_v):
+    """BertEncoder.forward interleaving schedule, vilbert.py:934-1107 (fixed layers, in_batch_pairs,
+    FAST_MODE off; with_coattention honoured). Returns the per-connection-layer outputs too
+    (output_all_encoded_layers, :1075-1077)."""
+    t_start = v_start = 0
+    all_t, all_v = [], []
+    n_t, n_v = cfg["num_hidden_layers"], cfg["v_num_hidden_layers"]
+    for count, (v_end, t_end) in enumerate(zip(cfg["v_biattention_id"], cfg["t_biattention_id"])):
+        for i in range(t_start, t_end):
+            t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t)
+        for i in range(v_start, v_end):
+            v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v)
+        if cfg["with_coattention"]:
+            v, t = connection_layer(P, f"{pre}.c_layer.{count}", cfg, v, mask_v, t, mask_t)
+        v_start, t_start = v_end, t_end
+        all_t.append(t)
+        all_v.append(v)
+    for i in range(v_start, n_v):
+        v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v)
+    for i in range(t_start, n_t):
+        t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t)
+    return t, v, all_t, all_v
+
+
+# --------------------------------------------------------------------------- embeddings / model
+def text_embeddings(P, pre, cfg, input_ids, token_type_ids, task_ids):
+    """BertEmbeddings.forward, vilbert.py:346-367. Positions are always arange(seq) (:349-352); the task
+    embedding row is inserted at index 1 after the sum (:358-362); LN after the concat. padding_idx=0 on
+    the word embeddings (:328-330) only zeroes that row's gradient."""
+    B, N = input_ids.shape
+    pos = torch.arange(N, device=input_ids.device).unsqueeze(0).expand(B, N)
+    e = (F.embedding(input_ids, P[pre + ".word_embeddings.weight"], padding_idx=0) + F.embedding(pos, P[pre + ".position_embeddings.weight"])
+         + F.embedding(token_type_ids, P[pre + ".token_type_embeddings.weight"]))
+    if cfg["task_specific_tokens"]:
+        te = F.embedding(task_ids, P[pre + ".task_embeddings.weight"])
+        e = torch.cat([e[:, 0:1], te, e[:, 1:]], dim=1)
+    return layer_norm(e, P[pre + ".LayerNorm.weight"], P[pre + ".LayerNorm.bias"])
+
+
+def image_embeddings(P, pre, feat, loc):
+    """BertImageEmbeddings.forward, vilbert.py:1421-1432."""
+    return layer_norm(linear(P, pre + ".image_embeddings", feat) + linear(P, pre + ".image_location_embeddings", loc),
+                      P[pre + ".LayerNorm.weight"], P[pre + ".LayerNorm.bias"])
+
+
+def bert_model(P, cfg, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None,
+               image_attention_mask=None, co_attention_mask=None, task_ids=None, prefix="bert",
+               output_all_encoded_layers=False):
+    """BertModel.forward, vilbert.py:1309-1406: default masks :1322-1329, task-token mask extension
+    :1331-1334, additive masks (1-m)*-10000 :1341-1362, embeddings, encoder, poolers (:1116-1122,
+    :1131-1137: Linear+ReLU on token 0). co_attention_mask is accepted and unused (:774-775, :796-797)."""
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_txt)
+    if token_type_ids is None:
+        token_type_ids = torch.zeros_like(input_txt)
+    if image_attention_mask is None:
+        image_attention_mask = torch.ones(input_imgs.shape[0], input_imgs.shape[1], device=input_txt.device).type_as(input_txt)
+    if cfg["task_specific_tokens"]:
+        attention_mask = torch.cat([torch.ones_like(attention_mask[:, :1]), attention_mask], dim=1)
+    dt = P[prefix + ".embeddings.word_embeddings.weight"].dtype
+    mask_t = (1.0 - attention_mask[:, None, None, :].to(dt)) * -10000.0
+    mask_v = (1.0 - image_attention_mask[:, None, None, :].to(dt)) * -10000.0
+    t = text_embeddings(P, prefix + ".embeddings", cfg, input_txt, token_type_ids, task_ids)
+    v = image_embeddings(P, prefix + ".v_embeddings", input_imgs, image_loc)
+    t, v, all_t, all_v = encoder(P, prefix + ".encoder", cfg, t, v, mask_t, mask_v)
+    pooled_t = torch.relu(linear(P, prefix + ".t_pooler.dense", t[:, 0]))
+    pooled_v = torch.relu(linear(P, prefix + ".v_pooler.dense", v[:, 0]))
+    if output_all_encoded_layers:
+        return all_t, all_v, pooled_t, pooled_v
+    return t, v, pooled_t, pooled_v
+
+
+# --------------------------------------------------------------------------- heads
+def simple_classifier(P, pre, x):
+    """SimpleClassifier, vilbert.py:1711-1722: Linear -> GeLU -> LayerNorm -> Linear."""
+    h = gelu(linear(P, pre + ".logit_fc.0", x))
+    h = layer_norm(h, P[pre + ".logit_fc.2.weight"], P[pre + ".logit_fc.2.bias"])
+    return linear(P, pre + ".logit_fc.3", h)
+
+
+def pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v, prefix="cls"):
+    """BertPreTrainingHeads.forward, vilbert.py:1228-1243; LM head :1193-1196 (decoder tied to the word
+    embeddings, :1190, + output-only bias); image head :1255-1258; transforms :1152-1156, :1172-1176."""
+    pooled = pooled_t * pooled_v if cfg["fusion_method"] == "mul" else pooled_t + pooled_v
+    ht = layer_norm(gelu(linear(P, prefix + ".predictions.transform.dense", seq_t)),
+                    P[prefix + ".predictions.transform.LayerNorm.weight"], P[prefix + ".predictions.transform.LayerNorm.bias"])
+    dec_w = P.get(prefix + ".predictions.decoder.weight", P["bert.embeddings.word_embeddings.weight"])
+    scores_t = F.linear(ht, dec_w) + P[prefix + ".predictions.bias"]
+    seq_rel = linear(P, prefix + ".bi_seq_relationship", pooled)
+    hv = layer_norm(gelu(linear(P, prefix + ".imagePredictions.transform.dense", seq_v)),
+                    P[prefix + ".imagePredictions.transform.LayerNorm.weight"], P[prefix + ".imagePredictions.transform.LayerNorm.bias"])
+    scores_v = linear(P, prefix + ".imagePredictions.decoder", hv)
+    return scores_t, scores_v, seq_rel
+
+
+def vilbert_for_vl_tasks(P, cfg, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None,
+                         image_attention_mask=None, co_attention_mask=None, task_ids=None):
+    """VILBertForVLTasks.forward, vilbert.py:1638-1708 (eval mode: every dropout is identity). Returns
+    the reference's tuple order (:1697-1708) minus all_attention_mask, preceded by the BertModel outputs:
+    (seq_t, seq_v, pooled_t, pooled_v), (vil_prediction, vil_prediction_gqa, vil_logit,
+    vil_binary_prediction, vil_tri_prediction, vision_prediction, vision_logit, linguisic_prediction,
+    linguisic_logit)."""
+    seq_t, seq_v, pooled_t, pooled_v = bert_model(P, cfg, input_txt, input_imgs, image_loc, token_type_ids, attention_mask,
+                                                  image_attention_mask, co_attention_mask, task_ids)
+    linguisic_prediction, vision_prediction, vil_binary_prediction = pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v)
+    pooled = pooled_t * pooled_v if cfg["fusion_method"] == "mul" else pooled_t + pooled_v
+    vil_prediction = simple_classifier(P, "vil_prediction", pooled)
+    vil_prediction_gqa = simple_classifier(P, "vil_prediction_gqa", pooled)
+    if pooled.shape[0] % 2 == 0:  # :1686-1689 — pairs consecutive samples; odd B keeps the NSP-style output
+        vil_binary_prediction = simple_classifier(P, "vil_binary_prediction", pooled.view(-1, pooled.shape[1] * 2))
+    vil_logit = linear(P, "vil_logit", pooled)
+    vil_tri_prediction = linear(P, "vil_tri_prediction", pooled)
+    dt = seq_v.dtype
+    vision_logit = linear(P, "vision_logit", seq_v) + ((1.0 - image_attention_mask.to(dt)) * -10000.0).unsqueeze(2)
+    linguisic_logit = linear(P, "linguisic_logit", seq_t)
+    return (seq_t, seq_v, pooled_t, pooled_v), (vil_prediction, vil_prediction_gqa, vil_logit, vil_binary_prediction,
+                                                vil_tri_prediction, vision_prediction, vision_logit, linguisic_prediction,
+                                                linguisic_logit)
+
+
+HEAD_NAMES = ("vil_prediction", "vil_prediction_gqa", "vil_logit", "vil_binary_prediction", "vil_tri_prediction",
+              "vision_prediction", "vision_logit", "linguisic_prediction", "linguisic_logit")
+BERT_OUT_NAMES = ("sequence_output_t", "sequence_output_v", "pooled_output_t", "pooled_output_v")
+
+
+def pretraining_losses(P, cfg, input_ids, image_feat, image_loc, token_type_ids, attention_mask, image_attention_mask,
+                       masked_lm_labels, image_label, image_target, next_sentence_label):
+    """BertForMultiModalPreTraining.forward with labels, visual_target == 0, vilbert.py:1471-1590:
+    masked-LM CE (ignore_index -1), masked-region KL-div against the soft target (global region dropped,
+    :1506; normalised by max(sum(image_label == 1), 0) as written at :1521), NSP/alignment CE."""
+    seq_t, seq_v, pooled_t, pooled_v = bert_model(P, cfg, input_ids, image_feat, image_loc, token_type_ids, attention_mask,
+                                                  image_attention_mask)
+    scores_t, scores_v, seq_rel = pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v)
+    scores_v = scores_v[:, 1:]
+    img_loss = F.kl_div(F.log_softmax(scores_v, dim=2), image_target, reduction="none")
+    masked_img_loss = torch.sum(img_loss * (image_label == 1).unsqueeze(2).float()) / max(torch.sum(image_label == 1), 0)
+    masked_lm_loss = F.cross_entropy(scores_t.view(-1, scores_t.shape[-1]), masked_lm_labels.view(-1), ignore_index=-1)
+    nsp_loss = F.cross_entropy(seq_rel.view(-1, 2), next_sentence_label.view(-1), ignore_index=-1)
+    return masked_lm_loss, masked_img_loss, nsp_loss
+
+
+# --------------------------------------------------------------------------- parameters / inputs
+def param_shapes(cfg, with_task_heads=True):
+    """Reference state_dict names -> shapes. nn.Linear.weight is [out, in]."""
+    Ht, It, Hv, Iv, Hb = cfg["hidden_size"], cfg["intermediate_size"], cfg["v_hidden_size"], cfg["v_intermediate_size"], cfg["bi_hidden_size"]
+    S = {}
+
+    def lin(n, o, i):
+        S[n + ".weight"] = (o, i); S[n + ".bias"] = (o,)
+
+    def ln(n, h):
+        S[n + ".weight"] = (h,); S[n + ".bias"] = (h,)
+
+    S["bert.embeddings.word_embeddings.weight"] = (cfg["vocab_size"], Ht)
+    S["bert.embeddings.position_embeddings.weight"] = (cfg["max_position_embeddings"], Ht)
+    S["bert.embeddings.token_type_embeddings.weight"] = (cfg["type_vocab_size"], Ht)
+    ln("bert.embeddings.LayerNorm", Ht)
+    if cfg["task_specific_tokens"]:
+        S["bert.embeddings.task_embeddings.weight"] = (20, Ht)
+    lin("bert.v_embeddings.image_embeddings", Hv, cfg["v_feature_size"])
+    lin("bert.v_embeddings.image_location_embeddings", Hv, 5)
+    ln("bert.v_embeddings.LayerNorm", Hv)
+    for kind, n, H, I in (("layer", cfg["num_hidden_layers"], Ht, It), ("v_layer", cfg["v_num_hidden_layers"], Hv, Iv)):
+        for i in range(n):
+            p = f"bert.encoder.{kind}.{i}"
+            for nm in ("query", "key", "value"):
+                lin(f"{p}.attention.self.{nm}", H, H)
+            lin(f"{p}.attention.output.dense", H, H); ln(f"{p}.attention.output.LayerNorm", H)
+            lin(f"{p}.intermediate.dense", I, H)
+            lin(f"{p}.output.dense", H, I); ln(f"{p}.output.LayerNorm", H)
+    for i in range(len(cfg["v_biattention_id"])):
+        p = f"bert.encoder.c_layer.{i}"
+        for nm in ("query1", "key1", "value1"):
+            lin(f"{p}.biattention.{nm}", Hb, Hv)
+        for nm in ("query2", "key2", "value2"):
+            lin(f"{p}.biattention.{nm}", Hb, Ht)
+        lin(f"{p}.biOutput.dense1", Hv, Hb); ln(f"{p}.biOutput.LayerNorm1", Hv); lin(f"{p}.biOutput.q_dense1", Hv, Hb)
+        lin(f"{p}.biOutput.dense2", Ht, Hb); ln(f"{p}.biOutput.LayerNorm2", Ht); lin(f"{p}.biOutput.q_dense2", Ht, Hb)
+        lin(f"{p}.v_intermediate.dense", Iv, Hv); lin(f"{p}.v_output.dense", Hv, Iv); ln(f"{p}.v_output.LayerNorm", Hv)
+        lin(f"{p}.t_intermediate.dense", It, Ht); lin(f"{p}.t_output.dense", Ht, It); ln(f"{p}.t_output.LayerNorm", Ht)
+    lin("bert.t_pooler.dense", Hb, Ht); lin("bert.v_pooler.dense", Hb, Hv)
+    S["cls.predictions.bias"] = (cfg["vocab_size"],)
+    lin("cls.predictions.transform.dense", Ht, Ht); ln("cls.predictions.transform.LayerNorm", Ht)
+    S["cls.predictions.decoder.weight"] = (cfg["vocab_size"], Ht)   # tied to the word embeddings
+    lin("cls.bi_seq_relationship", 2, Hb)
+    lin("cls.imagePredictions.transform.dense", Hv, Hv); ln("cls.imagePredictions.transform.LayerNorm", Hv)
+    lin("cls.imagePredictions.decoder", cfg["v_target_size"], Hv)
+    if with_task_heads:
+        for nm, i, o in (("vil_prediction", Hb, 3129), ("vil_prediction_gqa", Hb, 1533), ("vil_binary_prediction", 2 * Hb, 2)):
+            lin(f"{nm}.logit_fc.0", 2 * Hb, i); ln(f"{nm}.logit_fc.2", 2 * Hb); lin(f"{nm}.logit_fc.3", o, 2 * Hb)
+        lin("vil_logit", 1, Hb); lin("vil_tri_prediction", 3, Hb); lin("vision_logit", 1, Hv); lin("linguisic_logit", 1, Ht)
+    return S
+
+
+def synth_params(cfg, seed=0, dtype=torch.float32, device="cpu", with_task_heads=True, qk_scale=1.0):
+    """Deterministic parameters independent of module construction order: each tensor is drawn from its
+    own generator seeded by (seed, name). Weights ~ N(0, 0.02) like init_weights (vilbert.py:1274-1285) but
+    biases and LayerNorm affine are also randomised so that they are exercised. qk_scale > 1 multiplies
+    the query/key weights to create peaked softmax rows (SURVEY.md §8c adversarial case i)."""
+    import zlib
+    P = {}
+    for name, shape in param_shapes(cfg, with_task_heads).items():
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) & 0x7FFFFFFF)
+        if name == "cls.predictions.decoder.weight":
+            continue
+        if ".LayerNorm" in name or ".logit_fc.2." in name:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g) if name.endswith("weight") else 0.05 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        else:
+            t = 0.02 * torch.randn(shape, generator=g)
+            if qk_scale != 1.0 and any(k in name for k in (".query", ".key")):
+                t = t * qk_scale
+        P[name] = t.to(dtype).to(device)
+    P["cls.predictions.decoder.weight"] = P["bert.embeddings.word_embeddings.weight"]
+    return P
+
+
+def synth_inputs(cfg, B, Nv, Nt, seed=1234, device="cpu", ragged=True, task_id=None):
+    """Synthetic (region-feature, token-id) batch, SURVEY.md §8d "Synthetic inputs": post-ReLU features,
+    row 0 = mean of the valid rows / (0,0,1,1,1) box, prefix-valid masks."""
+    g = torch.Generator().manual_seed(seed)
+    V = cfg["vocab_size"]
+    ids = torch.randint(0, V, (B, Nt), generator=g)
+    ids[:, 0] = 101 % V
+    if ragged:
+        lt = torch.randint((Nt + 1) // 2, Nt + 1, (B,), generator=g)
+        lv = torch.randint(min(10, Nv), Nv + 1, (B,), generator=g)
+        lt[0] = 1 if B > 2 else lt[0]       # a length-1 text row (only CLS valid)
+    else:
+        lt = torch.full((B,), Nt); lv = torch.full((B,), Nv)
+    am = (torch.arange(Nt)[None] < lt[:, None]).long()
+    im = (torch.arange(Nv)[None] < lv[:, None]).long()
+    feat = torch.relu(torch.randn(B, Nv, cfg["v_feature_size"], generator=g)) * im[..., None]
+    denom = (im[:, 1:].sum(1, keepdim=True).clamp_min(1)).float()
+    feat[:, 0] = (feat[:, 1:] * im[:, 1:, None]).sum(1) / denom
+    xy = torch.rand(B, Nv, 2, generator=g) * 0.7
+    wh = 0.05 + torch.rand(B, Nv, 2, generator=g) * 0.25
+    loc = torch.cat([xy, xy + wh, (wh[..., :1] * wh[..., 1:])], dim=-1) * im[..., None]
+    loc[:, 0] = torch.tensor([0.0, 0.0, 1.0, 1.0, 1.0])
+    out = dict(input_txt=ids, input_imgs=feat, image_loc=loc, token_type_ids=torch.zeros_like(ids), attention_mask=am,
+               image_attention_mask=im, co_attention_mask=torch.zeros(B, Nv, Nt), task_ids=None)
+    if cfg["task_specific_tokens"]:
+        out["task_ids"] = torch.full((B, 1), 1 if task_id is None else task_id, dtype=torch.long)
+    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
+def vqa_loss(vil_prediction, target):
+    """task_utils.py:325-327 — BCE-with-logits, mean, times the number of answers."""
+    return F.binary_cross_entropy_with_logits(vil_prediction, target, reduction="mean") * target.shape[1]
+
+
+def synth_vqa_target(B, n_ans=3129, seed=99, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    tgt = torch.zeros(B, n_ans)
+    idx = torch.randint(0, n_ans, (B, 3), generator=g)
+    val = torch.tensor([0.3, 0.6, 0.9, 1.0])[torch.randint(0, 4, (B, 3), generator=g)]
+    tgt.scatter_(1, idx, val)
+    return tgt.to(device)
