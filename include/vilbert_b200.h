@@ -94,6 +94,110 @@ typedef struct vb_gemm_args {
 
 vb_status vb_gemm_bf16(const vb_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention:  P = softmax(Q K^T * scale + mask[b, key]),  O = P V, heads merged in the output.
+ * Replaces BertSelfAttention.forward (vilbert.py:424-460), BertImageSelfAttention.forward (:571-619,
+ * dynamic_attention off) and both directions of BertBiAttention.forward (:771-809), including the
+ * transpose_for_scores / permute().contiguous() layout ops (:416-422, :447-449).
+ *   Q: bf16, element (b, i, h, d) at Q[(b*Nq + i)*ldq + h*D + d]   (read in place from a packed QKV buffer)
+ *   K, V: same with Nk / ldk / ldv;  O: bf16 [B*Nq, H*D] with ldo
+ *   mask: f32 [B, Nk] additive (0 / -10000, vilbert.py:1350-1362) or NULL
+ *   lse:  f32 [B, H, Nq] row log-sum-exp in the log2 domain (saved for backward; may be NULL in fwd)
+ * Backward recomputes P from lse: needs dO (bf16), writes dQ/dK/dV (bf16, same indexing as Q/K/V with
+ * their own ld) and uses delta [B, H, Nq] f32 as scratch. D in {16, 32, 64, 128}; Nq, Nk <= ~320.
+ */
+typedef struct vb_attn_args {
+  int32_t B, H, Nq, Nk, D;
+  const void* Q; int64_t ldq;
+  const void* K; int64_t ldk;
+  const void* V; int64_t ldv;
+  const float* mask;
+  float scale;
+  void* O; int64_t ldo;
+  float* lse;
+  const void* dO; int64_t lddo;
+  void* dQ; int64_t lddq;
+  void* dK; int64_t lddk;
+  void* dV; int64_t lddv;
+  float* delta;
+} vb_attn_args;
+
+vb_status vb_attention_fwd(const vb_attn_args* args, void* stream);
+vb_status vb_attention_bwd(const vb_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise (HBM-bound) kernels. One warp per row, 128-bit accesses.
+ */
+
+/* BertLayerNorm.forward (vilbert.py:304-317): biased variance, eps inside the sqrt, affine after.
+ * x f32 [M,H] (ldx); writes y as f32 and/or bf16 (either may be NULL; both use ldy) and the row
+ * statistics mean/rstd [M] (may be NULL). H % 4 == 0, H <= 2048. */
+vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                           float* y_f32, void* y_bf16, int64_t ldy, float* mean, float* rstd,
+                           int32_t M, int32_t H, void* stream);
+/* Autograd of the above. dx as f32 and/or bf16; dgamma/dbeta are ACCUMULATED (atomics) and may be NULL.
+ * If gelu_pre (bf16 [M,H]) is given, dx_bf16 is additionally multiplied by gelu'(gelu_pre) — the
+ * Linear -> GELU -> LayerNorm head transforms (vilbert.py:1152-1156, 1172-1176, 1714-1718). */
+vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                           const float* mean, const float* rstd, float* dx_f32, void* dx_bf16, int64_t lddx,
+                           const void* gelu_pre, int64_t ld_pre, float* dgamma, float* dbeta,
+                           int32_t M, int32_t H, void* stream);
+
+/* fp32 -> bf16 casts: flat (weights shadow, region-feature ingest) and 2-D with independent leading
+ * dimensions and a scale (pads operands whose row length is not a multiple of 8). */
+vb_status vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+vb_status vb_cast2d_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows, int32_t cols,
+                                float scale, void* stream);
+
+/* BertEmbeddings.forward before its LayerNorm (vilbert.py:346-362): out[b,p,:] = word[ids] + pos[arange] +
+ * type[token_type_ids]; if task_ids != NULL the task embedding row is inserted at position 1 (no pos/type
+ * term) and the output has Nt+1 rows per sample. ids / token_type_ids [B,Nt] int64, task_ids [B] int64.
+ * Backward scatter-adds into the tables (word row 0 = padding_idx gets no gradient, :328-330). */
+vb_status vb_embed_text_fwd(const int64_t* ids, const int64_t* token_type_ids, const int64_t* task_ids,
+                            const float* word, const float* pos, const float* type, const float* task,
+                            float* out, int32_t B, int32_t Nt, int32_t H, void* stream);
+vb_status vb_embed_text_bwd(const float* dout, const int64_t* ids, const int64_t* token_type_ids,
+                            const int64_t* task_ids, float* dword, float* dpos, float* dtype, float* dtask,
+                            int32_t B, int32_t Nt, int32_t H, void* stream);
+
+/* BertImageEmbeddings.image_location_embeddings (vilbert.py:1416,1424): out[m,:] = loc[m,:5] W^T + b,
+ * W [H,5]; consumed as the residual of the 2048 -> Hv region-feature GEMM. Backward accumulates dW, db. */
+vb_status vb_loc_proj_fwd(const float* loc, const float* W, const float* b, float* out, int32_t M, int32_t H, void* stream);
+vb_status vb_loc_proj_bwd(const float* dy, const float* loc, float* dW, float* db, int32_t M, int32_t H, void* stream);
+
+/* Bias gradients: out[n] += sum_m X[m,n]; X is bf16 (is_bf16 != 0) or f32, [M,N] with ld. */
+vb_status vb_colsum(const void* X, int32_t is_bf16, int64_t ld, float* out, int32_t M, int32_t N, void* stream);
+
+/* Linears with 1..8 outputs (vil_logit, vil_tri_prediction, vision_logit, linguisic_logit,
+ * bi_seq_relationship, the 2-way output of vil_binary_prediction; vilbert.py:1231,1620-1628,1684-1695):
+ * y[m,j] = x[m,:] . W[j,:] + b[j] (+ row_addend[m]). Backward: dx (=, or += when accumulate_dx),
+ * dW and db ACCUMULATED. */
+vb_status vb_small_linear_fwd(const float* x, int64_t ldx, const float* W, const float* b, const float* row_addend,
+                              float* y, int32_t M, int32_t K, int32_t N, void* stream);
+vb_status vb_small_linear_bwd(const float* dy, const float* x, int64_t ldx, const float* W, float* dx, int64_t lddx,
+                              int32_t accumulate_dx, float* dW, float* db, int32_t M, int32_t K, int32_t N, void* stream);
+
+/* pooled_output = pooled_t (*|+) pooled_v (fusion_method, vilbert.py:1677-1682, 1236-1241); backward
+ * ACCUMULATES into da / db. */
+vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul, void* stream);
+vb_status vb_fuse_pooled_bwd(const float* d, const float* a, const float* b, float* da, float* db, int64_t n, int32_t mul, void* stream);
+/* ReLU backward of the poolers (vilbert.py:1121,1136): dx = dy * (y > 0). */
+vb_status vb_relu_bwd(const float* dy, const float* y, void* dx_bf16, float* dx_f32, int64_t n, void* stream);
+/* y += alpha * x (f32): merges gradient contributions. */
+vb_status vb_axpy_f32(const float* x, float* y, int64_t n, float alpha, void* stream);
+
+/* VQA objective (task_utils.py:325-327): loss = mean(BCEWithLogits(logits, target)) * cols, written to
+ * *loss (device scalar); dlogits = grad_scale * d loss / d logits as f32 and/or bf16 (ld). */
+vb_status vb_bce_logits_loss(const float* logits, const float* target, float* loss, float* dlogits_f32, void* dlogits_bf16,
+                             int64_t ld_dlogits_bf16, int32_t rows, int32_t cols, float grad_scale, void* stream);
+
+/* Additive attention masks of BertModel.forward (vilbert.py:1341-1362): out[b,j] = (1 - mask[b,j]) * -10000,
+ * mask int64 0/1 [B,N]; prepend_one != 0 emits N+1 entries per row with a leading 0 (task-token mask
+ * extension, :1331-1334). */
+vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_t B, int32_t N, int32_t prepend_one, void* stream);
+
+vb_status vb_memset_zero(void* ptr, int64_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,47 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    """Mirror of ``struct vb_attn_args``."""
+
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("D", C.c_int32),
+        ("Q", C.c_void_p), ("ldq", C.c_int64), ("K", C.c_void_p), ("ldk", C.c_int64), ("V", C.c_void_p), ("ldv", C.c_int64),
+        ("mask", C.c_void_p), ("scale", C.c_float),
+        ("O", C.c_void_p), ("ldo", C.c_int64), ("lse", C.c_void_p),
+        ("dO", C.c_void_p), ("lddo", C.c_int64), ("dQ", C.c_void_p), ("lddq", C.c_int64),
+        ("dK", C.c_void_p), ("lddk", C.c_int64), ("dV", C.c_void_p), ("lddv", C.c_int64),
+        ("delta", C.c_void_p),
+    ]
+
+
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+# argument types of every entry point of include/vilbert_b200.h (the trailing void* is the stream)
+_SIGNATURES = {
+    "vb_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "vb_gemm_bf16": [C.POINTER(GemmArgs), _P],
+    "vb_attention_fwd": [C.POINTER(AttnArgs), _P],
+    "vb_attention_bwd": [C.POINTER(AttnArgs), _P],
+    "vb_layernorm_fwd": [_P, _I64, _P, _P, _F, _P, _P, _I64, _P, _P, _I32, _I32, _P],
+    "vb_layernorm_bwd": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _I32, _I32, _P],
+    "vb_cast_f32_to_bf16": [_P, _P, _I64, _P],
+    "vb_cast2d_f32_to_bf16": [_P, _I64, _P, _I64, _I32, _I32, _F, _P],
+    "vb_embed_text_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "vb_embed_text_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "vb_loc_proj_fwd": [_P, _P, _P, _P, _I32, _I32, _P],
+    "vb_loc_proj_bwd": [_P, _P, _P, _P, _I32, _I32, _P],
+    "vb_colsum": [_P, _I32, _I64, _P, _I32, _I32, _P],
+    "vb_small_linear_fwd": [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "vb_small_linear_bwd": [_P, _P, _I64, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P],
+    "vb_fuse_pooled_fwd": [_P, _P, _P, _P, _I64, _I32, _P],
+    "vb_fuse_pooled_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _P],
+    "vb_relu_bwd": [_P, _P, _P, _P, _I64, _P],
+    "vb_axpy_f32": [_P, _P, _I64, _F, _P],
+    "vb_bce_logits_loss": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
+    "vb_mask_to_additive": [_P, _P, _I32, _I32, _I32, _P],
+    "vb_memset_zero": [_P, _I64, _P],
+}
+
 _lib = None
 
 
@@ -50,6 +91,10 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.vb_last_error.restype = C.c_char_p
         _lib.vb_version.restype = C.c_int
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(_lib, name)   # AttributeError here = stale build: fail loudly
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
     return _lib
 
 

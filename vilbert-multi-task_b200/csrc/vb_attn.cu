@@ -1,0 +1,453 @@
+// vb_attn.cu — fused QK^T * scale + additive key mask -> softmax -> PV for the three attention
+// flavours of ViLBERT (text self-attention vilbert.py:424-460, image self-attention :571-619,
+// cross-modal BertBiAttention :771-809), forward and backward.
+//
+// Problem sizes are tiny per (batch, head): Nq, Nk <= ~320, head dim 64/128, so a whole K/V panel
+// lives in shared memory and S / P never touch HBM. One CTA = (64-row query tile, head, batch) with
+// 4 warps x 16 rows; tensor-core work uses warp-level mma.sync m16n8k16 (bf16 -> fp32) with ldmatrix
+// operand fetch, row statistics via warp-shuffle online softmax over 64-key blocks. 1.8 % of the
+// model FLOPs live here; the tcgen05 path is reserved for the dense contractions.
+// Q/K/V are read in place from the packed QKV GEMM output (row stride = ld, head offset h*D), so the
+// reference's permute().contiguous() copies (vilbert.py:416-422, 447) never materialise.
+//
+// Backward (FlashAttention-2 style recompute): P = exp2(S*c + mask*log2e - lse2),
+//   delta = rowsum(dO o O), dS = P o (dO V^T - delta), dQ = scale dS K, dK = scale dS^T Q, dV = P^T dO.
+// Kernel "dq" owns a query tile and loops over key blocks; kernel "dkv" owns a key tile and loops over
+// query blocks with the transposed products so that no atomics are needed (deterministic).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "vb_internal.h"
+#include "vb_ptx.cuh"
+
+namespace vb {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int ATT_THREADS = 128;
+constexpr int TQ = 64;  // rows per CTA tile (4 warps x 16)
+constexpr int KB = 64;  // keys per online-softmax block
+
+struct AttnParams {
+  int B, H, Nq, Nk;
+  const __nv_bfloat16 *Q, *K, *V;
+  long long ldq, ldk, ldv;
+  const float* mask;
+  float scale;
+  __nv_bfloat16* O;
+  long long ldo;
+  float* lse;  // [B,H,Nq], log2 domain
+  const __nv_bfloat16* dO;
+  long long lddo;
+  __nv_bfloat16 *dQ, *dK, *dV;
+  long long lddq, lddk, lddv;
+  float* delta;  // [B,H,Nq]
+};
+
+// Copies `rows_valid` rows of D bf16 (row stride ld) into smem rows of stride D+8; rows beyond are zeroed.
+template <int D>
+__device__ __forceinline__ void load_panel(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows_valid,
+                                           int rows_total) {
+  constexpr int LD = D + 8;
+  constexpr int CH = D / 8;  // 16-byte chunks per row
+  for (int idx = threadIdx.x; idx < rows_total * CH; idx += ATT_THREADS) {
+    const int r = idx / CH, c = idx % CH;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * ld + c * 8));
+    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+  }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// acc[nt][4] (16 x 64 block, 8 n-tiles) = A(16 x D from sA rows a_row0..) * B^T where B rows b_row0.. (64 rows) of sB.
+template <int D>
+__device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16* sA, int a_row0, const __nv_bfloat16* sB,
+                                         int b_row0, int lane) {
+  constexpr int LD = D + 8;
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+    uint32_t a[4];
+    ldmatrix_x4(a, smem_u32(sA + (a_row0 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8));
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      const int mi = lane >> 3;
+      ldmatrix_x4(b, smem_u32(sB + (b_row0 + np * 16 + (mi >> 1) * 8 + (lane & 7)) * LD + kk * 16 + (mi & 1) * 8));
+      mma_bf16_16816(acc[2 * np], a, b[0], b[1]);
+      mma_bf16_16816(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// acc[D/8][4] (16 x D) += P(16 x 64, given as C-fragments pf[8][4] converted to bf16) * B where B rows b_row0.. (64 rows, k index) of sB [row][D].
+template <int D>
+__device__ __forceinline__ void mma_p_b(float (&acc)[D / 8][4], const float (&pf)[8][4], const __nv_bfloat16* sB, int b_row0,
+                                        int lane) {
+  constexpr int LD = D + 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(pf[2 * kk][0], pf[2 * kk][1]);
+    a[1] = pack_bf16(pf[2 * kk][2], pf[2 * kk][3]);
+    a[2] = pack_bf16(pf[2 * kk + 1][0], pf[2 * kk + 1][1]);
+    a[3] = pack_bf16(pf[2 * kk + 1][2], pf[2 * kk + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < D / 16; ++dp) {
+      uint32_t b[4];
+      const int mi = lane >> 3;
+      ldmatrix_x4_trans(b, smem_u32(sB + (b_row0 + kk * 16 + (mi & 1) * 8 + (lane & 7)) * LD + dp * 16 + (mi >> 1) * 8));
+      mma_bf16_16816(acc[2 * dp], a, b[0], b[1]);
+      mma_bf16_16816(acc[2 * dp + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// Stores a 16 x D fp32 C-fragment tile (scaled) as bf16 rows; rows >= rows_valid are skipped.
+template <int D>
+__device__ __forceinline__ void store_tile(__nv_bfloat16* dst, long long ld, const float (&acc)[D / 8][4], float s0, float s1,
+                                           int row0, int rows_valid, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < D / 8; ++nt) {
+    const int col = nt * 8 + 2 * t;
+    if (row0 + g < rows_valid)
+      *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g) * ld + col) = pack_bf16(acc[nt][0] * s0, acc[nt][1] * s0);
+    if (row0 + g + 8 < rows_valid)
+      *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g + 8) * ld + col) = pack_bf16(acc[nt][2] * s1, acc[nt][3] * s1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams p) {
+  constexpr int LD = D + 8;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int nkp = (p.Nk + KB - 1) / KB * KB;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sK = sQ + TQ * LD;
+  __nv_bfloat16* sV = sK + nkp * LD;
+  float* sMask = reinterpret_cast<float*>(sV + nkp * LD);
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  load_panel<D>(sQ, p.Q + ((long long)b * p.Nq + q0) * p.ldq + h * D, p.ldq, min(TQ, p.Nq - q0), TQ);
+  load_panel<D>(sK, p.K + (long long)b * p.Nk * p.ldk + h * D, p.ldk, p.Nk, nkp);
+  load_panel<D>(sV, p.V + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
+  for (int j = threadIdx.x; j < nkp; j += ATT_THREADS)
+    sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  if (q0 + r0 >= p.Nq) return;  // whole warp out of range (no later block-wide sync)
+
+  const float c = p.scale * LOG2E;
+  float m[2] = {-CUDART_INF_F, -CUDART_INF_F}, l[2] = {0.f, 0.f};
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+
+  for (int kb = 0; kb < nkp; kb += KB) {
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    mma_a_bt<D>(s, sQ, r0, sK, kb, lane);
+    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float mk0 = sMask[kb + nt * 8 + 2 * t], mk1 = sMask[kb + nt * 8 + 2 * t + 1];
+      s[nt][0] = s[nt][0] * c + mk0; s[nt][1] = s[nt][1] * c + mk1;
+      s[nt][2] = s[nt][2] * c + mk0; s[nt][3] = s[nt][3] * c + mk1;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+    const float mn0 = fmaxf(m[0], mx0), mn1 = fmaxf(m[1], mx1);
+    const float al0 = exp2f(m[0] - mn0), al1 = exp2f(m[1] - mn1);
+    m[0] = mn0; m[1] = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
+      s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+      rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
+    }
+    l[0] = l[0] * al0 + rs0; l[1] = l[1] * al1 + rs1;
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
+    mma_p_b<D>(o, s, sV, kb, lane);
+  }
+  l[0] = quad_sum(l[0]); l[1] = quad_sum(l[1]);
+  const int rows_valid = p.Nq - q0;
+  store_tile<D>(p.O + ((long long)b * p.Nq + q0) * p.ldo + h * D, p.ldo, o, 1.f / l[0], 1.f / l[1], r0, rows_valid, lane);
+  if (p.lse && t == 0) {
+    float* lse = p.lse + ((long long)b * p.H + h) * p.Nq + q0;
+    if (r0 + g < rows_valid) lse[r0 + g] = m[0] + log2f(l[0]);
+    if (r0 + g + 8 < rows_valid) lse[r0 + g + 8] = m[1] + log2f(l[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward: dQ
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnParams p) {
+  constexpr int LD = D + 8;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int nkp = (p.Nk + KB - 1) / KB * KB;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sdO = sQ + TQ * LD;
+  __nv_bfloat16* sK = sdO + TQ * LD;
+  __nv_bfloat16* sV = sK + nkp * LD;
+  float* sMask = reinterpret_cast<float*>(sV + nkp * LD);
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int rows_valid = min(TQ, p.Nq - q0);
+
+  load_panel<D>(sQ, p.Q + ((long long)b * p.Nq + q0) * p.ldq + h * D, p.ldq, rows_valid, TQ);
+  load_panel<D>(sdO, p.dO + ((long long)b * p.Nq + q0) * p.lddo + h * D, p.lddo, rows_valid, TQ);
+  load_panel<D>(sK, p.K + (long long)b * p.Nk * p.ldk + h * D, p.ldk, p.Nk, nkp);
+  load_panel<D>(sV, p.V + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
+  for (int j = threadIdx.x; j < nkp; j += ATT_THREADS)
+    sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  if (r0 >= rows_valid) return;
+
+  // delta = rowsum(dO o O) for rows g, g+8 of this warp; each quad lane sums a quarter of the columns.
+  float dl[2] = {0.f, 0.f};
+  {
+    const __nv_bfloat16* Og = p.O + ((long long)b * p.Nq + q0) * p.ldo + h * D;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int r = r0 + g + hh * 8;
+      if (r < rows_valid) {
+        float acc = 0.f;
+        for (int cidx = t * 8; cidx < D; cidx += 32) {
+          const uint4 ov = __ldg(reinterpret_cast<const uint4*>(Og + (long long)r * p.ldo + cidx));
+          const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * LD + cidx);
+          const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+          const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 of = __bfloat1622float2(o2[i]), df = __bfloat1622float2(d2[i]);
+            acc += of.x * df.x + of.y * df.y;
+          }
+        }
+        dl[hh] = acc;
+      }
+    }
+    dl[0] = quad_sum(dl[0]); dl[1] = quad_sum(dl[1]);
+  }
+  float ls[2] = {0.f, 0.f};
+  {
+    const float* lse = p.lse + ((long long)b * p.H + h) * p.Nq + q0;
+    if (r0 + g < rows_valid) ls[0] = lse[r0 + g];
+    if (r0 + g + 8 < rows_valid) ls[1] = lse[r0 + g + 8];
+    if (t == 0) {
+      float* dg = p.delta + ((long long)b * p.H + h) * p.Nq + q0;
+      if (r0 + g < rows_valid) dg[r0 + g] = dl[0];
+      if (r0 + g + 8 < rows_valid) dg[r0 + g + 8] = dl[1];
+    }
+  }
+
+  const float c = p.scale * LOG2E;
+  float dq[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+
+  for (int kb = 0; kb < nkp; kb += KB) {
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+    mma_a_bt<D>(s, sQ, r0, sK, kb, lane);
+    mma_a_bt<D>(dp, sdO, r0, sV, kb, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float mk0 = sMask[kb + nt * 8 + 2 * t], mk1 = sMask[kb + nt * 8 + 2 * t + 1];
+      const float p0 = exp2f(s[nt][0] * c + mk0 - ls[0]), p1 = exp2f(s[nt][1] * c + mk1 - ls[0]);
+      const float p2 = exp2f(s[nt][2] * c + mk0 - ls[1]), p3 = exp2f(s[nt][3] * c + mk1 - ls[1]);
+      s[nt][0] = p0 * (dp[nt][0] - dl[0]); s[nt][1] = p1 * (dp[nt][1] - dl[0]);
+      s[nt][2] = p2 * (dp[nt][2] - dl[1]); s[nt][3] = p3 * (dp[nt][3] - dl[1]);
+    }
+    mma_p_b<D>(dq, s, sK, kb, lane);
+  }
+  store_tile<D>(p.dQ + ((long long)b * p.Nq + q0) * p.lddq + h * D, p.lddq, dq, p.scale, p.scale, r0, rows_valid, lane);
+}
+
+// ------------------------------------------------------------------------------------------ backward: dK, dV
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnParams p) {
+  constexpr int LD = D + 8;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int nqp = (p.Nq + KB - 1) / KB * KB;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sV = sK + TQ * LD;
+  __nv_bfloat16* sQ = sV + TQ * LD;
+  __nv_bfloat16* sdO = sQ + nqp * LD;
+  float* sLse = reinterpret_cast<float*>(sdO + nqp * LD);
+  float* sDelta = sLse + nqp;
+
+  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * TQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int rows_valid = min(TQ, p.Nk - k0);
+
+  load_panel<D>(sK, p.K + ((long long)b * p.Nk + k0) * p.ldk + h * D, p.ldk, rows_valid, TQ);
+  load_panel<D>(sV, p.V + ((long long)b * p.Nk + k0) * p.ldv + h * D, p.ldv, rows_valid, TQ);
+  load_panel<D>(sQ, p.Q + (long long)b * p.Nq * p.ldq + h * D, p.ldq, p.Nq, nqp);
+  load_panel<D>(sdO, p.dO + (long long)b * p.Nq * p.lddo + h * D, p.lddo, p.Nq, nqp);
+  {
+    const float* lse = p.lse + ((long long)b * p.H + h) * p.Nq;
+    const float* dg = p.delta + ((long long)b * p.H + h) * p.Nq;
+    for (int i = threadIdx.x; i < nqp; i += ATT_THREADS) {
+      sLse[i] = (i < p.Nq) ? lse[i] : CUDART_INF_F;  // +inf -> P = 0 for padded query columns
+      sDelta[i] = (i < p.Nq) ? dg[i] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  if (r0 >= rows_valid) return;
+
+  float mk[2];
+  mk[0] = (r0 + g < rows_valid && p.mask) ? p.mask[(long long)b * p.Nk + k0 + r0 + g] * LOG2E : 0.f;
+  mk[1] = (r0 + g + 8 < rows_valid && p.mask) ? p.mask[(long long)b * p.Nk + k0 + r0 + g + 8] * LOG2E : 0.f;
+
+  const float c = p.scale * LOG2E;
+  float dk[D / 8][4], dv[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+
+  for (int qb = 0; qb < nqp; qb += KB) {
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+    }
+    mma_a_bt<D>(st, sK, r0, sQ, qb, lane);     // S^T  = K Q^T   (rows = keys, cols = queries)
+    mma_a_bt<D>(dpt, sV, r0, sdO, qb, lane);   // dP^T = V dO^T
+    // P^T, then dV += P^T dO ; overwrite st with dS^T afterwards
+    float pt[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int q = qb + nt * 8 + 2 * t;
+      const float l0 = sLse[q], l1 = sLse[q + 1];
+      pt[nt][0] = exp2f(st[nt][0] * c + mk[0] - l0); pt[nt][1] = exp2f(st[nt][1] * c + mk[0] - l1);
+      pt[nt][2] = exp2f(st[nt][2] * c + mk[1] - l0); pt[nt][3] = exp2f(st[nt][3] * c + mk[1] - l1);
+      const float d0 = sDelta[q], d1 = sDelta[q + 1];
+      st[nt][0] = pt[nt][0] * (dpt[nt][0] - d0); st[nt][1] = pt[nt][1] * (dpt[nt][1] - d1);
+      st[nt][2] = pt[nt][2] * (dpt[nt][2] - d0); st[nt][3] = pt[nt][3] * (dpt[nt][3] - d1);
+    }
+    mma_p_b<D>(dv, pt, sdO, qb, lane);
+    mma_p_b<D>(dk, st, sQ, qb, lane);
+  }
+  store_tile<D>(p.dV + ((long long)b * p.Nk + k0) * p.lddv + h * D, p.lddv, dv, 1.f, 1.f, r0, rows_valid, lane);
+  store_tile<D>(p.dK + ((long long)b * p.Nk + k0) * p.lddk + h * D, p.lddk, dk, p.scale, p.scale, r0, rows_valid, lane);
+}
+
+// ------------------------------------------------------------------------------------------ host
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int validate(const vb_attn_args* a, bool bwd) {
+  if (!a) return set_error(VB_ERR_INVALID, "vb_attention: null args");
+  if (a->B <= 0 || a->H <= 0 || a->Nq <= 0 || a->Nk <= 0) return set_error(VB_ERR_INVALID, "vb_attention: empty problem");
+  if (a->D != 16 && a->D != 32 && a->D != 64 && a->D != 128)
+    return set_error(VB_ERR_UNSUPPORTED, "vb_attention: head dim %d not in {16,32,64,128}", a->D);
+  if (!a->Q || !a->K || !a->V || !a->O) return set_error(VB_ERR_INVALID, "vb_attention: null tensor");
+  if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8) || !al16(a->Q) || !al16(a->K) || !al16(a->V) || !al16(a->O))
+    return set_error(VB_ERR_INVALID, "vb_attention: tensors need ld %% 8 == 0 and 16-byte aligned bases");
+  if (bwd) {
+    if (!a->dO || !a->dQ || !a->dK || !a->dV || !a->lse || !a->delta) return set_error(VB_ERR_INVALID, "vb_attention_bwd: null tensor");
+    if ((a->lddo % 8) || (a->lddq % 8) || (a->lddk % 8) || (a->lddv % 8) || !al16(a->dO) || !al16(a->dQ) || !al16(a->dK) || !al16(a->dV))
+      return set_error(VB_ERR_INVALID, "vb_attention_bwd: gradient tensors need ld %% 8 == 0 and 16-byte aligned bases");
+  }
+  return VB_OK;
+}
+
+static AttnParams to_params(const vb_attn_args* a) {
+  AttnParams p;
+  p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk;
+  p.Q = (const __nv_bfloat16*)a->Q; p.K = (const __nv_bfloat16*)a->K; p.V = (const __nv_bfloat16*)a->V;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv;
+  p.mask = a->mask; p.scale = a->scale;
+  p.O = (__nv_bfloat16*)a->O; p.ldo = a->ldo; p.lse = a->lse;
+  p.dO = (const __nv_bfloat16*)a->dO; p.lddo = a->lddo;
+  p.dQ = (__nv_bfloat16*)a->dQ; p.dK = (__nv_bfloat16*)a->dK; p.dV = (__nv_bfloat16*)a->dV;
+  p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.delta = a->delta;
+  return p;
+}
+
+template <typename Kern>
+static int launch_att(Kern kern, dim3 grid, size_t smem, const AttnParams& p, cudaStream_t s, const char* what) {
+  if (smem > 227 * 1024) return set_error(VB_ERR_UNSUPPORTED, "%s: sequence too long for the smem-resident panel (%zu bytes)", what, smem);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+  }
+  kern<<<grid, ATT_THREADS, smem, s>>>(p);
+  return check_launch(what);
+}
+
+}  // namespace vb
+
+extern "C" vb_status vb_attention_fwd(const vb_attn_args* a, void* stream) {
+  using namespace vb;
+  if (int s = validate(a, false)) return s;
+  const AttnParams p = to_params(a);
+  const int nkp = (a->Nk + KB - 1) / KB * KB;
+  const size_t smem = (size_t)(TQ + 2 * nkp) * (a->D + 8) * 2 + (size_t)nkp * 4;
+  dim3 grid((a->Nq + TQ - 1) / TQ, a->H, a->B);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->D) {
+    case 16: return launch_att(attn_fwd_kernel<16>, grid, smem, p, st, "vb_attention_fwd");
+    case 32: return launch_att(attn_fwd_kernel<32>, grid, smem, p, st, "vb_attention_fwd");
+    case 64: return launch_att(attn_fwd_kernel<64>, grid, smem, p, st, "vb_attention_fwd");
+    default: return launch_att(attn_fwd_kernel<128>, grid, smem, p, st, "vb_attention_fwd");
+  }
+}
+
+extern "C" vb_status vb_attention_bwd(const vb_attn_args* a, void* stream) {
+  using namespace vb;
+  if (int s = validate(a, true)) return s;
+  const AttnParams p = to_params(a);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nkp = (a->Nk + KB - 1) / KB * KB, nqp = (a->Nq + KB - 1) / KB * KB;
+  const size_t smem_q = (size_t)(2 * TQ + 2 * nkp) * (a->D + 8) * 2 + (size_t)nkp * 4;
+  const size_t smem_k = (size_t)(2 * TQ + 2 * nqp) * (a->D + 8) * 2 + (size_t)nqp * 8;
+  dim3 gq((a->Nq + TQ - 1) / TQ, a->H, a->B), gk((a->Nk + TQ - 1) / TQ, a->H, a->B);
+  int s;
+  switch (a->D) {
+    case 16:
+      if ((s = launch_att(attn_bwd_dq_kernel<16>, gq, smem_q, p, st, "vb_attention_bwd(dq)"))) return s;
+      return launch_att(attn_bwd_dkv_kernel<16>, gk, smem_k, p, st, "vb_attention_bwd(dkv)");
+    case 32:
+      if ((s = launch_att(attn_bwd_dq_kernel<32>, gq, smem_q, p, st, "vb_attention_bwd(dq)"))) return s;
+      return launch_att(attn_bwd_dkv_kernel<32>, gk, smem_k, p, st, "vb_attention_bwd(dkv)");
+    case 64:
+      if ((s = launch_att(attn_bwd_dq_kernel<64>, gq, smem_q, p, st, "vb_attention_bwd(dq)"))) return s;
+      return launch_att(attn_bwd_dkv_kernel<64>, gk, smem_k, p, st, "vb_attention_bwd(dkv)");
+    default:
+      if ((s = launch_att(attn_bwd_dq_kernel<128>, gq, smem_q, p, st, "vb_attention_bwd(dq)"))) return s;
+      return launch_att(attn_bwd_dkv_kernel<128>, gk, smem_k, p, st, "vb_attention_bwd(dkv)");
+  }
+}

@@ -1,0 +1,609 @@
+// vb_rowops.cu — the HBM-bound row-wise kernels around the tensor-core contractions: LayerNorm
+// forward/backward (vilbert.py:304-317), text / image embedding assembly (:346-367, :1421-1432),
+// bias-gradient column sums, tiny-N linears (1-3 logits), pooled fusion, casts, VQA BCE loss.
+// All are 128-bit vectorised, one warp per row, sized in multiples of the SM count.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vb_internal.h"
+#include "vb_ptx.cuh"
+
+namespace vb {
+
+constexpr int ROW_WARPS = 8;                 // warps per CTA for warp-per-row kernels
+constexpr int ROW_THREADS = ROW_WARPS * 32;
+constexpr int MAX_V4 = 16;                   // float4 chunks per lane -> H <= 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int row_grid(long long rows) {
+  long long blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  long long cap = (long long)sm_count() * 8;
+  if (cap <= 0) cap = 148 * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm fwd
+template <int NV4>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, long long ldy, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, int M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int n4 = H >> 2;
+  const float inv_h = 1.f / (float)H;
+  for (long long row = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * ROW_WARPS) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    float4 v[NV4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      v[i] = (c < n4) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(s) * inv_h;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < n4) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + cc * cc + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_h + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < n4) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+        const float4 b = reinterpret_cast<const float4*>(beta)[c];
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (y32) reinterpret_cast<float4*>(y32 + row * ldy)[c] = o;
+        if (y16) reinterpret_cast<uint2*>(y16 + row * ldy)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm bwd
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma; dgamma += sum dy * xhat; dbeta += sum dy.
+// Optional: dx16 additionally multiplied by gelu'(pre) (head transforms: Linear -> GELU -> LayerNorm).
+template <int NV4>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+              const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16, long long lddx,
+              const __nv_bfloat16* __restrict__ pre, long long ldpre, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              int M, int H) {
+  __shared__ float red[ROW_WARPS][32 * 4 + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n4 = H >> 2;
+  const float inv_h = 1.f / (float)H;
+  float4 ag[NV4], ab[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (long long row = (long long)blockIdx.x * ROW_WARPS + warp; row < M; row += (long long)gridDim.x * ROW_WARPS) {
+    const float4* dyr = reinterpret_cast<const float4*>(dy + row * lddy);
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float4 g[NV4], xh[NV4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < n4) {
+        const float4 d = dyr[c], xv = xr[c], gm = reinterpret_cast<const float4*>(gamma)[c];
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      } else {
+        g[i] = xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_h, c2 = warp_sum(s2) * inv_h;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < n4) {
+        float4 o;
+        o.x = (g[i].x - c1 - xh[i].x * c2) * rstd;
+        o.y = (g[i].y - c1 - xh[i].y * c2) * rstd;
+        o.z = (g[i].z - c1 - xh[i].z * c2) * rstd;
+        o.w = (g[i].w - c1 - xh[i].w * c2) * rstd;
+        if (dx32) reinterpret_cast<float4*>(dx32 + row * lddx)[c] = o;
+        if (dx16) {
+          if (pre) {
+            const uint2 pk = reinterpret_cast<const uint2*>(pre + row * ldpre)[c];
+            const float2 p01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+            const float2 p23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+            o.x *= gelu_erf_grad(p01.x); o.y *= gelu_erf_grad(p01.y);
+            o.z *= gelu_erf_grad(p23.x); o.w *= gelu_erf_grad(p23.y);
+          }
+          reinterpret_cast<uint2*>(dx16 + row * lddx)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        }
+      }
+    }
+  }
+  if (!dgamma && !dbeta) return;
+  // block reduction of the per-warp column partials, then one atomic per column per CTA
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = lane + i * 32;
+    if (i * 32 >= n4) break;  // uniform
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const float4 v = pass == 0 ? ag[i] : ab[i];
+      float* dst = pass == 0 ? dgamma : dbeta;
+      __syncthreads();
+      red[warp][lane * 4 + 0] = v.x; red[warp][lane * 4 + 1] = v.y; red[warp][lane * 4 + 2] = v.z; red[warp][lane * 4 + 3] = v.w;
+      __syncthreads();
+      if (dst && threadIdx.x < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < ROW_WARPS; ++w) s += red[w][threadIdx.x];
+        const int col = (i * 32 + (threadIdx.x >> 2)) * 4 + (threadIdx.x & 3);
+        if (col < H) atomicAdd(dst + col, s);
+      }
+    }
+    (void)c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ casts
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
+// rows x cols with independent leading dims (pads bf16 operands whose row size is not a multiple of 8)
+__global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
+                                       int rows, int cols, float scale) {
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y)
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+      dst[r * ldd + c] = __float2bfloat16(src[r * lds + c] * scale);
+}
+
+// ------------------------------------------------------------------------------------------ text embeddings
+// out[b, p, :] = word[ids[b, t]] + pos[t] + type[tt[b, t]]  for the original token t; with task tokens the
+// task embedding row is inserted at output position 1 and carries no pos/type term (vilbert.py:358-362).
+__global__ void __launch_bounds__(ROW_THREADS)
+embed_text_fwd_kernel(const long long* __restrict__ ids, const long long* __restrict__ tts, const long long* __restrict__ task_ids,
+                      const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
+                      const float* __restrict__ task, float* __restrict__ out, int B, int Nt, int H, int has_task) {
+  const int lane = threadIdx.x & 31;
+  const int No = Nt + (has_task ? 1 : 0);
+  const long long rows = (long long)B * No;
+  const int n4 = H >> 2;
+  for (long long row = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * ROW_WARPS) {
+    const int b = (int)(row / No), p = (int)(row % No);
+    float4* o = reinterpret_cast<float4*>(out + row * H);
+    if (has_task && p == 1) {
+      const float4* te = reinterpret_cast<const float4*>(task + task_ids[b] * H);
+      for (int c = lane; c < n4; c += 32) o[c] = te[c];
+      continue;
+    }
+    const int t = (has_task && p > 1) ? p - 1 : p;
+    const float4* w = reinterpret_cast<const float4*>(word + ids[(long long)b * Nt + t] * H);
+    const float4* pe = reinterpret_cast<const float4*>(pos + (long long)t * H);
+    const float4* ty = reinterpret_cast<const float4*>(type + tts[(long long)b * Nt + t] * H);
+    for (int c = lane; c < n4; c += 32) {
+      const float4 a = w[c], bb = pe[c], cc = ty[c];
+      o[c] = make_float4(a.x + bb.x + cc.x, a.y + bb.y + cc.y, a.z + bb.z + cc.z, a.w + bb.w + cc.w);
+    }
+  }
+}
+
+// scatter-add of d(out) into the embedding tables; word row 0 is padding_idx (no gradient, vilbert.py:328-330)
+__global__ void __launch_bounds__(ROW_THREADS)
+embed_text_bwd_kernel(const float* __restrict__ dout, const long long* __restrict__ ids, const long long* __restrict__ tts,
+                      const long long* __restrict__ task_ids, float* __restrict__ dword, float* __restrict__ dpos,
+                      float* __restrict__ dtype, float* __restrict__ dtask, int B, int Nt, int H, int has_task) {
+  const int lane = threadIdx.x & 31;
+  const int No = Nt + (has_task ? 1 : 0);
+  const long long rows = (long long)B * No;
+  for (long long row = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * ROW_WARPS) {
+    const int b = (int)(row / No), p = (int)(row % No);
+    const float* d = dout + row * H;
+    if (has_task && p == 1) {
+      float* dt = dtask + task_ids[b] * H;
+      for (int c = lane; c < H; c += 32) atomicAdd(dt + c, d[c]);
+      continue;
+    }
+    const int t = (has_task && p > 1) ? p - 1 : p;
+    const long long id = ids[(long long)b * Nt + t];
+    float* dw = dword + id * H;
+    float* dp = dpos + (long long)t * H;
+    float* dty = dtype + tts[(long long)b * Nt + t] * H;
+    for (int c = lane; c < H; c += 32) {
+      const float v = d[c];
+      if (id != 0) atomicAdd(dw + c, v);
+      atomicAdd(dp + c, v);
+      atomicAdd(dty + c, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ image location projection
+// out[m, h] = sum_j loc[m, j] * W[h, j] + b[h],  j < 5  (BertImageEmbeddings.image_location_embeddings, vilbert.py:1416,1424)
+__global__ void loc_proj_fwd_kernel(const float* __restrict__ loc, const float* __restrict__ W, const float* __restrict__ b,
+                                    float* __restrict__ out, int M, int H) {
+  extern __shared__ float sw[];  // [H][5] + [H]
+  for (int i = threadIdx.x; i < H * 5; i += blockDim.x) sw[i] = W[i];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) sw[H * 5 + i] = b[i];
+  __syncthreads();
+  for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+    float l[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) l[j] = loc[m * 5 + j];
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+      float acc = sw[H * 5 + h];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) acc += l[j] * sw[h * 5 + j];
+      out[m * H + h] = acc;
+    }
+  }
+}
+
+// dW[h, j] += sum_m dy[m, h] * loc[m, j];  db[h] += sum_m dy[m, h]
+__global__ void loc_proj_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ loc, float* __restrict__ dW,
+                                    float* __restrict__ db, int M, int H, int rows_per_block) {
+  const long long m0 = (long long)blockIdx.y * rows_per_block;
+  const long long m1 = min((long long)M, m0 + rows_per_block);
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long m = m0; m < m1; ++m) {
+    const float d = dy[m * H + h];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) acc[j] += d * __ldg(loc + m * 5 + j);
+    acc[5] += d;
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) atomicAdd(dW + (long long)h * 5 + j, acc[j]);
+  atomicAdd(db + h, acc[5]);
+}
+
+// ------------------------------------------------------------------------------------------ column sums (bias grads)
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// out[n] += sum_m X[m, n]; block = 32 x 8 threads: 32 consecutive columns, 8 row lanes.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ X, long long ld, float* __restrict__ out, int M, int N, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const long long m0 = (long long)blockIdx.y * rows_per_block;
+  const long long m1 = min((long long)M, m0 + rows_per_block);
+  float acc = 0.f;
+  if (col < N)
+    for (long long m = m0 + threadIdx.y; m < m1; m += 8) acc += to_f<T>(X[m * ld + col]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + col, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tiny-N linear (N <= 8)
+// y[m, j] = x[m, :] . W[j, :] + b[j] (+ addend[m]) — vil_logit / vil_tri_prediction / vision_logit /
+// linguisic_logit / bi_seq_relationship / the 2-way output of vil_binary_prediction (vilbert.py:1620-1628,1684-1695).
+__global__ void __launch_bounds__(ROW_THREADS)
+small_linear_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W, const float* __restrict__ b,
+                        const float* __restrict__ addend, float* __restrict__ y, int M, int K, int N) {
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * ROW_WARPS) {
+    const float* xr = x + row * ldx;
+    for (int j = 0; j < N; ++j) {
+      float acc = 0.f;
+      for (int k = lane; k < K; k += 32) acc += xr[k] * __ldg(W + (long long)j * K + k);
+      acc = warp_sum(acc);
+      if (lane == 0) y[row * N + j] = acc + (b ? b[j] : 0.f) + (addend ? addend[row] : 0.f);
+    }
+  }
+}
+
+// dx[m, :] (+)= sum_j dy[m, j] W[j, :];  dW[j, :] += sum_m dy[m, j] x[m, :];  db[j] += sum_m dy[m, j]
+__global__ void __launch_bounds__(ROW_THREADS)
+small_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long ldx, const float* __restrict__ W,
+                        float* __restrict__ dx, long long lddx, int accumulate_dx, float* __restrict__ dW, float* __restrict__ db,
+                        int M, int K, int N) {
+  // one CTA handles a strided set of rows; per-thread partial dW over columns k = threadIdx.x + i*ROW_THREADS
+  for (int j = 0; j < N; ++j) {
+    float dbp = 0.f;
+    for (int k = threadIdx.x; k < K; k += ROW_THREADS) {
+      float acc = 0.f;
+      for (long long m = blockIdx.x; m < M; m += gridDim.x) acc += dy[m * N + j] * x[m * ldx + k];
+      atomicAdd(dW + (long long)j * K + k, acc);
+    }
+    if (threadIdx.x == 0) {
+      for (long long m = blockIdx.x; m < M; m += gridDim.x) dbp += dy[m * N + j];
+      atomicAdd(db + j, dbp);
+    }
+  }
+  if (dx) {
+    for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+      for (int k = threadIdx.x; k < K; k += ROW_THREADS) {
+        float acc = 0.f;
+        for (int j = 0; j < N; ++j) acc += dy[m * N + j] * __ldg(W + (long long)j * K + k);
+        float* d = dx + m * lddx + k;
+        *d = accumulate_dx ? (*d + acc) : acc;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ elementwise helpers
+// out = a * b (fusion_method "mul") or a + b ("sum"), f32 + bf16 copies (vilbert.py:1677-1682, 1236-1241)
+__global__ void fuse_pooled_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o32,
+                                       __nv_bfloat16* __restrict__ o16, long long n, int mul) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = mul ? a[i] * b[i] : a[i] + b[i];
+    if (o32) o32[i] = v;
+    if (o16) o16[i] = __float2bfloat16(v);
+  }
+}
+// da += d * b, db += d * a (mul) or da += d, db += d (sum)
+__global__ void fuse_pooled_bwd_kernel(const float* __restrict__ d, const float* __restrict__ a, const float* __restrict__ b,
+                                       float* __restrict__ da, float* __restrict__ db, long long n, int mul) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = d[i];
+    da[i] += mul ? g * b[i] : g;
+    db[i] += mul ? g * a[i] : g;
+  }
+}
+// dx = dy * (y > 0) -> bf16 (pooler ReLU, vilbert.py:1121,1136)
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, __nv_bfloat16* __restrict__ dx16,
+                                float* __restrict__ dx32, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = y[i] > 0.f ? dy[i] : 0.f;
+    if (dx16) dx16[i] = __float2bfloat16(v);
+    if (dx32) dx32[i] = v;
+  }
+}
+// y (+)= x  (f32), used to merge gradient contributions
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float alpha) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += alpha * x[i];
+}
+
+// ------------------------------------------------------------------------------------------ VQA loss
+// loss = mean(BCEWithLogits(z, t)) * n_cols  (task_utils.py:325-327); dz = (sigmoid(z) - t) / n_rows * grad_scale
+__global__ void bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ t, float* __restrict__ loss,
+                                  float* __restrict__ dz32, __nv_bfloat16* __restrict__ dz16, long long lddz16, int rows, int cols,
+                                  float grad_scale) {
+  __shared__ float red[32];
+  const long long n = (long long)rows * cols;
+  float acc = 0.f;
+  const float inv_rows = 1.f / (float)rows;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = z[i], y = t[i];
+    acc += fmaxf(x, 0.f) - x * y + log1pf(__expf(-fabsf(x)));
+    const float g = (1.f / (1.f + __expf(-x)) - y) * inv_rows * grad_scale;
+    if (dz32) dz32[i] = g;
+    if (dz16) dz16[(i / cols) * lddz16 + (i % cols)] = __float2bfloat16(g);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss, v * inv_rows);
+  }
+}
+
+// additive attention mask (vilbert.py:1341-1362): out[b, j] = (1 - m[b, j]) * -10000; with prepend_one the
+// output row has N+1 entries and a leading 0 (task-token mask extension, :1331-1334)
+__global__ void mask_to_additive_kernel(const long long* __restrict__ m, float* __restrict__ out, int B, int N, int prepend) {
+  const int No = N + prepend;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * No; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / No), j = (int)(i % No);
+    float v = 0.f;
+    if (!(prepend && j == 0)) v = (1.0f - (float)m[(long long)b * N + (j - prepend)]) * -10000.0f;
+    out[i] = v;
+  }
+}
+
+static inline int ew_grid(long long n, int threads = 256) {
+  long long blocks = (n + threads - 1) / threads;
+  long long cap = (long long)sm_count() * 8;
+  if (cap <= 0) cap = 148 * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace vb
+
+using namespace vb;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* y_f32,
+                                      void* y_bf16, int64_t ldy, float* mean, float* rstd, int32_t M, int32_t H, void* stream) {
+  if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_layernorm_fwd: empty problem");
+  if ((H & 3) || H > MAX_V4 * 128 || (ldx & 3) || (ldy & 3) || !al16(x) || !al16(gamma) || !al16(beta) || (y_f32 && !al16(y_f32)) ||
+      (y_bf16 && (reinterpret_cast<uintptr_t>(y_bf16) & 7)))
+    return set_error(VB_ERR_INVALID, "vb_layernorm_fwd: need H %% 4 == 0, H <= %d, ld %% 4 == 0, 16-byte aligned rows", MAX_V4 * 128);
+  const int nv4 = (H / 4 + 31) / 32;
+  const int grid = row_grid(M);
+  __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
+#define LN_F(NV) ln_fwd_kernel<NV><<<grid, ROW_THREADS, 0, ST(stream)>>>(x, ldx, gamma, beta, eps, y_f32, y16, ldy, mean, rstd, M, H)
+  if (nv4 <= 1) LN_F(1); else if (nv4 <= 2) LN_F(2); else if (nv4 <= 4) LN_F(4); else if (nv4 <= 6) LN_F(6);
+  else if (nv4 <= 8) LN_F(8); else LN_F(16);
+#undef LN_F
+  return check_launch("vb_layernorm_fwd");
+}
+
+extern "C" vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma, const float* mean,
+                                      const float* rstd, float* dx_f32, void* dx_bf16, int64_t lddx, const void* gelu_pre,
+                                      int64_t ld_pre, float* dgamma, float* dbeta, int32_t M, int32_t H, void* stream) {
+  if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: empty problem");
+  if ((H & 3) || H > MAX_V4 * 128 || (ldx & 3) || (lddy & 3) || (lddx & 3) || (gelu_pre && (ld_pre & 3)) || !al16(dy) || !al16(x) || !al16(gamma))
+    return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: need H %% 4 == 0, H <= %d, ld %% 4 == 0, 16-byte aligned rows", MAX_V4 * 128);
+  const int nv4 = (H / 4 + 31) / 32;
+  int grid = row_grid(M);
+  const int cap = sm_count() * 2;   // fewer CTAs -> fewer dgamma/dbeta atomics
+  if (grid > cap && cap > 0) grid = cap;
+  __nv_bfloat16* dx16 = static_cast<__nv_bfloat16*>(dx_bf16);
+  const __nv_bfloat16* pre = static_cast<const __nv_bfloat16*>(gelu_pre);
+#define LN_B(NV) ln_bwd_kernel<NV><<<grid, ROW_THREADS, 0, ST(stream)>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx_f32, dx16, lddx, pre, ld_pre, dgamma, dbeta, M, H)
+  if (nv4 <= 1) LN_B(1); else if (nv4 <= 2) LN_B(2); else if (nv4 <= 4) LN_B(4); else if (nv4 <= 6) LN_B(6);
+  else if (nv4 <= 8) LN_B(8); else LN_B(16);
+#undef LN_B
+  return check_launch("vb_layernorm_bwd");
+}
+
+extern "C" vb_status vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n <= 0) return VB_OK;
+  if (!al16(src) || (reinterpret_cast<uintptr_t>(dst) & 7)) return set_error(VB_ERR_INVALID, "vb_cast_f32_to_bf16: misaligned buffers");
+  cast_f32_bf16_kernel<<<ew_grid(n / 4 + 1), 256, 0, ST(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n / 4, n);
+  return check_launch("vb_cast_f32_to_bf16");
+}
+
+extern "C" vb_status vb_cast2d_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows, int32_t cols, float scale,
+                                           void* stream) {
+  if (rows <= 0 || cols <= 0) return VB_OK;
+  dim3 grid((cols + 255) / 256 > 64 ? 64 : (cols + 255) / 256, rows > 4096 ? 4096 : rows);
+  cast2d_f32_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols, scale);
+  return check_launch("vb_cast2d_f32_to_bf16");
+}
+
+extern "C" vb_status vb_embed_text_fwd(const int64_t* ids, const int64_t* token_type_ids, const int64_t* task_ids, const float* word,
+                                       const float* pos, const float* type, const float* task, float* out, int32_t B, int32_t Nt,
+                                       int32_t H, void* stream) {
+  if (B <= 0 || Nt <= 0 || (H & 3)) return set_error(VB_ERR_INVALID, "vb_embed_text_fwd: bad shape");
+  const int has_task = task_ids != nullptr;
+  if (has_task && !task) return set_error(VB_ERR_INVALID, "vb_embed_text_fwd: task ids without a task table");
+  const long long rows = (long long)B * (Nt + has_task);
+  embed_text_fwd_kernel<<<row_grid(rows), ROW_THREADS, 0, ST(stream)>>>(
+      reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(token_type_ids),
+      reinterpret_cast<const long long*>(task_ids), word, pos, type, task, out, B, Nt, H, has_task);
+  return check_launch("vb_embed_text_fwd");
+}
+
+extern "C" vb_status vb_embed_text_bwd(const float* dout, const int64_t* ids, const int64_t* token_type_ids, const int64_t* task_ids,
+                                       float* dword, float* dpos, float* dtype, float* dtask, int32_t B, int32_t Nt, int32_t H,
+                                       void* stream) {
+  if (B <= 0 || Nt <= 0) return set_error(VB_ERR_INVALID, "vb_embed_text_bwd: bad shape");
+  const int has_task = task_ids != nullptr;
+  const long long rows = (long long)B * (Nt + has_task);
+  embed_text_bwd_kernel<<<row_grid(rows), ROW_THREADS, 0, ST(stream)>>>(
+      dout, reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(token_type_ids),
+      reinterpret_cast<const long long*>(task_ids), dword, dpos, dtype, dtask, B, Nt, H, has_task);
+  return check_launch("vb_embed_text_bwd");
+}
+
+extern "C" vb_status vb_loc_proj_fwd(const float* loc, const float* W, const float* b, float* out, int32_t M, int32_t H, void* stream) {
+  if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_loc_proj_fwd: bad shape");
+  const size_t smem = (size_t)H * 6 * sizeof(float);
+  if (smem > 48 * 1024) return set_error(VB_ERR_UNSUPPORTED, "vb_loc_proj_fwd: H too large");
+  int grid = sm_count() * 4; if (grid > M) grid = M; if (grid <= 0) grid = 1;
+  loc_proj_fwd_kernel<<<grid, 256, smem, ST(stream)>>>(loc, W, b, out, M, H);
+  return check_launch("vb_loc_proj_fwd");
+}
+
+extern "C" vb_status vb_loc_proj_bwd(const float* dy, const float* loc, float* dW, float* db, int32_t M, int32_t H, void* stream) {
+  if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_loc_proj_bwd: bad shape");
+  const int rpb = 64;
+  dim3 grid((H + 127) / 128, (M + rpb - 1) / rpb);
+  loc_proj_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(dy, loc, dW, db, M, H, rpb);
+  return check_launch("vb_loc_proj_bwd");
+}
+
+extern "C" vb_status vb_colsum(const void* X, int32_t is_bf16, int64_t ld, float* out, int32_t M, int32_t N, void* stream) {
+  if (M <= 0 || N <= 0) return set_error(VB_ERR_INVALID, "vb_colsum: bad shape");
+  int rpb = (M + 31) / 32; if (rpb < 64) rpb = 64;
+  dim3 grid((N + 31) / 32, (M + rpb - 1) / rpb), block(32, 8);
+  if (is_bf16) colsum_kernel<__nv_bfloat16><<<grid, block, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(X), ld, out, M, N, rpb);
+  else colsum_kernel<float><<<grid, block, 0, ST(stream)>>>(static_cast<const float*>(X), ld, out, M, N, rpb);
+  return check_launch("vb_colsum");
+}
+
+extern "C" vb_status vb_small_linear_fwd(const float* x, int64_t ldx, const float* W, const float* b, const float* row_addend, float* y,
+                                         int32_t M, int32_t K, int32_t N, void* stream) {
+  if (M <= 0 || K <= 0 || N <= 0 || N > 8) return set_error(VB_ERR_INVALID, "vb_small_linear_fwd: bad shape (N <= 8)");
+  small_linear_fwd_kernel<<<row_grid(M), ROW_THREADS, 0, ST(stream)>>>(x, ldx, W, b, row_addend, y, M, K, N);
+  return check_launch("vb_small_linear_fwd");
+}
+
+extern "C" vb_status vb_small_linear_bwd(const float* dy, const float* x, int64_t ldx, const float* W, float* dx, int64_t lddx,
+                                         int32_t accumulate_dx, float* dW, float* db, int32_t M, int32_t K, int32_t N, void* stream) {
+  if (M <= 0 || K <= 0 || N <= 0 || N > 8) return set_error(VB_ERR_INVALID, "vb_small_linear_bwd: bad shape (N <= 8)");
+  int grid = sm_count(); if (grid > M) grid = M; if (grid <= 0) grid = 1;
+  small_linear_bwd_kernel<<<grid, ROW_THREADS, 0, ST(stream)>>>(dy, x, ldx, W, dx, lddx, accumulate_dx, dW, db, M, K, N);
+  return check_launch("vb_small_linear_bwd");
+}
+
+extern "C" vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul, void* stream) {
+  if (n <= 0) return VB_OK;
+  fuse_pooled_fwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(a, b, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n, mul);
+  return check_launch("vb_fuse_pooled_fwd");
+}
+extern "C" vb_status vb_fuse_pooled_bwd(const float* d, const float* a, const float* b, float* da, float* db, int64_t n, int32_t mul,
+                                        void* stream) {
+  if (n <= 0) return VB_OK;
+  fuse_pooled_bwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(d, a, b, da, db, n, mul);
+  return check_launch("vb_fuse_pooled_bwd");
+}
+extern "C" vb_status vb_relu_bwd(const float* dy, const float* y, void* dx_bf16, float* dx_f32, int64_t n, void* stream) {
+  if (n <= 0) return VB_OK;
+  relu_bwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(dy, y, static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, n);
+  return check_launch("vb_relu_bwd");
+}
+extern "C" vb_status vb_axpy_f32(const float* x, float* y, int64_t n, float alpha, void* stream) {
+  if (n <= 0) return VB_OK;
+  axpy_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(x, y, n, alpha);
+  return check_launch("vb_axpy_f32");
+}
+extern "C" vb_status vb_bce_logits_loss(const float* logits, const float* target, float* loss, float* dlogits_f32, void* dlogits_bf16,
+                                        int64_t ld_dlogits_bf16, int32_t rows, int32_t cols, float grad_scale, void* stream) {
+  if (rows <= 0 || cols <= 0) return set_error(VB_ERR_INVALID, "vb_bce_logits_loss: bad shape");
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), ST(stream));
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_bce_logits_loss: memset: %s", cudaGetErrorString(e));
+  bce_logits_kernel<<<ew_grid((long long)rows * cols), 256, 0, ST(stream)>>>(logits, target, loss, dlogits_f32,
+                                                                              static_cast<__nv_bfloat16*>(dlogits_bf16), ld_dlogits_bf16, rows,
+                                                                              cols, grad_scale);
+  return check_launch("vb_bce_logits_loss");
+}
+extern "C" vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_t B, int32_t N, int32_t prepend_one, void* stream) {
+  if (B <= 0 || N <= 0) return set_error(VB_ERR_INVALID, "vb_mask_to_additive: bad shape");
+  mask_to_additive_kernel<<<ew_grid((long long)B * (N + 1)), 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(mask), out, B, N, prepend_one ? 1 : 0);
+  return check_launch("vb_mask_to_additive");
+}
+extern "C" vb_status vb_memset_zero(void* ptr, int64_t bytes, void* stream) {
+  if (bytes <= 0) return VB_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, ST(stream));
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_memset_zero: %s", cudaGetErrorString(e));
+  return VB_OK;
+}

@@ -1,0 +1,805 @@
+"""Execution engine of the B200 ViLBERT hot path.
+
+Mirrors, operation for operation, what the reference's eager modules do in
+VILBertForVLTasks.forward -> BertModel.forward -> BertEncoder.forward (vilbert/vilbert.py:1638-1708,
+:1309-1406, :934-1107) and what autograd derives from them, but as a static *plan*: for a given
+(B, Nt, Nv) shape every activation buffer is allocated once and the forward and backward passes
+become flat lists of C-ABI calls into libvilbert_b200.so (tcgen05 GEMMs, fused attention, row-wise
+kernels). A plan can be replayed eagerly (a tight loop of ctypes calls) or captured into one CUDA
+graph per pass. PyTorch is used for device memory, streams and (optionally) graph capture only.
+
+Numerics ("bf16 mode"): GEMM operands bf16, accumulation fp32 (TMEM); the residual
+stream, LayerNorm statistics/outputs, softmax statistics, biases and every gradient accumulation
+are fp32; bf16 copies of activations exist only as GEMM / attention operands.
+"""
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import _lib as L
+
+F32, BF16, I64 = torch.float32, torch.bfloat16, torch.int64
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+# ------------------------------------------------------------------------------------------ parameters
+class ParamStore:
+    """All parameters live in ONE flat fp32 buffer (reference state_dict names map to views of it), with a
+    flat fp32 gradient buffer of the same layout (what the data-parallel all-reduce operates on) and a flat
+    bf16 shadow used as GEMM operands. query/key/value weights of one attention are allocated contiguously
+    so that the fused [3H, H] QKV GEMM reads them in place."""
+
+    def __init__(self, cfg, device, heads="vl"):
+        """heads: "vl" = pre-training heads + the 7 task heads (VILBertForVLTasks), "pretraining" = cls.* only
+        (BertForMultiModalPreTraining), "none" = bare BertModel."""
+        assert heads in ("vl", "pretraining", "none")
+        self.heads = heads
+        with_task_heads = heads == "vl"
+        self.cfg = cfg
+        self.device = device
+        self.entries = OrderedDict()   # reference name -> (offset, shape)
+        self.fused = {}                # fused qkv name -> (offset, shape)
+        self._off = 0
+        c = cfg
+        Ht, It, Hv, Iv, Hb = c.hidden_size, c.intermediate_size, c.v_hidden_size, c.v_intermediate_size, c.bi_hidden_size
+        for h in (Ht, It, Hv, Iv, Hb, c.v_feature_size):
+            if h % 8:
+                raise ValueError("vilbert_b200: hidden sizes must be multiples of 8 (TMA row pitch)")
+        add, lin, ln = self._add, self._lin, self._ln
+        add("bert.embeddings.word_embeddings.weight", (c.vocab_size, Ht))
+        add("bert.embeddings.position_embeddings.weight", (c.max_position_embeddings, Ht))
+        add("bert.embeddings.token_type_embeddings.weight", (c.type_vocab_size, Ht))
+        ln("bert.embeddings.LayerNorm", Ht)
+        if c.task_specific_tokens:
+            add("bert.embeddings.task_embeddings.weight", (20, Ht))
+        lin("bert.v_embeddings.image_embeddings", Hv, c.v_feature_size)
+        lin("bert.v_embeddings.image_location_embeddings", Hv, 5)
+        ln("bert.v_embeddings.LayerNorm", Hv)
+        for kind, n, H, I in (("layer", c.num_hidden_layers, Ht, It), ("v_layer", c.v_num_hidden_layers, Hv, Iv)):
+            for i in range(n):
+                p = f"bert.encoder.{kind}.{i}"
+                self._qkv(f"{p}.attention.self", ("query", "key", "value"), H, H)
+                lin(f"{p}.attention.output.dense", H, H); ln(f"{p}.attention.output.LayerNorm", H)
+                lin(f"{p}.intermediate.dense", I, H)
+                lin(f"{p}.output.dense", H, I); ln(f"{p}.output.LayerNorm", H)
+        for i in range(len(c.v_biattention_id)):
+            p = f"bert.encoder.c_layer.{i}"
+            self._qkv(f"{p}.biattention", ("query1", "key1", "value1"), Hb, Hv, fused="qkv1")
+            self._qkv(f"{p}.biattention", ("query2", "key2", "value2"), Hb, Ht, fused="qkv2")
+            lin(f"{p}.biOutput.dense1", Hv, Hb); ln(f"{p}.biOutput.LayerNorm1", Hv); lin(f"{p}.biOutput.q_dense1", Hv, Hb)
+            lin(f"{p}.biOutput.dense2", Ht, Hb); ln(f"{p}.biOutput.LayerNorm2", Ht); lin(f"{p}.biOutput.q_dense2", Ht, Hb)
+            lin(f"{p}.v_intermediate.dense", Iv, Hv); lin(f"{p}.v_output.dense", Hv, Iv); ln(f"{p}.v_output.LayerNorm", Hv)
+            lin(f"{p}.t_intermediate.dense", It, Ht); lin(f"{p}.t_output.dense", Ht, It); ln(f"{p}.t_output.LayerNorm", Ht)
+        lin("bert.t_pooler.dense", Hb, Ht); lin("bert.v_pooler.dense", Hb, Hv)
+        if heads != "none":
+            add("cls.predictions.bias", (c.vocab_size,))
+            lin("cls.predictions.transform.dense", Ht, Ht); ln("cls.predictions.transform.LayerNorm", Ht)
+            lin("cls.bi_seq_relationship", 2, Hb)
+            lin("cls.imagePredictions.transform.dense", Hv, Hv); ln("cls.imagePredictions.transform.LayerNorm", Hv)
+            lin("cls.imagePredictions.decoder", c.v_target_size, Hv)
+        self.with_task_heads = with_task_heads
+        if with_task_heads:
+            for nm, i, o in (("vil_prediction", Hb, 3129), ("vil_prediction_gqa", Hb, 1533), ("vil_binary_prediction", 2 * Hb, 2)):
+                lin(f"{nm}.logit_fc.0", 2 * Hb, i); ln(f"{nm}.logit_fc.2", 2 * Hb); lin(f"{nm}.logit_fc.3", o, 2 * Hb)
+            lin("vil_logit", 1, Hb); lin("vil_tri_prediction", 3, Hb); lin("vision_logit", 1, Hv); lin("linguisic_logit", 1, Ht)
+        self.numel = self._off
+        self.flat = torch.zeros(self.numel, dtype=F32, device=device)
+        self.grad = torch.zeros(self.numel, dtype=F32, device=device)
+        self.shadow = torch.zeros(self.numel, dtype=BF16, device=device)
+        self.shadow_version = None
+
+    def _add(self, name, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        self.entries[name] = (self._off, tuple(shape))
+        self._off += _pad8(n)
+
+    def _lin(self, name, o, i):
+        self._add(name + ".weight", (o, i)); self._add(name + ".bias", (o,))
+
+    def _ln(self, name, h):
+        self._add(name + ".weight", (h,)); self._add(name + ".bias", (h,))
+
+    def _qkv(self, prefix, names, o, i, fused="qkv"):
+        assert (o * i) % 8 == 0 and o % 8 == 0
+        w0 = self._off
+        for nm in names:
+            self._add(f"{prefix}.{nm}.weight", (o, i))
+        b0 = self._off
+        for nm in names:
+            self._add(f"{prefix}.{nm}.bias", (o,))
+        self.fused[f"{prefix}.{fused}.weight"] = (w0, (3 * o, i))
+        self.fused[f"{prefix}.{fused}.bias"] = (b0, (3 * o,))
+
+    def _view(self, flat, name):
+        off, shape = self.entries[name] if name in self.entries else self.fused[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return flat[off:off + n].view(shape)
+
+    def p(self, name):
+        return self._view(self.flat, name)
+
+    def g(self, name):
+        return self._view(self.grad, name)
+
+    def w16(self, name):
+        return self._view(self.shadow, name)
+
+    def refresh_shadow(self, stream):
+        """bf16 copy of every parameter in one launch (belongs with the optimizer step in training)."""
+        L.check(L.lib().vb_cast_f32_to_bf16(self.flat.data_ptr(), self.shadow.data_ptr(), self.numel, stream), "vb_cast_f32_to_bf16")
+
+
+# ------------------------------------------------------------------------------------------ plan
+class Act:
+    """A residual-stream activation: fp32 values, bf16 operand copy, fp32 gradient (lazily allocated)."""
+    __slots__ = ("f32", "b16", "g32", "gw", "M", "H")
+
+    def __init__(self, f32, b16, M, H):
+        self.f32, self.b16, self.M, self.H = f32, b16, M, H
+        self.g32, self.gw = None, False
+
+
+HEAD_NAMES = ("vil_prediction", "vil_prediction_gqa", "vil_logit", "vil_binary_prediction", "vil_tri_prediction",
+              "vision_prediction", "vision_logit", "linguisic_prediction", "linguisic_logit")
+BERT_OUT_NAMES = ("sequence_output_t", "sequence_output_v", "pooled_output_t", "pooled_output_v")
+
+
+class Plan:
+    """Static execution plan for one input shape. `grad_outputs` names the outputs that will receive a
+    gradient in backward (dead branches are not emitted); `vqa_loss` fuses the VQA BCE objective
+    (task_utils.py:325-327) and its gradient after the forward."""
+
+    def __init__(self, engine, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None):
+        self.e, self.ps, self.cfg = engine, engine.ps, engine.cfg
+        self.lib = L.lib()
+        self.dev = engine.device
+        self.B, self.Nt_in, self.Nv = B, Nt, Nv
+        self.has_task = bool(self.cfg.task_specific_tokens)
+        self.Nt = Nt + (1 if self.has_task else 0)
+        self.grad_outputs = frozenset(grad_outputs)
+        self.vqa_loss = vqa_loss
+        self.heads = engine.ps.heads if heads is None else heads   # "vl" | "pretraining" | "none"
+        self.fwd_id = 0
+        self.fwd, self.bwd = [], []
+        self.cur = self.fwd
+        self._keep = []          # ctypes structs / tensors referenced by raw pointer
+        self._scratch = {}
+        self._bwd_emitters = []
+        self.n_kernels_fwd = self.n_kernels_bwd = 0
+        self.graph_fwd = self.graph_bwd = self.graph_step = None
+        self._build()
+
+    # ------------------------------------------------------------------ infrastructure
+    def buf(self, shape, dtype=F32, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
+        self._keep.append(t)
+        return t
+
+    def scratch(self, tag, shape, dtype):
+        key = (tag, tuple(shape), dtype)
+        if key not in self._scratch:
+            self._scratch[key] = self.buf(shape, dtype)
+        return self._scratch[key]
+
+    def emit(self, fn, *args):
+        self.cur.append((fn, args))
+
+    @staticmethod
+    def _ptr(t):
+        if t is None:
+            return None
+        return t.data_ptr() if torch.is_tensor(t) else int(t)
+
+    def gemm(self, M, N, K, A, lda, B, ldb, a_mn=0, b_mn=0, bias=None, residual=None, ld_res=0, aux=None, ld_aux=0, act=0,
+             out_f32=None, ld_of=0, out_bf16=None, ld_ob=0, out_pre=None, ld_op=0, atomic=0, split_k=1, alpha=1.0):
+        g = L.GemmArgs()
+        g.M, g.N, g.K = M, N, K
+        g.A, g.lda, g.a_mn_major = self._ptr(A), lda, a_mn
+        g.B, g.ldb, g.b_mn_major = self._ptr(B), ldb, b_mn
+        g.alpha = alpha
+        g.bias = self._ptr(bias)
+        g.residual, g.ld_res = self._ptr(residual), ld_res
+        g.aux, g.ld_aux = self._ptr(aux), ld_aux
+        g.act = act
+        g.out_f32, g.ld_out_f32 = self._ptr(out_f32), ld_of
+        g.out_bf16, g.ld_out_bf16 = self._ptr(out_bf16), ld_ob
+        g.out_pre, g.ld_out_pre = self._ptr(out_pre), ld_op
+        g.atomic_out, g.split_k, g.block_n, g.max_ctas = atomic, split_k, 0, 0
+        self._keep.append(g)
+        self.emit(self.lib.vb_gemm_bf16, C.byref(g))
+
+    def attention(self, bwd, B, H, Nq, Nk, D, Q, ldq, K, ldk, V, ldv, mask, O, ldo, lse, dO=None, lddo=0, dQ=None, lddq=0,
+                  dK=None, lddk=0, dV=None, lddv=0, delta=None):
+        a = L.AttnArgs()
+        a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
+        a.Q, a.ldq, a.K, a.ldk, a.V, a.ldv = self._ptr(Q), ldq, self._ptr(K), ldk, self._ptr(V), ldv
+        a.mask, a.scale = self._ptr(mask), 1.0 / math.sqrt(D)
+        a.O, a.ldo, a.lse = self._ptr(O), ldo, self._ptr(lse)
+        a.dO, a.lddo, a.dQ, a.lddq = self._ptr(dO), lddo, self._ptr(dQ), lddq
+        a.dK, a.lddk, a.dV, a.lddv, a.delta = self._ptr(dK), lddk, self._ptr(dV), lddv, self._ptr(delta)
+        self._keep.append(a)
+        self.emit(self.lib.vb_attention_bwd if bwd else self.lib.vb_attention_fwd, C.byref(a))
+
+    def ln_fwd(self, x, gamma, beta, M, H, want_f32=True):
+        y32 = self.buf((M, H), F32) if want_f32 else None
+        y16 = self.buf((M, H), BF16)
+        mean, rstd = self.buf((M,), F32), self.buf((M,), F32)
+        self.emit(self.lib.vb_layernorm_fwd, x.data_ptr(), H, gamma.data_ptr(), beta.data_ptr(), 1e-12, self._ptr(y32), y16.data_ptr(), H,
+                  mean.data_ptr(), rstd.data_ptr(), M, H)
+        return y32, y16, mean, rstd
+
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dx32, dx16, M, H, ggamma, gbeta, pre=None):
+        self.emit(self.lib.vb_layernorm_bwd, dy.data_ptr(), H, x.data_ptr(), H, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                  self._ptr(dx32), self._ptr(dx16), H, self._ptr(pre), H, ggamma.data_ptr(), gbeta.data_ptr(), M, H)
+
+    def colsum(self, X, ld, out, M, N):
+        self.emit(self.lib.vb_colsum, X.data_ptr(), 1 if X.dtype == BF16 else 0, ld, out.data_ptr(), M, N)
+
+    def grad_of(self, act):
+        if act.g32 is None:
+            act.g32 = self.buf((act.M, act.H), F32)
+        return act.g32
+
+    # dW, db of y = x W^T + b given dy (bf16 operand copy + a source for the bias column sums)
+    def linear_wgrad(self, dy16, ld_dy, dy_bias, ld_dyb, x16, ld_x, M, N_out, K_in, wname):
+        if dy_bias is not None:
+            self.colsum(dy_bias, ld_dyb, self.ps.g(wname + ".bias"), M, N_out)
+        self.gemm(N_out, K_in, M, dy16, ld_dy, x16, ld_x, a_mn=1, b_mn=1, out_f32=self.ps.g(wname + ".weight"), ld_of=K_in, atomic=1,
+                  split_k=0)
+
+    # act.g32 (+)= dy16 @ W (+ extra32)
+    def dgrad_into(self, act, dy16, ld_dy, W16, M, N_out, K_in, extra32=None):
+        g = self.grad_of(act)
+        if not act.gw:
+            self.gemm(M, K_in, N_out, dy16, ld_dy, W16, K_in, b_mn=1, residual=extra32, ld_res=K_in, out_f32=g, ld_of=K_in)
+            act.gw = True
+        else:
+            if extra32 is not None:
+                self.emit(self.lib.vb_axpy_f32, extra32.data_ptr(), g.data_ptr(), M * K_in, 1.0)
+            self.gemm(M, K_in, N_out, dy16, ld_dy, W16, K_in, b_mn=1, residual=g, ld_res=K_in, out_f32=g, ld_of=K_in)
+
+    def add_grad(self, act, src32):
+        g = self.grad_of(act)
+        if not act.gw:
+            self.emit(self.lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
+            act.gw = True
+        self.emit(self.lib.vb_axpy_f32, src32.data_ptr(), g.data_ptr(), g.numel(), 1.0)
+
+    # ------------------------------------------------------------------ blocks
+    def dense_res_ln(self, a16, K_in, res, wname, lnname, tag):
+        """LN(dense(a) + residual)  — BertSelfOutput / BertOutput / BertBiOutput halves (vilbert.py:470-474, 513-517, 844-855)."""
+        ps, M, H = self.ps, res.M, res.H
+        y = self.buf((M, H), F32)
+        self.gemm(M, H, K_in, a16, K_in, ps.w16(wname + ".weight"), K_in, bias=ps.p(wname + ".bias"), residual=res.f32, ld_res=H,
+                  out_f32=y, ld_of=H)
+        o32, o16, mean, rstd = self.ln_fwd(y, ps.p(lnname + ".weight"), ps.p(lnname + ".bias"), M, H)
+        out = Act(o32, o16, M, H)
+
+        def bwd():
+            """returns (dy16, dy32) of the dense output (== grad of the LN input); adds dy32 to res."""
+            if not out.gw:
+                return None
+            dy32 = self.scratch(tag + ".dy32", (M, H), F32)
+            dy16 = self.scratch(tag + ".dy16", (M, H), BF16)
+            self.ln_bwd(out.g32, y, ps.p(lnname + ".weight"), mean, rstd, dy32, dy16, M, H, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"))
+            self.linear_wgrad(dy16, H, dy32, H, a16, K_in, M, H, K_in, wname)
+            return dy16, dy32
+        return out, bwd
+
+    def ffn(self, x, I, w1, w2, lnname, tag):
+        """LN(dense2(gelu(dense1(x))) + x) — BertIntermediate + BertOutput (vilbert.py:500-503, 513-517)."""
+        ps, M, H = self.ps, x.M, x.H
+        pre16, f16 = self.buf((M, I), BF16), self.buf((M, I), BF16)
+        self.gemm(M, I, H, x.b16, H, ps.w16(w1 + ".weight"), H, bias=ps.p(w1 + ".bias"), act=L.VB_ACT_GELU, out_bf16=f16, ld_ob=I,
+                  out_pre=pre16, ld_op=I)
+        out, out_bwd = self.dense_res_ln(f16, I, x, w2, lnname, tag + ".o")
+
+        def bwd():
+            r = out_bwd()
+            if r is None:
+                return
+            dy16, dy32 = r
+            dpre16 = self.scratch(tag + ".dpre16", (M, I), BF16)
+            # d pre = (dy W2) * gelu'(pre)
+            self.gemm(M, I, H, dy16, H, ps.w16(w2 + ".weight"), I, b_mn=1, aux=pre16, ld_aux=I, act=L.VB_ACT_DGELU, out_bf16=dpre16, ld_ob=I)
+            self.linear_wgrad(dpre16, I, dpre16, I, x.b16, H, M, I, H, w1)
+            self.dgrad_into(x, dpre16, I, ps.w16(w1 + ".weight"), M, I, H, extra32=dy32)
+        self._bwd_emitters.append(bwd)
+        return out
+
+    def self_attention_block(self, x, B, N, nh, mask, prefix, tag):
+        """BertAttention (self-attention + output), text or image stream (vilbert.py:424-474, 571-633)."""
+        ps, M, H = self.ps, x.M, x.H
+        D = H // nh
+        qkv = self.buf((M, 3 * H), BF16)
+        self.gemm(M, 3 * H, H, x.b16, H, ps.w16(prefix + ".self.qkv.weight"), H, bias=ps.p(prefix + ".self.qkv.bias"), out_bf16=qkv, ld_ob=3 * H)
+        ctx = self.buf((M, H), BF16)
+        lse = self.buf((B, nh, N), F32)
+        q, k, v = qkv[:, 0:H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+        self.attention(False, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse)
+        out, out_bwd = self.dense_res_ln(ctx, H, x, prefix + ".output.dense", prefix + ".output.LayerNorm", tag + ".ao")
+
+        def bwd():
+            r = out_bwd()
+            if r is None:
+                return
+            dy16, dy32 = r
+            dctx = self.scratch(tag + ".dctx", (M, H), BF16)
+            self.gemm(M, H, H, dy16, H, ps.w16(prefix + ".output.dense.weight"), H, b_mn=1, out_bf16=dctx, ld_ob=H)
+            dqkv = self.scratch(tag + ".dqkv", (M, 3 * H), BF16)
+            delta = self.scratch(tag + ".delta", (B, nh, N), F32)
+            self.attention(True, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dO=dctx, lddo=H,
+                           dQ=dqkv[:, 0:H], lddq=3 * H, dK=dqkv[:, H:2 * H], lddk=3 * H, dV=dqkv[:, 2 * H:], lddv=3 * H, delta=delta)
+            self.linear_wgrad(dqkv, 3 * H, dqkv, 3 * H, x.b16, H, M, 3 * H, H, prefix + ".self.qkv")
+            self.dgrad_into(x, dqkv, 3 * H, ps.w16(prefix + ".self.qkv.weight"), M, 3 * H, H, extra32=dy32)
+        self._bwd_emitters.append(bwd)
+        return out
+
+    def connection_layer(self, v, t, idx):
+        """BertConnectionLayer.forward (vilbert.py:871-900): co-attention both ways + dual FFN."""
+        ps, c, B = self.ps, self.cfg, self.B
+        p = f"bert.encoder.c_layer.{idx}"
+        Hb, nh = c.bi_hidden_size, c.bi_num_attention_heads
+        D = Hb // nh
+        Mv, Mt, Hv, Ht, Nv, Nt = v.M, t.M, v.H, t.H, self.Nv, self.Nt
+        qkv1 = self.buf((Mv, 3 * Hb), BF16)
+        qkv2 = self.buf((Mt, 3 * Hb), BF16)
+        self.gemm(Mv, 3 * Hb, Hv, v.b16, Hv, ps.w16(p + ".biattention.qkv1.weight"), Hv, bias=ps.p(p + ".biattention.qkv1.bias"), out_bf16=qkv1, ld_ob=3 * Hb)
+        self.gemm(Mt, 3 * Hb, Ht, t.b16, Ht, ps.w16(p + ".biattention.qkv2.weight"), Ht, bias=ps.p(p + ".biattention.qkv2.bias"), out_bf16=qkv2, ld_ob=3 * Hb)
+        q1, k1, v1 = qkv1[:, 0:Hb], qkv1[:, Hb:2 * Hb], qkv1[:, 2 * Hb:]
+        q2, k2, v2 = qkv2[:, 0:Hb], qkv2[:, Hb:2 * Hb], qkv2[:, 2 * Hb:]
+        ctx1 = self.buf((Mt, Hb), BF16); lse1 = self.buf((B, nh, Nt), F32)   # text queries over vision keys/values
+        ctx2 = self.buf((Mv, Hb), BF16); lse2 = self.buf((B, nh, Nv), F32)   # vision queries over text keys/values
+        L3 = 3 * Hb
+        self.attention(False, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1)
+        self.attention(False, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2)
+        # biOutput: ctx2 -> vision stream (dense1 / LayerNorm1), ctx1 -> text stream (dense2 / LayerNorm2) (:890-892)
+        v1o, v1_bwd = self.dense_res_ln(ctx2, Hb, v, p + ".biOutput.dense1", p + ".biOutput.LayerNorm1", "c.v.bo")
+        t1o, t1_bwd = self.dense_res_ln(ctx1, Hb, t, p + ".biOutput.dense2", p + ".biOutput.LayerNorm2", "c.t.bo")
+
+        def bwd():
+            if not (v1o.gw or t1o.gw):
+                return
+            for a in (v1o, t1o):   # a stream without downstream gradient contributes zeros
+                if not a.gw:
+                    g = self.grad_of(a)
+                    self.emit(self.lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
+                    a.gw = True
+            rv, rt = v1_bwd(), t1_bwd()
+            dqkv1 = self.scratch("c.dqkv1", (Mv, L3), BF16)
+            dqkv2 = self.scratch("c.dqkv2", (Mt, L3), BF16)
+            dctx2 = self.scratch("c.dctx2", (Mv, Hb), BF16)
+            dctx1 = self.scratch("c.dctx1", (Mt, Hb), BF16)
+            dyv16, dyv32 = rv
+            dyt16, dyt32 = rt
+            self.gemm(Mv, Hb, Hv, dyv16, Hv, ps.w16(p + ".biOutput.dense1.weight"), Hb, b_mn=1, out_bf16=dctx2, ld_ob=Hb)
+            self.gemm(Mt, Hb, Ht, dyt16, Ht, ps.w16(p + ".biOutput.dense2.weight"), Hb, b_mn=1, out_bf16=dctx1, ld_ob=Hb)
+            d1 = self.scratch("c.delta1", (B, nh, Nt), F32)
+            d2 = self.scratch("c.delta2", (B, nh, Nv), F32)
+            self.attention(True, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1, dO=dctx1, lddo=Hb,
+                           dQ=dqkv2[:, 0:Hb], lddq=L3, dK=dqkv1[:, Hb:2 * Hb], lddk=L3, dV=dqkv1[:, 2 * Hb:], lddv=L3, delta=d1)
+            self.attention(True, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dO=dctx2, lddo=Hb,
+                           dQ=dqkv1[:, 0:Hb], lddq=L3, dK=dqkv2[:, Hb:2 * Hb], lddk=L3, dV=dqkv2[:, 2 * Hb:], lddv=L3, delta=d2)
+            self.linear_wgrad(dqkv1, L3, dqkv1, L3, v.b16, Hv, Mv, L3, Hv, p + ".biattention.qkv1")
+            self.linear_wgrad(dqkv2, L3, dqkv2, L3, t.b16, Ht, Mt, L3, Ht, p + ".biattention.qkv2")
+            self.dgrad_into(v, dqkv1, L3, ps.w16(p + ".biattention.qkv1.weight"), Mv, L3, Hv, extra32=dyv32)
+            self.dgrad_into(t, dqkv2, L3, ps.w16(p + ".biattention.qkv2.weight"), Mt, L3, Ht, extra32=dyt32)
+        self._bwd_emitters.append(bwd)
+        v2o = self.ffn(v1o, c.v_intermediate_size, p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", "c.v.ffn")
+        t2o = self.ffn(t1o, c.intermediate_size, p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", "c.t.ffn")
+        return v2o, t2o
+
+    def text_layer(self, x, i):
+        p = f"bert.encoder.layer.{i}"
+        c = self.cfg
+        h1 = self.self_attention_block(x, self.B, self.Nt, c.num_attention_heads, self.mask_t, p + ".attention", "t")
+        return self.ffn(h1, c.intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "t.ffn")
+
+    def image_layer(self, x, i):
+        p = f"bert.encoder.v_layer.{i}"
+        c = self.cfg
+        h1 = self.self_attention_block(x, self.B, self.Nv, c.v_num_attention_heads, self.mask_v, p + ".attention", "v")
+        return self.ffn(h1, c.v_intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "v.ffn")
+
+    # ------------------------------------------------------------------ embeddings
+    def embeddings(self):
+        ps, c, B, lib = self.ps, self.cfg, self.B, self.lib
+        Ht, Hv, Nt, Nv, Fv = c.hidden_size, c.v_hidden_size, self.Nt, self.Nv, c.v_feature_size
+        Mt, Mv = B * Nt, B * Nv
+        # static inputs
+        self.in_ids = self.buf((B, self.Nt_in), I64, zero=True)
+        self.in_tt = self.buf((B, self.Nt_in), I64, zero=True)
+        self.in_task = self.buf((B,), I64, zero=True) if self.has_task else None
+        self.in_amask = self.buf((B, self.Nt_in), I64, zero=True)
+        self.in_imask = self.buf((B, Nv), I64, zero=True)
+        self.in_feat = self.buf((B, Nv, Fv), F32, zero=True)
+        self.in_loc = self.buf((B, Nv, 5), F32, zero=True)
+        self.mask_t = self.buf((B, Nt), F32)
+        self.mask_v = self.buf((B, Nv), F32)
+        self.emit(lib.vb_mask_to_additive, self.in_amask.data_ptr(), self.mask_t.data_ptr(), B, self.Nt_in, 1 if self.has_task else 0)
+        self.emit(lib.vb_mask_to_additive, self.in_imask.data_ptr(), self.mask_v.data_ptr(), B, Nv, 0)
+        # text: gather-sum (+ task row) then LayerNorm (vilbert.py:346-367)
+        xe = self.buf((Mt, Ht), F32)
+        e = "bert.embeddings"
+        self.emit(lib.vb_embed_text_fwd, self.in_ids.data_ptr(), self.in_tt.data_ptr(), self._ptr(self.in_task), ps.p(e + ".word_embeddings.weight").data_ptr(),
+                  ps.p(e + ".position_embeddings.weight").data_ptr(), ps.p(e + ".token_type_embeddings.weight").data_ptr(),
+                  ps.p(e + ".task_embeddings.weight").data_ptr() if self.has_task else None, xe.data_ptr(), B, self.Nt_in, Ht)
+        t32, t16, tmean, trstd = self.ln_fwd(xe, ps.p(e + ".LayerNorm.weight"), ps.p(e + ".LayerNorm.bias"), Mt, Ht)
+        t = Act(t32, t16, Mt, Ht)
+        # image: region features fp32 -> bf16 ingest, 2048 -> Hv GEMM with the 5 -> Hv box projection as residual, LayerNorm (:1421-1432)
+        ve = "bert.v_embeddings"
+        feat16 = self.buf((Mv, Fv), BF16)
+        self.emit(lib.vb_cast_f32_to_bf16, self.in_feat.data_ptr(), feat16.data_ptr(), Mv * Fv)
+        locp = self.buf((Mv, Hv), F32)
+        self.emit(lib.vb_loc_proj_fwd, self.in_loc.data_ptr(), ps.p(ve + ".image_location_embeddings.weight").data_ptr(),
+                  ps.p(ve + ".image_location_embeddings.bias").data_ptr(), locp.data_ptr(), Mv, Hv)
+        yv = self.buf((Mv, Hv), F32)
+        self.gemm(Mv, Hv, Fv, feat16, Fv, ps.w16(ve + ".image_embeddings.weight"), Fv, bias=ps.p(ve + ".image_embeddings.bias"),
+                  residual=locp, ld_res=Hv, out_f32=yv, ld_of=Hv)
+        v32, v16, vmean, vrstd = self.ln_fwd(yv, ps.p(ve + ".LayerNorm.weight"), ps.p(ve + ".LayerNorm.bias"), Mv, Hv)
+        v = Act(v32, v16, Mv, Hv)
+
+        def bwd():
+            if t.gw:
+                dxe = self.scratch("emb.dxe", (Mt, Ht), F32)
+                self.ln_bwd(t.g32, xe, ps.p(e + ".LayerNorm.weight"), tmean, trstd, dxe, None, Mt, Ht, ps.g(e + ".LayerNorm.weight"), ps.g(e + ".LayerNorm.bias"))
+                self.emit(lib.vb_embed_text_bwd, dxe.data_ptr(), self.in_ids.data_ptr(), self.in_tt.data_ptr(), self._ptr(self.in_task),
+                          ps.g(e + ".word_embeddings.weight").data_ptr(), ps.g(e + ".position_embeddings.weight").data_ptr(),
+                          ps.g(e + ".token_type_embeddings.weight").data_ptr(),
+                          ps.g(e + ".task_embeddings.weight").data_ptr() if self.has_task else None, B, self.Nt_in, Ht)
+            if v.gw:
+                dyv32 = self.scratch("emb.dyv32", (Mv, Hv), F32)
+                dyv16 = self.scratch("emb.dyv16", (Mv, Hv), BF16)
+                self.ln_bwd(v.g32, yv, ps.p(ve + ".LayerNorm.weight"), vmean, vrstd, dyv32, dyv16, Mv, Hv, ps.g(ve + ".LayerNorm.weight"), ps.g(ve + ".LayerNorm.bias"))
+                self.linear_wgrad(dyv16, Hv, dyv32, Hv, feat16, Fv, Mv, Hv, Fv, ve + ".image_embeddings")
+                self.emit(lib.vb_loc_proj_bwd, dyv32.data_ptr(), self.in_loc.data_ptr(), ps.g(ve + ".image_location_embeddings.weight").data_ptr(),
+                          ps.g(ve + ".image_location_embeddings.bias").data_ptr(), Mv, Hv)
+        self._bwd_emitters.append(bwd)
+        return t, v
+
+    # ------------------------------------------------------------------ poolers and heads
+    def pooler(self, seq, N, wname):
+        """Linear + ReLU on token 0 (vilbert.py:1116-1122, 1131-1137); A is read with row pitch N*H."""
+        ps, B, H, Hb = self.ps, self.B, seq.H, self.cfg.bi_hidden_size
+        p32, p16 = self.buf((B, Hb), F32), self.buf((B, Hb), BF16)
+        self.gemm(B, Hb, H, seq.b16, N * H, ps.w16(wname + ".weight"), H, bias=ps.p(wname + ".bias"), act=L.VB_ACT_RELU, out_f32=p32, ld_of=Hb,
+                  out_bf16=p16, ld_ob=Hb)
+        pooled = Act(p32, p16, B, Hb)
+
+        def bwd():
+            if not pooled.gw:
+                return
+            dpre = self.scratch("pool.dpre", (B, Hb), BF16)
+            dpre32 = self.scratch("pool.dpre32", (B, Hb), F32)
+            self.emit(self.lib.vb_relu_bwd, pooled.g32.data_ptr(), p32.data_ptr(), dpre.data_ptr(), dpre32.data_ptr(), B * Hb)
+            self.linear_wgrad(dpre, Hb, dpre32, Hb, seq.b16, N * H, B, Hb, H, wname)
+            g = self.grad_of(seq)
+            if not seq.gw:
+                self.emit(self.lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
+                seq.gw = True
+            # rows b*N of the sequence gradient += dpre @ W
+            self.gemm(B, H, Hb, dpre, Hb, ps.w16(wname + ".weight"), H, b_mn=1, residual=g, ld_res=N * H, out_f32=g, ld_of=N * H)
+        self._bwd_emitters.append(bwd)
+        return pooled
+
+    def out_grad_buffer(self, name, shape):
+        """Static fp32 buffer the caller's d(loss)/d(output) is copied into before backward."""
+        if name not in self.gout:
+            self.gout[name] = self.buf(shape, F32, zero=True)
+        return self.gout[name]
+
+    def big_head(self, name, x16, ld_x, x_act, M, K_in, N_out, wname, bias_name, w16=None, gw=None):
+        """Wide linear head (N_out in the thousands): logits = x W^T + b as fp32 [M, N_out]; backward from a
+        caller-supplied fp32 d(logits) (cast to a bf16 operand with an 8-padded row pitch)."""
+        ps = self.ps
+        W16 = w16 if w16 is not None else ps.w16(wname + ".weight")
+        logits = self.buf((M, N_out), F32)
+        self.gemm(M, N_out, K_in, x16, ld_x, W16, K_in, bias=ps.p(bias_name), out_f32=logits, ld_of=N_out)
+        self.outputs[name] = logits
+
+        def bwd():
+            if name not in self.grad_outputs:
+                return None
+            ldp = _pad8(N_out)
+            if self.vqa_loss and name == "vil_prediction":
+                dl32, dl16 = self.vqa_dl32, self.vqa_dl16
+            else:
+                dl32 = self.out_grad_buffer(name, (M, N_out))
+                dl16 = self.scratch("head.dl16." + name, (M, ldp), BF16)
+                self.emit(self.lib.vb_cast2d_f32_to_bf16, dl32.data_ptr(), N_out, dl16.data_ptr(), ldp, M, N_out, 1.0)
+            self.colsum(dl32, N_out, ps.g(bias_name), M, N_out)
+            gW = gw if gw is not None else ps.g(wname + ".weight")
+            self.gemm(N_out, K_in, M, dl16, ldp, x16, ld_x, a_mn=1, b_mn=1, out_f32=gW, ld_of=K_in, atomic=1, split_k=0)
+            return dl16, ldp, W16
+        return bwd
+
+    def transform(self, x, wdense, lnname, tag):
+        """Linear -> GELU -> LayerNorm (BertPredictionHeadTransform / BertImgPredictionHeadTransform / the first three
+        stages of SimpleClassifier; vilbert.py:1152-1156, 1172-1176, 1714-1718). x: Act or (b16, M, K) for a plain operand."""
+        ps = self.ps
+        M, K = x.M, x.H
+        Hh = ps.p(wdense + ".weight").shape[0]
+        g32, pre16 = self.buf((M, Hh), F32), self.buf((M, Hh), BF16)
+        self.gemm(M, Hh, K, x.b16, K, ps.w16(wdense + ".weight"), K, bias=ps.p(wdense + ".bias"), act=L.VB_ACT_GELU, out_f32=g32, ld_of=Hh,
+                  out_pre=pre16, ld_op=Hh)
+        _, h16, mean, rstd = self.ln_fwd(g32, ps.p(lnname + ".weight"), ps.p(lnname + ".bias"), M, Hh, want_f32=False)
+        hn = Act(None, h16, M, Hh)
+
+        def bwd():
+            if not hn.gw:
+                return
+            dpre16 = self.scratch(tag + ".dpre16", (M, Hh), BF16)
+            self.ln_bwd(hn.g32, g32, ps.p(lnname + ".weight"), mean, rstd, None, dpre16, M, Hh, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"), pre=pre16)
+            self.linear_wgrad(dpre16, Hh, dpre16, Hh, x.b16, K, M, Hh, K, wdense)
+            self.dgrad_into(x, dpre16, Hh, ps.w16(wdense + ".weight"), M, Hh, K)
+        return hn, bwd
+
+    def small_head(self, name, x, wname, N_out, addend=None, x32=None, M=None, K=None):
+        ps = self.ps
+        M = x.M if M is None else M
+        K = x.H if K is None else K
+        xin = x.f32 if x32 is None else x32
+        y = self.buf((M, N_out), F32)
+        self.emit(self.lib.vb_small_linear_fwd, xin.data_ptr(), K, ps.p(wname + ".weight").data_ptr(), ps.p(wname + ".bias").data_ptr(),
+                  self._ptr(addend), y.data_ptr(), M, K, N_out)
+        self.outputs[name] = y
+
+        def bwd():
+            if name not in self.grad_outputs:
+                return
+            dy = self.out_grad_buffer(name, (M, N_out))
+            g = self.grad_of(x)
+            acc = 1 if x.gw else 0
+            x.gw = True
+            self.emit(self.lib.vb_small_linear_bwd, dy.data_ptr(), xin.data_ptr(), K, ps.p(wname + ".weight").data_ptr(), g.data_ptr(), K, acc,
+                      ps.g(wname + ".weight").data_ptr(), ps.g(wname + ".bias").data_ptr(), M, K, N_out)
+        self._bwd_emitters.append(bwd)
+
+    def build_heads(self, seq_t, seq_v, pooled_t, pooled_v):
+        """VILBertForVLTasks.forward after self.bert (vilbert.py:1673-1708) + BertPreTrainingHeads (:1228-1243).
+        Dropout layers are identity (eval-mode / p = 0 parity protocol)."""
+        ps, c, B, lib = self.ps, self.cfg, self.B, self.lib
+        Hb, Ht, Hv, Nt, Nv = c.bi_hidden_size, c.hidden_size, c.v_hidden_size, self.Nt, self.Nv
+        mul = 1 if c.fusion_method == "mul" else 0
+        f32, f16 = self.buf((B, Hb), F32), self.buf((B, Hb), BF16)
+        self.emit(lib.vb_fuse_pooled_fwd, pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), f32.data_ptr(), f16.data_ptr(), B * Hb, mul)
+        fused = Act(f32, f16, B, Hb)
+
+        def fused_bwd():
+            if not fused.gw:
+                return
+            for a in (pooled_t, pooled_v):
+                g = self.grad_of(a)
+                if not a.gw:
+                    self.emit(lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
+                    a.gw = True
+            self.emit(lib.vb_fuse_pooled_bwd, fused.g32.data_ptr(), pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), pooled_t.g32.data_ptr(),
+                      pooled_v.g32.data_ptr(), B * Hb, mul)
+        self._bwd_emitters.append(fused_bwd)
+
+        # --- cls: masked-LM head (decoder tied to the word embeddings), image-region head, alignment head
+        ht, ht_bwd = self.transform(seq_t, "cls.predictions.transform.dense", "cls.predictions.transform.LayerNorm", "lm.tr")
+        lm_bwd = self.big_head("linguisic_prediction", ht.b16, Ht, ht, B * Nt, Ht, c.vocab_size, None, "cls.predictions.bias",
+                               w16=ps.w16("bert.embeddings.word_embeddings.weight"), gw=ps.g("bert.embeddings.word_embeddings.weight"))
+        hv, hv_bwd = self.transform(seq_v, "cls.imagePredictions.transform.dense", "cls.imagePredictions.transform.LayerNorm", "im.tr")
+        im_bwd = self.big_head("vision_prediction", hv.b16, Hv, hv, B * Nv, Hv, c.v_target_size, "cls.imagePredictions.decoder",
+                               "cls.imagePredictions.decoder.bias")
+
+        def wide_bwd(head_bwd, hn, tr_bwd, K, N_out):
+            def f():
+                r = head_bwd()
+                if r is None:
+                    return
+                dl16, ldp, W16 = r
+                g = self.grad_of(hn)
+                self.gemm(hn.M, K, N_out, dl16, ldp, W16, K, b_mn=1, out_f32=g, ld_of=K)
+                hn.gw = True
+                tr_bwd()
+            return f
+        self._bwd_emitters.append(wide_bwd(lm_bwd, ht, ht_bwd, Ht, c.vocab_size))
+        self._bwd_emitters.append(wide_bwd(im_bwd, hv, hv_bwd, Hv, c.v_target_size))
+
+        if self.heads == "pretraining":
+            # BertForMultiModalPreTraining returns the alignment score of self.cls (vilbert.py:1497)
+            self.small_head("seq_relationship_score", fused, "cls.bi_seq_relationship", 2)
+            return
+        if B % 2 == 0:
+            # vil_binary_prediction pairs consecutive samples: pooled.view(-1, 2*Hb) (:1686-1689)
+            pair = Act(f32.view(B // 2, 2 * Hb), f16.view(B // 2, 2 * Hb), B // 2, 2 * Hb)
+            hb, hb_bwd = self.transform(pair, "vil_binary_prediction.logit_fc.0", "vil_binary_prediction.logit_fc.2", "bin.tr")
+            # LayerNorm output is needed in fp32 for the 2-way linear: recompute it from the bf16 copy is lossy, so run the small
+            # linear on an fp32 LayerNorm output
+            hb32 = self.buf((B // 2, 2 * Hb), F32)
+            # re-emit LN with an fp32 output (cheap: B/2 rows)
+            fwd_fn, fwd_args = self.fwd[-1]
+            args = list(fwd_args); args[5] = hb32.data_ptr(); self.fwd[-1] = (fwd_fn, tuple(args))
+            hb.f32 = hb32
+
+            def bin_bwd():
+                if not hb.gw:
+                    return
+                hb_bwd()
+                if pair.gw:   # gradient landed in pair.g32 [B/2, 2Hb] == [B, Hb]
+                    self.add_grad(fused, pair.g32.view(B, Hb))
+            self._bwd_emitters.append(bin_bwd)   # registered first => runs after the 2-way linear's backward
+            self.small_head("vil_binary_prediction", hb, "vil_binary_prediction.logit_fc.3", 2)
+        else:
+            # odd batch: the reference returns the [B, 2] alignment output of self.cls here (:1673, 1686)
+            self.small_head("vil_binary_prediction", fused, "cls.bi_seq_relationship", 2)
+
+        for nm, n_out in (("vil_prediction", 3129), ("vil_prediction_gqa", 1533)):
+            hh, hh_bwd = self.transform(fused, nm + ".logit_fc.0", nm + ".logit_fc.2", nm + ".tr")
+            head_bwd = self.big_head(nm, hh.b16, 2 * Hb, hh, B, 2 * Hb, n_out, nm + ".logit_fc.3", nm + ".logit_fc.3.bias")
+            self._bwd_emitters.append(wide_bwd(head_bwd, hh, hh_bwd, 2 * Hb, n_out))
+        self.small_head("vil_logit", fused, "vil_logit", 1)
+        self.small_head("vil_tri_prediction", fused, "vil_tri_prediction", 3)
+        self.small_head("vision_logit", seq_v, "vision_logit", 1, addend=self.mask_v)
+        self.small_head("linguisic_logit", seq_t, "linguisic_logit", 1)
+
+    # ------------------------------------------------------------------ whole model
+    def _build(self):
+        c, B = self.cfg, self.B
+        self.outputs, self.gout = OrderedDict(), {}
+        t, v = self.embeddings()
+        # BertEncoder.forward interleaving schedule (vilbert.py:960-1096)
+        t_start = v_start = 0
+        for count, (v_end, t_end) in enumerate(zip(c.v_biattention_id, c.t_biattention_id)):
+            for i in range(t_start, t_end):
+                t = self.text_layer(t, i)
+            for i in range(v_start, v_end):
+                v = self.image_layer(v, i)
+            if c.with_coattention:
+                v, t = self.connection_layer(v, t, count)
+            v_start, t_start = v_end, t_end
+        for i in range(v_start, c.v_num_hidden_layers):
+            v = self.image_layer(v, i)
+        for i in range(t_start, c.num_hidden_layers):
+            t = self.text_layer(t, i)
+        self.seq_t, self.seq_v = t, v
+        self.pooled_t = self.pooler(t, self.Nt, "bert.t_pooler.dense")
+        self.pooled_v = self.pooler(v, self.Nv, "bert.v_pooler.dense")
+        self.outputs["sequence_output_t"] = t.f32.view(B, self.Nt, -1)
+        self.outputs["sequence_output_v"] = v.f32.view(B, self.Nv, -1)
+        self.outputs["pooled_output_t"] = self.pooled_t.f32
+        self.outputs["pooled_output_v"] = self.pooled_v.f32
+        if self.heads != "none":
+            self.build_heads(t, v, self.pooled_t, self.pooled_v)
+            for nm in ("vision_prediction", "vision_logit"):
+                if nm in self.outputs:
+                    self.outputs[nm] = self.outputs[nm].view(B, self.Nv, -1)
+            for nm in ("linguisic_prediction", "linguisic_logit"):
+                if nm in self.outputs:
+                    self.outputs[nm] = self.outputs[nm].view(B, self.Nt, -1)
+        self.n_kernels_fwd = len(self.fwd)
+
+        # ---------------- backward
+        self.cur = self.bwd
+        if self.vqa_loss:
+            lg = self.outputs["vil_prediction"]
+            self.vqa_target = self.buf(tuple(lg.shape), F32, zero=True)
+            self.loss = self.buf((1,), F32, zero=True)
+            self.vqa_dl32 = self.buf(tuple(lg.shape), F32)
+            self.vqa_dl16 = self.buf((lg.shape[0], _pad8(lg.shape[1])), BF16, zero=True)
+            self.emit(self.lib.vb_bce_logits_loss, lg.data_ptr(), self.vqa_target.data_ptr(), self.loss.data_ptr(), self.vqa_dl32.data_ptr(),
+                      self.vqa_dl16.data_ptr(), _pad8(lg.shape[1]), lg.shape[0], lg.shape[1], 1.0)
+        # gradients flowing into the BertModel outputs themselves
+        for nm, act in (("sequence_output_t", self.seq_t), ("sequence_output_v", self.seq_v), ("pooled_output_t", self.pooled_t),
+                        ("pooled_output_v", self.pooled_v)):
+            if nm in self.grad_outputs:
+                self.add_grad(act, self.out_grad_buffer(nm, (act.M, act.H)))
+        for emitter in reversed(self._bwd_emitters):
+            emitter()
+        self.n_kernels_bwd = len(self.bwd)
+        self.cur = self.fwd
+
+    # ------------------------------------------------------------------ execution
+    def load_inputs(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
+                    task_ids=None, non_blocking=True):
+        """Host (ideally pinned) or device tensors -> the plan's static input buffers."""
+        self.in_ids.copy_(input_txt, non_blocking=non_blocking)
+        if token_type_ids is None:
+            self.in_tt.zero_()
+        else:
+            self.in_tt.copy_(token_type_ids, non_blocking=non_blocking)
+        if attention_mask is None:
+            self.in_amask.fill_(1)
+        else:
+            self.in_amask.copy_(attention_mask, non_blocking=non_blocking)
+        if image_attention_mask is None:
+            self.in_imask.fill_(1)
+        else:
+            self.in_imask.copy_(image_attention_mask, non_blocking=non_blocking)
+        self.in_feat.copy_(input_imgs, non_blocking=non_blocking)
+        self.in_loc.copy_(image_loc, non_blocking=non_blocking)
+        if self.has_task:
+            if task_ids is None:
+                raise ValueError("task_specific_tokens is set: task_ids is required")
+            self.in_task.copy_(task_ids.reshape(-1), non_blocking=non_blocking)
+
+    def _run(self, ops):
+        stream = torch.cuda.current_stream().cuda_stream
+        check = L.check
+        for fn, args in ops:
+            st = fn(*args, stream)
+            if st:
+                check(st, fn.__name__)
+
+    def run_forward(self):
+        self.fwd_id += 1
+        if self.graph_fwd is not None:
+            self.graph_fwd.replay()
+        else:
+            self._run(self.fwd)
+
+    def run_backward(self):
+        if self.graph_bwd is not None:
+            self.graph_bwd.replay()
+        else:
+            self._run(self.bwd)
+
+    def run_step(self):
+        """forward + (loss) + backward; gradients accumulate into ParamStore.grad."""
+        if self.graph_step is not None:
+            self.graph_step.replay()
+        else:
+            self._run(self.fwd)
+            self._run(self.bwd)
+
+    def capture(self, separate=False):
+        """Captures the plan into CUDA graphs (one for the whole step, or one per pass)."""
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):   # warm-up outside capture (module load, smem attribute calls)
+            self._run(self.fwd)
+            self._run(self.bwd)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if separate:
+            self.graph_fwd, self.graph_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fwd):
+                self._run(self.fwd)
+            with torch.cuda.graph(self.graph_bwd):
+                self._run(self.bwd)
+        else:
+            self.graph_step = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_step):
+                self._run(self.fwd)
+                self._run(self.bwd)
+        torch.cuda.synchronize()
+
+
+class Engine:
+    """Owns the parameters and the per-shape plans."""
+
+    def __init__(self, cfg, device="cuda", heads="vl", _build_only=False):
+        """_build_only=True (tests) allows a CPU device: plans can be constructed and inspected but never run."""
+        cfg.check_supported()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and not _build_only:
+            raise L.VBError("vilbert_b200 runs on sm_100a GPUs only; there is no CPU path (device=%s)" % device)
+        L.lib()  # fail loudly now if the extension is missing
+        self.ps = ParamStore(cfg, self.device, heads)
+        self.plans = {}
+
+    def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None):
+        key = (B, Nt, Nv, frozenset(grad_outputs), vqa_loss, heads)
+        if key not in self.plans:
+            self.plans[key] = Plan(self, B, Nt, Nv, grad_outputs, vqa_loss, heads)
+        return self.plans[key]
+
+    def refresh_weights(self):
+        self.ps.refresh_shadow(torch.cuda.current_stream().cuda_stream)
+
+    def zero_grad(self):
+        L.check(L.lib().vb_memset_zero(self.ps.grad.data_ptr(), self.ps.grad.numel() * 4, torch.cuda.current_stream().cuda_stream))

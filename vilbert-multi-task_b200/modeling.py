@@ -1,0 +1,263 @@
+"""Drop-in module surface: BertModel, VILBertForVLTasks, BertForMultiModalPreTraining with the
+reference's constructor / forward signatures, output tuples and state_dict key names
+(vilbert/vilbert.py:1288-1406, :1435-1597, :1600-1708), executing on the B200 engine
+(engine.py -> libvilbert_b200.so). There is no PyTorch / CPU fallback: constructing a model on a
+non-CUDA device or without the built extension raises.
+"""
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from .config import BertConfig
+from .engine import BERT_OUT_NAMES, HEAD_NAMES, Engine
+
+
+class _Node(nn.Module):
+    """Container whose children / parameters are registered under the reference's dotted names."""
+
+
+def _register_tree(root, store):
+    params = {}
+    for name in store.entries:
+        view = store.p(name)
+        prm = nn.Parameter(view, requires_grad=True)
+        prm.grad = store.g(name)
+        params[name] = prm
+        _attach(root, name, prm)
+    # tied decoder: the same Parameter object under its reference name (vilbert.py:1190, 1634-1636)
+    _attach(root, "cls.predictions.decoder.weight", params["bert.embeddings.word_embeddings.weight"])
+    return params
+
+
+def _attach(root, dotted, prm):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Node())
+        mod = getattr(mod, p)
+    mod.register_parameter(parts[-1], prm)
+
+
+class _EngineFn(torch.autograd.Function):
+    """Bridges the engine's static plans into torch.autograd: forward runs the plan's forward pass and returns
+    its outputs; backward copies d(loss)/d(outputs) into the plan's static buffers and runs the hand-written
+    backward pass, which accumulates parameter gradients directly into the flat gradient buffer (the
+    Parameters' .grad are views of it). A plan is specialised on the set of outputs that receive a gradient;
+    the set seen in the previous backward of a shape is used as the hint for the next forward, so in a
+    steady training loop forward and backward share one plan and nothing is recomputed."""
+
+    @staticmethod
+    def forward(ctx, model, names, anchor, inputs):
+        B, Nt = inputs["input_txt"].shape
+        Nv = inputs["input_imgs"].shape[1]
+        hint = model._grad_hint.get((B, Nt, Nv, names), ())
+        plan = model.engine.plan(B, Nt, Nv, grad_outputs=hint, heads=model._heads_for(names))
+        model._sync_weights()
+        plan.load_inputs(**inputs)
+        plan.run_forward()
+        ctx.model, ctx.names, ctx.inputs, ctx.plan, ctx.fwd_id = model, names, inputs, plan, plan.fwd_id
+        ctx.set_materialize_grads(False)
+        return tuple(plan.outputs[n].clone() for n in names)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        model, names, inputs, plan = ctx.model, ctx.names, ctx.inputs, ctx.plan
+        live = tuple(n for n, g in zip(names, grads) if g is not None)
+        if live:
+            B, Nt = inputs["input_txt"].shape
+            Nv = inputs["input_imgs"].shape[1]
+            if frozenset(live) != plan.grad_outputs or plan.fwd_id != ctx.fwd_id:
+                model._grad_hint[(B, Nt, Nv, names)] = live
+                plan = model.engine.plan(B, Nt, Nv, grad_outputs=live, heads=model._heads_for(names))
+                plan.load_inputs(**inputs)     # different plan (or overwritten activations): recompute the forward
+                plan.run_forward()
+            for n, g in zip(names, grads):
+                if g is not None:
+                    plan.gout[n].copy_(g.reshape(plan.gout[n].shape))
+            plan.run_backward()
+        return None, None, None, None
+
+
+class BertPreTrainedModel(nn.Module):
+    """Weight handling of the reference's PreTrainedModel (vilbert/utils.py:703-1032) restricted to local
+    files: state_dict with the reference key names, legacy gamma/beta renaming, eval mode after loading."""
+
+    config_class = BertConfig
+    _heads = "vl"          # which heads own parameters: "vl" | "pretraining" | "none"
+
+    def __init__(self, config, device=None):
+        super().__init__()
+        if not isinstance(config, BertConfig):
+            raise ValueError("Parameter config should be an instance of class `BertConfig`.")
+        self.config = config
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        if dev.type != "cuda" or not torch.cuda.is_available():
+            raise L.VBError("vilbert_b200 models run on sm_100a GPUs only; there is no CPU path")
+        self.engine = Engine(config, dev, heads=self._heads)
+        self._params = _register_tree(self, self.engine.ps)
+        self._grad_hint = {}
+        self._anchor = torch.zeros((), device=dev, requires_grad=True)
+        self._shadow_version = None
+        self.init_weights()
+
+    # ---- reference init (vilbert.py:1274-1285): N(0, initializer_range) for Linear/Embedding weights, zero bias, LN 1/0
+    def init_weights(self):
+        std = self.config.initializer_range
+        with torch.no_grad():
+            for name, prm in self._params.items():
+                if "LayerNorm" in name or ".logit_fc.2." in name:
+                    prm.fill_(1.0) if name.endswith("weight") else prm.zero_()
+                elif name.endswith(".bias"):
+                    prm.zero_()
+                else:
+                    prm.normal_(mean=0.0, std=std)
+
+    def tie_weights(self):
+        pass  # the decoder weight IS the word-embedding Parameter (registered twice)
+
+    def _heads_for(self, names):
+        """BertModel-only outputs never need the heads' forward."""
+        return "none" if all(n in BERT_OUT_NAMES for n in names) else self._heads
+
+    def _sync_weights(self):
+        v = self.engine.ps.flat._version
+        if v != self._shadow_version:
+            self.engine.refresh_weights()
+            self._shadow_version = v
+
+    def zero_grad(self, set_to_none=False):
+        self.engine.zero_grad()
+
+    def _apply(self, fn, recurse=True):
+        raise L.VBError("vilbert_b200 models own flat CUDA parameter buffers; .to()/.cuda()/.half() are not supported "
+                        "(construct the model on the target GPU)")
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, config=None, state_dict=None, **kwargs):
+        """Local files only (no network): a directory containing pytorch_model.bin (+ config.json) or a .bin file.
+        Returns an eval-mode model like the reference (vilbert/utils.py:1022)."""
+        kwargs.pop("default_gpu", None)
+        if config is None:
+            cfg_path = os.path.join(pretrained_model_name_or_path, "config.json")
+            config = BertConfig.from_json_file(cfg_path)
+        model = cls(config, *model_args, **kwargs)
+        if state_dict is None:
+            path = pretrained_model_name_or_path
+            if os.path.isdir(path):
+                path = os.path.join(path, "pytorch_model.bin")
+            state_dict = torch.load(path, map_location="cpu")
+        renamed = {}
+        for k, v in state_dict.items():
+            nk = k.replace("gamma", "weight") if "gamma" in k else k
+            nk = nk.replace("beta", "bias") if "beta" in nk else nk
+            if nk.startswith("module."):
+                nk = nk[len("module."):]
+            renamed[nk] = v
+        own = model.state_dict()
+        if not any(k.startswith("bert.") for k in renamed) and any(("bert." + k) in own for k in renamed):
+            renamed = {"bert." + k: v for k, v in renamed.items()}   # base-model checkpoint into a model with heads
+        model.load_state_dict({k: v for k, v in renamed.items() if k in own}, strict=False)
+        model.eval()
+        return model
+
+    # ---- shared forward machinery
+    def _run(self, names, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids):
+        inputs = dict(input_txt=input_txt, input_imgs=input_imgs, image_loc=image_loc, token_type_ids=token_type_ids,
+                      attention_mask=attention_mask, image_attention_mask=image_attention_mask, task_ids=task_ids)
+        outs = _EngineFn.apply(self, tuple(names), self._anchor, inputs)
+        return dict(zip(names, outs))
+
+
+class BertModel(BertPreTrainedModel):
+    """Reference: vilbert/vilbert.py:1288-1406. Parameters live under the bare names (embeddings.*, encoder.*)."""
+    _heads = "none"
+
+    def state_dict(self, *a, **k):
+        sd = super().state_dict(*a, **k)
+        return type(sd)((key[len("bert."):], v) for key, v in sd.items() if key.startswith("bert."))
+
+    def load_state_dict(self, state_dict, strict=True):
+        return super().load_state_dict({"bert." + k: v for k, v in state_dict.items()}, strict=False)
+
+    def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
+                co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
+        if output_all_attention_masks:
+            raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
+        if output_all_encoded_layers:
+            raise NotImplementedError("output_all_encoded_layers=True is not supported by the B200 engine yet")
+        o = self._run(BERT_OUT_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
+        return (o["sequence_output_t"], o["sequence_output_v"], o["pooled_output_t"], o["pooled_output_v"], ([], [], []))
+
+
+class VILBertForVLTasks(BertPreTrainedModel):
+    """Reference: vilbert/vilbert.py:1600-1708. forward returns the same 10-tuple in the same order
+    (:1697-1708). co_attention_mask is accepted and ignored exactly like the reference (:774-775, 796-797)."""
+    _heads = "vl"
+
+    def __init__(self, config, num_labels=1, dropout_prob=0.1, default_gpu=True, device=None):
+        super().__init__(config, device)
+        self.num_labels = num_labels
+        self.dropout_prob = dropout_prob
+        self.fusion_method = config.fusion_method
+
+    @property
+    def bert(self):
+        return _BertView(self)
+
+    def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
+                co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
+        if output_all_attention_masks or output_all_encoded_layers:
+            raise NotImplementedError("output_all_encoded_layers / output_all_attention_masks are not supported by the B200 engine")
+        if image_attention_mask is None:
+            raise TypeError("image_attention_mask is required by VILBertForVLTasks.forward (vilbert.py:1693)")
+        o = self._run(HEAD_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
+        return tuple(o[n] for n in HEAD_NAMES) + (([], [], []),)
+
+
+class _BertView:
+    """`model.bert(...)` on a model with heads: runs the same engine and returns the BertModel 5-tuple."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def __call__(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
+                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
+        o = self._o._run(BERT_OUT_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
+        return (o["sequence_output_t"], o["sequence_output_v"], o["pooled_output_t"], o["pooled_output_v"], ([], [], []))
+
+
+class BertForMultiModalPreTraining(BertPreTrainedModel):
+    """Reference: vilbert/vilbert.py:1435-1597 (visual_target == 0: KL-divergence region objective). The encoder
+    and the three heads run on the engine; the three scalar losses are formed with torch on the head outputs
+    exactly as the reference does (:1506-1590) and their gradients re-enter the engine through autograd."""
+    _heads = "pretraining"
+
+    def __init__(self, config, device=None):
+        super().__init__(config, device)
+        self.visual_target = config.visual_target
+        if self.visual_target != 0:
+            raise NotImplementedError("only visual_target == 0 (KLDiv) is supported")
+
+    @property
+    def bert(self):
+        return _BertView(self)
+
+    def forward(self, input_ids, image_feat, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
+                masked_lm_labels=None, image_label=None, image_target=None, next_sentence_label=None, output_all_attention_masks=False):
+        if output_all_attention_masks:
+            raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
+        names = ("linguisic_prediction", "vision_prediction", "seq_relationship_score")
+        o = self._run(names, input_ids, image_feat, image_loc, token_type_ids, attention_mask, image_attention_mask, None)
+        prediction_scores_t, prediction_scores_v, seq_relationship_score = (o[n] for n in names)
+        if masked_lm_labels is not None and next_sentence_label is not None and image_target is not None:
+            prediction_scores_v = prediction_scores_v[:, 1:]
+            img_loss = F.kl_div(F.log_softmax(prediction_scores_v, dim=2), image_target, reduction="none")
+            masked_img_loss = torch.sum(img_loss * (image_label == 1).unsqueeze(2).float()) / max(torch.sum((image_label == 1)), 0)
+            masked_lm_loss = F.cross_entropy(prediction_scores_t.view(-1, self.config.vocab_size), masked_lm_labels.view(-1), ignore_index=-1)
+            next_sentence_loss = F.cross_entropy(seq_relationship_score.view(-1, 2), next_sentence_label.view(-1), ignore_index=-1)
+            return masked_lm_loss.unsqueeze(0), masked_img_loss.unsqueeze(0), next_sentence_loss.unsqueeze(0)
+        return prediction_scores_t, prediction_scores_v, seq_relationship_score, ([], [], [])
