@@ -1,0 +1,236 @@
+"""Shared GPU check helpers (used by the -m gpu tests and by the tools/ probe drivers).
+Every check runs the CUDA path through the C ABI (ctypes) and compares with torch fp32 / the oracle."""
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import vilbert_oracle as O
+from vilbert_b200 import _lib as L
+
+BF = torch.bfloat16
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-20)).item()
+
+
+def rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm_case(M, N, K, a_mn=False, b_mn=False, bias=False, res=False, act=0, out_bf16=False, atomic=False, split_k=1, block_n=0,
+              alpha=1.0, check=True, iters=0, seed=0):
+    """Returns (max relative error vs fp32 matmul of the bf16 operands, ms per launch or None)."""
+    dev = torch.device("cuda")
+    g_ = torch.Generator(device=dev).manual_seed(seed)
+    lib = L.lib()
+    A = (torch.randn(M, K, device=dev, generator=g_) * 0.5).to(BF)
+    B = (torch.randn(N, K, device=dev, generator=g_) * 0.5).to(BF)
+    pad8 = lambda x: (x + 7) // 8 * 8
+    if a_mn:
+        A_st = torch.zeros(K, pad8(M), device=dev, dtype=BF); A_st[:, :M] = A.t(); lda = pad8(M)
+    else:
+        A_st = torch.zeros(M, pad8(K), device=dev, dtype=BF); A_st[:, :K] = A; lda = pad8(K)
+    if b_mn:
+        B_st = torch.zeros(K, pad8(N), device=dev, dtype=BF); B_st[:, :N] = B.t(); ldb = pad8(N)
+    else:
+        B_st = torch.zeros(N, pad8(K), device=dev, dtype=BF); B_st[:, :K] = B; ldb = pad8(K)
+    bias_t = torch.randn(N, device=dev, generator=g_) if bias else None
+    res_t = torch.randn(M, N, device=dev, generator=g_) if res else None
+    aux_t = torch.randn(M, N, device=dev, generator=g_).to(BF) if act == L.VB_ACT_DGELU else None
+    out32 = torch.full((M, N), 0.0 if atomic else float("nan"), device=dev)
+    out16 = torch.empty(M, N, device=dev, dtype=BF) if out_bf16 else None
+    pre16 = torch.empty(M, N, device=dev, dtype=BF) if (act == L.VB_ACT_GELU and out_bf16 and N % 8 == 0) else None
+    g = L.GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.A, g.lda, g.a_mn_major = A_st.data_ptr(), lda, int(a_mn)
+    g.B, g.ldb, g.b_mn_major = B_st.data_ptr(), ldb, int(b_mn)
+    g.alpha = alpha
+    g.bias = bias_t.data_ptr() if bias else None
+    g.residual, g.ld_res = (res_t.data_ptr(), N) if res else (None, 0)
+    g.aux, g.ld_aux = (aux_t.data_ptr(), N) if aux_t is not None else (None, 0)
+    g.act = act
+    g.out_f32, g.ld_out_f32 = out32.data_ptr(), N
+    g.out_bf16, g.ld_out_bf16 = (out16.data_ptr(), N) if out_bf16 and not atomic else (None, 0)
+    g.out_pre, g.ld_out_pre = (pre16.data_ptr(), N) if pre16 is not None else (None, 0)
+    g.atomic_out, g.split_k, g.block_n, g.max_ctas = int(atomic), split_k, block_n, 0
+    L.check(lib.vb_gemm_bf16(C.byref(g), stream()), "vb_gemm_bf16")
+    torch.cuda.synchronize()
+    err = None
+    if check:
+        ref = alpha * (A.float() @ B.float().t())
+        if bias: ref = ref + bias_t
+        if act == L.VB_ACT_GELU:
+            pre_ref = ref.clone(); ref = O.gelu(ref)
+        elif act == L.VB_ACT_RELU:
+            ref = ref.clamp_min(0)
+        elif act == L.VB_ACT_DGELU:
+            x = aux_t.float()
+            ref = ref * (0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi))
+        if res: ref = ref + res_t
+        scale = ref.abs().max().item() + 1e-9
+        err = ((out32 - ref).abs().max() / scale).item()
+        if out16 is not None and not atomic:
+            err = max(err, ((out16.float() - ref).abs().max() / scale).item() - 4e-3)   # bf16 output rounding
+        if pre16 is not None:
+            err = max(err, ((pre16.float() - pre_ref).abs().max() / (pre_ref.abs().max() + 1e-9)).item() - 4e-3)
+        if err != err: err = float("inf")
+    ms = None
+    if iters:
+        if atomic: out32.zero_()
+        for _ in range(3): lib.vb_gemm_bf16(C.byref(g), stream())
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(iters): lib.vb_gemm_bf16(C.byref(g), stream())
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+    return err, ms
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attn_case(B, H, Nq, Nk, D, cross, peaked=1.0, iters=0, seed=0):
+    """Returns (dict of relative errors of O, dQ, dK, dV, lse vs fp32 torch on the same bf16 inputs, timing str)."""
+    dev = torch.device("cuda"); lib = L.lib()
+    g_ = torch.Generator(device=dev).manual_seed(seed)
+    Hd = H * D
+    if cross:
+        qsrc = (torch.randn(B * Nq, 3 * Hd, device=dev, generator=g_) * peaked).to(BF)
+        ksrc = (torch.randn(B * Nk, 3 * Hd, device=dev, generator=g_) * peaked).to(BF)
+    else:
+        qsrc = ksrc = (torch.randn(B * Nq, 3 * Hd, device=dev, generator=g_) * peaked).to(BF)
+    q, k, v = qsrc[:, :Hd], ksrc[:, Hd:2 * Hd], ksrc[:, 2 * Hd:]
+    lens = torch.randint(1, Nk + 1, (B,), device=dev, generator=g_); lens[0] = Nk
+    if B > 1: lens[1] = 1                                                 # a row with a single valid key
+    mask = ((torch.arange(Nk, device=dev)[None] >= lens[:, None]).float() * -10000.0).contiguous()
+    Ot = torch.zeros(B * Nq, Hd, device=dev, dtype=BF); lse = torch.zeros(B, H, Nq, device=dev)
+    dO = torch.randn(B * Nq, Hd, device=dev, generator=g_).to(BF)
+    dqb = torch.zeros(B * Nq, 3 * Hd, device=dev, dtype=BF); dkb = torch.zeros(B * Nk, 3 * Hd, device=dev, dtype=BF)
+    delta = torch.zeros(B, H, Nq, device=dev)
+    a = L.AttnArgs()
+    a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
+    a.Q, a.ldq, a.K, a.ldk, a.V, a.ldv = q.data_ptr(), 3 * Hd, k.data_ptr(), 3 * Hd, v.data_ptr(), 3 * Hd
+    a.mask, a.scale = mask.data_ptr(), 1.0 / math.sqrt(D)
+    a.O, a.ldo, a.lse = Ot.data_ptr(), Hd, lse.data_ptr()
+    a.dO, a.lddo = dO.data_ptr(), Hd
+    a.dQ, a.lddq = dqb[:, :Hd].data_ptr(), 3 * Hd
+    a.dK, a.lddk = dkb[:, Hd:2 * Hd].data_ptr(), 3 * Hd
+    a.dV, a.lddv = dkb[:, 2 * Hd:].data_ptr(), 3 * Hd
+    a.delta = delta.data_ptr()
+    L.check(lib.vb_attention_fwd(C.byref(a), stream()), "vb_attention_fwd")
+    L.check(lib.vb_attention_bwd(C.byref(a), stream()), "vb_attention_bwd")
+    torch.cuda.synchronize()
+    qf = q.float().view(B, Nq, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
+    kf = k.float().view(B, Nk, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
+    vf = v.float().view(B, Nk, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
+    s = qf @ kf.transpose(-1, -2) / math.sqrt(D) + mask[:, None, None, :]
+    p = torch.softmax(s, -1)
+    o = (p @ vf).permute(0, 2, 1, 3).reshape(B * Nq, Hd)
+    o.backward(dO.float())
+    errs = dict(O=rel(Ot, o), dQ=rel(dqb[:, :Hd].view(B, Nq, H, D).permute(0, 2, 1, 3), qf.grad),
+                dK=rel(dkb[:, Hd:2 * Hd].view(B, Nk, H, D).permute(0, 2, 1, 3), kf.grad),
+                dV=rel(dkb[:, 2 * Hd:].view(B, Nk, H, D).permute(0, 2, 1, 3), vf.grad),
+                lse=rel(lse * math.log(2.0), torch.logsumexp(s, -1)))
+    timing = ""
+    if iters:
+        for fn, nm in ((lib.vb_attention_fwd, "fwd"), (lib.vb_attention_bwd, "bwd")):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            for _ in range(3): fn(C.byref(a), stream())
+            e0.record()
+            for _ in range(iters): fn(C.byref(a), stream())
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            fl = 4.0 * B * H * Nq * Nk * D * (1 if nm == "fwd" else 2.5)
+            timing += f" {nm} {ms*1e3:.1f}us {fl/ms/1e9:.1f}TF"
+    return errs, timing
+
+
+# ------------------------------------------------------------------------------------------ full model
+def build_engine(cfgj, P, device):
+    from vilbert_b200.config import BertConfig
+    from vilbert_b200.engine import Engine
+    eng = Engine(BertConfig.from_dict(cfgj), device)
+    for k in eng.ps.entries:
+        eng.ps.p(k).copy_(P[k])
+    eng.refresh_weights()
+    return eng
+
+
+def oracle_args(inp):
+    return (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+            inp["image_attention_mask"], inp["co_attention_mask"], inp["task_ids"])
+
+
+def probe_loss(heads, names, tgt):
+    """VQA loss on vil_prediction + a small quadratic on every other requested head (touches every grad path)."""
+    l = 0
+    for n, h in zip(O.HEAD_NAMES, heads):
+        if n in names:
+            l = l + (O.vqa_loss(h, tgt) if n == "vil_prediction" else 0.1 * h.float().clamp(-50, 50).pow(2).mean())
+    return l
+
+
+def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, device="cuda"):
+    """Engine vs the oracle in fp32 and in bf16-operand mode. Returns dict(out_fp32, out_bf16, grad_fp32, grad_bf16, ...)
+    where each is {tensor name: error}; gradient errors are (max-rel with floor, rel-L2)."""
+    dev = torch.device(device)
+    cfg = O.make_config(cfgj)
+    names = O.HEAD_NAMES if names is None else names
+    P = O.synth_params(cfg, seed=seed, device=dev, qk_scale=qk_scale)
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=1234 + seed, device=dev)
+    eng = build_engine(cfgj, P, dev)
+    plan = eng.plan(B, Nt, Nv, grad_outputs=names if grads else ())
+    plan.load_inputs(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+                     inp["image_attention_mask"], inp["task_ids"])
+    plan.run_forward()
+    torch.cuda.synchronize()
+    tgt = O.synth_vqa_target(B, 3129, device=dev)
+    result = dict(plan=plan, engine=eng)
+    mine_heads = [plan.outputs[n].detach().clone().requires_grad_(True) for n in O.HEAD_NAMES]
+    if grads:
+        lm = probe_loss(mine_heads, names, tgt); lm.backward()
+        eng.zero_grad()
+        for n, t in zip(O.HEAD_NAMES, mine_heads):
+            if n in names:
+                plan.gout[n].copy_(t.grad.reshape(plan.gout[n].shape))
+        plan.run_backward()
+        torch.cuda.synchronize()
+        result["loss"] = lm.item()
+    for mode in ("fp32", "bf16"):
+        Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+        Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+        if mode == "bf16":
+            with O.bf16_operand_mode():
+                bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, *oracle_args(inp))
+                if grads:
+                    lo = probe_loss(heads_o, names, tgt); lo.backward()
+        else:
+            bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, *oracle_args(inp))
+            if grads:
+                lo = probe_loss(heads_o, names, tgt); lo.backward()
+        oe = {}
+        for n, r in list(zip(O.BERT_OUT_NAMES, bert_o)) + list(zip(O.HEAD_NAMES, heads_o)):
+            oe[n] = rel(plan.outputs[n].reshape(r.shape), r)
+        result["out_" + mode] = oe
+        if grads:
+            result["loss_" + mode] = lo.item()
+            gmax = max(v.grad.abs().max().item() for v in Pg.values() if v.grad is not None)
+            ge = {}
+            for k in eng.ps.entries:
+                rg, mg = Pg[k].grad, eng.ps.g(k)
+                if rg is None:
+                    ge[k] = (0.0 if mg.abs().max().item() == 0 else float("inf"), 0.0)
+                    continue
+                # gradients that are ~0 in exact arithmetic (key biases: softmax shift invariance) are compared
+                # against a floor of 1e-3 of the largest gradient in the model
+                floor = 1e-3 * gmax
+                ge[k] = (((mg - rg).abs().max() / max(rg.abs().max().item(), floor)).item(),
+                         ((mg - rg).norm() / max(rg.norm().item(), floor * math.sqrt(rg.numel()) * 0.1)).item())
+            result["grad_" + mode] = ge
+    return result

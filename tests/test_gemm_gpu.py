@@ -1,0 +1,56 @@
+"""tcgen05 GEMM (vb_gemm_bf16) through the C ABI vs torch fp32 matmul of the same bf16 operands.
+Tolerance: 2e-3 of max|ref| (fp32 accumulation-order noise; bf16 output rounding is discounted in the helper)."""
+import pytest
+
+from vilbert_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (128, 256, 64, 256), (384, 512, 256, 0), (2304, 768, 768, 0),
+                                       (2304, 2304, 768, 0), (6400, 1024, 1024, 128), (6400, 3072, 1024, 256), (100, 72, 40, 0),
+                                       (333, 1601, 1024, 0), (130, 30522, 768, 0), (64, 1024, 768, 0), (1, 8, 8, 0)])
+def test_forward_layout_plain(M, N, K, bn):
+    """nn.Linear forward layout (both operands K-major), incl. ragged edges and the 30522/1601-wide heads."""
+    from _gpu_util import gemm_case
+    err, _ = gemm_case(M, N, K, block_n=bn)
+    assert err < TOL
+
+
+@pytest.mark.parametrize("kw", [dict(bias=True), dict(bias=True, act=L.VB_ACT_GELU, out_bf16=True), dict(bias=True, res=True),
+                                dict(act=L.VB_ACT_DGELU, out_bf16=True), dict(bias=True, act=L.VB_ACT_RELU, out_bf16=True),
+                                dict(atomic=True, split_k=3), dict(atomic=True, split_k=0), dict(alpha=0.125, res=True)])
+@pytest.mark.parametrize("shape", [(2304, 768, 768), (300, 200, 136)])
+def test_fused_epilogues(kw, shape):
+    """bias / erf-GELU (+ saved pre-activation) / ReLU / GELU' / fp32 residual / split-K atomics."""
+    from _gpu_util import gemm_case
+    err, _ = gemm_case(*shape, **kw)
+    assert err < TOL
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (256, 256, 128, 256), (768, 768, 2304, 0), (1000, 520, 200, 0), (3072, 768, 6400, 0)])
+def test_mn_major_operands(a_mn, b_mn, M, N, K, bn):
+    """dgrad (B MN-major) and wgrad (A and B MN-major) operand layouts, read in place through TMA."""
+    from _gpu_util import gemm_case
+    err, _ = gemm_case(M, N, K, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+    assert err < TOL
+
+
+def test_invalid_arguments_are_rejected():
+    import ctypes as C
+    import torch
+    lib = L.lib()
+    g = L.GemmArgs()
+    x = torch.zeros(64, 64, device="cuda", dtype=torch.bfloat16)
+    o = torch.zeros(64, 64, device="cuda")
+    g.M, g.N, g.K = 64, 64, 60
+    g.A, g.lda, g.B, g.ldb = x.data_ptr(), 60, x.data_ptr(), 64      # lda not a multiple of 8
+    g.out_f32, g.ld_out_f32, g.alpha, g.split_k = o.data_ptr(), 64, 1.0, 1
+    assert lib.vb_gemm_bf16(C.byref(g), None) == 1
+    assert b"ld % 8" in lib.vb_last_error()
+    g.lda, g.out_f32 = 64, None
+    assert lib.vb_gemm_bf16(C.byref(g), None) == 1                      # no output
+    with pytest.raises(L.VBError):
+        L.check(lib.vb_gemm_bf16(C.byref(g), None), "vb_gemm_bf16")

@@ -1,0 +1,93 @@
+"""CPU-side checks of the host code: C-ABI exports, config semantics, parameter layout, plan construction."""
+import ctypes
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import vilbert_oracle as O
+from vilbert_b200 import _lib as L
+from vilbert_b200.config import BertConfig
+from vilbert_b200.engine import Engine, ParamStore
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    declared = L.exported_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vilbert_b200.h but not exported"
+    assert set(L._SIGNATURES) <= set(declared)
+    assert lib.vb_version() == 1
+    assert ctypes.sizeof(L.GemmArgs) >= 160 and ctypes.sizeof(L.AttnArgs) >= 150
+
+
+def test_no_fallback_without_gpu():
+    """The product must fail loudly when it cannot run on the GPU: no CPU path."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vilbert_b200 import modeling
+    cfg = BertConfig.from_dict(json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tiny_b4.json")))["config"])
+    with pytest.raises(L.VBError):
+        modeling.VILBertForVLTasks(cfg, num_labels=1)
+    with pytest.raises(L.VBError):
+        Engine(cfg, "cpu")
+
+
+def test_config_semantics(tmp_path, golden_dir):
+    cfgj = json.load(open(os.path.join(golden_dir, "base_6layer_6conect_b4.json")))["config"]
+    p = tmp_path / "c.json"
+    p.write_text(json.dumps(cfgj))
+    c = BertConfig.from_json_file(str(p))
+    assert c.hidden_size == 768 and c.v_hidden_size == 1024 and c.bi_num_attention_heads == 8
+    assert c.v_biattention_id == [0, 1, 2, 3, 4, 5] and c.t_biattention_id == [6, 7, 8, 9, 10, 11]
+    # defaults the JSON does not carry (vilbert.py:158-184) and post-hoc mutation
+    assert c.fusion_method == "mul" and c.task_specific_tokens is False and c.with_coattention is True
+    c.task_specific_tokens = True
+    assert json.loads(c.to_json_string())["task_specific_tokens"] is True
+    c2 = BertConfig(30522, hidden_size=768)
+    assert c2.vocab_size == 30522 and c2.v_feature_size == 2048
+    with pytest.raises(ValueError):
+        BertConfig(3.5)
+    bad = BertConfig.from_dict(dict(cfgj, dynamic_attention=True))
+    with pytest.raises(NotImplementedError):
+        bad.check_supported()
+
+
+def test_param_store_layout(golden_dir):
+    cfgj = json.load(open(os.path.join(golden_dir, "base_6layer_6conect_b4.json")))["config"]
+    cfg = BertConfig.from_dict(cfgj)
+    ps = ParamStore(cfg, "cpu")
+    ref = O.param_shapes(O.make_config(cfgj))
+    ref.pop("cls.predictions.decoder.weight")
+    assert {k: tuple(v[1]) for k, v in ps.entries.items()} == {k: tuple(v) for k, v in ref.items()}
+    # fused QKV views alias the three reference tensors, in order
+    p = "bert.encoder.layer.3.attention.self"
+    ps.p(p + ".query.weight").fill_(1.0); ps.p(p + ".key.weight").fill_(2.0); ps.p(p + ".value.weight").fill_(3.0)
+    w = ps.p(p + ".qkv.weight")
+    assert w.shape == (3 * 768, 768)
+    assert w[:768].eq(1).all() and w[768:1536].eq(2).all() and w[1536:].eq(3).all()
+    for name, (off, shape) in list(ps.entries.items()) + list(ps.fused.items()):
+        assert off % 8 == 0, name     # 16-byte aligned bf16 shadow / 32-byte aligned fp32
+    assert ps.p("bert.encoder.c_layer.0.biattention.qkv2.weight").shape == (3 * 1024, 768)
+
+
+@pytest.mark.parametrize("task_tokens,B", [(False, 4), (True, 3)])
+def test_plan_builds_on_cpu(golden_dir, task_tokens, B):
+    """Plans are pure host data (buffers + C-ABI call records): build them here without a GPU and check structure."""
+    cfgj = dict(json.load(open(os.path.join(golden_dir, "tiny_b4.json")))["config"], task_specific_tokens=task_tokens)
+    eng = Engine(BertConfig.from_dict(cfgj), "cpu", _build_only=True)
+    fwd_only = eng.plan(B, 9, 11)
+    assert fwd_only.n_kernels_bwd == 0 and fwd_only.n_kernels_fwd > 50
+    full = eng.plan(B, 9, 11, grad_outputs=O.HEAD_NAMES)
+    vqa = eng.plan(B, 9, 11, grad_outputs=("vil_prediction",), vqa_loss=True)
+    assert full.n_kernels_fwd == fwd_only.n_kernels_fwd == vqa.n_kernels_fwd
+    assert full.n_kernels_bwd > vqa.n_kernels_bwd > full.n_kernels_fwd      # dead head branches are not emitted
+    assert set(O.HEAD_NAMES) | set(O.BERT_OUT_NAMES) == set(full.outputs)
+    nt = 9 + int(task_tokens)
+    assert tuple(full.outputs["sequence_output_t"].shape) == (B, nt, cfgj["hidden_size"])
+    assert tuple(full.outputs["linguisic_prediction"].shape) == (B, nt, cfgj["vocab_size"])
+    assert tuple(full.outputs["vil_binary_prediction"].shape) == ((B // 2, 2) if B % 2 == 0 else (B, 2))
+    bert_only = eng.plan(B, 9, 11, heads="none")
+    assert set(bert_only.outputs) == set(O.BERT_OUT_NAMES)

@@ -1,0 +1,96 @@
+"""The oracle (oracle/vilbert_oracle.py) against the fixtures that oracle/make_golden.py produced from the
+UNMODIFIED reference (vilbert/vilbert.py) in the build container. Runs anywhere (CPU, no reference needed)."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import vilbert_oracle as O
+
+CASES_FULL = ["tiny_b4", "tiny_tasktok_odd_b3", "tiny_peaked_b2"]
+CASES_SUMMARY = ["base_2layer_2conect_cfg1"]
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def _run(meta, grads):
+    cfg = O.make_config(meta["config"])
+    P = O.synth_params(cfg, seed=meta["seed"], qk_scale=meta["qk_scale"])
+    inp = O.synth_inputs(cfg, meta["B"], meta["Nv"], meta["Nt"], seed=1234 + meta["seed"])
+    Pg = {k: v.clone().requires_grad_(grads) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"],
+                                             inp["attention_mask"], inp["image_attention_mask"], inp["co_attention_mask"], inp["task_ids"])
+    if grads:
+        tgt = O.synth_vqa_target(meta["B"], 3129)
+        l = O.vqa_loss(heads_o[0], tgt)
+        for h in heads_o[1:]:
+            l = l + 0.1 * h.float().clamp(-50, 50).pow(2).mean()
+        l.backward()
+    return inp, Pg, dict(zip(O.BERT_OUT_NAMES, bert_o)), dict(zip(O.HEAD_NAMES, heads_o))
+
+
+@pytest.mark.parametrize("name", CASES_FULL)
+def test_oracle_matches_reference_tensors(name, golden_dir):
+    """Full tensors saved from the reference: outputs and parameter gradients (fp32, 1e-5 relative)."""
+    meta = json.load(open(os.path.join(golden_dir, name + ".json")))
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"))
+    inp, Pg, bert_o, heads_o = _run(meta, grads=True)
+    for k, v in gold["inputs"].items():          # the synthetic inputs themselves are part of the contract
+        assert torch.equal(inp[k], v), k
+    for k, v in gold["bert"].items():
+        assert rel(bert_o[k], v) < 1e-5, k
+    for k, v in gold["heads"].items():
+        assert rel(heads_o[k], v) < 1e-5, k
+    for k, v in gold["grads"].items():
+        assert rel(Pg[k].grad, v) < 1e-5, k
+    # q_dense1/2 never receive a gradient (vilbert.py:834,841)
+    assert all(Pg[k].grad is None for k in Pg if "q_dense" in k)
+
+
+@pytest.mark.parametrize("name", CASES_SUMMARY)
+def test_oracle_matches_reference_summaries(name, golden_dir):
+    """BASELINE.json configs[0] (bert_base_2layer_2conect forward, B=2, 36 regions, 20 tokens): sampled values and
+    norms of every output recorded from the reference."""
+    meta = json.load(open(os.path.join(golden_dir, name + ".json")))
+    _, _, bert_o, heads_o = _run(meta, grads=False)
+    outs = {**bert_o, **heads_o}
+    for k, s in meta["outputs"].items():
+        t = outs[k].detach().double().flatten()
+        assert list(outs[k].shape) == s["shape"], k
+        got = t[torch.tensor(s["sample_idx"])]
+        ref = torch.tensor(s["samples"], dtype=torch.float64)
+        assert (got - ref).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), k
+        assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
+
+
+def test_pretraining_losses_golden(golden_dir):
+    meta = json.load(open(os.path.join(golden_dir, "tiny_pretraining_losses.json")))
+    cfg = O.make_config(meta["config"])
+    B, Nv, Nt = meta["B"], meta["Nv"], meta["Nt"]
+    P = O.synth_params(cfg, seed=3, with_task_heads=False)
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=77)
+    g = torch.Generator().manual_seed(5)
+    lm = torch.full((B, Nt), -1, dtype=torch.long)
+    sel = torch.rand(B, Nt, generator=g) < 0.15; sel[:, 1] = True
+    lm[sel] = torch.randint(0, cfg["vocab_size"], (int(sel.sum()),), generator=g)
+    il = torch.full((B, Nv - 1), -1, dtype=torch.long); il[torch.rand(B, Nv - 1, generator=g) < 0.15] = 1; il[:, 0] = 1
+    it = torch.softmax(torch.randn(B, Nv - 1, cfg["v_target_size"], generator=g), -1)
+    ns = torch.randint(0, 2, (B,), generator=g)
+    losses = O.pretraining_losses(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+                                  inp["image_attention_mask"], lm, il, it, ns)
+    for got, ref in zip(losses, meta["losses"]):
+        assert abs(got.item() - ref) <= 1e-5 * abs(ref)
+
+
+def test_param_inventory_matches_reference_names(golden_dir):
+    """The oracle's parameter inventory equals the reference state_dict recorded in the fixture grads + never-grad params."""
+    meta = json.load(open(os.path.join(golden_dir, "base_6layer_6conect_b4.json")))
+    shapes = O.param_shapes(O.make_config(meta["config"]))
+    for k, s in meta["grads"].items():
+        assert list(shapes[k]) == s["shape"], k
+    n = sum(int(torch.tensor(v).prod()) for k, v in shapes.items() if k != "cls.predictions.decoder.weight")
+    assert abs(n / 1e6 - 268.0) < 0.1   # 268.0 M parameters for base-6-6

@@ -170,6 +170,7 @@ class Plan:
         self.heads = engine.ps.heads if heads is None else heads   # "vl" | "pretraining" | "none"
         self.fwd_id = 0
         self.fwd, self.bwd = [], []
+        self.prologue = []       # optional per-step ops run before the forward (see enable_training_prologue)
         self.cur = self.fwd
         self._keep = []          # ctypes structs / tensors referenced by raw pointer
         self._scratch = {}
@@ -746,11 +747,28 @@ class Plan:
         else:
             self._run(self.bwd)
 
+    def enable_training_prologue(self, zero_grad=True, refresh_weights=True):
+        """Makes run_step a complete training-step body: zero the flat gradient buffer and refresh the bf16
+        weight shadow from the fp32 master parameters (what an optimizer step invalidates) before the forward."""
+        ps, lib = self.ps, self.lib
+        self.prologue = []
+        if zero_grad:
+            self.prologue.append((lib.vb_memset_zero, (ps.grad.data_ptr(), ps.grad.numel() * 4)))
+        if refresh_weights:
+            self.prologue.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr(), ps.shadow.data_ptr(), ps.numel)))
+        self.graph_step = None
+
+    @property
+    def n_launches_step(self):
+        return len(self.prologue) + len(self.fwd) + len(self.bwd)
+
     def run_step(self):
-        """forward + (loss) + backward; gradients accumulate into ParamStore.grad."""
+        """(prologue) + forward + (loss) + backward; gradients accumulate into ParamStore.grad."""
+        self.fwd_id += 1
         if self.graph_step is not None:
             self.graph_step.replay()
         else:
+            self._run(self.prologue)
             self._run(self.fwd)
             self._run(self.bwd)
 
@@ -760,6 +778,7 @@ class Plan:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):   # warm-up outside capture (module load, smem attribute calls)
+            self._run(self.prologue)
             self._run(self.fwd)
             self._run(self.bwd)
         torch.cuda.current_stream().wait_stream(s)
@@ -773,6 +792,7 @@ class Plan:
         else:
             self.graph_step = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_step):
+                self._run(self.prologue)
                 self._run(self.fwd)
                 self._run(self.bwd)
         torch.cuda.synchronize()
