@@ -85,6 +85,7 @@ typedef struct vb_gemm_args {
   void* out_pre;         /* bf16 pre-activation (GELU) or NULL */
   int64_t ld_out_pre;
   int32_t atomic_out;    /* 0 store, 1 red.add into out_f32 */
+  float* out_colsum;     /* [N] or NULL: += column sums of the epilogue value before the residual add (bias gradients) */
   int32_t split_k;       /* >= 1; > 1 requires atomic_out and no act / bf16 outputs */
   int32_t block_n;       /* 0 = auto, else 128 or 256 */
   int32_t max_ctas;      /* 0 = one persistent CTA per SM */
@@ -137,10 +138,12 @@ vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, cons
                            int32_t M, int32_t H, void* stream);
 /* Autograd of the above. dx as f32 and/or bf16; dgamma/dbeta are ACCUMULATED (atomics) and may be NULL.
  * If gelu_pre (bf16 [M,H]) is given, dx_bf16 is additionally multiplied by gelu'(gelu_pre) — the
- * Linear -> GELU -> LayerNorm head transforms (vilbert.py:1152-1156, 1172-1176, 1714-1718). */
+ * Linear -> GELU -> LayerNorm head transforms (vilbert.py:1152-1156, 1172-1176, 1714-1718).
+ * dbias (may be NULL) += column sums of the dx value written to dx_bf16 (or of dx when dx_bf16 is NULL): the
+ * bias gradient of the Linear that produced the LayerNorm input. */
 vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
                            const float* mean, const float* rstd, float* dx_f32, void* dx_bf16, int64_t lddx,
-                           const void* gelu_pre, int64_t ld_pre, float* dgamma, float* dbeta,
+                           const void* gelu_pre, int64_t ld_pre, float* dgamma, float* dbeta, float* dbias,
                            int32_t M, int32_t H, void* stream);
 
 /* fp32 -> bf16 casts: flat (weights shadow, region-feature ingest) and 2-D with independent leading

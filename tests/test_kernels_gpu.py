@@ -51,7 +51,7 @@ def test_layernorm_fwd_bwd(M, H):
     dy = torch.randn(M, H, device=dev); yr.backward(dy)
     dx32 = torch.empty(M, H, device=dev); dx16 = torch.empty(M, H, device=dev, dtype=BF); dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
     L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx32.data_ptr(), dx16.data_ptr(), H, None, 0,
-                                 dg.data_ptr(), db.data_ptr(), M, H, S()))
+                                 dg.data_ptr(), db.data_ptr(), None, M, H, S()))
     torch.cuda.synchronize()
     assert rel(y32, yr) < 1e-5 and rel(y16, yr) < 5e-3
     assert rel(dx32, xr.grad) < 1e-5 and rel(dx16, xr.grad) < 5e-3 and rel(dg, gr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
@@ -66,7 +66,7 @@ def test_layernorm_bwd_fused_gelu_grad():
     pf = pre.float(); gp = 0.5 * (1 + torch.erf(pf / 2 ** 0.5)) + pf * torch.exp(-0.5 * pf * pf) / math.sqrt(2 * math.pi)
     dx16 = torch.empty(M, H, device=dev, dtype=BF); dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
     L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, dx16.data_ptr(), H, pre.data_ptr(), H,
-                                 dg.data_ptr(), db.data_ptr(), M, H, S()))
+                                 dg.data_ptr(), db.data_ptr(), None, M, H, S()))
     torch.cuda.synchronize()
     assert rel(dx16, xr.grad * gp) < 5e-3
 

@@ -93,7 +93,7 @@ for (M, H) in [(37, 64), (50, 96), (2304, 768), (6400, 1024), (33, 2048), (128, 
     dy = torch.randn(M, H, device=dev); yr.backward(dy)
     dx32 = torch.empty(M, H, device=dev); dx16 = torch.empty(M, H, device=dev, dtype=BF); dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
     L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx32.data_ptr(), dx16.data_ptr(), H, None, 0,
-                                 dg.data_ptr(), db.data_ptr(), M, H, ST()))
+                                 dg.data_ptr(), db.data_ptr(), None, M, H, ST()))
     torch.cuda.synchronize()
     report(f"layernorm M{M} H{H}", dict(y=rel(y32, yr), y16=max(rel(y16, yr) - 4e-3, 0), dx=rel(dx32, xr.grad), dg=rel(dg, gr.grad), db=rel(db, br.grad)), 1e-4)
 # LN bwd with gelu' fusion
@@ -103,7 +103,7 @@ mean = x.mean(-1); rstd = 1 / torch.sqrt(x.var(-1, unbiased=False) + 1e-12); dy 
 xr = x.clone().requires_grad_(True); F.layer_norm(xr, (H,), g, b, 1e-12).backward(dy)
 pf = pre.float(); gp = 0.5 * (1 + torch.erf(pf / 2 ** 0.5)) + pf * torch.exp(-0.5 * pf * pf) / math.sqrt(2 * math.pi)
 dx16 = torch.empty(M, H, device=dev, dtype=BF); dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
-L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, dx16.data_ptr(), H, pre.data_ptr(), H, dg.data_ptr(), db.data_ptr(), M, H, ST()))
+L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, dx16.data_ptr(), H, pre.data_ptr(), H, dg.data_ptr(), db.data_ptr(), None, M, H, ST()))
 torch.cuda.synchronize()
 report("layernorm bwd + gelu'", dict(dx16=max(rel(dx16, xr.grad * gp) - 4e-3, 0)), 1e-3)
 

@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
         ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int64),
         ("out_bf16", C.c_void_p), ("ld_out_bf16", C.c_int64),
         ("out_pre", C.c_void_p), ("ld_out_pre", C.c_int64),
-        ("atomic_out", C.c_int32), ("split_k", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
+        ("atomic_out", C.c_int32), ("out_colsum", C.c_void_p), ("split_k", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
         ("dbg_lbo_a", C.c_uint32), ("dbg_sbo_a", C.c_uint32), ("dbg_lbo_b", C.c_uint32), ("dbg_sbo_b", C.c_uint32),
     ]
 
@@ -58,7 +58,7 @@ _SIGNATURES = {
     "vb_attention_fwd": [C.POINTER(AttnArgs), _P],
     "vb_attention_bwd": [C.POINTER(AttnArgs), _P],
     "vb_layernorm_fwd": [_P, _I64, _P, _P, _F, _P, _P, _I64, _P, _P, _I32, _I32, _P],
-    "vb_layernorm_bwd": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _I32, _I32, _P],
+    "vb_layernorm_bwd": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I32, _I32, _P],
     "vb_cast_f32_to_bf16": [_P, _P, _I64, _P],
     "vb_cast2d_f32_to_bf16": [_P, _I64, _P, _I64, _I32, _I32, _F, _P],
     "vb_embed_text_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],

@@ -28,7 +28,7 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle span of bf16
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
 constexpr int GEMM_THREADS = 192;
-constexpr int STAGE_PAD = 33;    // fp32 staging row stride (conflict-free transpose)
+constexpr int STAGE_PAD = 36;    // fp32 staging row stride: 144 B rows keep 128-bit accesses aligned and conflict-free
 constexpr int STAGING_BYTES_PER_WARP = 32 * STAGE_PAD * 4;
 
 template <int BN>
@@ -60,6 +60,7 @@ struct GemmKernelParams {
   __nv_bfloat16* out_pre;
   long long ld_op;
   int atomic_out;
+  float* out_colsum;
   int vec_f32, vec_bf16, vec_pre, vec_res, vec_aux;  // 128/64-bit access legal for that buffer
   uint64_t desc_base_a, desc_base_b;                 // smem descriptor without the address field
   uint32_t kadv_a, kadv_b;                           // descriptor address advance per UMMA_K (bytes)
@@ -183,6 +184,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // ================================================================ epilogue (warps 2..5)
+    // Per 32-column chunk: (1) issue the global reads of this chunk (fp32 residual / bf16 GELU pre-activation)
+    // so their latency overlaps the TMEM read, (2) tcgen05.ld 32 lanes x 32 columns -> registers (thread = row),
+    // (3) 128-bit stores into a padded smem tile, (4) row-wise pass where a lane owns 4 consecutive columns of
+    // rows {rr, rr+4, ...}: 128-bit smem reads, fused math, 128-bit coalesced global stores.
     const int lane_grp = warp_idx & 3;  // TMEM lanes [32*lane_grp, +32) are visible to this warp
     float* stg = staging + (warp_idx - 2) * (32 * STAGE_PAD);
     const int rr = lane >> 3;           // row within a 4-row group of the coalesced pass
@@ -194,15 +199,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = t2 / p.num_m_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
-      tc_fence_after();
       const int m_base = m_blk * BM + lane_grp * 32;
       const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16) + as * BN;
+      bool waited = false;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n_chunk = n_blk * BN + c * 32;
+        const bool chunk_live = n_chunk < p.N;  // warp-uniform
+        const int n = n_chunk + cc;
+        const bool full4 = (n + 3 < p.N);
+        const int nv = full4 ? 4 : (p.N - n);   // may be <= 0 for dead lanes
+        // ---- (1) prefetch per-element global operands
+        float4 resv[8];
+        uint2 auxv[8];
+        const bool vres = p.residual && p.vec_res && full4;
+        const bool vaux = (p.act == VB_ACT_DGELU) && p.vec_aux && full4;
+        if (chunk_live) {
+          if (vres) {
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const long long m = m_base + ps * 4 + rr;
+              if (m < p.M) resv[ps] = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
+            }
+          }
+          if (vaux) {
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const long long m = m_base + ps * 4 + rr;
+              if (m < p.M) auxv[ps] = *reinterpret_cast<const uint2*>(p.aux + m * p.ld_aux + n);
+            }
+          }
+        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (chunk_live && p.bias && nv > 0) {
+          if (full4) {
+            b4 = *reinterpret_cast<const float4*>(p.bias + n);   // bias base is 16B aligned (host check), n % 4 == 0
+          } else {
+            b4.x = p.bias[n];
+            if (nv > 1) b4.y = p.bias[n + 1];
+            if (nv > 2) b4.z = p.bias[n + 2];
+          }
+        }
+        if (!waited) {
+          mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+          tc_fence_after();
+          waited = true;
+        }
+        // ---- (2) TMEM -> registers
         uint32_t r[32];
-        if (n_chunk < p.N) {  // warp-uniform
+        if (chunk_live) {
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
         }
@@ -211,36 +256,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tc_fence_before();
           mbar_arrive(smem_u32(&tmem_empty_bar[as]));
         }
-        if (n_chunk >= p.N) continue;
+        if (!chunk_live) continue;
+        // ---- (3) registers -> padded smem tile (row = lane)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * STAGE_PAD + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * STAGE_PAD + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
-        const int n = n_chunk + cc;
-#pragma unroll 2
+        // ---- (4) coalesced row pass
+        float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;   // column sums of this lane's 4 columns (bias gradients)
+#pragma unroll
         for (int ps = 0; ps < 8; ++ps) {
           const int row = ps * 4 + rr;
           const long long m = m_base + row;
-          if (m >= p.M || n >= p.N) continue;
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = stg[row * STAGE_PAD + cc + j] * p.alpha;
-          const bool full4 = (n + 3 < p.N);
-          const int nv = full4 ? 4 : (p.N - n);
-          if (p.bias) {
-            if (full4) {
-              // bias base is 16B aligned (checked on host) and n % 4 == 0
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n);
-              v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
-            } else {
-              for (int j = 0; j < nv; ++j) v[j] += p.bias[n + j];
-            }
-          }
+          if (m >= p.M || nv <= 0) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * STAGE_PAD + cc);
+          float v[4] = {a4.x * p.alpha + b4.x, a4.y * p.alpha + b4.y, a4.z * p.alpha + b4.z, a4.w * p.alpha + b4.w};
           if (p.act == VB_ACT_GELU) {
             if (p.out_pre) {
               __nv_bfloat16* dst = p.out_pre + m * p.ld_op + n;
               if (full4 && p.vec_pre) {
-                uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-                *reinterpret_cast<uint2*>(dst) = pk;
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
               } else {
                 for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16(v[j]);
               }
@@ -251,33 +286,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
           } else if (p.act == VB_ACT_DGELU) {
-            const __nv_bfloat16* src = p.aux + m * p.ld_aux + n;
             float x[4] = {0.f, 0.f, 0.f, 0.f};
-            if (full4 && p.vec_aux) {
-              const uint2 pk = *reinterpret_cast<const uint2*>(src);
-              const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
-              const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+            if (vaux) {
+              const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].x);
+              const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].y);
               x[0] = __low2float(lo); x[1] = __high2float(lo);
               x[2] = __low2float(hi); x[3] = __high2float(hi);
             } else {
+              const __nv_bfloat16* src = p.aux + m * p.ld_aux + n;
               for (int j = 0; j < nv; ++j) x[j] = __bfloat162float(src[j]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(x[j]);
           }
+          if (p.out_colsum) { cs0 += v[0]; cs1 += v[1]; cs2 += v[2]; cs3 += v[3]; }
           if (p.residual) {
-            const float* src = p.residual + m * p.ld_res + n;
-            if (full4 && p.vec_res) {
-              const float4 r4 = *reinterpret_cast<const float4*>(src);
-              v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+            if (vres) {
+              v[0] += resv[ps].x; v[1] += resv[ps].y; v[2] += resv[ps].z; v[3] += resv[ps].w;
             } else {
+              const float* src = p.residual + m * p.ld_res + n;
               for (int j = 0; j < nv; ++j) v[j] += src[j];
             }
           }
           if (p.out_f32) {
             float* dst = p.out_f32 + m * p.ld_of + n;
             if (p.atomic_out) {
-              for (int j = 0; j < nv; ++j) atomicAdd(dst + j, v[j]);
+              if (full4 && p.vec_f32) {
+                asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+              } else {
+                for (int j = 0; j < nv; ++j) atomicAdd(dst + j, v[j]);
+              }
             } else if (full4 && p.vec_f32) {
               *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
@@ -287,11 +325,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (p.out_bf16) {
             __nv_bfloat16* dst = p.out_bf16 + m * p.ld_ob + n;
             if (full4 && p.vec_bf16) {
-              uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-              *reinterpret_cast<uint2*>(dst) = pk;
+              *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
             } else {
               for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16(v[j]);
             }
+          }
+        }
+        if (p.out_colsum) {
+          // reduce over the 4 row-lanes that share these columns (lane bits 3,4), then one atomic per column
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+          if (rr == 0 && nv > 0) {
+            atomicAdd(p.out_colsum + n, cs0);
+            if (nv > 1) atomicAdd(p.out_colsum + n + 1, cs1);
+            if (nv > 2) atomicAdd(p.out_colsum + n + 2, cs2);
+            if (nv > 3) atomicAdd(p.out_colsum + n + 3, cs3);
           }
         }
         __syncwarp();
@@ -407,7 +457,7 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
       if (split_k < 1) split_k = 1;
     }
   }
-  if (split_k > 1 && (!a->atomic_out || a->act != VB_ACT_NONE || a->bias || a->residual))
+  if (split_k > 1 && (!a->atomic_out || a->act != VB_ACT_NONE || a->bias || a->residual || a->out_colsum))
     return set_error(VB_ERR_INVALID, "vb_gemm_bf16: split_k > 1 needs atomic_out and a plain epilogue");
   int kps = (num_k + split_k - 1) / split_k;
   split_k = (num_k + kps - 1) / kps;  // no empty splits
@@ -425,6 +475,7 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); p.ld_ob = a->ld_out_bf16;
   p.out_pre = static_cast<__nv_bfloat16*>(a->out_pre); p.ld_op = a->ld_out_pre;
   p.atomic_out = a->atomic_out;
+  p.out_colsum = a->out_colsum;
   p.vec_f32 = a->out_f32 && aligned(a->out_f32, 16) && (a->ld_out_f32 % 4 == 0);
   p.vec_bf16 = a->out_bf16 && aligned(a->out_bf16, 8) && (a->ld_out_bf16 % 4 == 0);
   p.vec_pre = a->out_pre && aligned(a->out_pre, 8) && (a->ld_out_pre % 4 == 0);

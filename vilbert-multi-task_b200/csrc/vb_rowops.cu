@@ -89,14 +89,14 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16, long long lddx,
               const __nv_bfloat16* __restrict__ pre, long long ldpre, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              int M, int H) {
+              float* __restrict__ dbias, int M, int H) {
   __shared__ float red[ROW_WARPS][32 * 4 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n4 = H >> 2;
   const float inv_h = 1.f / (float)H;
-  float4 ag[NV4], ab[NV4];
+  float4 ag[NV4], ab[NV4], ad[NV4];   // column partials: dgamma, dbeta, and the bias gradient of the producing Linear
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV4; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (long long row = (long long)blockIdx.x * ROW_WARPS + warp; row < M; row += (long long)gridDim.x * ROW_WARPS) {
     const float4* dyr = reinterpret_cast<const float4*>(dy + row * lddy);
@@ -130,7 +130,7 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
         o.z = (g[i].z - c1 - xh[i].z * c2) * rstd;
         o.w = (g[i].w - c1 - xh[i].w * c2) * rstd;
         if (dx32) reinterpret_cast<float4*>(dx32 + row * lddx)[c] = o;
-        if (dx16) {
+        if (dx16 || dbias) {
           if (pre) {
             const uint2 pk = reinterpret_cast<const uint2*>(pre + row * ldpre)[c];
             const float2 p01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
@@ -138,21 +138,22 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
             o.x *= gelu_erf_grad(p01.x); o.y *= gelu_erf_grad(p01.y);
             o.z *= gelu_erf_grad(p23.x); o.w *= gelu_erf_grad(p23.y);
           }
-          reinterpret_cast<uint2*>(dx16 + row * lddx)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+          if (dx16) reinterpret_cast<uint2*>(dx16 + row * lddx)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+          ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
         }
       }
     }
   }
-  if (!dgamma && !dbeta) return;
+  if (!dgamma && !dbeta && !dbias) return;
   // block reduction of the per-warp column partials, then one atomic per column per CTA
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
     const int c = lane + i * 32;
     if (i * 32 >= n4) break;  // uniform
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const float4 v = pass == 0 ? ag[i] : ab[i];
-      float* dst = pass == 0 ? dgamma : dbeta;
+    for (int pass = 0; pass < 3; ++pass) {
+      const float4 v = pass == 0 ? ag[i] : (pass == 1 ? ab[i] : ad[i]);
+      float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
       __syncthreads();
       red[warp][lane * 4 + 0] = v.x; red[warp][lane * 4 + 1] = v.y; red[warp][lane * 4 + 2] = v.z; red[warp][lane * 4 + 3] = v.w;
       __syncthreads();
@@ -467,7 +468,7 @@ extern "C" vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* 
 
 extern "C" vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma, const float* mean,
                                       const float* rstd, float* dx_f32, void* dx_bf16, int64_t lddx, const void* gelu_pre,
-                                      int64_t ld_pre, float* dgamma, float* dbeta, int32_t M, int32_t H, void* stream) {
+                                      int64_t ld_pre, float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H, void* stream) {
   if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: empty problem");
   if ((H & 3) || H > MAX_V4 * 128 || (ldx & 3) || (lddy & 3) || (lddx & 3) || (gelu_pre && (ld_pre & 3)) || !al16(dy) || !al16(x) || !al16(gamma))
     return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: need H %% 4 == 0, H <= %d, ld %% 4 == 0, 16-byte aligned rows", MAX_V4 * 128);
@@ -477,7 +478,7 @@ extern "C" vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float
   if (grid > cap && cap > 0) grid = cap;
   __nv_bfloat16* dx16 = static_cast<__nv_bfloat16*>(dx_bf16);
   const __nv_bfloat16* pre = static_cast<const __nv_bfloat16*>(gelu_pre);
-#define LN_B(NV) ln_bwd_kernel<NV><<<grid, ROW_THREADS, 0, ST(stream)>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx_f32, dx16, lddx, pre, ld_pre, dgamma, dbeta, M, H)
+#define LN_B(NV) ln_bwd_kernel<NV><<<grid, ROW_THREADS, 0, ST(stream)>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx_f32, dx16, lddx, pre, ld_pre, dgamma, dbeta, dbias, M, H)
   if (nv4 <= 1) LN_B(1); else if (nv4 <= 2) LN_B(2); else if (nv4 <= 4) LN_B(4); else if (nv4 <= 6) LN_B(6);
   else if (nv4 <= 8) LN_B(8); else LN_B(16);
 #undef LN_B

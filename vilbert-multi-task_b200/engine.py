@@ -201,7 +201,7 @@ class Plan:
         return t.data_ptr() if torch.is_tensor(t) else int(t)
 
     def gemm(self, M, N, K, A, lda, B, ldb, a_mn=0, b_mn=0, bias=None, residual=None, ld_res=0, aux=None, ld_aux=0, act=0,
-             out_f32=None, ld_of=0, out_bf16=None, ld_ob=0, out_pre=None, ld_op=0, atomic=0, split_k=1, alpha=1.0):
+             out_f32=None, ld_of=0, out_bf16=None, ld_ob=0, out_pre=None, ld_op=0, atomic=0, split_k=1, alpha=1.0, out_colsum=None):
         g = L.GemmArgs()
         g.M, g.N, g.K = M, N, K
         g.A, g.lda, g.a_mn_major = self._ptr(A), lda, a_mn
@@ -215,6 +215,7 @@ class Plan:
         g.out_bf16, g.ld_out_bf16 = self._ptr(out_bf16), ld_ob
         g.out_pre, g.ld_out_pre = self._ptr(out_pre), ld_op
         g.atomic_out, g.split_k, g.block_n, g.max_ctas = atomic, split_k, 0, 0
+        g.out_colsum = self._ptr(out_colsum)
         self._keep.append(g)
         self.emit(self.lib.vb_gemm_bf16, C.byref(g))
 
@@ -238,9 +239,10 @@ class Plan:
                   mean.data_ptr(), rstd.data_ptr(), M, H)
         return y32, y16, mean, rstd
 
-    def ln_bwd(self, dy, x, gamma, mean, rstd, dx32, dx16, M, H, ggamma, gbeta, pre=None):
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dx32, dx16, M, H, ggamma, gbeta, pre=None, gbias=None):
+        """gbias: bias gradient of the Linear feeding this LayerNorm (column sums of dx), fused into the same pass."""
         self.emit(self.lib.vb_layernorm_bwd, dy.data_ptr(), H, x.data_ptr(), H, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                  self._ptr(dx32), self._ptr(dx16), H, self._ptr(pre), H, ggamma.data_ptr(), gbeta.data_ptr(), M, H)
+                  self._ptr(dx32), self._ptr(dx16), H, self._ptr(pre), H, ggamma.data_ptr(), gbeta.data_ptr(), self._ptr(gbias), M, H)
 
     def colsum(self, X, ld, out, M, N):
         self.emit(self.lib.vb_colsum, X.data_ptr(), 1 if X.dtype == BF16 else 0, ld, out.data_ptr(), M, N)
@@ -291,8 +293,9 @@ class Plan:
                 return None
             dy32 = self.scratch(tag + ".dy32", (M, H), F32)
             dy16 = self.scratch(tag + ".dy16", (M, H), BF16)
-            self.ln_bwd(out.g32, y, ps.p(lnname + ".weight"), mean, rstd, dy32, dy16, M, H, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"))
-            self.linear_wgrad(dy16, H, dy32, H, a16, K_in, M, H, K_in, wname)
+            self.ln_bwd(out.g32, y, ps.p(lnname + ".weight"), mean, rstd, dy32, dy16, M, H, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"),
+                        gbias=ps.g(wname + ".bias"))
+            self.linear_wgrad(dy16, H, None, 0, a16, K_in, M, H, K_in, wname)
             return dy16, dy32
         return out, bwd
 
@@ -311,8 +314,9 @@ class Plan:
             dy16, dy32 = r
             dpre16 = self.scratch(tag + ".dpre16", (M, I), BF16)
             # d pre = (dy W2) * gelu'(pre)
-            self.gemm(M, I, H, dy16, H, ps.w16(w2 + ".weight"), I, b_mn=1, aux=pre16, ld_aux=I, act=L.VB_ACT_DGELU, out_bf16=dpre16, ld_ob=I)
-            self.linear_wgrad(dpre16, I, dpre16, I, x.b16, H, M, I, H, w1)
+            self.gemm(M, I, H, dy16, H, ps.w16(w2 + ".weight"), I, b_mn=1, aux=pre16, ld_aux=I, act=L.VB_ACT_DGELU, out_bf16=dpre16, ld_ob=I,
+                      out_colsum=ps.g(w1 + ".bias"))
+            self.linear_wgrad(dpre16, I, None, 0, x.b16, H, M, I, H, w1)
             self.dgrad_into(x, dpre16, I, ps.w16(w1 + ".weight"), M, I, H, extra32=dy32)
         self._bwd_emitters.append(bwd)
         return out
@@ -460,8 +464,9 @@ class Plan:
             if v.gw:
                 dyv32 = self.scratch("emb.dyv32", (Mv, Hv), F32)
                 dyv16 = self.scratch("emb.dyv16", (Mv, Hv), BF16)
-                self.ln_bwd(v.g32, yv, ps.p(ve + ".LayerNorm.weight"), vmean, vrstd, dyv32, dyv16, Mv, Hv, ps.g(ve + ".LayerNorm.weight"), ps.g(ve + ".LayerNorm.bias"))
-                self.linear_wgrad(dyv16, Hv, dyv32, Hv, feat16, Fv, Mv, Hv, Fv, ve + ".image_embeddings")
+                self.ln_bwd(v.g32, yv, ps.p(ve + ".LayerNorm.weight"), vmean, vrstd, dyv32, dyv16, Mv, Hv, ps.g(ve + ".LayerNorm.weight"), ps.g(ve + ".LayerNorm.bias"),
+                            gbias=ps.g(ve + ".image_embeddings.bias"))
+                self.linear_wgrad(dyv16, Hv, None, 0, feat16, Fv, Mv, Hv, Fv, ve + ".image_embeddings")
                 self.emit(lib.vb_loc_proj_bwd, dyv32.data_ptr(), self.in_loc.data_ptr(), ps.g(ve + ".image_location_embeddings.weight").data_ptr(),
                           ps.g(ve + ".image_location_embeddings.bias").data_ptr(), Mv, Hv)
         self._bwd_emitters.append(bwd)
@@ -539,8 +544,9 @@ class Plan:
             if not hn.gw:
                 return
             dpre16 = self.scratch(tag + ".dpre16", (M, Hh), BF16)
-            self.ln_bwd(hn.g32, g32, ps.p(lnname + ".weight"), mean, rstd, None, dpre16, M, Hh, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"), pre=pre16)
-            self.linear_wgrad(dpre16, Hh, dpre16, Hh, x.b16, K, M, Hh, K, wdense)
+            self.ln_bwd(hn.g32, g32, ps.p(lnname + ".weight"), mean, rstd, None, dpre16, M, Hh, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"), pre=pre16,
+                        gbias=ps.g(wdense + ".bias"))
+            self.linear_wgrad(dpre16, Hh, None, 0, x.b16, K, M, Hh, K, wdense)
             self.dgrad_into(x, dpre16, Hh, ps.w16(wdense + ".weight"), M, Hh, K)
         return hn, bwd
 
