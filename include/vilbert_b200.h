@@ -91,6 +91,7 @@ typedef struct vb_gemm_args {
   int32_t max_ctas;      /* 0 = one persistent CTA per SM */
   /* debug/test overrides for the smem matrix descriptors (0 = library default) */
   uint32_t dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b;
+  void* dbg_timeline;    /* NULL, or u64 [grid][8]: per-CTA clock64 stamps (development only) */
 } vb_gemm_args;
 
 vb_status vb_gemm_bf16(const vb_gemm_args* args, void* stream);

@@ -65,9 +65,109 @@ struct GemmKernelParams {
   uint64_t desc_base_a, desc_base_b;                 // smem descriptor without the address field
   uint32_t kadv_a, kadv_b;                           // descriptor address advance per UMMA_K (bytes)
   uint32_t idesc;
+  int a_mn, b_mn;            // operand majors (runtime: only the TMA producer cares)
+  int fast_ok;               // every buffer the specialised epilogue touches allows 128/64-bit accesses
+  unsigned long long* dbg;   // optional per-CTA timeline [grid][8] (clock64), NULL in production
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// Epilogue specialisations. Each instantiation keeps ONE compact, fully unrolled fast path (whole 32x32 chunk inside
+// the matrix, 128/64-bit aligned buffers) plus a shared non-inlined generic path for ragged edges / odd layouts.
+// (A single kernel with every variant inlined is ~180 KB of SASS and thrashes the instruction cache: the epilogue
+// of one 128x128 tile then costs ~29k cycles instead of ~2k — measured with the clock64 timeline, profiles/.)
+enum { EPI_F32 = 0,     // v = alpha*acc (+bias) (+fp32 residual) -> out_f32                (out-proj / FFN2 / dgrad-into-residual / logits)
+       EPI_BF16 = 1,    // v = alpha*acc (+bias) -> out_bf16                                 (QKV, plain dgrads)
+       EPI_GELU = 2,    // pre = acc + bias -> out_pre (bf16); gelu(pre) -> out_bf16 / out_f32
+       EPI_DGELU = 3,   // v = acc * gelu'(aux) -> out_bf16 (+ column sums)
+       EPI_ATOMIC = 4,  // red.global.add.v4.f32 into out_f32 (split-K wgrad)
+       EPI_GENERIC = 5, // runtime flags only (ReLU poolers, unusual output combinations)
+       EPI_COUNT = 6 };
+
+struct EpiCtx {
+  int m_base, n, nv, rr, cc;
+  bool full4;
+};
+
+// Generic, compact (non-unrolled) path: any flags, any alignment, ragged rows / columns.
+__device__ __noinline__ void epi_generic_chunk(const GemmKernelParams& p, const float* stg, int m_base, int n, int rr, int cc) {
+  const int nv = min(4, p.N - n);
+  if (nv <= 0) return;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int ps = 0; ps < 8; ++ps) {
+    const int row = ps * 4 + rr;
+    const long long m = m_base + row;
+    if (m >= p.M) break;
+#pragma unroll 1
+    for (int j = 0; j < nv; ++j) {
+      float v = stg[row * STAGE_PAD + cc + j] * p.alpha;
+      if (p.bias) v += p.bias[n + j];
+      if (p.act == VB_ACT_GELU) {
+        if (p.out_pre) p.out_pre[m * p.ld_op + n + j] = __float2bfloat16(v);
+        v = gelu_erf(v);
+      } else if (p.act == VB_ACT_RELU) {
+        v = fmaxf(v, 0.f);
+      } else if (p.act == VB_ACT_DGELU) {
+        v *= gelu_erf_grad(__bfloat162float(p.aux[m * p.ld_aux + n + j]));
+      }
+      cs[j] += v;
+      if (p.residual) v += p.residual[m * p.ld_res + n + j];
+      if (p.out_f32) {
+        if (p.atomic_out) atomicAdd(p.out_f32 + m * p.ld_of + n + j, v);
+        else p.out_f32[m * p.ld_of + n + j] = v;
+      }
+      if (p.out_bf16) p.out_bf16[m * p.ld_ob + n + j] = __float2bfloat16(v);
+    }
+  }
+  if (p.out_colsum) {
+#pragma unroll 1
+    for (int j = 0; j < nv; ++j) atomicAdd(p.out_colsum + n + j, cs[j]);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const float* stg, int m_base, int n, int rr, int cc,
+                                               const float4 (&resv)[8], const uint2 (&auxv)[8], const float4 b4) {
+  float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+#pragma unroll
+  for (int ps = 0; ps < 8; ++ps) {
+    const int row = ps * 4 + rr;
+    const long long m = m_base + row;
+    const float4 a4 = *reinterpret_cast<const float4*>(stg + row * STAGE_PAD + cc);
+    float v0 = fmaf(a4.x, p.alpha, b4.x), v1 = fmaf(a4.y, p.alpha, b4.y), v2 = fmaf(a4.z, p.alpha, b4.z), v3 = fmaf(a4.w, p.alpha, b4.w);
+    if (EPI == EPI_GELU) {
+      *reinterpret_cast<uint2*>(p.out_pre + m * p.ld_op + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+      v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_of + n) = make_float4(v0, v1, v2, v3);
+      if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+    } else if (EPI == EPI_DGELU) {
+      const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].x));
+      const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].y));
+      v0 *= gelu_erf_grad(x01.x); v1 *= gelu_erf_grad(x01.y); v2 *= gelu_erf_grad(x23.x); v3 *= gelu_erf_grad(x23.y);
+      cs0 += v0; cs1 += v1; cs2 += v2; cs3 += v3;
+      *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+    } else if (EPI == EPI_F32) {
+      if (p.residual) { v0 += resv[ps].x; v1 += resv[ps].y; v2 += resv[ps].z; v3 += resv[ps].w; }
+      *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_of + n) = make_float4(v0, v1, v2, v3);
+    } else if (EPI == EPI_BF16) {
+      *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+    } else if (EPI == EPI_ATOMIC) {
+      asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p.out_f32 + m * p.ld_of + n), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+    }
+  }
+  if (EPI == EPI_DGELU && p.out_colsum) {
+    // reduce over the 4 row-lanes sharing these columns (lane bits 3,4), then one atomic per column
+    cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+    cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+    cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+    cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+    if (rr == 0) {
+      atomicAdd(p.out_colsum + n, cs0); atomicAdd(p.out_colsum + n + 1, cs1);
+      atomicAdd(p.out_colsum + n + 2, cs2); atomicAdd(p.out_colsum + n + 3, cs3);
+    }
+  }
+}
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
@@ -88,6 +188,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#define VB_DBG(slot) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+  if (threadIdx.x == 0) VB_DBG(0);
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -102,6 +204,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     fence_mbar_init();
   }
+  __syncwarp();
   if (warp_idx == 1) {
     tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
     tmem_relinquish();
@@ -110,64 +213,69 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) VB_DBG(1);
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int total_tiles = tiles_mn * p.split_k;
 
   if (warp_idx == 0) {
-    // ================================================================ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = tile % p.split_k;
-        const int t2 = tile / p.split_k;
-        const int m_blk = t2 % p.num_m_blocks;
-        const int n_blk = t2 / p.num_m_blocks;
-        const int kb0 = split * p.k_blocks_per_split;
-        const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
-        for (int kb = kb0; kb < kb1; ++kb) {
+    // ================================================================ TMA producer (lane 0 issues; the warp stays converged)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile % p.split_k;
+      const int t2 = tile / p.split_k;
+      const int m_blk = t2 % p.num_m_blocks;
+      const int n_blk = t2 / p.num_m_blocks;
+      const int kb0 = split * p.k_blocks_per_split;
+      const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (lane == 0) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
           const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
-          if (A_MN) {
+          if (p.a_mn) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, fb);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, fb);
           } else {
             tma_load_2d(sa, &tmap_a, kb * BK, m_blk * BM, fb);
           }
-          if (B_MN) {
+          if (p.b_mn) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmap_b, n_blk * BN + j * 64, kb * BK, fb);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmap_b, n_blk * BN + j * 64, kb * BK, fb);
           } else {
             tma_load_2d(sb, &tmap_b, kb * BK, n_blk * BN, fb);
           }
-          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+          if (kb == kb0 && tile == blockIdx.x) VB_DBG(2);
         }
+        __syncwarp();
+        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp_idx == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int split = tile % p.split_k;
-        const int kb0 = split * p.k_blocks_per_split;
-        const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+    // ================================================================ MMA issuer (lane 0 issues; the warp stays converged)
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int split = tile % p.split_k;
+      const int kb0 = split * p.k_blocks_per_split;
+      const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t tmem_d = tmem_base + as * BN;
+      if (lane == 0) {
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
+      }
+      __syncwarp();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (lane == 0) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
+          if (kb == kb0 && tile == blockIdx.x) VB_DBG(3);
           const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
@@ -177,17 +285,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             umma_bf16(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(smem_u32(&empty_bar[stage]));  // smem slot free once these MMAs retire
-          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete
+        __syncwarp();
+        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (lane == 0) {
+        umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete
+        if (tile == blockIdx.x) VB_DBG(4);
+      }
+      __syncwarp();
     }
   } else {
     // ================================================================ epilogue (warps 2..5)
-    // Per 32-column chunk: (1) issue the global reads of this chunk (fp32 residual / bf16 GELU pre-activation)
-    // so their latency overlaps the TMEM read, (2) tcgen05.ld 32 lanes x 32 columns -> registers (thread = row),
-    // (3) 128-bit stores into a padded smem tile, (4) row-wise pass where a lane owns 4 consecutive columns of
-    // rows {rr, rr+4, ...}: 128-bit smem reads, fused math, 128-bit coalesced global stores.
+    // Per 32-column chunk: (1) issue the global reads of this chunk (fp32 residual / bf16 GELU pre-activation) so their
+    // latency overlaps the TMEM read, (2) tcgen05.ld 32 lanes x 32 columns -> registers (thread = row), (3) 128-bit
+    // stores into a padded smem tile, (4) row-wise pass where a lane owns 4 consecutive columns of rows {rr, rr+4, ..}:
+    // 128-bit smem reads, fused math, 128-bit coalesced global stores.
     const int lane_grp = warp_idx & 3;  // TMEM lanes [32*lane_grp, +32) are visible to this warp
     float* stg = staging + (warp_idx - 2) * (32 * STAGE_PAD);
     const int rr = lane >> 3;           // row within a 4-row group of the coalesced pass
@@ -201,55 +314,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t aphase = (it >> 1) & 1;
       const int m_base = m_blk * BM + lane_grp * 32;
       const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16) + as * BN;
+      const bool rows_full = (m_base + 32 <= p.M);
       bool waited = false;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n_chunk = n_blk * BN + c * 32;
-        const bool chunk_live = n_chunk < p.N;  // warp-uniform
+        const bool chunk_live = (n_chunk < p.N) && (m_base < p.M);  // warp-uniform
         const int n = n_chunk + cc;
-        const bool full4 = (n + 3 < p.N);
-        const int nv = full4 ? 4 : (p.N - n);   // may be <= 0 for dead lanes
-        // ---- (1) prefetch per-element global operands
+        const bool fast = (EPI != EPI_GENERIC) && p.fast_ok && rows_full && (n_chunk + 32 <= p.N);  // warp-uniform
+        // ---- (1) prefetch per-element global operands of the fast path
         float4 resv[8];
         uint2 auxv[8];
-        const bool vres = p.residual && p.vec_res && full4;
-        const bool vaux = (p.act == VB_ACT_DGELU) && p.vec_aux && full4;
-        if (chunk_live) {
-          if (vres) {
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const long long m = m_base + ps * 4 + rr;
-              if (m < p.M) resv[ps] = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
-            }
-          }
-          if (vaux) {
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const long long m = m_base + ps * 4 + rr;
-              if (m < p.M) auxv[ps] = *reinterpret_cast<const uint2*>(p.aux + m * p.ld_aux + n);
-            }
-          }
-        }
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (chunk_live && p.bias && nv > 0) {
-          if (full4) {
-            b4 = *reinterpret_cast<const float4*>(p.bias + n);   // bias base is 16B aligned (host check), n % 4 == 0
-          } else {
-            b4.x = p.bias[n];
-            if (nv > 1) b4.y = p.bias[n + 1];
-            if (nv > 2) b4.z = p.bias[n + 2];
+        if (chunk_live && fast) {
+          if (EPI == EPI_F32 && p.residual) {
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps)
+              resv[ps] = *reinterpret_cast<const float4*>(p.residual + (long long)(m_base + ps * 4 + rr) * p.ld_res + n);
           }
+          if (EPI == EPI_DGELU) {
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps)
+              auxv[ps] = *reinterpret_cast<const uint2*>(p.aux + (long long)(m_base + ps * 4 + rr) * p.ld_aux + n);
+          }
+          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + n);
         }
         if (!waited) {
           mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
           tc_fence_after();
           waited = true;
+          if (tile == blockIdx.x && warp_idx == 2 && lane == 0) VB_DBG(5);
         }
-        // ---- (2) TMEM -> registers
-        uint32_t r[32];
+        // ---- (2) TMEM -> registers -> (3) padded smem tile (row = lane)
         if (chunk_live) {
+          uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * STAGE_PAD + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
         if (c == BN / 32 - 1) {
           // every TMEM read of this accumulator stage has landed in registers
@@ -257,101 +360,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_arrive(smem_u32(&tmem_empty_bar[as]));
         }
         if (!chunk_live) continue;
-        // ---- (3) registers -> padded smem tile (row = lane)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * STAGE_PAD + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
         // ---- (4) coalesced row pass
-        float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;   // column sums of this lane's 4 columns (bias gradients)
-#pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-          const int row = ps * 4 + rr;
-          const long long m = m_base + row;
-          if (m >= p.M || nv <= 0) continue;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * STAGE_PAD + cc);
-          float v[4] = {a4.x * p.alpha + b4.x, a4.y * p.alpha + b4.y, a4.z * p.alpha + b4.z, a4.w * p.alpha + b4.w};
-          if (p.act == VB_ACT_GELU) {
-            if (p.out_pre) {
-              __nv_bfloat16* dst = p.out_pre + m * p.ld_op + n;
-              if (full4 && p.vec_pre) {
-                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-              } else {
-                for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16(v[j]);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.act == VB_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act == VB_ACT_DGELU) {
-            float x[4] = {0.f, 0.f, 0.f, 0.f};
-            if (vaux) {
-              const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].x);
-              const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].y);
-              x[0] = __low2float(lo); x[1] = __high2float(lo);
-              x[2] = __low2float(hi); x[3] = __high2float(hi);
-            } else {
-              const __nv_bfloat16* src = p.aux + m * p.ld_aux + n;
-              for (int j = 0; j < nv; ++j) x[j] = __bfloat162float(src[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(x[j]);
-          }
-          if (p.out_colsum) { cs0 += v[0]; cs1 += v[1]; cs2 += v[2]; cs3 += v[3]; }
-          if (p.residual) {
-            if (vres) {
-              v[0] += resv[ps].x; v[1] += resv[ps].y; v[2] += resv[ps].z; v[3] += resv[ps].w;
-            } else {
-              const float* src = p.residual + m * p.ld_res + n;
-              for (int j = 0; j < nv; ++j) v[j] += src[j];
-            }
-          }
-          if (p.out_f32) {
-            float* dst = p.out_f32 + m * p.ld_of + n;
-            if (p.atomic_out) {
-              if (full4 && p.vec_f32) {
-                asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-              } else {
-                for (int j = 0; j < nv; ++j) atomicAdd(dst + j, v[j]);
-              }
-            } else if (full4 && p.vec_f32) {
-              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-              for (int j = 0; j < nv; ++j) dst[j] = v[j];
-            }
-          }
-          if (p.out_bf16) {
-            __nv_bfloat16* dst = p.out_bf16 + m * p.ld_ob + n;
-            if (full4 && p.vec_bf16) {
-              *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-            } else {
-              for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16(v[j]);
-            }
-          }
-        }
-        if (p.out_colsum) {
-          // reduce over the 4 row-lanes that share these columns (lane bits 3,4), then one atomic per column
-          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
-          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
-          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
-          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
-          if (rr == 0 && nv > 0) {
-            atomicAdd(p.out_colsum + n, cs0);
-            if (nv > 1) atomicAdd(p.out_colsum + n + 1, cs1);
-            if (nv > 2) atomicAdd(p.out_colsum + n + 2, cs2);
-            if (nv > 3) atomicAdd(p.out_colsum + n + 3, cs3);
-          }
-        }
+        if (fast) epi_fast_chunk<EPI>(p, stg, m_base, n, rr, cc, resv, auxv, b4);
+        else      epi_generic_chunk(p, stg, m_base, n, rr, cc);
         __syncwarp();
       }
+      if (tile == blockIdx.x && warp_idx == 2 && lane == 0) VB_DBG(6);
     }
   }
 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) VB_DBG(7);
   if (warp_idx == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -392,10 +414,10 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
   return VB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
                        cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
@@ -406,6 +428,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return VB_OK;
+}
+
+template <int BN>
+static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid, cudaStream_t stream) {
+  switch (epi) {
+    case EPI_F32: return launch_gemm<BN, EPI_F32>(ta, tb, p, grid, stream);
+    case EPI_BF16: return launch_gemm<BN, EPI_BF16>(ta, tb, p, grid, stream);
+    case EPI_GELU: return launch_gemm<BN, EPI_GELU>(ta, tb, p, grid, stream);
+    case EPI_DGELU: return launch_gemm<BN, EPI_DGELU>(ta, tb, p, grid, stream);
+    case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC>(ta, tb, p, grid, stream);
+    default: return launch_gemm<BN, EPI_GENERIC>(ta, tb, p, grid, stream);
+  }
 }
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
@@ -494,6 +528,10 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   p.kadv_a = a->a_mn_major ? 2 * 1024 : UK * 2;
   p.kadv_b = a->b_mn_major ? 2 * 1024 : UK * 2;
   p.idesc = umma_idesc_bf16(BM, bn, a->a_mn_major ? 1 : 0, a->b_mn_major ? 1 : 0);
+  p.dbg = reinterpret_cast<unsigned long long*>(a->dbg_timeline);
+  p.a_mn = a->a_mn_major ? 1 : 0;
+  p.b_mn = a->b_mn_major ? 1 : 0;
+  p.fast_ok = 0;
 
   CUtensorMap ta, tb;
   int st;
@@ -507,17 +545,21 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   const long long total_tiles = (long long)num_m * num_n * split_k;
   const int grid = (int)(total_tiles < max_ctas ? total_tiles : max_ctas);
 
-#define VB_LAUNCH(BN_, AM_, BM_) return launch_gemm<BN_, AM_, BM_>(ta, tb, p, grid, stream)
-  if (bn == 256) {
-    if (!a->a_mn_major && !a->b_mn_major) VB_LAUNCH(256, false, false);
-    if (!a->a_mn_major && a->b_mn_major) VB_LAUNCH(256, false, true);
-    if (a->a_mn_major && !a->b_mn_major) VB_LAUNCH(256, true, false);
-    VB_LAUNCH(256, true, true);
-  } else {
-    if (!a->a_mn_major && !a->b_mn_major) VB_LAUNCH(128, false, false);
-    if (!a->a_mn_major && a->b_mn_major) VB_LAUNCH(128, false, true);
-    if (a->a_mn_major && !a->b_mn_major) VB_LAUNCH(128, true, false);
-    VB_LAUNCH(128, true, true);
+  // pick the epilogue specialisation; anything unusual runs the generic one
+  int epi = EPI_GENERIC;
+  const bool no_extra = !a->out_colsum;
+  if (a->atomic_out) {
+    if (a->act == VB_ACT_NONE && !a->bias && !a->residual && no_extra) { epi = EPI_ATOMIC; p.fast_ok = p.vec_f32; }
+  } else if (a->act == VB_ACT_GELU) {
+    if (a->out_pre && !a->residual && no_extra && (a->out_bf16 || a->out_f32)) {
+      epi = EPI_GELU; p.fast_ok = p.vec_pre && (!a->out_bf16 || p.vec_bf16) && (!a->out_f32 || p.vec_f32);
+    }
+  } else if (a->act == VB_ACT_DGELU) {
+    if (a->out_bf16 && !a->out_f32 && !a->residual && !a->bias) { epi = EPI_DGELU; p.fast_ok = p.vec_bf16 && p.vec_aux; }
+  } else if (a->act == VB_ACT_NONE) {
+    if (a->out_f32 && !a->out_bf16 && no_extra) { epi = EPI_F32; p.fast_ok = p.vec_f32 && (!a->residual || p.vec_res); }
+    else if (a->out_bf16 && !a->out_f32 && !a->residual && no_extra) { epi = EPI_BF16; p.fast_ok = p.vec_bf16; }
   }
-#undef VB_LAUNCH
+  if (bn == 256) return launch_gemm_epi<256>(epi, ta, tb, p, grid, stream);
+  return launch_gemm_epi<128>(epi, ta, tb, p, grid, stream);
 }
