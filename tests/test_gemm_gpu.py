@@ -20,8 +20,10 @@ def test_forward_layout_plain(M, N, K, bn):
 
 @pytest.mark.parametrize("kw", [dict(bias=True), dict(bias=True, act=L.VB_ACT_GELU, out_bf16=True), dict(bias=True, res=True),
                                 dict(act=L.VB_ACT_DGELU, out_bf16=True), dict(bias=True, act=L.VB_ACT_RELU, out_bf16=True),
-                                dict(atomic=True, split_k=3), dict(atomic=True, split_k=0), dict(alpha=0.125, res=True)])
-@pytest.mark.parametrize("shape", [(2304, 768, 768), (300, 200, 136)])
+                                dict(atomic=True, split_k=3), dict(atomic=True, split_k=0), dict(alpha=0.125, res=True),
+                                dict(bias=True, out_bf16=True), dict(bias=True, out_bf16=True, both_outputs=True),
+                                dict(bias=True, act=L.VB_ACT_GELU, out_bf16=True, both_outputs=True)])
+@pytest.mark.parametrize("shape", [(2304, 768, 768), (300, 200, 136), (256, 1601, 128)])
 def test_fused_epilogues(kw, shape):
     """bias / erf-GELU (+ saved pre-activation) / ReLU / GELU' / fp32 residual / split-K atomics."""
     from _gpu_util import gemm_case

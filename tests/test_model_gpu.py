@@ -95,7 +95,9 @@ def test_base_2layer_2conect_config1(golden_dir):
     """BASELINE.json configs[0] shape (B=2, 36 regions, 20 tokens) on the real 2-connection-layer config."""
     from _gpu_util import model_case
     r = model_case(_cfg(golden_dir, "base_2layer_2conect_cfg1"), 2, 36, 20)
-    _check(r, grad_max=8e-2, grad_l2=4e-2)       # 12+2+2 layers at B=2: see module docstring
+    # 12+2+2 layers at B=2: vil_binary_prediction is ONE row of two logits here (max-norm over 2 numbers); the bf16-operand
+    # emulation of the reference itself is off by 2.7e-2 on it (tools/bf16_budget_cpu.py)
+    _check(r, small_tol=6e-2, grad_max=8e-2, grad_l2=4e-2)
 
 
 def test_base_6layer_6conect_vqa_shape(golden_dir):

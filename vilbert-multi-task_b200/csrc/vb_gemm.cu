@@ -147,7 +147,12 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
       *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
     } else if (EPI == EPI_F32) {
       if (p.residual) { v0 += resv[ps].x; v1 += resv[ps].y; v2 += resv[ps].z; v3 += resv[ps].w; }
-      *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_of + n) = make_float4(v0, v1, v2, v3);
+      float* dst = p.out_f32 + m * p.ld_of + n;
+      if (p.vec_f32) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
+      } else {   // row pitch not a multiple of 4 floats (30522-/1601-/3129-wide logits): same bytes, 32-bit stores
+        dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
+      }
     } else if (EPI == EPI_BF16) {
       *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
     } else if (EPI == EPI_ATOMIC) {
@@ -329,8 +334,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (chunk_live && fast) {
           if (EPI == EPI_F32 && p.residual) {
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps)
-              resv[ps] = *reinterpret_cast<const float4*>(p.residual + (long long)(m_base + ps * 4 + rr) * p.ld_res + n);
+            for (int ps = 0; ps < 8; ++ps) {
+              const float* src = p.residual + (long long)(m_base + ps * 4 + rr) * p.ld_res + n;
+              if (p.vec_res) resv[ps] = *reinterpret_cast<const float4*>(src);
+              else resv[ps] = make_float4(src[0], src[1], src[2], src[3]);
+            }
           }
           if (EPI == EPI_DGELU) {
 #pragma unroll
@@ -557,7 +565,7 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   } else if (a->act == VB_ACT_DGELU) {
     if (a->out_bf16 && !a->out_f32 && !a->residual && !a->bias) { epi = EPI_DGELU; p.fast_ok = p.vec_bf16 && p.vec_aux; }
   } else if (a->act == VB_ACT_NONE) {
-    if (a->out_f32 && !a->out_bf16 && no_extra) { epi = EPI_F32; p.fast_ok = p.vec_f32 && (!a->residual || p.vec_res); }
+    if (a->out_f32 && !a->out_bf16 && no_extra) { epi = EPI_F32; p.fast_ok = 1; }   // unaligned pitches use 32-bit accesses
     else if (a->out_bf16 && !a->out_f32 && !a->residual && no_extra) { epi = EPI_BF16; p.fast_ok = p.vec_bf16; }
   }
   if (bn == 256) return launch_gemm_epi<256>(epi, ta, tb, p, grid, stream);

@@ -172,6 +172,9 @@ class Plan:
         self.fwd, self.bwd = [], []
         self.prologue = []       # optional per-step ops run before the forward (see enable_training_prologue)
         self.cur = self.fwd
+        self.sid = 0             # stream the next emitted op goes to: 0 = text/main stream, 1 = vision stream
+        self.two_streams = engine.two_streams
+        self._aux = None
         self._keep = []          # ctypes structs / tensors referenced by raw pointer
         self._scratch = {}
         self._bwd_emitters = []
@@ -192,7 +195,36 @@ class Plan:
         return self._scratch[key]
 
     def emit(self, fn, *args):
-        self.cur.append((fn, args))
+        self.cur.append((fn, args, self.sid if self.two_streams else 0))
+
+    def sync_streams(self, mirror=True):
+        """Both streams wait for each other here. Between two connection layers the text and the vision segments are
+        data-independent (vilbert.py:977-1006), so they run on two CUDA streams (and as parallel branches of the
+        captured graph). mirror=True also places a barrier at the mirrored position of the backward pass."""
+        if not self.two_streams:
+            return
+        self.cur.append((None, (), 0))
+        if mirror and self.cur is self.fwd:
+            self._bwd_emitters.append(None)
+
+    class _On:
+        def __init__(self, plan, sid):
+            self.plan, self.sid = plan, sid
+
+        def __enter__(self):
+            self.prev = self.plan.sid
+            self.plan.sid = self.sid
+
+        def __exit__(self, *exc):
+            self.plan.sid = self.prev
+            return False
+
+    def on(self, sid):
+        return Plan._On(self, sid)
+
+    def push_bwd(self, fn):
+        """Registers a backward emitter; it will emit on the stream that is current now."""
+        self._bwd_emitters.append((self.sid, fn))
 
     @staticmethod
     def _ptr(t):
@@ -318,7 +350,7 @@ class Plan:
                       out_colsum=ps.g(w1 + ".bias"))
             self.linear_wgrad(dpre16, I, None, 0, x.b16, H, M, I, H, w1)
             self.dgrad_into(x, dpre16, I, ps.w16(w1 + ".weight"), M, I, H, extra32=dy32)
-        self._bwd_emitters.append(bwd)
+        self.push_bwd(bwd)
         return out
 
     def self_attention_block(self, x, B, N, nh, mask, prefix, tag):
@@ -346,7 +378,7 @@ class Plan:
                            dQ=dqkv[:, 0:H], lddq=3 * H, dK=dqkv[:, H:2 * H], lddk=3 * H, dV=dqkv[:, 2 * H:], lddv=3 * H, delta=delta)
             self.linear_wgrad(dqkv, 3 * H, dqkv, 3 * H, x.b16, H, M, 3 * H, H, prefix + ".self.qkv")
             self.dgrad_into(x, dqkv, 3 * H, ps.w16(prefix + ".self.qkv.weight"), M, 3 * H, H, extra32=dy32)
-        self._bwd_emitters.append(bwd)
+        self.push_bwd(bwd)
         return out
 
     def connection_layer(self, v, t, idx):
@@ -358,17 +390,21 @@ class Plan:
         Mv, Mt, Hv, Ht, Nv, Nt = v.M, t.M, v.H, t.H, self.Nv, self.Nt
         qkv1 = self.buf((Mv, 3 * Hb), BF16)
         qkv2 = self.buf((Mt, 3 * Hb), BF16)
-        self.gemm(Mv, 3 * Hb, Hv, v.b16, Hv, ps.w16(p + ".biattention.qkv1.weight"), Hv, bias=ps.p(p + ".biattention.qkv1.bias"), out_bf16=qkv1, ld_ob=3 * Hb)
+        with self.on(1):
+            self.gemm(Mv, 3 * Hb, Hv, v.b16, Hv, ps.w16(p + ".biattention.qkv1.weight"), Hv, bias=ps.p(p + ".biattention.qkv1.bias"), out_bf16=qkv1, ld_ob=3 * Hb)
         self.gemm(Mt, 3 * Hb, Ht, t.b16, Ht, ps.w16(p + ".biattention.qkv2.weight"), Ht, bias=ps.p(p + ".biattention.qkv2.bias"), out_bf16=qkv2, ld_ob=3 * Hb)
+        self.sync_streams()      # each direction needs the other stream's keys / values
         q1, k1, v1 = qkv1[:, 0:Hb], qkv1[:, Hb:2 * Hb], qkv1[:, 2 * Hb:]
         q2, k2, v2 = qkv2[:, 0:Hb], qkv2[:, Hb:2 * Hb], qkv2[:, 2 * Hb:]
         ctx1 = self.buf((Mt, Hb), BF16); lse1 = self.buf((B, nh, Nt), F32)   # text queries over vision keys/values
         ctx2 = self.buf((Mv, Hb), BF16); lse2 = self.buf((B, nh, Nv), F32)   # vision queries over text keys/values
         L3 = 3 * Hb
         self.attention(False, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1)
-        self.attention(False, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2)
+        with self.on(1):
+            self.attention(False, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2)
         # biOutput: ctx2 -> vision stream (dense1 / LayerNorm1), ctx1 -> text stream (dense2 / LayerNorm2) (:890-892)
-        v1o, v1_bwd = self.dense_res_ln(ctx2, Hb, v, p + ".biOutput.dense1", p + ".biOutput.LayerNorm1", "c.v.bo")
+        with self.on(1):
+            v1o, v1_bwd = self.dense_res_ln(ctx2, Hb, v, p + ".biOutput.dense1", p + ".biOutput.LayerNorm1", "c.v.bo")
         t1o, t1_bwd = self.dense_res_ln(ctx1, Hb, t, p + ".biOutput.dense2", p + ".biOutput.LayerNorm2", "c.t.bo")
 
         def bwd():
@@ -398,8 +434,12 @@ class Plan:
             self.linear_wgrad(dqkv2, L3, dqkv2, L3, t.b16, Ht, Mt, L3, Ht, p + ".biattention.qkv2")
             self.dgrad_into(v, dqkv1, L3, ps.w16(p + ".biattention.qkv1.weight"), Mv, L3, Hv, extra32=dyv32)
             self.dgrad_into(t, dqkv2, L3, ps.w16(p + ".biattention.qkv2.weight"), Mt, L3, Ht, extra32=dyt32)
-        self._bwd_emitters.append(bwd)
-        v2o = self.ffn(v1o, c.v_intermediate_size, p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", "c.v.ffn")
+        # the cross-modal backward touches both streams' tensors: it runs on the main stream between two barriers
+        self._bwd_emitters.append(None)
+        self.push_bwd(bwd)
+        self._bwd_emitters.append(None)
+        with self.on(1):
+            v2o = self.ffn(v1o, c.v_intermediate_size, p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", "c.v.ffn")
         t2o = self.ffn(t1o, c.intermediate_size, p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", "c.t.ffn")
         return v2o, t2o
 
@@ -432,6 +472,7 @@ class Plan:
         self.mask_v = self.buf((B, Nv), F32)
         self.emit(lib.vb_mask_to_additive, self.in_amask.data_ptr(), self.mask_t.data_ptr(), B, self.Nt_in, 1 if self.has_task else 0)
         self.emit(lib.vb_mask_to_additive, self.in_imask.data_ptr(), self.mask_v.data_ptr(), B, Nv, 0)
+        self.sync_streams()
         # text: gather-sum (+ task row) then LayerNorm (vilbert.py:346-367)
         xe = self.buf((Mt, Ht), F32)
         e = "bert.embeddings"
@@ -440,20 +481,8 @@ class Plan:
                   ps.p(e + ".task_embeddings.weight").data_ptr() if self.has_task else None, xe.data_ptr(), B, self.Nt_in, Ht)
         t32, t16, tmean, trstd = self.ln_fwd(xe, ps.p(e + ".LayerNorm.weight"), ps.p(e + ".LayerNorm.bias"), Mt, Ht)
         t = Act(t32, t16, Mt, Ht)
-        # image: region features fp32 -> bf16 ingest, 2048 -> Hv GEMM with the 5 -> Hv box projection as residual, LayerNorm (:1421-1432)
-        ve = "bert.v_embeddings"
-        feat16 = self.buf((Mv, Fv), BF16)
-        self.emit(lib.vb_cast_f32_to_bf16, self.in_feat.data_ptr(), feat16.data_ptr(), Mv * Fv)
-        locp = self.buf((Mv, Hv), F32)
-        self.emit(lib.vb_loc_proj_fwd, self.in_loc.data_ptr(), ps.p(ve + ".image_location_embeddings.weight").data_ptr(),
-                  ps.p(ve + ".image_location_embeddings.bias").data_ptr(), locp.data_ptr(), Mv, Hv)
-        yv = self.buf((Mv, Hv), F32)
-        self.gemm(Mv, Hv, Fv, feat16, Fv, ps.w16(ve + ".image_embeddings.weight"), Fv, bias=ps.p(ve + ".image_embeddings.bias"),
-                  residual=locp, ld_res=Hv, out_f32=yv, ld_of=Hv)
-        v32, v16, vmean, vrstd = self.ln_fwd(yv, ps.p(ve + ".LayerNorm.weight"), ps.p(ve + ".LayerNorm.bias"), Mv, Hv)
-        v = Act(v32, v16, Mv, Hv)
 
-        def bwd():
+        def bwd_text():
             if t.gw:
                 dxe = self.scratch("emb.dxe", (Mt, Ht), F32)
                 self.ln_bwd(t.g32, xe, ps.p(e + ".LayerNorm.weight"), tmean, trstd, dxe, None, Mt, Ht, ps.g(e + ".LayerNorm.weight"), ps.g(e + ".LayerNorm.bias"))
@@ -461,15 +490,31 @@ class Plan:
                           ps.g(e + ".word_embeddings.weight").data_ptr(), ps.g(e + ".position_embeddings.weight").data_ptr(),
                           ps.g(e + ".token_type_embeddings.weight").data_ptr(),
                           ps.g(e + ".task_embeddings.weight").data_ptr() if self.has_task else None, B, self.Nt_in, Ht)
-            if v.gw:
-                dyv32 = self.scratch("emb.dyv32", (Mv, Hv), F32)
-                dyv16 = self.scratch("emb.dyv16", (Mv, Hv), BF16)
-                self.ln_bwd(v.g32, yv, ps.p(ve + ".LayerNorm.weight"), vmean, vrstd, dyv32, dyv16, Mv, Hv, ps.g(ve + ".LayerNorm.weight"), ps.g(ve + ".LayerNorm.bias"),
-                            gbias=ps.g(ve + ".image_embeddings.bias"))
-                self.linear_wgrad(dyv16, Hv, None, 0, feat16, Fv, Mv, Hv, Fv, ve + ".image_embeddings")
-                self.emit(lib.vb_loc_proj_bwd, dyv32.data_ptr(), self.in_loc.data_ptr(), ps.g(ve + ".image_location_embeddings.weight").data_ptr(),
-                          ps.g(ve + ".image_location_embeddings.bias").data_ptr(), Mv, Hv)
-        self._bwd_emitters.append(bwd)
+        self.push_bwd(bwd_text)
+        # image: region features fp32 -> bf16 ingest, 2048 -> Hv GEMM with the 5 -> Hv box projection as residual, LayerNorm (:1421-1432)
+        ve = "bert.v_embeddings"
+        with self.on(1):
+            feat16 = self.buf((Mv, Fv), BF16)
+            self.emit(lib.vb_cast_f32_to_bf16, self.in_feat.data_ptr(), feat16.data_ptr(), Mv * Fv)
+            locp = self.buf((Mv, Hv), F32)
+            self.emit(lib.vb_loc_proj_fwd, self.in_loc.data_ptr(), ps.p(ve + ".image_location_embeddings.weight").data_ptr(),
+                      ps.p(ve + ".image_location_embeddings.bias").data_ptr(), locp.data_ptr(), Mv, Hv)
+            yv = self.buf((Mv, Hv), F32)
+            self.gemm(Mv, Hv, Fv, feat16, Fv, ps.w16(ve + ".image_embeddings.weight"), Fv, bias=ps.p(ve + ".image_embeddings.bias"),
+                      residual=locp, ld_res=Hv, out_f32=yv, ld_of=Hv)
+            v32, v16, vmean, vrstd = self.ln_fwd(yv, ps.p(ve + ".LayerNorm.weight"), ps.p(ve + ".LayerNorm.bias"), Mv, Hv)
+            v = Act(v32, v16, Mv, Hv)
+
+            def bwd_image():
+                if v.gw:
+                    dyv32 = self.scratch("emb.dyv32", (Mv, Hv), F32)
+                    dyv16 = self.scratch("emb.dyv16", (Mv, Hv), BF16)
+                    self.ln_bwd(v.g32, yv, ps.p(ve + ".LayerNorm.weight"), vmean, vrstd, dyv32, dyv16, Mv, Hv, ps.g(ve + ".LayerNorm.weight"), ps.g(ve + ".LayerNorm.bias"),
+                                gbias=ps.g(ve + ".image_embeddings.bias"))
+                    self.linear_wgrad(dyv16, Hv, None, 0, feat16, Fv, Mv, Hv, Fv, ve + ".image_embeddings")
+                    self.emit(lib.vb_loc_proj_bwd, dyv32.data_ptr(), self.in_loc.data_ptr(), ps.g(ve + ".image_location_embeddings.weight").data_ptr(),
+                              ps.g(ve + ".image_location_embeddings.bias").data_ptr(), Mv, Hv)
+            self.push_bwd(bwd_image)
         return t, v
 
     # ------------------------------------------------------------------ poolers and heads
@@ -494,7 +539,7 @@ class Plan:
                 seq.gw = True
             # rows b*N of the sequence gradient += dpre @ W
             self.gemm(B, H, Hb, dpre, Hb, ps.w16(wname + ".weight"), H, b_mn=1, residual=g, ld_res=N * H, out_f32=g, ld_of=N * H)
-        self._bwd_emitters.append(bwd)
+        self.push_bwd(bwd)
         return pooled
 
     def out_grad_buffer(self, name, shape):
@@ -569,7 +614,7 @@ class Plan:
             x.gw = True
             self.emit(self.lib.vb_small_linear_bwd, dy.data_ptr(), xin.data_ptr(), K, ps.p(wname + ".weight").data_ptr(), g.data_ptr(), K, acc,
                       ps.g(wname + ".weight").data_ptr(), ps.g(wname + ".bias").data_ptr(), M, K, N_out)
-        self._bwd_emitters.append(bwd)
+        self.push_bwd(bwd)
 
     def build_heads(self, seq_t, seq_v, pooled_t, pooled_v):
         """VILBertForVLTasks.forward after self.bert (vilbert.py:1673-1708) + BertPreTrainingHeads (:1228-1243).
@@ -591,7 +636,7 @@ class Plan:
                     a.gw = True
             self.emit(lib.vb_fuse_pooled_bwd, fused.g32.data_ptr(), pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), pooled_t.g32.data_ptr(),
                       pooled_v.g32.data_ptr(), B * Hb, mul)
-        self._bwd_emitters.append(fused_bwd)
+        self.push_bwd(fused_bwd)
 
         # --- cls: masked-LM head (decoder tied to the word embeddings), image-region head, alignment head
         ht, ht_bwd = self.transform(seq_t, "cls.predictions.transform.dense", "cls.predictions.transform.LayerNorm", "lm.tr")
@@ -612,8 +657,8 @@ class Plan:
                 hn.gw = True
                 tr_bwd()
             return f
-        self._bwd_emitters.append(wide_bwd(lm_bwd, ht, ht_bwd, Ht, c.vocab_size))
-        self._bwd_emitters.append(wide_bwd(im_bwd, hv, hv_bwd, Hv, c.v_target_size))
+        self.push_bwd(wide_bwd(lm_bwd, ht, ht_bwd, Ht, c.vocab_size))
+        self.push_bwd(wide_bwd(im_bwd, hv, hv_bwd, Hv, c.v_target_size))
 
         if self.heads == "pretraining":
             # BertForMultiModalPreTraining returns the alignment score of self.cls (vilbert.py:1497)
@@ -627,8 +672,8 @@ class Plan:
             # linear on an fp32 LayerNorm output
             hb32 = self.buf((B // 2, 2 * Hb), F32)
             # re-emit LN with an fp32 output (cheap: B/2 rows)
-            fwd_fn, fwd_args = self.fwd[-1]
-            args = list(fwd_args); args[5] = hb32.data_ptr(); self.fwd[-1] = (fwd_fn, tuple(args))
+            fwd_fn, fwd_args, fwd_sid = self.fwd[-1]
+            args = list(fwd_args); args[5] = hb32.data_ptr(); self.fwd[-1] = (fwd_fn, tuple(args), fwd_sid)
             hb.f32 = hb32
 
             def bin_bwd():
@@ -637,7 +682,7 @@ class Plan:
                 hb_bwd()
                 if pair.gw:   # gradient landed in pair.g32 [B/2, 2Hb] == [B, Hb]
                     self.add_grad(fused, pair.g32.view(B, Hb))
-            self._bwd_emitters.append(bin_bwd)   # registered first => runs after the 2-way linear's backward
+            self.push_bwd(bin_bwd)   # registered first => runs after the 2-way linear's backward
             self.small_head("vil_binary_prediction", hb, "vil_binary_prediction.logit_fc.3", 2)
         else:
             # odd batch: the reference returns the [B, 2] alignment output of self.cls here (:1673, 1686)
@@ -646,7 +691,7 @@ class Plan:
         for nm, n_out in (("vil_prediction", 3129), ("vil_prediction_gqa", 1533)):
             hh, hh_bwd = self.transform(fused, nm + ".logit_fc.0", nm + ".logit_fc.2", nm + ".tr")
             head_bwd = self.big_head(nm, hh.b16, 2 * Hb, hh, B, 2 * Hb, n_out, nm + ".logit_fc.3", nm + ".logit_fc.3.bias")
-            self._bwd_emitters.append(wide_bwd(head_bwd, hh, hh_bwd, 2 * Hb, n_out))
+            self.push_bwd(wide_bwd(head_bwd, hh, hh_bwd, 2 * Hb, n_out))
         self.small_head("vil_logit", fused, "vil_logit", 1)
         self.small_head("vil_tri_prediction", fused, "vil_tri_prediction", 3)
         self.small_head("vision_logit", seq_v, "vision_logit", 1, addend=self.mask_v)
@@ -662,15 +707,18 @@ class Plan:
         for count, (v_end, t_end) in enumerate(zip(c.v_biattention_id, c.t_biattention_id)):
             for i in range(t_start, t_end):
                 t = self.text_layer(t, i)
-            for i in range(v_start, v_end):
-                v = self.image_layer(v, i)
+            with self.on(1):
+                for i in range(v_start, v_end):
+                    v = self.image_layer(v, i)
             if c.with_coattention:
                 v, t = self.connection_layer(v, t, count)
             v_start, t_start = v_end, t_end
-        for i in range(v_start, c.v_num_hidden_layers):
-            v = self.image_layer(v, i)
+        with self.on(1):
+            for i in range(v_start, c.v_num_hidden_layers):
+                v = self.image_layer(v, i)
         for i in range(t_start, c.num_hidden_layers):
             t = self.text_layer(t, i)
+        self.sync_streams()      # poolers and heads read both streams; they run on the main stream
         self.seq_t, self.seq_v = t, v
         self.pooled_t = self.pooler(t, self.Nt, "bert.t_pooler.dense")
         self.pooled_v = self.pooler(v, self.Nv, "bert.v_pooler.dense")
@@ -686,7 +734,8 @@ class Plan:
             for nm in ("linguisic_prediction", "linguisic_logit"):
                 if nm in self.outputs:
                     self.outputs[nm] = self.outputs[nm].view(B, self.Nt, -1)
-        self.n_kernels_fwd = len(self.fwd)
+        self.sync_streams(mirror=False)
+        self.n_kernels_fwd = sum(1 for op in self.fwd if op[0] is not None)
 
         # ---------------- backward
         self.cur = self.bwd
@@ -703,9 +752,16 @@ class Plan:
                         ("pooled_output_v", self.pooled_v)):
             if nm in self.grad_outputs:
                 self.add_grad(act, self.out_grad_buffer(nm, (act.M, act.H)))
-        for emitter in reversed(self._bwd_emitters):
-            emitter()
-        self.n_kernels_bwd = len(self.bwd)
+        self.sync_streams()
+        for entry in reversed(self._bwd_emitters):
+            if entry is None:
+                self.sync_streams()
+            else:
+                self.sid, emitter = entry
+                emitter()
+        self.sid = 0
+        self.sync_streams()
+        self.n_kernels_bwd = sum(1 for op in self.bwd if op[0] is not None)
         self.cur = self.fwd
 
     # ------------------------------------------------------------------ execution
@@ -733,10 +789,18 @@ class Plan:
             self.in_task.copy_(task_ids.reshape(-1), non_blocking=non_blocking)
 
     def _run(self, ops):
-        stream = torch.cuda.current_stream().cuda_stream
+        main = torch.cuda.current_stream()
+        if self.two_streams and self._aux is None:
+            self._aux = torch.cuda.Stream(device=self.dev)
+        aux = self._aux if self.two_streams else main
+        handles = (main.cuda_stream, aux.cuda_stream)
         check = L.check
-        for fn, args in ops:
-            st = fn(*args, stream)
+        for fn, args, sid in ops:
+            if fn is None:      # barrier between the two streams
+                e1 = torch.cuda.Event(); e1.record(main); aux.wait_event(e1)
+                e2 = torch.cuda.Event(); e2.record(aux); main.wait_event(e2)
+                continue
+            st = fn(*args, handles[sid])
             if st:
                 check(st, fn.__name__)
 
@@ -759,14 +823,14 @@ class Plan:
         ps, lib = self.ps, self.lib
         self.prologue = []
         if zero_grad:
-            self.prologue.append((lib.vb_memset_zero, (ps.grad.data_ptr(), ps.grad.numel() * 4)))
+            self.prologue.append((lib.vb_memset_zero, (ps.grad.data_ptr(), ps.grad.numel() * 4), 0))
         if refresh_weights:
-            self.prologue.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr(), ps.shadow.data_ptr(), ps.numel)))
+            self.prologue.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr(), ps.shadow.data_ptr(), ps.numel), 0))
         self.graph_step = None
 
     @property
     def n_launches_step(self):
-        return len(self.prologue) + len(self.fwd) + len(self.bwd)
+        return len(self.prologue) + self.n_kernels_fwd + self.n_kernels_bwd
 
     def run_step(self):
         """(prologue) + forward + (loss) + backward; gradients accumulate into ParamStore.grad."""
@@ -807,7 +871,7 @@ class Plan:
 class Engine:
     """Owns the parameters and the per-shape plans."""
 
-    def __init__(self, cfg, device="cuda", heads="vl", _build_only=False):
+    def __init__(self, cfg, device="cuda", heads="vl", _build_only=False, two_streams=True):
         """_build_only=True (tests) allows a CPU device: plans can be constructed and inspected but never run."""
         cfg.check_supported()
         self.cfg = cfg
@@ -816,6 +880,7 @@ class Engine:
             raise L.VBError("vilbert_b200 runs on sm_100a GPUs only; there is no CPU path (device=%s)" % device)
         L.lib()  # fail loudly now if the extension is missing
         self.ps = ParamStore(cfg, self.device, heads)
+        self.two_streams = two_streams   # text / vision segments on two CUDA streams (parallel graph branches)
         self.plans = {}
 
     def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None):
