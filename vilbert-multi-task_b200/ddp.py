@@ -1,0 +1,43 @@
+"""Data-parallel plumbing: the only distributed step of the path is the gradient all-reduce
+(reference: apex DistributedDataParallel(model, delay_allreduce=True) at train_tasks.py:497 — one flattened
+all-reduce after backward, averaged over the world size; batch split per rank at task_utils.py:435-437).
+
+Here the gradients already live in ONE flat fp32 buffer (engine.ParamStore.grad), so the all-reduce runs in place
+on contiguous, fixed-address buckets (NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradAllReducer:
+    def __init__(self, flat_grad, n_buckets=8, group=None, align=1024):
+        self.flat = flat_grad
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n = flat_grad.numel()
+        step = max(align, (n + n_buckets - 1) // n_buckets)
+        step = (step + align - 1) // align * align
+        self.buckets = [flat_grad[i:min(i + step, n)] for i in range(0, n, step)]
+        # NCCL has a fused average; gloo only sums
+        self.use_avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
+
+    def allreduce(self, stream=None):
+        """Averages the flat gradient buffer over all ranks, bucket by bucket (in place)."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if self.use_avg:
+                dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group)
+                b.div_(self.world)
+
+    def broadcast_params(self, flat_params, src=0):
+        """Rank-`src` parameters to every rank (what apex DDP does at wrap time)."""
+        if self.world > 1:
+            dist.broadcast(flat_params, src=src, group=self.group)
+
+
+def shard_batch(global_batch, rank, world):
+    """Per-rank batch like the reference: batch_size // world_size samples each (task_utils.py:435-437)."""
+    per = global_batch // world
+    return rank * per, per
