@@ -296,6 +296,19 @@ def main():
                 aa = args[0]._obj
                 d["flops"] += 4.0 * aa.B * aa.H * aa.Nq * aa.Nk * aa.D * (2.5 if name.endswith("bwd") else 1.0)
         if a.profile_ops:
+            # GEMM launches grouped by problem signature
+            shapes = {}
+            for (fn, args, _sid), (s0, s1) in zip(ops, evs):
+                if fn.__name__ == "vb_gemm_bf16":
+                    ga = args[0]._obj
+                    key = (ga.M, ga.N, ga.K, "A^T" if ga.a_mn_major else "A", "B^T" if ga.b_mn_major else "B", ga.act, int(bool(ga.out_f32)), int(bool(ga.out_bf16)),
+                           int(bool(ga.residual)), ga.atomic_out)
+                    d = shapes.setdefault(key, [0, 0.0])
+                    d[0] += 1; d[1] += s0.elapsed_time(s1)
+            print("  GEMM launches by signature (M N K majors act f32 bf16 res atomic): n, total ms, avg us, TFLOP/s", file=sys.stderr)
+            for key, (n, ms_) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:28]:
+                fl = 2.0 * key[0] * key[1] * key[2] * n
+                print(f"    {str(key):58s} n={n:3d} {ms_:7.3f} ms {ms_ / n * 1e3:7.1f} us {fl / ms_ / 1e9:7.1f}", file=sys.stderr)
             tot = sum(d["ms"] for d in prof.values())
             for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
                 tf = f"{d['flops'] / d['ms'] / 1e9:8.1f} TFLOP/s" if d["flops"] else ""

@@ -45,7 +45,9 @@ struct AttnParams {
   float* delta;  // [B,H,Nq]
 };
 
-// Copies `rows_valid` rows of D bf16 (row stride ld) into smem rows of stride D+8; rows beyond are zeroed.
+// Copies `rows_valid` rows of D bf16 (row stride ld) into smem rows of stride D+8 with cp.async (16-byte LDGSTS, no
+// register staging: every request of the panel is in flight at once); rows beyond rows_valid are zero-filled
+// (src-size 0). Completion: cp_async_wait_all() + __syncthreads().
 template <int D>
 __device__ __forceinline__ void load_panel(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows_valid,
                                            int rows_total) {
@@ -53,10 +55,15 @@ __device__ __forceinline__ void load_panel(__nv_bfloat16* dst, const __nv_bfloat
   constexpr int CH = D / 8;  // 16-byte chunks per row
   for (int idx = threadIdx.x; idx < rows_total * CH; idx += ATT_THREADS) {
     const int r = idx / CH, c = idx % CH;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * ld + c * 8));
-    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+    const bool ok = r < rows_valid;
+    const __nv_bfloat16* g = src + (long long)(ok ? r : 0) * ld + c * 8;
+    const uint32_t d = smem_u32(dst + r * LD + c * 8);
+    const int nbytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(nbytes) : "memory");
   }
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ float quad_max(float v) {
@@ -146,6 +153,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
   load_panel<D>(sV, p.V + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
   for (int j = threadIdx.x; j < nkp; j += ATT_THREADS)
     sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
+  cp_async_wait_all();
   __syncthreads();
 
   const int r0 = warp * 16;
@@ -220,6 +228,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
   load_panel<D>(sV, p.V + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
   for (int j = threadIdx.x; j < nkp; j += ATT_THREADS)
     sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
+  cp_async_wait_all();
   __syncthreads();
 
   const int r0 = warp * 16;
@@ -319,6 +328,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
       sDelta[i] = (i < p.Nq) ? dg[i] : 0.f;
     }
   }
+  cp_async_wait_all();
   __syncthreads();
 
   const int r0 = warp * 16;

@@ -476,15 +476,19 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   const int num_k = (a->K + BK - 1) / BK;
   int max_ctas = a->max_ctas > 0 ? a->max_ctas : dev_sms;
 
-  // tile width: minimise (waves x tile width); ties go to the wider tile (less smem traffic per flop)
+  // tile width: minimise the modelled per-CTA time (cycles, from the clock64 timelines in profiles/): a 128x128 k-block
+  // costs ~580 cycles (bound by L2 -> smem operand traffic), a 128x256 one ~640; the epilogue of a tile (~4.5k / ~8.5k
+  // cycles) overlaps the next tile's main loop, the last one is exposed.
   int bn = a->block_n;
   if (bn == 0) {
     auto cost = [&](int w) {
-      long long tiles = (long long)num_m * ((a->N + w - 1) / w);
-      long long waves = (tiles + max_ctas - 1) / max_ctas;
-      return waves * w;
+      const long long tiles = (long long)num_m * ((a->N + w - 1) / w);
+      const long long rounds = (tiles + max_ctas - 1) / max_ctas;
+      const long long ml = (long long)num_k * (w == 256 ? 640 : 580);
+      const long long epi = (w == 256 ? 8500 : 4500);
+      return 2500 + rounds * (ml > epi ? ml : epi) + epi;
     };
-    bn = (a->N > 128 && cost(256) <= cost(128)) ? 256 : 128;
+    bn = (a->N > 128 && cost(256) < cost(128)) ? 256 : 128;
   }
   if (bn != 128 && bn != 256) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: block_n must be 0, 128 or 256");
   const int num_n = (a->N + bn - 1) / bn;
