@@ -81,32 +81,40 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm bwd
-// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma; dgamma += sum dy * xhat; dbeta += sum dy.
-// Optional: dx16 additionally multiplied by gelu'(pre) (head transforms: Linear -> GELU -> LayerNorm).
-template <int NV4>
-__global__ void __launch_bounds__(ROW_THREADS)
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma; dgamma += sum dy * xhat; dbeta += sum dy;
+// dbias += sum dx (bias gradient of the Linear that produced the LayerNorm input).
+// Optional: dx16 (and dbias) additionally multiplied by gelu'(pre) (head transforms: Linear -> GELU -> LayerNorm).
+//
+// A row is handled by a TEAM of two warps (64 lanes x NV float4 chunks) so that the three per-column accumulators fit in
+// ~110 registers and two 256-thread CTAs (16 warps) stay resident per SM; the two row sums cross the warps through a
+// double-buffered smem slot and one 64-thread named barrier per row.
+template <int NV>
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16, long long lddx,
               const __nv_bfloat16* __restrict__ pre, long long ldpre, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dbias, int M, int H) {
-  __shared__ float red[ROW_WARPS][32 * 4 + 4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int TEAMS = ROW_THREADS / 64;
+  __shared__ float xch[TEAMS][2][2][2];
+  __shared__ float red[TEAMS][64 * 4 + 4];
+  const int team = threadIdx.x >> 6, tl = threadIdx.x & 63, wih = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
   const int n4 = H >> 2;
   const float inv_h = 1.f / (float)H;
-  float4 ag[NV4], ab[NV4], ad[NV4];   // column partials: dgamma, dbeta, and the bias gradient of the producing Linear
+  float4 ag[NV], ab[NV], ad[NV];
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (long long row = (long long)blockIdx.x * ROW_WARPS + warp; row < M; row += (long long)gridDim.x * ROW_WARPS) {
+  int it = 0;
+  for (long long row = (long long)blockIdx.x * TEAMS + team; row < M; row += (long long)gridDim.x * TEAMS, ++it) {
     const float4* dyr = reinterpret_cast<const float4*>(dy + row * lddy);
     const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float4 g[NV4], xh[NV4];
+    float4 g[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) {
-      const int c = lane + i * 32;
+    for (int i = 0; i < NV; ++i) {
+      const int c = tl + i * 64;
       if (c < n4) {
         const float4 d = dyr[c], xv = xr[c], gm = reinterpret_cast<const float4*>(gamma)[c];
         xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
@@ -119,10 +127,14 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
         g[i] = xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    const float c1 = warp_sum(s1) * inv_h, c2 = warp_sum(s2) * inv_h;
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { xch[team][it & 1][wih][0] = s1; xch[team][it & 1][wih][1] = s2; }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + team) : "memory");
+    const float c1 = (xch[team][it & 1][0][0] + xch[team][it & 1][1][0]) * inv_h;
+    const float c2 = (xch[team][it & 1][0][1] + xch[team][it & 1][1][1]) * inv_h;
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) {
-      const int c = lane + i * 32;
+    for (int i = 0; i < NV; ++i) {
+      const int c = tl + i * 64;
       if (c < n4) {
         float4 o;
         o.x = (g[i].x - c1 - xh[i].x * c2) * rstd;
@@ -145,27 +157,25 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
     }
   }
   if (!dgamma && !dbeta && !dbias) return;
-  // block reduction of the per-warp column partials, then one atomic per column per CTA
+  // CTA reduction of the per-team column partials, then one atomic per column per CTA
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) {
-    const int c = lane + i * 32;
-    if (i * 32 >= n4) break;  // uniform
+  for (int i = 0; i < NV; ++i) {
+    if (i * 64 >= n4) break;  // uniform
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
       const float4 v = pass == 0 ? ag[i] : (pass == 1 ? ab[i] : ad[i]);
       float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
       __syncthreads();
-      red[warp][lane * 4 + 0] = v.x; red[warp][lane * 4 + 1] = v.y; red[warp][lane * 4 + 2] = v.z; red[warp][lane * 4 + 3] = v.w;
+      red[team][tl * 4 + 0] = v.x; red[team][tl * 4 + 1] = v.y; red[team][tl * 4 + 2] = v.z; red[team][tl * 4 + 3] = v.w;
       __syncthreads();
-      if (dst && threadIdx.x < 128) {
-        float s = 0.f;
+      if (dst) {
+        float sacc = 0.f;
 #pragma unroll
-        for (int w = 0; w < ROW_WARPS; ++w) s += red[w][threadIdx.x];
-        const int col = (i * 32 + (threadIdx.x >> 2)) * 4 + (threadIdx.x & 3);
-        if (col < H) atomicAdd(dst + col, s);
+        for (int w = 0; w < TEAMS; ++w) sacc += red[w][threadIdx.x];
+        const int col = (i * 64 + (threadIdx.x >> 2)) * 4 + (threadIdx.x & 3);
+        if (col < H) atomicAdd(dst + col, sacc);
       }
     }
-    (void)c;
   }
 }
 
@@ -472,15 +482,14 @@ extern "C" vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float
   if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: empty problem");
   if ((H & 3) || H > MAX_V4 * 128 || (ldx & 3) || (lddy & 3) || (lddx & 3) || (gelu_pre && (ld_pre & 3)) || !al16(dy) || !al16(x) || !al16(gamma))
     return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: need H %% 4 == 0, H <= %d, ld %% 4 == 0, 16-byte aligned rows", MAX_V4 * 128);
-  const int nv4 = (H / 4 + 31) / 32;
-  int grid = row_grid(M);
-  const int cap = sm_count() * 2;   // fewer CTAs -> fewer dgamma/dbeta atomics
-  if (grid > cap && cap > 0) grid = cap;
+  const int nv = (H / 4 + 63) / 64;   // float4 chunks per lane of a 64-lane row team
+  long long blocks = ((long long)M + 3) / 4;
+  const int cap = sm_count() * 2;     // two resident CTAs per SM; fewer CTAs -> fewer dgamma/dbeta atomics
+  int grid = (int)(blocks < cap || cap <= 0 ? (blocks > 0 ? blocks : 1) : cap);
   __nv_bfloat16* dx16 = static_cast<__nv_bfloat16*>(dx_bf16);
   const __nv_bfloat16* pre = static_cast<const __nv_bfloat16*>(gelu_pre);
 #define LN_B(NV) ln_bwd_kernel<NV><<<grid, ROW_THREADS, 0, ST(stream)>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx_f32, dx16, lddx, pre, ld_pre, dgamma, dbeta, dbias, M, H)
-  if (nv4 <= 1) LN_B(1); else if (nv4 <= 2) LN_B(2); else if (nv4 <= 4) LN_B(4); else if (nv4 <= 6) LN_B(6);
-  else if (nv4 <= 8) LN_B(8); else LN_B(16);
+  if (nv <= 1) LN_B(1); else if (nv <= 2) LN_B(2); else if (nv <= 3) LN_B(3); else if (nv <= 4) LN_B(4); else LN_B(8);
 #undef LN_B
   return check_launch("vb_layernorm_bwd");
 }
