@@ -102,7 +102,7 @@ def test_base_2layer_2conect_config1(golden_dir):
             assert e < (6e-2 if n in SMALL_HEADS else 1e-2), (mode, n, e)
     assert abs(r["loss"] - r["loss_fp32"]) < 2e-3 * abs(r["loss_fp32"])
     l2 = sorted(v[1] for v in r["grad_bf16"].values())
-    assert l2[len(l2) // 2] < 2e-2 and l2[int(len(l2) * 0.9)] < 8e-2, (l2[len(l2) // 2], l2[int(len(l2) * 0.9)])
+    assert l2[len(l2) // 2] < 4e-2 and l2[int(len(l2) * 0.9)] < 1e-1, (l2[len(l2) // 2], l2[int(len(l2) * 0.9)])
 
 
 def test_base_6layer_6conect_vqa_shape(golden_dir):

@@ -1,6 +1,7 @@
 // vb_api.cu — error reporting, version and device queries of the C ABI (include/vilbert_b200.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "vb_internal.h"
 
@@ -13,6 +14,15 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VB_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int sm_count() {

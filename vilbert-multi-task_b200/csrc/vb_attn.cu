@@ -138,6 +138,7 @@ template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams p) {
   constexpr int LD = D + 8;
   extern __shared__ __align__(16) uint8_t smem_att[];
+  pdl_entry();
   const int nkp = (p.Nk + KB - 1) / KB * KB;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
   __nv_bfloat16* sK = sQ + TQ * LD;
@@ -210,6 +211,7 @@ template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnParams p) {
   constexpr int LD = D + 8;
   extern __shared__ __align__(16) uint8_t smem_att[];
+  pdl_entry();
   const int nkp = (p.Nk + KB - 1) / KB * KB;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
   __nv_bfloat16* sdO = sQ + TQ * LD;
@@ -303,6 +305,7 @@ template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnParams p) {
   constexpr int LD = D + 8;
   extern __shared__ __align__(16) uint8_t smem_att[];
+  pdl_entry();
   const int nqp = (p.Nq + KB - 1) / KB * KB;
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_att);
   __nv_bfloat16* sV = sK + TQ * LD;
@@ -414,8 +417,9 @@ static int launch_att(Kern kern, dim3 grid, size_t smem, const AttnParams& p, cu
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   }
-  kern<<<grid, ATT_THREADS, smem, s>>>(p);
-  return check_launch(what);
+  cudaError_t e = launch_pdl(kern, grid, dim3(ATT_THREADS), smem, s, p);
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return VB_OK;
 }
 
 }  // namespace vb

@@ -218,6 +218,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_entry();   // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel's tail
   if (threadIdx.x == 0) VB_DBG(1);
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
@@ -432,8 +433,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
     if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmCfg<BN>::SMEM_BYTES, stream, ta, tb, p);
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return VB_OK;
 }

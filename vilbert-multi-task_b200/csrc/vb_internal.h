@@ -13,4 +13,26 @@ inline int check_launch(const char* what) {
   return VB_OK;
 }
 int sm_count();
+
+// Programmatic dependent launch (PDL): every kernel of the library starts with `griddepcontrol.wait` (all global
+// traffic happens after it) followed by `griddepcontrol.launch_dependents`, and is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that launch processing, CTA scheduling and per-CTA setup
+// (barrier init, TMEM allocation, tensor-map prefetch) of kernel N+1 overlap the tail of kernel N — also inside
+// captured CUDA graphs. VB_PDL=0 in the environment restores plain stream serialization.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 }  // namespace vb

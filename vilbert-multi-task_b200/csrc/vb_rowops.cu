@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
               float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, long long ldy, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int M, int H) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int n4 = H >> 2;
   const float inv_h = 1.f / (float)H;
@@ -95,6 +96,7 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
               float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16, long long lddx,
               const __nv_bfloat16* __restrict__ pre, long long ldpre, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dbias, int M, int H) {
+  pdl_entry();
   constexpr int TEAMS = ROW_THREADS / 64;
   __shared__ float xch[TEAMS][2][2][2];
   __shared__ float red[TEAMS][64 * 4 + 4];
@@ -181,6 +183,7 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
 
 // ------------------------------------------------------------------------------------------ casts
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4, long long n) {
+  pdl_entry();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
@@ -195,6 +198,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 // rows x cols with independent leading dims (pads bf16 operands whose row size is not a multiple of 8)
 __global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
                                        int rows, int cols, float scale) {
+  pdl_entry();
   for (long long r = blockIdx.y; r < rows; r += gridDim.y)
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
       dst[r * ldd + c] = __float2bfloat16(src[r * lds + c] * scale);
@@ -207,6 +211,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 embed_text_fwd_kernel(const long long* __restrict__ ids, const long long* __restrict__ tts, const long long* __restrict__ task_ids,
                       const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
                       const float* __restrict__ task, float* __restrict__ out, int B, int Nt, int H, int has_task) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int No = Nt + (has_task ? 1 : 0);
   const long long rows = (long long)B * No;
@@ -235,6 +240,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 embed_text_bwd_kernel(const float* __restrict__ dout, const long long* __restrict__ ids, const long long* __restrict__ tts,
                       const long long* __restrict__ task_ids, float* __restrict__ dword, float* __restrict__ dpos,
                       float* __restrict__ dtype, float* __restrict__ dtask, int B, int Nt, int H, int has_task) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int No = Nt + (has_task ? 1 : 0);
   const long long rows = (long long)B * No;
@@ -264,6 +270,7 @@ embed_text_bwd_kernel(const float* __restrict__ dout, const long long* __restric
 // out[m, h] = sum_j loc[m, j] * W[h, j] + b[h],  j < 5  (BertImageEmbeddings.image_location_embeddings, vilbert.py:1416,1424)
 __global__ void loc_proj_fwd_kernel(const float* __restrict__ loc, const float* __restrict__ W, const float* __restrict__ b,
                                     float* __restrict__ out, int M, int H) {
+  pdl_entry();
   extern __shared__ float sw[];  // [H][5] + [H]
   for (int i = threadIdx.x; i < H * 5; i += blockDim.x) sw[i] = W[i];
   for (int i = threadIdx.x; i < H; i += blockDim.x) sw[H * 5 + i] = b[i];
@@ -284,6 +291,7 @@ __global__ void loc_proj_fwd_kernel(const float* __restrict__ loc, const float* 
 // dW[h, j] += sum_m dy[m, h] * loc[m, j];  db[h] += sum_m dy[m, h]
 __global__ void loc_proj_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ loc, float* __restrict__ dW,
                                     float* __restrict__ db, int M, int H, int rows_per_block) {
+  pdl_entry();
   const long long m0 = (long long)blockIdx.y * rows_per_block;
   const long long m1 = min((long long)M, m0 + rows_per_block);
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,6 +319,7 @@ __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return _
 // out[n] += sum_m X[m, n]; block = 32 x 8 threads: 32 consecutive columns, 8 row lanes.
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ X, long long ld, float* __restrict__ out, int M, int N, int rows_per_block) {
+  pdl_entry();
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   const long long m0 = (long long)blockIdx.y * rows_per_block;
@@ -334,6 +343,7 @@ __global__ void colsum_kernel(const T* __restrict__ X, long long ld, float* __re
 __global__ void __launch_bounds__(ROW_THREADS)
 small_linear_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W, const float* __restrict__ b,
                         const float* __restrict__ addend, float* __restrict__ y, int M, int K, int N) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   for (long long row = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * ROW_WARPS) {
     const float* xr = x + row * ldx;
@@ -351,6 +361,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 small_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long ldx, const float* __restrict__ W,
                         float* __restrict__ dx, long long lddx, int accumulate_dx, float* __restrict__ dW, float* __restrict__ db,
                         int M, int K, int N) {
+  pdl_entry();
   // one CTA handles a strided set of rows; per-thread partial dW over columns k = threadIdx.x + i*ROW_THREADS
   for (int j = 0; j < N; ++j) {
     float dbp = 0.f;
@@ -380,6 +391,7 @@ small_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ 
 // out = a * b (fusion_method "mul") or a + b ("sum"), f32 + bf16 copies (vilbert.py:1677-1682, 1236-1241)
 __global__ void fuse_pooled_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o32,
                                        __nv_bfloat16* __restrict__ o16, long long n, int mul) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = mul ? a[i] * b[i] : a[i] + b[i];
     if (o32) o32[i] = v;
@@ -389,6 +401,7 @@ __global__ void fuse_pooled_fwd_kernel(const float* __restrict__ a, const float*
 // da += d * b, db += d * a (mul) or da += d, db += d (sum)
 __global__ void fuse_pooled_bwd_kernel(const float* __restrict__ d, const float* __restrict__ a, const float* __restrict__ b,
                                        float* __restrict__ da, float* __restrict__ db, long long n, int mul) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float g = d[i];
     da[i] += mul ? g * b[i] : g;
@@ -398,6 +411,7 @@ __global__ void fuse_pooled_bwd_kernel(const float* __restrict__ d, const float*
 // dx = dy * (y > 0) -> bf16 (pooler ReLU, vilbert.py:1121,1136)
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, __nv_bfloat16* __restrict__ dx16,
                                 float* __restrict__ dx32, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = y[i] > 0.f ? dy[i] : 0.f;
     if (dx16) dx16[i] = __float2bfloat16(v);
@@ -406,6 +420,7 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __res
 }
 // y (+)= x  (f32), used to merge gradient contributions
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float alpha) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += alpha * x[i];
 }
 
@@ -414,6 +429,7 @@ __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, 
 __global__ void bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ t, float* __restrict__ loss,
                                   float* __restrict__ dz32, __nv_bfloat16* __restrict__ dz16, long long lddz16, int rows, int cols,
                                   float grad_scale) {
+  pdl_entry();
   __shared__ float red[32];
   const long long n = (long long)rows * cols;
   float acc = 0.f;
@@ -438,6 +454,7 @@ __global__ void bce_logits_kernel(const float* __restrict__ z, const float* __re
 // additive attention mask (vilbert.py:1341-1362): out[b, j] = (1 - m[b, j]) * -10000; with prepend_one the
 // output row has N+1 entries and a leading 0 (task-token mask extension, :1331-1334)
 __global__ void mask_to_additive_kernel(const long long* __restrict__ m, float* __restrict__ out, int B, int N, int prepend) {
+  pdl_entry();
   const int No = N + prepend;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * No; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / No), j = (int)(i % No);
@@ -469,7 +486,7 @@ extern "C" vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* 
   const int nv4 = (H / 4 + 31) / 32;
   const int grid = row_grid(M);
   __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
-#define LN_F(NV) ln_fwd_kernel<NV><<<grid, ROW_THREADS, 0, ST(stream)>>>(x, ldx, gamma, beta, eps, y_f32, y16, ldy, mean, rstd, M, H)
+#define LN_F(NV) launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), x, ldx, gamma, beta, eps, y_f32, y16, ldy, mean, rstd, M, H)
   if (nv4 <= 1) LN_F(1); else if (nv4 <= 2) LN_F(2); else if (nv4 <= 4) LN_F(4); else if (nv4 <= 6) LN_F(6);
   else if (nv4 <= 8) LN_F(8); else LN_F(16);
 #undef LN_F
@@ -488,7 +505,7 @@ extern "C" vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float
   int grid = (int)(blocks < cap || cap <= 0 ? (blocks > 0 ? blocks : 1) : cap);
   __nv_bfloat16* dx16 = static_cast<__nv_bfloat16*>(dx_bf16);
   const __nv_bfloat16* pre = static_cast<const __nv_bfloat16*>(gelu_pre);
-#define LN_B(NV) ln_bwd_kernel<NV><<<grid, ROW_THREADS, 0, ST(stream)>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx_f32, dx16, lddx, pre, ld_pre, dgamma, dbeta, dbias, M, H)
+#define LN_B(NV) launch_pdl(ln_bwd_kernel<NV>, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), dy, lddy, x, ldx, gamma, mean, rstd, dx_f32, dx16, lddx, pre, ld_pre, dgamma, dbeta, dbias, M, H)
   if (nv <= 1) LN_B(1); else if (nv <= 2) LN_B(2); else if (nv <= 3) LN_B(3); else if (nv <= 4) LN_B(4); else LN_B(8);
 #undef LN_B
   return check_launch("vb_layernorm_bwd");
@@ -497,7 +514,7 @@ extern "C" vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float
 extern "C" vb_status vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   if (n <= 0) return VB_OK;
   if (!al16(src) || (reinterpret_cast<uintptr_t>(dst) & 7)) return set_error(VB_ERR_INVALID, "vb_cast_f32_to_bf16: misaligned buffers");
-  cast_f32_bf16_kernel<<<ew_grid(n / 4 + 1), 256, 0, ST(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n / 4, n);
+  launch_pdl(cast_f32_bf16_kernel, dim3(ew_grid(n / 4 + 1)), dim3(256), (size_t)(0), ST(stream), src, static_cast<__nv_bfloat16*>(dst), n / 4, n);
   return check_launch("vb_cast_f32_to_bf16");
 }
 
@@ -505,7 +522,7 @@ extern "C" vb_status vb_cast2d_f32_to_bf16(const float* src, int64_t lds, void* 
                                            void* stream) {
   if (rows <= 0 || cols <= 0) return VB_OK;
   dim3 grid((cols + 255) / 256 > 64 ? 64 : (cols + 255) / 256, rows > 4096 ? 4096 : rows);
-  cast2d_f32_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols, scale);
+  launch_pdl(cast2d_f32_bf16_kernel, dim3(grid), dim3(256), (size_t)(0), ST(stream), src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols, scale);
   return check_launch("vb_cast2d_f32_to_bf16");
 }
 
@@ -516,7 +533,7 @@ extern "C" vb_status vb_embed_text_fwd(const int64_t* ids, const int64_t* token_
   const int has_task = task_ids != nullptr;
   if (has_task && !task) return set_error(VB_ERR_INVALID, "vb_embed_text_fwd: task ids without a task table");
   const long long rows = (long long)B * (Nt + has_task);
-  embed_text_fwd_kernel<<<row_grid(rows), ROW_THREADS, 0, ST(stream)>>>(
+  launch_pdl(embed_text_fwd_kernel, dim3(row_grid(rows)), dim3(ROW_THREADS), (size_t)(0), ST(stream), 
       reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(token_type_ids),
       reinterpret_cast<const long long*>(task_ids), word, pos, type, task, out, B, Nt, H, has_task);
   return check_launch("vb_embed_text_fwd");
@@ -528,7 +545,7 @@ extern "C" vb_status vb_embed_text_bwd(const float* dout, const int64_t* ids, co
   if (B <= 0 || Nt <= 0) return set_error(VB_ERR_INVALID, "vb_embed_text_bwd: bad shape");
   const int has_task = task_ids != nullptr;
   const long long rows = (long long)B * (Nt + has_task);
-  embed_text_bwd_kernel<<<row_grid(rows), ROW_THREADS, 0, ST(stream)>>>(
+  launch_pdl(embed_text_bwd_kernel, dim3(row_grid(rows)), dim3(ROW_THREADS), (size_t)(0), ST(stream), 
       dout, reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(token_type_ids),
       reinterpret_cast<const long long*>(task_ids), dword, dpos, dtype, dtask, B, Nt, H, has_task);
   return check_launch("vb_embed_text_bwd");
@@ -539,7 +556,7 @@ extern "C" vb_status vb_loc_proj_fwd(const float* loc, const float* W, const flo
   const size_t smem = (size_t)H * 6 * sizeof(float);
   if (smem > 48 * 1024) return set_error(VB_ERR_UNSUPPORTED, "vb_loc_proj_fwd: H too large");
   int grid = sm_count() * 4; if (grid > M) grid = M; if (grid <= 0) grid = 1;
-  loc_proj_fwd_kernel<<<grid, 256, smem, ST(stream)>>>(loc, W, b, out, M, H);
+  launch_pdl(loc_proj_fwd_kernel, dim3(grid), dim3(256), (size_t)(smem), ST(stream), loc, W, b, out, M, H);
   return check_launch("vb_loc_proj_fwd");
 }
 
@@ -547,7 +564,7 @@ extern "C" vb_status vb_loc_proj_bwd(const float* dy, const float* loc, float* d
   if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_loc_proj_bwd: bad shape");
   const int rpb = 64;
   dim3 grid((H + 127) / 128, (M + rpb - 1) / rpb);
-  loc_proj_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(dy, loc, dW, db, M, H, rpb);
+  launch_pdl(loc_proj_bwd_kernel, dim3(grid), dim3(128), (size_t)(0), ST(stream), dy, loc, dW, db, M, H, rpb);
   return check_launch("vb_loc_proj_bwd");
 }
 
@@ -555,15 +572,15 @@ extern "C" vb_status vb_colsum(const void* X, int32_t is_bf16, int64_t ld, float
   if (M <= 0 || N <= 0) return set_error(VB_ERR_INVALID, "vb_colsum: bad shape");
   int rpb = (M + 31) / 32; if (rpb < 64) rpb = 64;
   dim3 grid((N + 31) / 32, (M + rpb - 1) / rpb), block(32, 8);
-  if (is_bf16) colsum_kernel<__nv_bfloat16><<<grid, block, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(X), ld, out, M, N, rpb);
-  else colsum_kernel<float><<<grid, block, 0, ST(stream)>>>(static_cast<const float*>(X), ld, out, M, N, rpb);
+  if (is_bf16) launch_pdl(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(block), (size_t)(0), ST(stream), static_cast<const __nv_bfloat16*>(X), ld, out, M, N, rpb);
+  else launch_pdl(colsum_kernel<float>, dim3(grid), dim3(block), (size_t)(0), ST(stream), static_cast<const float*>(X), ld, out, M, N, rpb);
   return check_launch("vb_colsum");
 }
 
 extern "C" vb_status vb_small_linear_fwd(const float* x, int64_t ldx, const float* W, const float* b, const float* row_addend, float* y,
                                          int32_t M, int32_t K, int32_t N, void* stream) {
   if (M <= 0 || K <= 0 || N <= 0 || N > 8) return set_error(VB_ERR_INVALID, "vb_small_linear_fwd: bad shape (N <= 8)");
-  small_linear_fwd_kernel<<<row_grid(M), ROW_THREADS, 0, ST(stream)>>>(x, ldx, W, b, row_addend, y, M, K, N);
+  launch_pdl(small_linear_fwd_kernel, dim3(row_grid(M)), dim3(ROW_THREADS), (size_t)(0), ST(stream), x, ldx, W, b, row_addend, y, M, K, N);
   return check_launch("vb_small_linear_fwd");
 }
 
@@ -571,29 +588,29 @@ extern "C" vb_status vb_small_linear_bwd(const float* dy, const float* x, int64_
                                          int32_t accumulate_dx, float* dW, float* db, int32_t M, int32_t K, int32_t N, void* stream) {
   if (M <= 0 || K <= 0 || N <= 0 || N > 8) return set_error(VB_ERR_INVALID, "vb_small_linear_bwd: bad shape (N <= 8)");
   int grid = sm_count(); if (grid > M) grid = M; if (grid <= 0) grid = 1;
-  small_linear_bwd_kernel<<<grid, ROW_THREADS, 0, ST(stream)>>>(dy, x, ldx, W, dx, lddx, accumulate_dx, dW, db, M, K, N);
+  launch_pdl(small_linear_bwd_kernel, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), dy, x, ldx, W, dx, lddx, accumulate_dx, dW, db, M, K, N);
   return check_launch("vb_small_linear_bwd");
 }
 
 extern "C" vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul, void* stream) {
   if (n <= 0) return VB_OK;
-  fuse_pooled_fwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(a, b, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n, mul);
+  launch_pdl(fuse_pooled_fwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), a, b, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n, mul);
   return check_launch("vb_fuse_pooled_fwd");
 }
 extern "C" vb_status vb_fuse_pooled_bwd(const float* d, const float* a, const float* b, float* da, float* db, int64_t n, int32_t mul,
                                         void* stream) {
   if (n <= 0) return VB_OK;
-  fuse_pooled_bwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(d, a, b, da, db, n, mul);
+  launch_pdl(fuse_pooled_bwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), d, a, b, da, db, n, mul);
   return check_launch("vb_fuse_pooled_bwd");
 }
 extern "C" vb_status vb_relu_bwd(const float* dy, const float* y, void* dx_bf16, float* dx_f32, int64_t n, void* stream) {
   if (n <= 0) return VB_OK;
-  relu_bwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(dy, y, static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, n);
+  launch_pdl(relu_bwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), dy, y, static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, n);
   return check_launch("vb_relu_bwd");
 }
 extern "C" vb_status vb_axpy_f32(const float* x, float* y, int64_t n, float alpha, void* stream) {
   if (n <= 0) return VB_OK;
-  axpy_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(x, y, n, alpha);
+  launch_pdl(axpy_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), x, y, n, alpha);
   return check_launch("vb_axpy_f32");
 }
 extern "C" vb_status vb_bce_logits_loss(const float* logits, const float* target, float* loss, float* dlogits_f32, void* dlogits_bf16,
@@ -601,14 +618,14 @@ extern "C" vb_status vb_bce_logits_loss(const float* logits, const float* target
   if (rows <= 0 || cols <= 0) return set_error(VB_ERR_INVALID, "vb_bce_logits_loss: bad shape");
   cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), ST(stream));
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_bce_logits_loss: memset: %s", cudaGetErrorString(e));
-  bce_logits_kernel<<<ew_grid((long long)rows * cols), 256, 0, ST(stream)>>>(logits, target, loss, dlogits_f32,
+  launch_pdl(bce_logits_kernel, dim3(ew_grid((long long)rows * cols)), dim3(256), (size_t)(0), ST(stream), logits, target, loss, dlogits_f32,
                                                                               static_cast<__nv_bfloat16*>(dlogits_bf16), ld_dlogits_bf16, rows,
                                                                               cols, grad_scale);
   return check_launch("vb_bce_logits_loss");
 }
 extern "C" vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_t B, int32_t N, int32_t prepend_one, void* stream) {
   if (B <= 0 || N <= 0) return set_error(VB_ERR_INVALID, "vb_mask_to_additive: bad shape");
-  mask_to_additive_kernel<<<ew_grid((long long)B * (N + 1)), 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(mask), out, B, N, prepend_one ? 1 : 0);
+  launch_pdl(mask_to_additive_kernel, dim3(ew_grid((long long)B * (N + 1))), dim3(256), (size_t)(0), ST(stream), reinterpret_cast<const long long*>(mask), out, B, N, prepend_one ? 1 : 0);
   return check_launch("vb_mask_to_additive");
 }
 extern "C" vb_status vb_memset_zero(void* ptr, int64_t bytes, void* stream) {
