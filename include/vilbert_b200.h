@@ -59,8 +59,8 @@ vb_status vb_device_info(int* sm_count, int* cc);
  *   mn-major : element (r, k) at ptr[k*ld + r]
  * Requirements: ld % 8 == 0, base pointers 16-byte aligned. M, N, K arbitrary (TMA zero-fills the
  * edges, stores are predicated).
- * act: VB_ACT_GELU = exact erf GELU (vilbert.py:111-117), out_pre receives the pre-activation;
- *      VB_ACT_DGELU multiplies by gelu'(aux[m,n]) (aux = saved pre-activation);
+ * act: VB_ACT_GELU = erf GELU (vilbert.py:111-117; erf by Abramowitz-Stegun 7.1.26, |err| < 5e-7), out_pre receives
+ *      gelu'(pre-activation) as bf16 (what the backward needs); VB_ACT_DGELU multiplies by aux[m,n] (that buffer);
  * atomic_out: accumulate into out_f32 with red.global.add (needed when split_k > 1).
  */
 typedef struct vb_gemm_args {
@@ -75,14 +75,14 @@ typedef struct vb_gemm_args {
   const float* bias;     /* [N] or NULL */
   const float* residual; /* f32 [M,N] or NULL; may alias out_f32 */
   int64_t ld_res;
-  const void* aux;       /* bf16 [M,N] for VB_ACT_DGELU, else NULL */
+  const void* aux;       /* bf16 [M,N] saved gelu'(pre) for VB_ACT_DGELU, else NULL */
   int64_t ld_aux;
   int32_t act;
   float* out_f32;        /* or NULL */
   int64_t ld_out_f32;
   void* out_bf16;        /* or NULL */
   int64_t ld_out_bf16;
-  void* out_pre;         /* bf16 pre-activation (GELU) or NULL */
+  void* out_pre;         /* bf16 gelu'(pre-activation) (GELU) or NULL */
   int64_t ld_out_pre;
   int32_t atomic_out;    /* 0 store, 1 red.add into out_f32 */
   float* out_colsum;     /* [N] or NULL: += column sums of the epilogue value before the residual add (bias gradients) */
@@ -91,7 +91,7 @@ typedef struct vb_gemm_args {
   int32_t max_ctas;      /* 0 = one persistent CTA per SM */
   /* debug/test overrides for the smem matrix descriptors (0 = library default) */
   uint32_t dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b;
-  void* dbg_timeline;    /* NULL, or u64 [grid][8]: per-CTA clock64 stamps (development only) */
+  void* dbg_timeline;    /* NULL, or u64 [grid][10]: per-CTA clock64 / globaltimer stamps (development only) */
 } vb_gemm_args;
 
 vb_status vb_gemm_bf16(const vb_gemm_args* args, void* stream);
@@ -138,7 +138,7 @@ vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, cons
                            float* y_f32, void* y_bf16, int64_t ldy, float* mean, float* rstd,
                            int32_t M, int32_t H, void* stream);
 /* Autograd of the above. dx as f32 and/or bf16; dgamma/dbeta are ACCUMULATED (atomics) and may be NULL.
- * If gelu_pre (bf16 [M,H]) is given, dx_bf16 is additionally multiplied by gelu'(gelu_pre) — the
+ * If gelu_pre (bf16 [M,H], the GELU derivative saved by the forward GEMM) is given, dx_bf16 is multiplied by it — the
  * Linear -> GELU -> LayerNorm head transforms (vilbert.py:1152-1156, 1172-1176, 1714-1718).
  * dbias (may be NULL) += column sums of the dx value written to dx_bf16 (or of dx when dx_bf16 is NULL): the
  * bias gradient of the Linear that produced the LayerNorm input. */

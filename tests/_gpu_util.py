@@ -70,12 +70,12 @@ def gemm_case(M, N, K, a_mn=False, b_mn=False, bias=False, res=False, act=0, out
         ref = alpha * (A.float() @ B.float().t())
         if bias: ref = ref + bias_t
         if act == L.VB_ACT_GELU:
-            pre_ref = ref.clone(); ref = O.gelu(ref)
+            x_ = ref.clone(); ref = O.gelu(ref)
+            pre_ref = 0.5 * (1 + torch.erf(x_ / 2 ** 0.5)) + x_ * torch.exp(-0.5 * x_ * x_) / math.sqrt(2 * math.pi)   # saved gelu'(pre)
         elif act == L.VB_ACT_RELU:
             ref = ref.clamp_min(0)
         elif act == L.VB_ACT_DGELU:
-            x = aux_t.float()
-            ref = ref * (0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi))
+            ref = ref * aux_t.float()            # aux = saved gelu'(pre)
         if res: ref = ref + res_t
         scale = ref.abs().max().item() + 1e-9
         err = ((out32 - ref).abs().max() / scale).item() if want_f32 else 0.0

@@ -7,7 +7,7 @@ lib = L.lib(); dev = "cuda"; BF = torch.bfloat16
 def run(M, N, K, bn, res=False):
     A = torch.randn(M, K, device=dev).to(BF); B = torch.randn(N, K, device=dev).to(BF)
     out = torch.empty(M, N, device=dev); r = torch.randn(M, N, device=dev)
-    dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(148 * 10, dtype=torch.int64, device=dev)
     g = L.GemmArgs(); g.M, g.N, g.K = M, N, K
     g.A, g.lda, g.B, g.ldb = A.data_ptr(), K, B.data_ptr(), K
     g.alpha, g.out_f32, g.ld_out_f32, g.split_k, g.block_n = 1.0, out.data_ptr(), N, 1, bn
@@ -18,18 +18,20 @@ def run(M, N, K, bn, res=False):
     g.dbg_timeline = dbg.data_ptr()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record(); L.check(lib.vb_gemm_bf16(C.byref(g), st)); e1.record(); torch.cuda.synchronize()
-    t = dbg.view(148, 8).cpu()
-    live = t[:, 0] != 0
-    t = t[live]
+    full = dbg.view(148, 10).cpu()
+    live = full[:, 0] != 0
+    full = full[live]
+    t = full[:, :8]
+    ns0, ns1 = full[:, 8], full[:, 9]
     d = (t - t[:, :1]).float()
     names = ["entry", "setup done", "first TMA issued", "first full_bar", "last MMA committed", "epi: tmem_full", "epi: done", "exit sync"]
     print(f"--- M{M} N{N} K{K} bn{bn} res{int(res)}: event time {e0.elapsed_time(e1)*1e3:.1f} us, {int(live.sum())} CTAs; cycles since CTA entry (median / max over CTAs):")
     for i, n in enumerate(names):
         print(f"     {n:20s} {d[:, i].median().item():10.0f} {d[:, i].max().item():10.0f}")
-    print(f"     CTA entry spread (cycles): {(t[:,0].max() - t[:,0].min()).item()}")
-run(128, 128, 64, 128)
-run(2304, 768, 768, 128)
+    print(f"     globaltimer: CTA start spread {(ns0.max() - ns0.min()).item()} ns, first start -> last end {(ns1.max() - ns0.min()).item()} ns, "
+          f"median CTA lifetime {(ns1 - ns0).median().item()} ns")
 run(2304, 768, 768, 128, res=True)
 run(2304, 768, 3072, 128)
-run(6400, 1024, 1024, 128)
-run(6400, 1024, 1024, 256)
+run(6400, 1024, 1024, 128, res=True)
+run(6400, 1024, 1024, 256, res=True)
+run(6400, 3072, 1024, 256)

@@ -67,7 +67,7 @@ struct GemmKernelParams {
   uint32_t idesc;
   int a_mn, b_mn;            // operand majors (runtime: only the TMA producer cares)
   int fast_ok;               // every buffer the specialised epilogue touches allows 128/64-bit accesses
-  unsigned long long* dbg;   // optional per-CTA timeline [grid][8] (clock64), NULL in production
+  unsigned long long* dbg;   // optional per-CTA timeline [grid][10] (8 x clock64 + 2 x globaltimer ns), NULL in production
 };
 
 // Epilogue specialisations. Each instantiation keeps ONE compact, fully unrolled fast path (whole 32x32 chunk inside
@@ -76,8 +76,8 @@ struct GemmKernelParams {
 // of one 128x128 tile then costs ~29k cycles instead of ~2k — measured with the clock64 timeline, profiles/.)
 enum { EPI_F32 = 0,     // v = alpha*acc (+bias) (+fp32 residual) -> out_f32                (out-proj / FFN2 / dgrad-into-residual / logits)
        EPI_BF16 = 1,    // v = alpha*acc (+bias) -> out_bf16                                 (QKV, plain dgrads)
-       EPI_GELU = 2,    // pre = acc + bias -> out_pre (bf16); gelu(pre) -> out_bf16 / out_f32
-       EPI_DGELU = 3,   // v = acc * gelu'(aux) -> out_bf16 (+ column sums)
+       EPI_GELU = 2,    // pre = acc + bias; gelu(pre) -> out_bf16 / out_f32; gelu'(pre) -> out_pre (bf16, saved for backward)
+       EPI_DGELU = 3,   // v = acc * aux (aux = saved gelu'(pre)) -> out_bf16 (+ column sums)
        EPI_ATOMIC = 4,  // red.global.add.v4.f32 into out_f32 (split-K wgrad)
        EPI_GENERIC = 5, // runtime flags only (ReLU poolers, unusual output combinations)
        EPI_COUNT = 6 };
@@ -102,12 +102,14 @@ __device__ __noinline__ void epi_generic_chunk(const GemmKernelParams& p, const 
       float v = stg[row * STAGE_PAD + cc + j] * p.alpha;
       if (p.bias) v += p.bias[n + j];
       if (p.act == VB_ACT_GELU) {
-        if (p.out_pre) p.out_pre[m * p.ld_op + n + j] = __float2bfloat16(v);
-        v = gelu_erf(v);
+        float gg, dg;
+        gelu_erf_and_grad(v, gg, dg);
+        if (p.out_pre) p.out_pre[m * p.ld_op + n + j] = __float2bfloat16(dg);   // saved for backward: gelu'(pre)
+        v = gg;
       } else if (p.act == VB_ACT_RELU) {
         v = fmaxf(v, 0.f);
       } else if (p.act == VB_ACT_DGELU) {
-        v *= gelu_erf_grad(__bfloat162float(p.aux[m * p.ld_aux + n + j]));
+        v *= __bfloat162float(p.aux[m * p.ld_aux + n + j]);                      // aux = saved gelu'(pre)
       }
       cs[j] += v;
       if (p.residual) v += p.residual[m * p.ld_res + n + j];
@@ -135,14 +137,15 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
     const float4 a4 = *reinterpret_cast<const float4*>(stg + row * STAGE_PAD + cc);
     float v0 = fmaf(a4.x, p.alpha, b4.x), v1 = fmaf(a4.y, p.alpha, b4.y), v2 = fmaf(a4.z, p.alpha, b4.z), v3 = fmaf(a4.w, p.alpha, b4.w);
     if (EPI == EPI_GELU) {
-      *reinterpret_cast<uint2*>(p.out_pre + m * p.ld_op + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
-      v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+      float d0, d1, d2, d3;
+      gelu_erf_and_grad(v0, v0, d0); gelu_erf_and_grad(v1, v1, d1); gelu_erf_and_grad(v2, v2, d2); gelu_erf_and_grad(v3, v3, d3);
+      *reinterpret_cast<uint2*>(p.out_pre + m * p.ld_op + n) = make_uint2(pack_bf16(d0, d1), pack_bf16(d2, d3));   // gelu'(pre) for backward
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_of + n) = make_float4(v0, v1, v2, v3);
       if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
     } else if (EPI == EPI_DGELU) {
       const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].x));
       const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].y));
-      v0 *= gelu_erf_grad(x01.x); v1 *= gelu_erf_grad(x01.y); v2 *= gelu_erf_grad(x23.x); v3 *= gelu_erf_grad(x23.y);
+      v0 *= x01.x; v1 *= x01.y; v2 *= x23.x; v3 *= x23.y;   // aux = gelu'(pre) saved by the forward epilogue
       cs0 += v0; cs1 += v1; cs2 += v2; cs3 += v3;
       *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
     } else if (EPI == EPI_F32) {
@@ -193,8 +196,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-#define VB_DBG(slot) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
-  if (threadIdx.x == 0) VB_DBG(0);
+#define VB_DBG(slot) do { if (p.dbg) p.dbg[blockIdx.x * 10 + (slot)] = clock64(); } while (0)
+#define VB_DBG_NS(slot) do { if (p.dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[blockIdx.x * 10 + (slot)] = t_; } } while (0)
+  if (threadIdx.x == 0) { VB_DBG(0); VB_DBG_NS(8); }
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -321,40 +325,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int m_base = m_blk * BM + lane_grp * 32;
       const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16) + as * BN;
       const bool rows_full = (m_base + 32 <= p.M);
+      const bool rows_live = (m_base < p.M);
       bool waited = false;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n_chunk = n_blk * BN + c * 32;
-        const bool chunk_live = (n_chunk < p.N) && (m_base < p.M);  // warp-uniform
-        const int n = n_chunk + cc;
-        const bool fast = (EPI != EPI_GENERIC) && p.fast_ok && rows_full && (n_chunk + 32 <= p.N);  // warp-uniform
-        // ---- (1) prefetch per-element global operands of the fast path
-        float4 resv[8];
-        uint2 auxv[8];
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (chunk_live && fast) {
-          if (EPI == EPI_F32 && p.residual) {
+      constexpr int NC = BN / 32;
+      // software pipeline over chunk pairs: the global operands of chunk c+1 are in flight while chunk c is processed
+      float4 res0[8], res1[8];
+      uint2 aux0[8], aux1[8];
+      float4 bia0, bia1;
+      auto chunk_fast = [&](int c) -> bool {
+        return (EPI != EPI_GENERIC) && p.fast_ok && rows_full && (n_blk * BN + c * 32 + 32 <= p.N);
+      };
+      auto prefetch = [&](int c, float4 (&resv)[8], uint2 (&auxv)[8], float4& b4) {
+        b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c >= NC || !rows_live || !chunk_fast(c)) return;
+        const int n = n_blk * BN + c * 32 + cc;
+        if (EPI == EPI_F32 && p.residual) {
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const float* src = p.residual + (long long)(m_base + ps * 4 + rr) * p.ld_res + n;
-              if (p.vec_res) resv[ps] = *reinterpret_cast<const float4*>(src);
-              else resv[ps] = make_float4(src[0], src[1], src[2], src[3]);
-            }
+          for (int ps = 0; ps < 8; ++ps) {
+            const float* src = p.residual + (long long)(m_base + ps * 4 + rr) * p.ld_res + n;
+            if (p.vec_res) resv[ps] = *reinterpret_cast<const float4*>(src);
+            else resv[ps] = make_float4(src[0], src[1], src[2], src[3]);
           }
-          if (EPI == EPI_DGELU) {
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps)
-              auxv[ps] = *reinterpret_cast<const uint2*>(p.aux + (long long)(m_base + ps * 4 + rr) * p.ld_aux + n);
-          }
-          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + n);
         }
+        if (EPI == EPI_DGELU) {
+#pragma unroll
+          for (int ps = 0; ps < 8; ++ps)
+            auxv[ps] = *reinterpret_cast<const uint2*>(p.aux + (long long)(m_base + ps * 4 + rr) * p.ld_aux + n);
+        }
+        if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + n);
+      };
+      auto process = [&](int c, const float4 (&resv)[8], const uint2 (&auxv)[8], const float4 b4) {
+        const int n_chunk = n_blk * BN + c * 32;
+        const bool chunk_live = (n_chunk < p.N) && rows_live;  // warp-uniform
         if (!waited) {
           mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
           tc_fence_after();
           waited = true;
           if (tile == blockIdx.x && warp_idx == 2 && lane == 0) VB_DBG(5);
         }
-        // ---- (2) TMEM -> registers -> (3) padded smem tile (row = lane)
+        // TMEM -> registers -> padded smem tile (row = lane)
         if (chunk_live) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
@@ -363,17 +372,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * STAGE_PAD + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
-        if (c == BN / 32 - 1) {
+        if (c == NC - 1) {
           // every TMEM read of this accumulator stage has landed in registers
           tc_fence_before();
           mbar_arrive(smem_u32(&tmem_empty_bar[as]));
         }
-        if (!chunk_live) continue;
+        if (!chunk_live) return;
         __syncwarp();
-        // ---- (4) coalesced row pass
-        if (fast) epi_fast_chunk<EPI>(p, stg, m_base, n, rr, cc, resv, auxv, b4);
-        else      epi_generic_chunk(p, stg, m_base, n, rr, cc);
+        // coalesced row pass
+        if (chunk_fast(c)) epi_fast_chunk<EPI>(p, stg, m_base, n_chunk + cc, rr, cc, resv, auxv, b4);
+        else               epi_generic_chunk(p, stg, m_base, n_chunk + cc, rr, cc);
         __syncwarp();
+      };
+      prefetch(0, res0, aux0, bia0);
+#pragma unroll 1
+      for (int c = 0; c < NC; c += 2) {
+        prefetch(c + 1, res1, aux1, bia1);
+        process(c, res0, aux0, bia0);
+        prefetch(c + 2, res0, aux0, bia0);
+        process(c + 1, res1, aux1, bia1);
       }
       if (tile == blockIdx.x && warp_idx == 2 && lane == 0) VB_DBG(6);
     }
@@ -382,7 +399,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) VB_DBG(7);
+  if (threadIdx.x == 0) { VB_DBG(7); VB_DBG_NS(9); }
   if (warp_idx == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

@@ -204,11 +204,24 @@ __device__ __forceinline__ float erf_as(float x) {
 __device__ __forceinline__ float gelu_erf(float x) {
   return x * 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f));
 }
-// d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+// GELU and its derivative d/dx [x * Phi(x)] = Phi(x) + x * phi(x) in one go: erf(x/sqrt2) and phi(x) share exp(-x^2/2).
+__device__ __forceinline__ void gelu_erf_and_grad(float x, float& g, float& dg) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float e = __expf(-z * z);                                   // exp(-x^2 / 2)
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;
+  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float g, dg;
+  gelu_erf_and_grad(x, g, dg);
+  return dg;
 }
 
 }  // namespace vb

@@ -84,7 +84,8 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
 // ------------------------------------------------------------------------------------------ LayerNorm bwd
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma; dgamma += sum dy * xhat; dbeta += sum dy;
 // dbias += sum dx (bias gradient of the Linear that produced the LayerNorm input).
-// Optional: dx16 (and dbias) additionally multiplied by gelu'(pre) (head transforms: Linear -> GELU -> LayerNorm).
+// Optional: dx16 (and dbias) additionally multiplied by the saved GELU derivative `pre` (head transforms:
+// Linear -> GELU -> LayerNorm).
 //
 // A row is handled by a TEAM of two warps (64 lanes x NV float4 chunks) so that the three per-column accumulators fit in
 // ~110 registers and two 256-thread CTAs (16 warps) stay resident per SM; the two row sums cross the warps through a
@@ -149,8 +150,7 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
             const uint2 pk = reinterpret_cast<const uint2*>(pre + row * ldpre)[c];
             const float2 p01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
             const float2 p23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
-            o.x *= gelu_erf_grad(p01.x); o.y *= gelu_erf_grad(p01.y);
-            o.z *= gelu_erf_grad(p23.x); o.w *= gelu_erf_grad(p23.y);
+            o.x *= p01.x; o.y *= p01.y; o.z *= p23.x; o.w *= p23.y;   // pre = gelu'(pre-activation) saved by the forward GEMM
           }
           if (dx16) reinterpret_cast<uint2*>(dx16 + row * lddx)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
           ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;

@@ -19,6 +19,19 @@ class _Node(nn.Module):
     """Container whose children / parameters are registered under the reference's dotted names."""
 
 
+class _BertNode(_Node):
+    """The `bert` sub-module of a model with heads: owns the encoder parameters (names bert.*) and, when called like
+    the reference's `model.bert(...)` (vilbert.py:1652), runs the same engine and returns the BertModel 5-tuple."""
+
+    def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
+                co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
+        if output_all_attention_masks or output_all_encoded_layers:
+            raise NotImplementedError("output_all_encoded_layers / output_all_attention_masks are not supported by the B200 engine")
+        owner = self.__dict__["_owner_ref"]()
+        o = owner._run(BERT_OUT_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
+        return (o["sequence_output_t"], o["sequence_output_v"], o["pooled_output_t"], o["pooled_output_v"], ([], [], []))
+
+
 def _register_tree(root, store):
     params = {}
     for name in store.entries:
@@ -33,12 +46,18 @@ def _register_tree(root, store):
 
 
 def _attach(root, dotted, prm):
+    import weakref
     parts = dotted.split(".")
     mod = root
-    for p in parts[:-1]:
-        if not hasattr(mod, p):
-            mod.add_module(p, _Node())
-        mod = getattr(mod, p)
+    for i, p in enumerate(parts[:-1]):
+        if p not in mod._modules:
+            if i == 0 and p == "bert":
+                node = _BertNode()
+                node.__dict__["_owner_ref"] = weakref.ref(root)
+            else:
+                node = _Node()
+            mod.add_module(p, node)
+        mod = mod._modules[p]
     mod.register_parameter(parts[-1], prm)
 
 
@@ -204,10 +223,6 @@ class VILBertForVLTasks(BertPreTrainedModel):
         self.dropout_prob = dropout_prob
         self.fusion_method = config.fusion_method
 
-    @property
-    def bert(self):
-        return _BertView(self)
-
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
         if output_all_attention_masks or output_all_encoded_layers:
@@ -216,18 +231,6 @@ class VILBertForVLTasks(BertPreTrainedModel):
             raise TypeError("image_attention_mask is required by VILBertForVLTasks.forward (vilbert.py:1693)")
         o = self._run(HEAD_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
         return tuple(o[n] for n in HEAD_NAMES) + (([], [], []),)
-
-
-class _BertView:
-    """`model.bert(...)` on a model with heads: runs the same engine and returns the BertModel 5-tuple."""
-
-    def __init__(self, owner):
-        self._o = owner
-
-    def __call__(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
-                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
-        o = self._o._run(BERT_OUT_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
-        return (o["sequence_output_t"], o["sequence_output_v"], o["pooled_output_t"], o["pooled_output_v"], ([], [], []))
 
 
 class BertForMultiModalPreTraining(BertPreTrainedModel):
@@ -241,10 +244,6 @@ class BertForMultiModalPreTraining(BertPreTrainedModel):
         self.visual_target = config.visual_target
         if self.visual_target != 0:
             raise NotImplementedError("only visual_target == 0 (KLDiv) is supported")
-
-    @property
-    def bert(self):
-        return _BertView(self)
 
     def forward(self, input_ids, image_feat, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 masked_lm_labels=None, image_label=None, image_target=None, next_sentence_label=None, output_all_attention_masks=False):
