@@ -122,6 +122,8 @@ typedef struct vb_attn_args {
   void* dK; int64_t lddk;
   void* dV; int64_t lddv;
   float* delta;
+  /* optional (backward): += column sums of dQ / dK / dV, f32 [H*D] each — the bias gradients of the projections */
+  float* dbias_q; float* dbias_k; float* dbias_v;
 } vb_attn_args;
 
 vb_status vb_attention_fwd(const vb_attn_args* args, void* stream);

@@ -48,6 +48,7 @@ class AttnArgs(C.Structure):
         ("dO", C.c_void_p), ("lddo", C.c_int64), ("dQ", C.c_void_p), ("lddq", C.c_int64),
         ("dK", C.c_void_p), ("lddk", C.c_int64), ("dV", C.c_void_p), ("lddv", C.c_int64),
         ("delta", C.c_void_p),
+        ("dbias_q", C.c_void_p), ("dbias_k", C.c_void_p), ("dbias_v", C.c_void_p),
     ]
 
 

@@ -43,6 +43,7 @@ struct AttnParams {
   __nv_bfloat16 *dQ, *dK, *dV;
   long long lddq, lddk, lddv;
   float* delta;  // [B,H,Nq]
+  float *dbq, *dbk, *dbv;  // optional bias gradients [H*D] of the Q / K / V projections (+= column sums of dQ / dK / dV)
 };
 
 // Copies `rows_valid` rows of D bf16 (row stride ld) into smem rows of stride D+8 with cp.async (16-byte LDGSTS, no
@@ -118,18 +119,28 @@ __device__ __forceinline__ void mma_p_b(float (&acc)[D / 8][4], const float (&pf
   }
 }
 
-// Stores a 16 x D fp32 C-fragment tile (scaled) as bf16 rows; rows >= rows_valid are skipped.
+// Stores a 16 x D fp32 C-fragment tile (scaled) as bf16 rows; rows >= rows_valid are skipped. If colsum != nullptr the
+// column sums of the stored (valid, scaled) values are accumulated there (bias gradient of the projection).
 template <int D>
 __device__ __forceinline__ void store_tile(__nv_bfloat16* dst, long long ld, const float (&acc)[D / 8][4], float s0, float s1,
-                                           int row0, int rows_valid, int lane) {
+                                           int row0, int rows_valid, int lane, float* colsum = nullptr) {
   const int g = lane >> 2, t = lane & 3;
+  const bool v0 = row0 + g < rows_valid, v1 = row0 + g + 8 < rows_valid;
 #pragma unroll
   for (int nt = 0; nt < D / 8; ++nt) {
     const int col = nt * 8 + 2 * t;
-    if (row0 + g < rows_valid)
-      *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g) * ld + col) = pack_bf16(acc[nt][0] * s0, acc[nt][1] * s0);
-    if (row0 + g + 8 < rows_valid)
-      *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g + 8) * ld + col) = pack_bf16(acc[nt][2] * s1, acc[nt][3] * s1);
+    const float a0 = acc[nt][0] * s0, a1 = acc[nt][1] * s0, a2 = acc[nt][2] * s1, a3 = acc[nt][3] * s1;
+    if (v0) *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g) * ld + col) = pack_bf16(a0, a1);
+    if (v1) *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g + 8) * ld + col) = pack_bf16(a2, a3);
+    if (colsum) {
+      float c0 = (v0 ? a0 : 0.f) + (v1 ? a2 : 0.f), c1 = (v0 ? a1 : 0.f) + (v1 ? a3 : 0.f);
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {   // reduce over the 8 row groups (lane bits 2..4)
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      }
+      if (g == 0) { atomicAdd(colsum + col, c0); atomicAdd(colsum + col + 1, c1); }
+    }
   }
 }
 
@@ -297,7 +308,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
     }
     mma_p_b<D>(dq, s, sK, kb, lane);
   }
-  store_tile<D>(p.dQ + ((long long)b * p.Nq + q0) * p.lddq + h * D, p.lddq, dq, p.scale, p.scale, r0, rows_valid, lane);
+  store_tile<D>(p.dQ + ((long long)b * p.Nq + q0) * p.lddq + h * D, p.lddq, dq, p.scale, p.scale, r0, rows_valid, lane,
+                p.dbq ? p.dbq + h * D : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------ backward: dK, dV
@@ -373,8 +385,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
     mma_p_b<D>(dv, pt, sdO, qb, lane);
     mma_p_b<D>(dk, st, sQ, qb, lane);
   }
-  store_tile<D>(p.dV + ((long long)b * p.Nk + k0) * p.lddv + h * D, p.lddv, dv, 1.f, 1.f, r0, rows_valid, lane);
-  store_tile<D>(p.dK + ((long long)b * p.Nk + k0) * p.lddk + h * D, p.lddk, dk, p.scale, p.scale, r0, rows_valid, lane);
+  store_tile<D>(p.dV + ((long long)b * p.Nk + k0) * p.lddv + h * D, p.lddv, dv, 1.f, 1.f, r0, rows_valid, lane, p.dbv ? p.dbv + h * D : nullptr);
+  store_tile<D>(p.dK + ((long long)b * p.Nk + k0) * p.lddk + h * D, p.lddk, dk, p.scale, p.scale, r0, rows_valid, lane, p.dbk ? p.dbk + h * D : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -407,6 +419,7 @@ static AttnParams to_params(const vb_attn_args* a) {
   p.dQ = (__nv_bfloat16*)a->dQ; p.dK = (__nv_bfloat16*)a->dK; p.dV = (__nv_bfloat16*)a->dV;
   p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
   p.delta = a->delta;
+  p.dbq = a->dbias_q; p.dbk = a->dbias_k; p.dbv = a->dbias_v;
   return p;
 }
 

@@ -252,7 +252,7 @@ class Plan:
         self.emit(self.lib.vb_gemm_bf16, C.byref(g))
 
     def attention(self, bwd, B, H, Nq, Nk, D, Q, ldq, K, ldk, V, ldv, mask, O, ldo, lse, dO=None, lddo=0, dQ=None, lddq=0,
-                  dK=None, lddk=0, dV=None, lddv=0, delta=None):
+                  dK=None, lddk=0, dV=None, lddv=0, delta=None, dbq=None, dbk=None, dbv=None):
         a = L.AttnArgs()
         a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
         a.Q, a.ldq, a.K, a.ldk, a.V, a.ldv = self._ptr(Q), ldq, self._ptr(K), ldk, self._ptr(V), ldv
@@ -260,6 +260,7 @@ class Plan:
         a.O, a.ldo, a.lse = self._ptr(O), ldo, self._ptr(lse)
         a.dO, a.lddo, a.dQ, a.lddq = self._ptr(dO), lddo, self._ptr(dQ), lddq
         a.dK, a.lddk, a.dV, a.lddv, a.delta = self._ptr(dK), lddk, self._ptr(dV), lddv, self._ptr(delta)
+        a.dbias_q, a.dbias_k, a.dbias_v = self._ptr(dbq), self._ptr(dbk), self._ptr(dbv)
         self._keep.append(a)
         self.emit(self.lib.vb_attention_bwd if bwd else self.lib.vb_attention_fwd, C.byref(a))
 
@@ -374,9 +375,11 @@ class Plan:
             self.gemm(M, H, H, dy16, H, ps.w16(prefix + ".output.dense.weight"), H, b_mn=1, out_bf16=dctx, ld_ob=H)
             dqkv = self.scratch(tag + ".dqkv", (M, 3 * H), BF16)
             delta = self.scratch(tag + ".delta", (B, nh, N), F32)
+            gb = ps.g(prefix + ".self.qkv.bias")     # bias gradients = column sums of dQ|dK|dV, fused into the attention backward
             self.attention(True, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dO=dctx, lddo=H,
-                           dQ=dqkv[:, 0:H], lddq=3 * H, dK=dqkv[:, H:2 * H], lddk=3 * H, dV=dqkv[:, 2 * H:], lddv=3 * H, delta=delta)
-            self.linear_wgrad(dqkv, 3 * H, dqkv, 3 * H, x.b16, H, M, 3 * H, H, prefix + ".self.qkv")
+                           dQ=dqkv[:, 0:H], lddq=3 * H, dK=dqkv[:, H:2 * H], lddk=3 * H, dV=dqkv[:, 2 * H:], lddv=3 * H, delta=delta,
+                           dbq=gb[0:H], dbk=gb[H:2 * H], dbv=gb[2 * H:])
+            self.linear_wgrad(dqkv, 3 * H, None, 0, x.b16, H, M, 3 * H, H, prefix + ".self.qkv")
             self.dgrad_into(x, dqkv, 3 * H, ps.w16(prefix + ".self.qkv.weight"), M, 3 * H, H, extra32=dy32)
         self.push_bwd(bwd)
         return out
@@ -424,14 +427,17 @@ class Plan:
             dyt16, dyt32 = rt
             self.gemm(Mv, Hb, Hv, dyv16, Hv, ps.w16(p + ".biOutput.dense1.weight"), Hb, b_mn=1, out_bf16=dctx2, ld_ob=Hb)
             self.gemm(Mt, Hb, Ht, dyt16, Ht, ps.w16(p + ".biOutput.dense2.weight"), Hb, b_mn=1, out_bf16=dctx1, ld_ob=Hb)
+            gb1, gb2 = ps.g(p + ".biattention.qkv1.bias"), ps.g(p + ".biattention.qkv2.bias")
             d1 = self.scratch("c.delta1", (B, nh, Nt), F32)
             d2 = self.scratch("c.delta2", (B, nh, Nv), F32)
             self.attention(True, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1, dO=dctx1, lddo=Hb,
-                           dQ=dqkv2[:, 0:Hb], lddq=L3, dK=dqkv1[:, Hb:2 * Hb], lddk=L3, dV=dqkv1[:, 2 * Hb:], lddv=L3, delta=d1)
+                           dQ=dqkv2[:, 0:Hb], lddq=L3, dK=dqkv1[:, Hb:2 * Hb], lddk=L3, dV=dqkv1[:, 2 * Hb:], lddv=L3, delta=d1,
+                           dbq=gb2[0:Hb], dbk=gb1[Hb:2 * Hb], dbv=gb1[2 * Hb:])
             self.attention(True, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dO=dctx2, lddo=Hb,
-                           dQ=dqkv1[:, 0:Hb], lddq=L3, dK=dqkv2[:, Hb:2 * Hb], lddk=L3, dV=dqkv2[:, 2 * Hb:], lddv=L3, delta=d2)
-            self.linear_wgrad(dqkv1, L3, dqkv1, L3, v.b16, Hv, Mv, L3, Hv, p + ".biattention.qkv1")
-            self.linear_wgrad(dqkv2, L3, dqkv2, L3, t.b16, Ht, Mt, L3, Ht, p + ".biattention.qkv2")
+                           dQ=dqkv1[:, 0:Hb], lddq=L3, dK=dqkv2[:, Hb:2 * Hb], lddk=L3, dV=dqkv2[:, 2 * Hb:], lddv=L3, delta=d2,
+                           dbq=gb1[0:Hb], dbk=gb2[Hb:2 * Hb], dbv=gb2[2 * Hb:])
+            self.linear_wgrad(dqkv1, L3, None, 0, v.b16, Hv, Mv, L3, Hv, p + ".biattention.qkv1")
+            self.linear_wgrad(dqkv2, L3, None, 0, t.b16, Ht, Mt, L3, Ht, p + ".biattention.qkv2")
             self.dgrad_into(v, dqkv1, L3, ps.w16(p + ".biattention.qkv1.weight"), Mv, L3, Hv, extra32=dyv32)
             self.dgrad_into(t, dqkv2, L3, ps.w16(p + ".biattention.qkv2.weight"), Mt, L3, Ht, extra32=dyt32)
         # the cross-modal backward touches both streams' tensors: it runs on the main stream between two barriers
