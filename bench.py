@@ -7,8 +7,8 @@
 
 One "step" = one training-step body on one batch of synthetic input (BASELINE.json configs[1]:
 bert_base_6layer_6conect, per-GPU batch 64, 100 regions x 36 tokens, VQA head):
-zero the flat gradient buffer, refresh the bf16 weight shadow from the fp32 master weights, forward of the
-encoder and ALL heads (as VILBertForVLTasks.forward always computes them), BCE-with-logits VQA loss
+bump the dropout step counter, zero the flat gradient buffer, refresh the bf16 weight shadow from the fp32 master
+weights, train-mode forward (all dropout layers active, p = 0.1 as the reference trains) of the encoder and ALL heads (as VILBertForVLTasks.forward always computes them), BCE-with-logits VQA loss
 (task_utils.py:325-327), backward of everything with a gradient path, and for N > 1 the gradient all-reduce.
 The optimizer update is not part of the metric.
 
@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--regions", type=int, default=100)
     ap.add_argument("--tokens", type=int, default=36)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--eval-mode", action="store_true", help="disable the dropout layers (reference eval mode); default is train mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel-class time table to stderr")
@@ -166,7 +167,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout; keep stdout for the single JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     W = max(a.warmup, 3)
     cfg_o = O.make_config(cfgj)
     eng = Engine(BertConfig.from_dict(cfgj), dev)
@@ -178,7 +190,7 @@ def main():
             eng.ps.p(name).fill_(1.0 if name.endswith("weight") else 0.0)
         elif name.endswith(".bias"):
             eng.ps.p(name).zero_()
-    plan = eng.plan(B, Nt, Nv, grad_outputs=("vil_prediction",), vqa_loss=True)
+    plan = eng.plan(B, Nt, Nv, grad_outputs=("vil_prediction",), vqa_loss=True, train=not a.eval_mode)
     plan.enable_training_prologue()
     # synthetic batches (different per rank), host-pinned
     n_host = 4
@@ -330,7 +342,8 @@ def main():
         "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not a.no_graph,
                    "l2": "working set (activations + weights + grads ~6 GB/step) exceeds the 126 MB L2; no explicit flush",
                    "streams": "text and vision segments on two CUDA streams (parallel graph branches)" if eng.two_streams else "single stream",
-                   "numerics": "bf16 tensor-core operands, fp32 accumulate/residual/LayerNorm/softmax; dropout p=0 (parity protocol)",
+                   "numerics": "bf16 tensor-core operands, fp32 accumulate/residual/LayerNorm/softmax",
+                   "mode": "eval (dropout off)" if a.eval_mode else "train: every nn.Dropout of the reference active (p=0.1, in-kernel counter-based masks, new masks each step)",
                    "loss": loss_val},
         "samples_per_s": B * world / (ms_step / 1e3),
         "model_tflops_per_gpu": flops_step / (ms_step / 1e3) / 1e12,

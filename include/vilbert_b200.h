@@ -37,6 +37,18 @@ enum {
 
 enum { VB_ACT_NONE = 0, VB_ACT_GELU = 1, VB_ACT_RELU = 2, VB_ACT_DGELU = 3 };
 
+/* Dropout descriptor (nn.Dropout at vilbert.py:365,443,472,515,604,631,676,778,800,848-851,1233,1430,1678-1695).
+ * Masks are not stored: keep(element) = hash32(index ^ hash32(site + step * 0x9E3779B9)) >= p * 2^32 with
+ * hash32 = lowbias32 (x^=x>>16; x*=0x7feb352d; x^=x>>15; x*=0x846ca68b; x^=x>>16), kept values scaled by 1/(1-p).
+ * `step` is a device uint32 bumped once per training step; `site` names the dropout layer; `index` is the
+ * row-major element index of the tensor the reference applies nn.Dropout to (mod 2^32). step == NULL or p == 0
+ * disables dropout (the reference's eval mode). */
+typedef struct vb_dropout {
+  const uint32_t* step;
+  uint32_t site;
+  float p;
+} vb_dropout;
+
 /* ABI version of this header (bumped on incompatible change). */
 int vb_version(void);
 /* Message for the last non-OK status returned on this thread ("" if none). */
@@ -86,6 +98,7 @@ typedef struct vb_gemm_args {
   int64_t ld_out_pre;
   int32_t atomic_out;    /* 0 store, 1 red.add into out_f32 */
   float* out_colsum;     /* [N] or NULL: += column sums of the epilogue value before the residual add (bias gradients) */
+  vb_dropout dropout;    /* applied to the epilogue value before the residual add (index m*N + n): LN(dropout(dense(x)) + res) */
   int32_t split_k;       /* >= 1; > 1 requires atomic_out and no act / bf16 outputs */
   int32_t block_n;       /* 0 = auto, else 128 or 256 */
   int32_t max_ctas;      /* 0 = one persistent CTA per SM */
@@ -124,6 +137,7 @@ typedef struct vb_attn_args {
   float* delta;
   /* optional (backward): += column sums of dQ / dK / dV, f32 [H*D] each — the bias gradients of the projections */
   float* dbias_q; float* dbias_k; float* dbias_v;
+  vb_dropout dropout;   /* on the probabilities; element index ((b*H + h)*Nq + q)*Nk + k */
 } vb_attn_args;
 
 vb_status vb_attention_fwd(const vb_attn_args* args, void* stream);
@@ -138,7 +152,8 @@ vb_status vb_attention_bwd(const vb_attn_args* args, void* stream);
  * statistics mean/rstd [M] (may be NULL). H % 4 == 0, H <= 2048. */
 vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
                            float* y_f32, void* y_bf16, int64_t ldy, float* mean, float* rstd,
-                           int32_t M, int32_t H, void* stream);
+                           int32_t M, int32_t H, const vb_dropout* out_dropout /* may be NULL: dropout(LN(x)), embeddings */,
+                           void* stream);
 /* Autograd of the above. dx as f32 and/or bf16; dgamma/dbeta are ACCUMULATED (atomics) and may be NULL.
  * If gelu_pre (bf16 [M,H], the GELU derivative saved by the forward GEMM) is given, dx_bf16 is multiplied by it — the
  * Linear -> GELU -> LayerNorm head transforms (vilbert.py:1152-1156, 1172-1176, 1714-1718).
@@ -147,7 +162,10 @@ vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, cons
 vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
                            const float* mean, const float* rstd, float* dx_f32, void* dx_bf16, int64_t lddx,
                            const void* gelu_pre, int64_t ld_pre, float* dgamma, float* dbeta, float* dbias,
-                           int32_t M, int32_t H, void* stream);
+                           int32_t M, int32_t H,
+                           const vb_dropout* out_dropout /* NULL or the mask applied to this LN's OUTPUT in forward: dy is masked first */,
+                           const vb_dropout* in_dropout  /* NULL or the mask applied to the dense output feeding this LN: dx_bf16 / dbias are masked */,
+                           void* stream);
 
 /* fp32 -> bf16 casts: flat (weights shadow, region-feature ingest) and 2-D with independent leading
  * dimensions and a scale (pads operands whose row length is not a multiple of 8). */
@@ -179,14 +197,18 @@ vb_status vb_colsum(const void* X, int32_t is_bf16, int64_t ld, float* out, int3
  * y[m,j] = x[m,:] . W[j,:] + b[j] (+ row_addend[m]). Backward: dx (=, or += when accumulate_dx),
  * dW and db ACCUMULATED. */
 vb_status vb_small_linear_fwd(const float* x, int64_t ldx, const float* W, const float* b, const float* row_addend,
-                              float* y, int32_t M, int32_t K, int32_t N, void* stream);
+                              float* y, int32_t M, int32_t K, int32_t N,
+                              const vb_dropout* in_dropout /* NULL or dropout applied to x first (index m*K + k; needs ldx == K) */, void* stream);
 vb_status vb_small_linear_bwd(const float* dy, const float* x, int64_t ldx, const float* W, float* dx, int64_t lddx,
-                              int32_t accumulate_dx, float* dW, float* db, int32_t M, int32_t K, int32_t N, void* stream);
+                              int32_t accumulate_dx, float* dW, float* db, int32_t M, int32_t K, int32_t N,
+                              const vb_dropout* in_dropout, void* stream);
 
 /* pooled_output = pooled_t (*|+) pooled_v (fusion_method, vilbert.py:1677-1682, 1236-1241); backward
  * ACCUMULATES into da / db. */
-vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul, void* stream);
-vb_status vb_fuse_pooled_bwd(const float* d, const float* a, const float* b, float* da, float* db, int64_t n, int32_t mul, void* stream);
+vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul,
+                             const vb_dropout* dropout /* NULL or dropout on the fused vector (index i) */, void* stream);
+vb_status vb_fuse_pooled_bwd(const float* d, const float* a, const float* b, float* da, float* db, int64_t n, int32_t mul,
+                             const vb_dropout* dropout, void* stream);
 /* ReLU backward of the poolers (vilbert.py:1121,1136): dx = dy * (y > 0). */
 vb_status vb_relu_bwd(const float* dy, const float* y, void* dx_bf16, float* dx_f32, int64_t n, void* stream);
 /* y += alpha * x (f32): merges gradient contributions. */
@@ -201,6 +223,9 @@ vb_status vb_bce_logits_loss(const float* logits, const float* target, float* lo
  * mask int64 0/1 [B,N]; prepend_one != 0 emits N+1 entries per row with a leading 0 (task-token mask
  * extension, :1331-1334). */
 vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_t B, int32_t N, int32_t prepend_one, void* stream);
+
+/* step += 1 on the device (the dropout step counter; one launch per training step, capturable in a CUDA graph). */
+vb_status vb_step_counter_bump(uint32_t* step, void* stream);
 
 vb_status vb_memset_zero(void* ptr, int64_t bytes, void* stream);
 

@@ -40,6 +40,52 @@ def make_config(json_dict):
     return cfg
 
 
+# --------------------------------------------------------------------------- dropout masks (train mode)
+class DropMasks:
+    """Bit-exact Python restatement of the engine's stateless dropout RNG (include/vilbert_b200.h: vb_dropout):
+    keep(i) = hash32(i ^ hash32(site + step * 0x9E3779B9)) >= p * 2^32, hash32 = lowbias32, site = crc32(layer name),
+    i = row-major element index of the tensor nn.Dropout acts on. Passing `drop=DropMasks(step)` to the oracle functions
+    turns every nn.Dropout of the reference (train mode) into a multiplication with the engine's mask, so train-mode
+    parity can be checked exactly like eval-mode parity. drop=None is eval mode."""
+
+    M = 0xFFFFFFFF
+
+    def __init__(self, step, head_p=0.1):
+        self.step = int(step) & self.M
+        self.head_p = head_p
+
+    @classmethod
+    def _hash32(cls, x):
+        x = x & cls.M
+        x = x ^ (x >> 16); x = (x * 0x7feb352d) & cls.M
+        x = x ^ (x >> 15); x = (x * 0x846ca68b) & cls.M
+        x = x ^ (x >> 16)
+        return x
+
+    def mask(self, name, p, shape, device):
+        import zlib
+        import numpy as np
+        p32 = float(np.float32(p))
+        if p32 <= 0.0:
+            return None
+        site = zlib.crc32(name.encode()) & self.M
+        seed = int(self._hash32(torch.tensor([(site + self.step * 0x9E3779B9) & self.M], dtype=torch.int64))[0])
+        n = 1
+        for d in shape:
+            n *= d
+        idx = torch.arange(n, dtype=torch.int64, device=device) & self.M
+        keep = self._hash32(idx ^ seed) >= int(p32 * 4294967296.0)
+        scale = float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+        return keep.to(torch.float32).view(shape) * scale
+
+
+def _drop(x, drop, name, p):
+    if drop is None:
+        return x
+    m = drop.mask(name, p, tuple(x.shape), x.device)
+    return x if m is None else x * m
+
+
 # --------------------------------------------------------------------------- primitives
 def gelu(x):
     """vilbert.py:111-117 — exact erf GELU."""
@@ -63,7 +109,7 @@ def _heads(x, n_heads):
     return x.view(B, N, n_heads, H // n_heads).permute(0, 2, 1, 3)
 
 
-def attention(q, k, v, add_mask, n_heads):
+def attention(q, k, v, add_mask, n_heads, drop=None, drop_name=None, drop_p=0.0):
     """QK^T / sqrt(d) + mask -> softmax -> PV -> merge heads (vilbert.py:434-449, :593-608, :771-809).
     add_mask is the additive [B,1,1,Nk] mask (0 / -10000). Dropout on the probabilities is identity
     here (eval mode / p=0: the parity protocol of SURVEY.md §8c)."""
@@ -71,34 +117,41 @@ def attention(q, k, v, add_mask, n_heads):
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
     s = s + add_mask
     p = torch.softmax(s, dim=-1)
+    p = _drop(p, drop, drop_name, drop_p)
     ctx = torch.matmul(p, v).permute(0, 2, 1, 3).contiguous()
     return ctx.view(ctx.shape[0], ctx.shape[1], -1)
 
 
 # --------------------------------------------------------------------------- encoder blocks
-def text_layer(P, pre, cfg, h, mask):
+def text_layer(P, pre, cfg, h, mask, drop=None):
     """BertLayer.forward, vilbert.py:527-533 (= BertSelfAttention :424-460, BertSelfOutput :470-474,
     BertIntermediate :500-503, BertOutput :513-517)."""
     a = pre + ".attention"
     ctx = attention(linear(P, a + ".self.query", h), linear(P, a + ".self.key", h), linear(P, a + ".self.value", h),
-                    mask, cfg["num_attention_heads"])
-    h1 = layer_norm(linear(P, a + ".output.dense", ctx) + h, P[a + ".output.LayerNorm.weight"], P[a + ".output.LayerNorm.bias"])
+                    mask, cfg["num_attention_heads"], drop, a + ".self.dropout", cfg["attention_probs_dropout_prob"])
+    hp = cfg["hidden_dropout_prob"]
+    h1 = layer_norm(_drop(linear(P, a + ".output.dense", ctx), drop, a + ".output.dropout", hp) + h,
+                    P[a + ".output.LayerNorm.weight"], P[a + ".output.LayerNorm.bias"])
     f = gelu(linear(P, pre + ".intermediate.dense", h1))
-    return layer_norm(linear(P, pre + ".output.dense", f) + h1, P[pre + ".output.LayerNorm.weight"], P[pre + ".output.LayerNorm.bias"])
+    return layer_norm(_drop(linear(P, pre + ".output.dense", f), drop, pre + ".output.dropout", hp) + h1,
+                      P[pre + ".output.LayerNorm.weight"], P[pre + ".output.LayerNorm.bias"])
 
 
-def image_layer(P, pre, cfg, h, mask):
+def image_layer(P, pre, cfg, h, mask, drop=None):
     """BertImageLayer.forward, vilbert.py:688-694 (self-attn :571-619 with dynamic_attention off,
     :629-633, :661-664, :674-678). Same block on the visual stream."""
     a = pre + ".attention"
     ctx = attention(linear(P, a + ".self.query", h), linear(P, a + ".self.key", h), linear(P, a + ".self.value", h),
-                    mask, cfg["v_num_attention_heads"])
-    h1 = layer_norm(linear(P, a + ".output.dense", ctx) + h, P[a + ".output.LayerNorm.weight"], P[a + ".output.LayerNorm.bias"])
+                    mask, cfg["v_num_attention_heads"], drop, a + ".self.dropout", cfg["v_attention_probs_dropout_prob"])
+    hp = cfg["v_hidden_dropout_prob"]
+    h1 = layer_norm(_drop(linear(P, a + ".output.dense", ctx), drop, a + ".output.dropout", hp) + h,
+                    P[a + ".output.LayerNorm.weight"], P[a + ".output.LayerNorm.bias"])
     f = gelu(linear(P, pre + ".intermediate.dense", h1))
-    return layer_norm(linear(P, pre + ".output.dense", f) + h1, P[pre + ".output.LayerNorm.weight"], P[pre + ".output.LayerNorm.bias"])
+    return layer_norm(_drop(linear(P, pre + ".output.dense", f), drop, pre + ".output.dropout", hp) + h1,
+                      P[pre + ".output.LayerNorm.weight"], P[pre + ".output.LayerNorm.bias"])
 
 
-def connection_layer(P, pre, cfg, v, mask_v, t, mask_t):
+def connection_layer(P, pre, cfg, v, mask_v, t, mask_t, drop=None):
     """BertConnectionLayer.forward, vilbert.py:871-900. Subscript 1 = vision, 2 = text.
     BertBiAttention :738-823: ctx1 = text queries over vision keys/values, ctx2 = vision queries over
     text keys/values; BertBiOutput :844-855 with the argument swap of :890-892 (ctx2 -> vision stream
@@ -107,19 +160,23 @@ def connection_layer(P, pre, cfg, v, mask_v, t, mask_t):
     nh = cfg["bi_num_attention_heads"]
     q1, k1, v1 = linear(P, b + ".query1", v), linear(P, b + ".key1", v), linear(P, b + ".value1", v)
     q2, k2, v2 = linear(P, b + ".query2", t), linear(P, b + ".key2", t), linear(P, b + ".value2", t)
-    ctx1 = attention(q2, k1, v1, mask_v, nh)   # [B,Nt,Hb]
-    ctx2 = attention(q1, k2, v2, mask_t, nh)   # [B,Nv,Hb]
+    # dropout1 (v_attention_probs_dropout_prob) acts on probs1, dropout2 (attention_probs_dropout_prob) on probs2 (:730,:738,:778,:800)
+    ctx1 = attention(q2, k1, v1, mask_v, nh, drop, b + ".dropout1", cfg["v_attention_probs_dropout_prob"])   # [B,Nt,Hb]
+    ctx2 = attention(q1, k2, v2, mask_t, nh, drop, b + ".dropout2", cfg["attention_probs_dropout_prob"])     # [B,Nv,Hb]
     o = pre + ".biOutput"
-    v1_ = layer_norm(linear(P, o + ".dense1", ctx2) + v, P[o + ".LayerNorm1.weight"], P[o + ".LayerNorm1.bias"])
-    t1_ = layer_norm(linear(P, o + ".dense2", ctx1) + t, P[o + ".LayerNorm2.weight"], P[o + ".LayerNorm2.bias"])
+    vp, tp = cfg["v_hidden_dropout_prob"], cfg["hidden_dropout_prob"]
+    v1_ = layer_norm(_drop(linear(P, o + ".dense1", ctx2), drop, o + ".dropout1", vp) + v, P[o + ".LayerNorm1.weight"], P[o + ".LayerNorm1.bias"])
+    t1_ = layer_norm(_drop(linear(P, o + ".dense2", ctx1), drop, o + ".dropout2", tp) + t, P[o + ".LayerNorm2.weight"], P[o + ".LayerNorm2.bias"])
     fv = gelu(linear(P, pre + ".v_intermediate.dense", v1_))
-    v2_ = layer_norm(linear(P, pre + ".v_output.dense", fv) + v1_, P[pre + ".v_output.LayerNorm.weight"], P[pre + ".v_output.LayerNorm.bias"])
+    v2_ = layer_norm(_drop(linear(P, pre + ".v_output.dense", fv), drop, pre + ".v_output.dropout", vp) + v1_,
+                     P[pre + ".v_output.LayerNorm.weight"], P[pre + ".v_output.LayerNorm.bias"])
     ft = gelu(linear(P, pre + ".t_intermediate.dense", t1_))
-    t2_ = layer_norm(linear(P, pre + ".t_output.dense", ft) + t1_, P[pre + ".t_output.LayerNorm.weight"], P[pre + ".t_output.LayerNorm.bias"])
+    t2_ = layer_norm(_drop(linear(P, pre + ".t_output.dense", ft), drop, pre + ".t_output.dropout", tp) + t1_,
+                     P[pre + ".t_output.LayerNorm.weight"], P[pre + ".t_output.LayerNorm.bias"])
     return v2_, t2_
 
 
-def encoder(P, pre, cfg, t, v, mask_t, mask_v):
+def encoder(P, pre, cfg, t, v, mask_t, mask_v, drop=None):
     """BertEncoder.forward interleaving schedule, vilbert.py:934-1107 (fixed layers, in_batch_pairs,
     FAST_MODE off; with_coattention honoured). Returns the per-connection-layer outputs too
     (output_all_encoded_layers, :1075-1077)."""
@@ -128,23 +185,23 @@ def encoder(P, pre, cfg, t, v, mask_t, mask_v):
     n_t, n_v = cfg["num_hidden_layers"], cfg["v_num_hidden_layers"]
     for count, (v_end, t_end) in enumerate(zip(cfg["v_biattention_id"], cfg["t_biattention_id"])):
         for i in range(t_start, t_end):
-            t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t)
+            t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t, drop)
         for i in range(v_start, v_end):
-            v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v)
+            v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
         if cfg["with_coattention"]:
-            v, t = connection_layer(P, f"{pre}.c_layer.{count}", cfg, v, mask_v, t, mask_t)
+            v, t = connection_layer(P, f"{pre}.c_layer.{count}", cfg, v, mask_v, t, mask_t, drop)
         v_start, t_start = v_end, t_end
         all_t.append(t)
         all_v.append(v)
     for i in range(v_start, n_v):
-        v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v)
+        v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
     for i in range(t_start, n_t):
-        t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t)
+        t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t, drop)
     return t, v, all_t, all_v
 
 
 # --------------------------------------------------------------------------- embeddings / model
-def text_embeddings(P, pre, cfg, input_ids, token_type_ids, task_ids):
+def text_embeddings(P, pre, cfg, input_ids, token_type_ids, task_ids, drop=None):
     """BertEmbeddings.forward, vilbert.py:346-367. Positions are always arange(seq) (:349-352); the task
     embedding row is inserted at index 1 after the sum (:358-362); LN after the concat. padding_idx=0 on
     the word embeddings (:328-330) only zeroes that row's gradient."""
@@ -155,18 +212,18 @@ def text_embeddings(P, pre, cfg, input_ids, token_type_ids, task_ids):
     if cfg["task_specific_tokens"]:
         te = F.embedding(task_ids, P[pre + ".task_embeddings.weight"])
         e = torch.cat([e[:, 0:1], te, e[:, 1:]], dim=1)
-    return layer_norm(e, P[pre + ".LayerNorm.weight"], P[pre + ".LayerNorm.bias"])
+    return _drop(layer_norm(e, P[pre + ".LayerNorm.weight"], P[pre + ".LayerNorm.bias"]), drop, pre + ".dropout", cfg["hidden_dropout_prob"])
 
 
-def image_embeddings(P, pre, feat, loc):
-    """BertImageEmbeddings.forward, vilbert.py:1421-1432."""
-    return layer_norm(linear(P, pre + ".image_embeddings", feat) + linear(P, pre + ".image_location_embeddings", loc),
-                      P[pre + ".LayerNorm.weight"], P[pre + ".LayerNorm.bias"])
+def image_embeddings(P, pre, feat, loc, drop=None, p=0.0):
+    """BertImageEmbeddings.forward, vilbert.py:1421-1432 (its dropout uses hidden_dropout_prob, :1419)."""
+    return _drop(layer_norm(linear(P, pre + ".image_embeddings", feat) + linear(P, pre + ".image_location_embeddings", loc),
+                            P[pre + ".LayerNorm.weight"], P[pre + ".LayerNorm.bias"]), drop, pre + ".dropout", p)
 
 
 def bert_model(P, cfg, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None,
                image_attention_mask=None, co_attention_mask=None, task_ids=None, prefix="bert",
-               output_all_encoded_layers=False):
+               output_all_encoded_layers=False, drop=None):
     """BertModel.forward, vilbert.py:1309-1406: default masks :1322-1329, task-token mask extension
     :1331-1334, additive masks (1-m)*-10000 :1341-1362, embeddings, encoder, poolers (:1116-1122,
     :1131-1137: Linear+ReLU on token 0). co_attention_mask is accepted and unused (:774-775, :796-797)."""
@@ -181,9 +238,9 @@ def bert_model(P, cfg, input_txt, input_imgs, image_loc, token_type_ids=None, at
     dt = P[prefix + ".embeddings.word_embeddings.weight"].dtype
     mask_t = (1.0 - attention_mask[:, None, None, :].to(dt)) * -10000.0
     mask_v = (1.0 - image_attention_mask[:, None, None, :].to(dt)) * -10000.0
-    t = text_embeddings(P, prefix + ".embeddings", cfg, input_txt, token_type_ids, task_ids)
-    v = image_embeddings(P, prefix + ".v_embeddings", input_imgs, image_loc)
-    t, v, all_t, all_v = encoder(P, prefix + ".encoder", cfg, t, v, mask_t, mask_v)
+    t = text_embeddings(P, prefix + ".embeddings", cfg, input_txt, token_type_ids, task_ids, drop)
+    v = image_embeddings(P, prefix + ".v_embeddings", input_imgs, image_loc, drop, cfg["hidden_dropout_prob"])
+    t, v, all_t, all_v = encoder(P, prefix + ".encoder", cfg, t, v, mask_t, mask_v, drop)
     pooled_t = torch.relu(linear(P, prefix + ".t_pooler.dense", t[:, 0]))
     pooled_v = torch.relu(linear(P, prefix + ".v_pooler.dense", v[:, 0]))
     if output_all_encoded_layers:
@@ -199,10 +256,11 @@ def simple_classifier(P, pre, x):
     return linear(P, pre + ".logit_fc.3", h)
 
 
-def pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v, prefix="cls"):
+def pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v, prefix="cls", drop=None):
     """BertPreTrainingHeads.forward, vilbert.py:1228-1243; LM head :1193-1196 (decoder tied to the word
     embeddings, :1190, + output-only bias); image head :1255-1258; transforms :1152-1156, :1172-1176."""
     pooled = pooled_t * pooled_v if cfg["fusion_method"] == "mul" else pooled_t + pooled_v
+    pooled = _drop(pooled, drop, prefix + ".dropout", 0.1)      # BertPreTrainingHeads.dropout = nn.Dropout(0.1), :1233
     ht = layer_norm(gelu(linear(P, prefix + ".predictions.transform.dense", seq_t)),
                     P[prefix + ".predictions.transform.LayerNorm.weight"], P[prefix + ".predictions.transform.LayerNorm.bias"])
     dec_w = P.get(prefix + ".predictions.decoder.weight", P["bert.embeddings.word_embeddings.weight"])
@@ -215,16 +273,18 @@ def pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v, prefix="cls"):
 
 
 def vilbert_for_vl_tasks(P, cfg, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None,
-                         image_attention_mask=None, co_attention_mask=None, task_ids=None):
+                         image_attention_mask=None, co_attention_mask=None, task_ids=None, drop=None):
     """VILBertForVLTasks.forward, vilbert.py:1638-1708 (eval mode: every dropout is identity). Returns
     the reference's tuple order (:1697-1708) minus all_attention_mask, preceded by the BertModel outputs:
     (seq_t, seq_v, pooled_t, pooled_v), (vil_prediction, vil_prediction_gqa, vil_logit,
     vil_binary_prediction, vil_tri_prediction, vision_prediction, vision_logit, linguisic_prediction,
     linguisic_logit)."""
     seq_t, seq_v, pooled_t, pooled_v = bert_model(P, cfg, input_txt, input_imgs, image_loc, token_type_ids, attention_mask,
-                                                  image_attention_mask, co_attention_mask, task_ids)
-    linguisic_prediction, vision_prediction, vil_binary_prediction = pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v)
+                                                  image_attention_mask, co_attention_mask, task_ids, drop=drop)
+    linguisic_prediction, vision_prediction, vil_binary_prediction = pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v, drop=drop)
     pooled = pooled_t * pooled_v if cfg["fusion_method"] == "mul" else pooled_t + pooled_v
+    hp = drop.head_p if drop is not None else 0.0
+    pooled = _drop(pooled, drop, "dropout.pooled", hp)           # self.dropout(pooled), :1677-1682
     vil_prediction = simple_classifier(P, "vil_prediction", pooled)
     vil_prediction_gqa = simple_classifier(P, "vil_prediction_gqa", pooled)
     if pooled.shape[0] % 2 == 0:  # :1686-1689 — pairs consecutive samples; odd B keeps the NSP-style output
@@ -232,8 +292,8 @@ def vilbert_for_vl_tasks(P, cfg, input_txt, input_imgs, image_loc, token_type_id
     vil_logit = linear(P, "vil_logit", pooled)
     vil_tri_prediction = linear(P, "vil_tri_prediction", pooled)
     dt = seq_v.dtype
-    vision_logit = linear(P, "vision_logit", seq_v) + ((1.0 - image_attention_mask.to(dt)) * -10000.0).unsqueeze(2)
-    linguisic_logit = linear(P, "linguisic_logit", seq_t)
+    vision_logit = linear(P, "vision_logit", _drop(seq_v, drop, "dropout.seq_v", hp)) + ((1.0 - image_attention_mask.to(dt)) * -10000.0).unsqueeze(2)
+    linguisic_logit = linear(P, "linguisic_logit", _drop(seq_t, drop, "dropout.seq_t", hp))
     return (seq_t, seq_v, pooled_t, pooled_v), (vil_prediction, vil_prediction_gqa, vil_logit, vil_binary_prediction,
                                                 vil_tri_prediction, vision_prediction, vision_logit, linguisic_prediction,
                                                 linguisic_logit)

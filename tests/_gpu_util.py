@@ -180,16 +180,22 @@ def probe_loss(heads, names, tgt):
     return l
 
 
-def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, device="cuda"):
+def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, device="cuda", train_step=None):
     """Engine vs the oracle in fp32 and in bf16-operand mode. Returns dict(out_fp32, out_bf16, grad_fp32, grad_bf16, ...)
-    where each is {tensor name: error}; gradient errors are (max-rel with floor, rel-L2)."""
+    where each is {tensor name: error}; gradient errors are (max-rel with floor, rel-L2).
+    train_step=k runs the engine in TRAIN mode (every nn.Dropout of the reference active, dropout step counter = k) against
+    the oracle with the same stateless masks (oracle.DropMasks(k))."""
     dev = torch.device(device)
     cfg = O.make_config(cfgj)
     names = O.HEAD_NAMES if names is None else names
     P = O.synth_params(cfg, seed=seed, device=dev, qk_scale=qk_scale)
     inp = O.synth_inputs(cfg, B, Nv, Nt, seed=1234 + seed, device=dev)
     eng = build_engine(cfgj, P, dev)
-    plan = eng.plan(B, Nt, Nv, grad_outputs=names if grads else ())
+    drop = None
+    if train_step is not None:
+        eng.drop_step.fill_(int(train_step))
+        drop = O.DropMasks(train_step, head_p=eng.head_dropout_prob)
+    plan = eng.plan(B, Nt, Nv, grad_outputs=names if grads else (), train=train_step is not None)
     plan.load_inputs(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
                      inp["image_attention_mask"], inp["task_ids"])
     plan.run_forward()
@@ -211,11 +217,11 @@ def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, de
         Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
         if mode == "bf16":
             with O.bf16_operand_mode():
-                bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, *oracle_args(inp))
+                bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, *oracle_args(inp), drop=drop)
                 if grads:
                     lo = probe_loss(heads_o, names, tgt); lo.backward()
         else:
-            bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, *oracle_args(inp))
+            bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, *oracle_args(inp), drop=drop)
             if grads:
                 lo = probe_loss(heads_o, names, tgt); lo.backward()
         oe = {}

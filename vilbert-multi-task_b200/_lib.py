@@ -16,6 +16,12 @@ class VBError(RuntimeError):
     pass
 
 
+class Dropout(C.Structure):
+    """Mirror of ``struct vb_dropout``."""
+
+    _fields_ = [("step", C.c_void_p), ("site", C.c_uint32), ("p", C.c_float)]
+
+
 class GemmArgs(C.Structure):
     """Mirror of ``struct vb_gemm_args`` (include/vilbert_b200.h)."""
 
@@ -31,7 +37,7 @@ class GemmArgs(C.Structure):
         ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int64),
         ("out_bf16", C.c_void_p), ("ld_out_bf16", C.c_int64),
         ("out_pre", C.c_void_p), ("ld_out_pre", C.c_int64),
-        ("atomic_out", C.c_int32), ("out_colsum", C.c_void_p), ("split_k", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
+        ("atomic_out", C.c_int32), ("out_colsum", C.c_void_p), ("dropout", Dropout), ("split_k", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
         ("dbg_lbo_a", C.c_uint32), ("dbg_sbo_a", C.c_uint32), ("dbg_lbo_b", C.c_uint32), ("dbg_sbo_b", C.c_uint32),
         ("dbg_timeline", C.c_void_p),
     ]
@@ -49,6 +55,7 @@ class AttnArgs(C.Structure):
         ("dK", C.c_void_p), ("lddk", C.c_int64), ("dV", C.c_void_p), ("lddv", C.c_int64),
         ("delta", C.c_void_p),
         ("dbias_q", C.c_void_p), ("dbias_k", C.c_void_p), ("dbias_v", C.c_void_p),
+        ("dropout", Dropout),
     ]
 
 
@@ -59,8 +66,8 @@ _SIGNATURES = {
     "vb_gemm_bf16": [C.POINTER(GemmArgs), _P],
     "vb_attention_fwd": [C.POINTER(AttnArgs), _P],
     "vb_attention_bwd": [C.POINTER(AttnArgs), _P],
-    "vb_layernorm_fwd": [_P, _I64, _P, _P, _F, _P, _P, _I64, _P, _P, _I32, _I32, _P],
-    "vb_layernorm_bwd": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I32, _I32, _P],
+    "vb_layernorm_fwd": [_P, _I64, _P, _P, _F, _P, _P, _I64, _P, _P, _I32, _I32, _P, _P],
+    "vb_layernorm_bwd": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I32, _I32, _P, _P, _P],
     "vb_cast_f32_to_bf16": [_P, _P, _I64, _P],
     "vb_cast2d_f32_to_bf16": [_P, _I64, _P, _I64, _I32, _I32, _F, _P],
     "vb_embed_text_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
@@ -68,10 +75,11 @@ _SIGNATURES = {
     "vb_loc_proj_fwd": [_P, _P, _P, _P, _I32, _I32, _P],
     "vb_loc_proj_bwd": [_P, _P, _P, _P, _I32, _I32, _P],
     "vb_colsum": [_P, _I32, _I64, _P, _I32, _I32, _P],
-    "vb_small_linear_fwd": [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P],
-    "vb_small_linear_bwd": [_P, _P, _I64, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P],
-    "vb_fuse_pooled_fwd": [_P, _P, _P, _P, _I64, _I32, _P],
-    "vb_fuse_pooled_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _P],
+    "vb_small_linear_fwd": [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P],
+    "vb_small_linear_bwd": [_P, _P, _I64, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P],
+    "vb_fuse_pooled_fwd": [_P, _P, _P, _P, _I64, _I32, _P, _P],
+    "vb_fuse_pooled_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _P, _P],
+    "vb_step_counter_bump": [_P, _P],
     "vb_relu_bwd": [_P, _P, _P, _P, _I64, _P],
     "vb_axpy_f32": [_P, _P, _I64, _F, _P],
     "vb_bce_logits_loss": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],

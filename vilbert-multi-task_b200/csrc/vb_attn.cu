@@ -43,6 +43,7 @@ struct AttnParams {
   __nv_bfloat16 *dQ, *dK, *dV;
   long long lddq, lddk, lddv;
   float* delta;  // [B,H,Nq]
+  DropCfg drop;            // dropout on the attention probabilities (element index ((b*H + h)*Nq + q)*Nk + k)
   float *dbq, *dbk, *dbv;  // optional bias gradients [H*D] of the Q / K / V projections (+= column sums of dQ / dK / dV)
 };
 
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
   if (q0 + r0 >= p.Nq) return;  // whole warp out of range (no later block-wide sync)
 
   const float c = p.scale * LOG2E;
+  const uint32_t dseed = p.drop.ctr ? drop_seed(p.drop) : 0u;
   float m[2] = {-CUDART_INF_F, -CUDART_INF_F}, l[2] = {0.f, 0.f};
   float o[D / 8][4];
 #pragma unroll
@@ -205,6 +207,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
     l[0] = l[0] * al0 + rs0; l[1] = l[1] * al1 + rs1;
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
+    if (p.drop.ctr) {   // nn.Dropout on the probabilities (vilbert.py:443, 604, 778, 800): the row sum above stays undropped
+      const uint32_t e0 = (uint32_t)((((long long)b * p.H + h) * p.Nq + q0 + r0 + g) * p.Nk + kb + 2 * t);
+      const uint32_t e1 = e0 + 8u * (uint32_t)p.Nk;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] *= drop_factor(dseed, e0 + nt * 8, p.drop); s[nt][1] *= drop_factor(dseed, e0 + nt * 8 + 1, p.drop);
+        s[nt][2] *= drop_factor(dseed, e1 + nt * 8, p.drop); s[nt][3] *= drop_factor(dseed, e1 + nt * 8 + 1, p.drop);
+      }
+    }
     mma_p_b<D>(o, s, sV, kb, lane);
   }
   l[0] = quad_sum(l[0]); l[1] = quad_sum(l[1]);
@@ -285,6 +296,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
   }
 
   const float c = p.scale * LOG2E;
+  const uint32_t dseed = p.drop.ctr ? drop_seed(p.drop) : 0u;
   float dq[D / 8][4];
 #pragma unroll
   for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
@@ -303,6 +315,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
       const float mk0 = sMask[kb + nt * 8 + 2 * t], mk1 = sMask[kb + nt * 8 + 2 * t + 1];
       const float p0 = exp2f(s[nt][0] * c + mk0 - ls[0]), p1 = exp2f(s[nt][1] * c + mk1 - ls[0]);
       const float p2 = exp2f(s[nt][2] * c + mk0 - ls[1]), p3 = exp2f(s[nt][3] * c + mk1 - ls[1]);
+      if (p.drop.ctr) {   // dP = mask/(1-p) * (dO V^T); delta = rowsum(dO o O) already contains the mask through O
+        const uint32_t e0 = (uint32_t)((((long long)b * p.H + h) * p.Nq + q0 + r0 + g) * p.Nk + kb + nt * 8 + 2 * t);
+        const uint32_t e1 = e0 + 8u * (uint32_t)p.Nk;
+        dp[nt][0] *= drop_factor(dseed, e0, p.drop); dp[nt][1] *= drop_factor(dseed, e0 + 1, p.drop);
+        dp[nt][2] *= drop_factor(dseed, e1, p.drop); dp[nt][3] *= drop_factor(dseed, e1 + 1, p.drop);
+      }
       s[nt][0] = p0 * (dp[nt][0] - dl[0]); s[nt][1] = p1 * (dp[nt][1] - dl[0]);
       s[nt][2] = p2 * (dp[nt][2] - dl[1]); s[nt][3] = p3 * (dp[nt][3] - dl[1]);
     }
@@ -354,6 +372,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
   mk[1] = (r0 + g + 8 < rows_valid && p.mask) ? p.mask[(long long)b * p.Nk + k0 + r0 + g + 8] * LOG2E : 0.f;
 
   const float c = p.scale * LOG2E;
+  const uint32_t dseed = p.drop.ctr ? drop_seed(p.drop) : 0u;
   float dk[D / 8][4], dv[D / 8][4];
 #pragma unroll
   for (int i = 0; i < D / 8; ++i) {
@@ -379,8 +398,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
       pt[nt][0] = exp2f(st[nt][0] * c + mk[0] - l0); pt[nt][1] = exp2f(st[nt][1] * c + mk[0] - l1);
       pt[nt][2] = exp2f(st[nt][2] * c + mk[1] - l0); pt[nt][3] = exp2f(st[nt][3] * c + mk[1] - l1);
       const float d0 = sDelta[q], d1 = sDelta[q + 1];
-      st[nt][0] = pt[nt][0] * (dpt[nt][0] - d0); st[nt][1] = pt[nt][1] * (dpt[nt][1] - d1);
-      st[nt][2] = pt[nt][2] * (dpt[nt][2] - d0); st[nt][3] = pt[nt][3] * (dpt[nt][3] - d1);
+      float f0 = 1.f, f1 = 1.f, f2 = 1.f, f3 = 1.f;
+      if (p.drop.ctr) {   // transposed tile: row = key (g, g+8), column = query (q, q+1)
+        const uint32_t eq0 = (uint32_t)((((long long)b * p.H + h) * p.Nq + q) * p.Nk + k0 + r0 + g);
+        const uint32_t eq1 = eq0 + (uint32_t)p.Nk;
+        f0 = drop_factor(dseed, eq0, p.drop); f1 = drop_factor(dseed, eq1, p.drop);
+        f2 = drop_factor(dseed, eq0 + 8, p.drop); f3 = drop_factor(dseed, eq1 + 8, p.drop);
+      }
+      st[nt][0] = pt[nt][0] * (dpt[nt][0] * f0 - d0); st[nt][1] = pt[nt][1] * (dpt[nt][1] * f1 - d1);
+      st[nt][2] = pt[nt][2] * (dpt[nt][2] * f2 - d0); st[nt][3] = pt[nt][3] * (dpt[nt][3] * f3 - d1);
+      pt[nt][0] *= f0; pt[nt][1] *= f1; pt[nt][2] *= f2; pt[nt][3] *= f3;   // dV = (mask/(1-p) P)^T dO
     }
     mma_p_b<D>(dv, pt, sdO, qb, lane);
     mma_p_b<D>(dk, st, sQ, qb, lane);
@@ -420,6 +447,11 @@ static AttnParams to_params(const vb_attn_args* a) {
   p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
   p.delta = a->delta;
   p.dbq = a->dbias_q; p.dbk = a->dbias_k; p.dbv = a->dbias_v;
+  const bool on = a->dropout.step && a->dropout.p > 0.f;
+  p.drop.ctr = on ? a->dropout.step : nullptr;
+  p.drop.site = a->dropout.site;
+  p.drop.thresh = on ? (uint32_t)((double)a->dropout.p * 4294967296.0) : 0u;
+  p.drop.scale = on && a->dropout.p < 1.f ? 1.f / (1.f - a->dropout.p) : 1.f;
   return p;
 }
 

@@ -65,6 +65,7 @@ struct GemmKernelParams {
   uint64_t desc_base_a, desc_base_b;                 // smem descriptor without the address field
   uint32_t kadv_a, kadv_b;                           // descriptor address advance per UMMA_K (bytes)
   uint32_t idesc;
+  DropCfg drop;              // dropout on the epilogue value before the residual add (EPI_F32 / generic)
   int a_mn, b_mn;            // operand majors (runtime: only the TMA producer cares)
   int fast_ok;               // every buffer the specialised epilogue touches allows 128/64-bit accesses
   unsigned long long* dbg;   // optional per-CTA timeline [grid][10] (8 x clock64 + 2 x globaltimer ns), NULL in production
@@ -111,6 +112,7 @@ __device__ __noinline__ void epi_generic_chunk(const GemmKernelParams& p, const 
       } else if (p.act == VB_ACT_DGELU) {
         v *= __bfloat162float(p.aux[m * p.ld_aux + n + j]);                      // aux = saved gelu'(pre)
       }
+      if (p.drop.ctr) v = drop_apply(v, drop_seed(p.drop), (uint32_t)(m * p.N + n + j), p.drop);
       cs[j] += v;
       if (p.residual) v += p.residual[m * p.ld_res + n + j];
       if (p.out_f32) {
@@ -130,6 +132,7 @@ template <int EPI>
 __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const float* stg, int m_base, int n, int rr, int cc,
                                                const float4 (&resv)[8], const uint2 (&auxv)[8], const float4 b4) {
   float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+  const uint32_t dseed = (EPI == EPI_F32 && p.drop.ctr) ? drop_seed(p.drop) : 0u;
 #pragma unroll
   for (int ps = 0; ps < 8; ++ps) {
     const int row = ps * 4 + rr;
@@ -149,6 +152,11 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
       cs0 += v0; cs1 += v1; cs2 += v2; cs3 += v3;
       *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
     } else if (EPI == EPI_F32) {
+      if (p.drop.ctr) {   // LN(dropout(dense(x)) + residual): mask the dense output, element index m*N + n
+        const uint32_t e0 = (uint32_t)(m * p.N + n);
+        v0 = drop_apply(v0, dseed, e0, p.drop); v1 = drop_apply(v1, dseed, e0 + 1, p.drop);
+        v2 = drop_apply(v2, dseed, e0 + 2, p.drop); v3 = drop_apply(v3, dseed, e0 + 3, p.drop);
+      }
       if (p.residual) { v0 += resv[ps].x; v1 += resv[ps].y; v2 += resv[ps].z; v3 += resv[ps].w; }
       float* dst = p.out_f32 + m * p.ld_of + n;
       if (p.vec_f32) {
@@ -561,6 +569,10 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   p.a_mn = a->a_mn_major ? 1 : 0;
   p.b_mn = a->b_mn_major ? 1 : 0;
   p.fast_ok = 0;
+  p.drop.ctr = (a->dropout.step && a->dropout.p > 0.f) ? a->dropout.step : nullptr;
+  p.drop.site = a->dropout.site;
+  p.drop.thresh = (uint32_t)((double)a->dropout.p * 4294967296.0);
+  p.drop.scale = a->dropout.p < 1.f ? 1.f / (1.f - a->dropout.p) : 0.f;
 
   CUtensorMap ta, tb;
   int st;
@@ -577,17 +589,18 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   // pick the epilogue specialisation; anything unusual runs the generic one
   int epi = EPI_GENERIC;
   const bool no_extra = !a->out_colsum;
+  const bool has_drop = p.drop.ctr != nullptr;   // only the F32 specialisation (and the generic path) implement it
   if (a->atomic_out) {
-    if (a->act == VB_ACT_NONE && !a->bias && !a->residual && no_extra) { epi = EPI_ATOMIC; p.fast_ok = p.vec_f32; }
+    if (a->act == VB_ACT_NONE && !a->bias && !a->residual && no_extra && !has_drop) { epi = EPI_ATOMIC; p.fast_ok = p.vec_f32; }
   } else if (a->act == VB_ACT_GELU) {
-    if (a->out_pre && !a->residual && no_extra && (a->out_bf16 || a->out_f32)) {
+    if (a->out_pre && !a->residual && no_extra && !has_drop && (a->out_bf16 || a->out_f32)) {
       epi = EPI_GELU; p.fast_ok = p.vec_pre && (!a->out_bf16 || p.vec_bf16) && (!a->out_f32 || p.vec_f32);
     }
   } else if (a->act == VB_ACT_DGELU) {
-    if (a->out_bf16 && !a->out_f32 && !a->residual && !a->bias) { epi = EPI_DGELU; p.fast_ok = p.vec_bf16 && p.vec_aux; }
+    if (a->out_bf16 && !a->out_f32 && !a->residual && !a->bias && !has_drop) { epi = EPI_DGELU; p.fast_ok = p.vec_bf16 && p.vec_aux; }
   } else if (a->act == VB_ACT_NONE) {
     if (a->out_f32 && !a->out_bf16 && no_extra) { epi = EPI_F32; p.fast_ok = 1; }   // unaligned pitches use 32-bit accesses
-    else if (a->out_bf16 && !a->out_f32 && !a->residual && no_extra) { epi = EPI_BF16; p.fast_ok = p.vec_bf16; }
+    else if (a->out_bf16 && !a->out_f32 && !a->residual && no_extra && !has_drop) { epi = EPI_BF16; p.fast_ok = p.vec_bf16; }
   }
   if (bn == 256) return launch_gemm_epi<256>(epi, ta, tb, p, grid, stream);
   return launch_gemm_epi<128>(epi, ta, tb, p, grid, stream);

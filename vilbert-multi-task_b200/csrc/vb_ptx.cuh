@@ -31,6 +31,29 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_entry() { pdl_wait(); pdl_launch_dependents(); }
 
+// ---------------------------------------------------------------- counter-based dropout RNG
+// keep(element) = hash32(index ^ seed) >= threshold, seed = hash32(site + step * golden), threshold = p * 2^32.
+// Stateless: the backward kernels regenerate the mask of any element from (site id, step counter, element index),
+// nothing is stored. hash32 = "lowbias32" (two multiplies, full avalanche). The step counter lives in device memory
+// (bumped once per training step inside the captured graph), the site id names the dropout layer.
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+struct DropCfg {
+  const uint32_t* ctr;   // device step counter, NULL = dropout disabled
+  uint32_t site;         // id of the dropout layer
+  uint32_t thresh;       // p * 2^32
+  float scale;           // 1 / (1 - p)
+};
+__device__ __forceinline__ uint32_t drop_seed(const DropCfg& d) { return hash32(d.site + (*d.ctr) * 0x9E3779B9U); }
+__device__ __forceinline__ float drop_apply(float v, uint32_t seed, uint32_t idx, const DropCfg& d) {
+  return hash32(idx ^ seed) >= d.thresh ? v * d.scale : 0.f;
+}
+__device__ __forceinline__ float drop_factor(uint32_t seed, uint32_t idx, const DropCfg& d) {
+  return hash32(idx ^ seed) >= d.thresh ? d.scale : 0.f;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));

@@ -33,11 +33,12 @@ template <int NV4>
 __global__ void __launch_bounds__(ROW_THREADS)
 ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
               float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, long long ldy, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, int M, int H) {
+              float* __restrict__ rstd_out, int M, int H, const DropCfg drop) {
   pdl_entry();
   const int lane = threadIdx.x & 31;
   const int n4 = H >> 2;
   const float inv_h = 1.f / (float)H;
+  const uint32_t dseed = drop.ctr ? drop_seed(drop) : 0u;
   for (long long row = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * ROW_WARPS) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
     float4 v[NV4];
@@ -74,6 +75,11 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
         o.y = (v[i].y - mean) * rstd * g.y + b.y;
         o.z = (v[i].z - mean) * rstd * g.z + b.z;
         o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (drop.ctr) {   // dropout(LayerNorm(x)) of the embeddings (vilbert.py:365, 1430); element index row*H + col
+          const uint32_t e0 = (uint32_t)(row * H + c * 4);
+          o.x = drop_apply(o.x, dseed, e0, drop); o.y = drop_apply(o.y, dseed, e0 + 1, drop);
+          o.z = drop_apply(o.z, dseed, e0 + 2, drop); o.w = drop_apply(o.w, dseed, e0 + 3, drop);
+        }
         if (y32) reinterpret_cast<float4*>(y32 + row * ldy)[c] = o;
         if (y16) reinterpret_cast<uint2*>(y16 + row * ldy)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       }
@@ -96,9 +102,11 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16, long long lddx,
               const __nv_bfloat16* __restrict__ pre, long long ldpre, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              float* __restrict__ dbias, int M, int H) {
+              float* __restrict__ dbias, int M, int H, const DropCfg drop_out, const DropCfg drop_in) {
   pdl_entry();
   constexpr int TEAMS = ROW_THREADS / 64;
+  const uint32_t seed_out = drop_out.ctr ? drop_seed(drop_out) : 0u;   // mask applied to this LayerNorm's output in forward
+  const uint32_t seed_in = drop_in.ctr ? drop_seed(drop_in) : 0u;      // mask applied to the dense output feeding this LayerNorm
   __shared__ float xch[TEAMS][2][2][2];
   __shared__ float red[TEAMS][64 * 4 + 4];
   const int team = threadIdx.x >> 6, tl = threadIdx.x & 63, wih = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
@@ -119,7 +127,13 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
     for (int i = 0; i < NV; ++i) {
       const int c = tl + i * 64;
       if (c < n4) {
-        const float4 d = dyr[c], xv = xr[c], gm = reinterpret_cast<const float4*>(gamma)[c];
+        float4 d = dyr[c];
+        const float4 xv = xr[c], gm = reinterpret_cast<const float4*>(gamma)[c];
+        if (drop_out.ctr) {
+          const uint32_t e0 = (uint32_t)(row * H + c * 4);
+          d.x = drop_apply(d.x, seed_out, e0, drop_out); d.y = drop_apply(d.y, seed_out, e0 + 1, drop_out);
+          d.z = drop_apply(d.z, seed_out, e0 + 2, drop_out); d.w = drop_apply(d.w, seed_out, e0 + 3, drop_out);
+        }
         xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
         g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
         s1 += g[i].x + g[i].y + g[i].z + g[i].w;
@@ -151,6 +165,11 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
             const float2 p01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
             const float2 p23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
             o.x *= p01.x; o.y *= p01.y; o.z *= p23.x; o.w *= p23.y;   // pre = gelu'(pre-activation) saved by the forward GEMM
+          }
+          if (drop_in.ctr) {   // gradient of dropout(dense(x)): same mask as the forward GEMM epilogue (index row*H + col)
+            const uint32_t e0 = (uint32_t)(row * H + c * 4);
+            o.x = drop_apply(o.x, seed_in, e0, drop_in); o.y = drop_apply(o.y, seed_in, e0 + 1, drop_in);
+            o.z = drop_apply(o.z, seed_in, e0 + 2, drop_in); o.w = drop_apply(o.w, seed_in, e0 + 3, drop_in);
           }
           if (dx16) reinterpret_cast<uint2*>(dx16 + row * lddx)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
           ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
@@ -342,14 +361,19 @@ __global__ void colsum_kernel(const T* __restrict__ X, long long ld, float* __re
 // linguisic_logit / bi_seq_relationship / the 2-way output of vil_binary_prediction (vilbert.py:1620-1628,1684-1695).
 __global__ void __launch_bounds__(ROW_THREADS)
 small_linear_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W, const float* __restrict__ b,
-                        const float* __restrict__ addend, float* __restrict__ y, int M, int K, int N) {
+                        const float* __restrict__ addend, float* __restrict__ y, int M, int K, int N, const DropCfg drop) {
   pdl_entry();
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = drop.ctr ? drop_seed(drop) : 0u;   // dropout on the input x (vilbert.py:1692, 1695), index m*K + k
   for (long long row = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * ROW_WARPS) {
     const float* xr = x + row * ldx;
     for (int j = 0; j < N; ++j) {
       float acc = 0.f;
-      for (int k = lane; k < K; k += 32) acc += xr[k] * __ldg(W + (long long)j * K + k);
+      for (int k = lane; k < K; k += 32) {
+        float xv = xr[k];
+        if (drop.ctr) xv = drop_apply(xv, dseed, (uint32_t)(row * K + k), drop);
+        acc += xv * __ldg(W + (long long)j * K + k);
+      }
       acc = warp_sum(acc);
       if (lane == 0) y[row * N + j] = acc + (b ? b[j] : 0.f) + (addend ? addend[row] : 0.f);
     }
@@ -360,14 +384,19 @@ small_linear_fwd_kernel(const float* __restrict__ x, long long ldx, const float*
 __global__ void __launch_bounds__(ROW_THREADS)
 small_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long ldx, const float* __restrict__ W,
                         float* __restrict__ dx, long long lddx, int accumulate_dx, float* __restrict__ dW, float* __restrict__ db,
-                        int M, int K, int N) {
+                        int M, int K, int N, const DropCfg drop) {
   pdl_entry();
+  const uint32_t dseed = drop.ctr ? drop_seed(drop) : 0u;
   // one CTA handles a strided set of rows; per-thread partial dW over columns k = threadIdx.x + i*ROW_THREADS
   for (int j = 0; j < N; ++j) {
     float dbp = 0.f;
     for (int k = threadIdx.x; k < K; k += ROW_THREADS) {
       float acc = 0.f;
-      for (long long m = blockIdx.x; m < M; m += gridDim.x) acc += dy[m * N + j] * x[m * ldx + k];
+      for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+        float xv = x[m * ldx + k];
+        if (drop.ctr) xv = drop_apply(xv, dseed, (uint32_t)(m * K + k), drop);
+        acc += dy[m * N + j] * xv;
+      }
       atomicAdd(dW + (long long)j * K + k, acc);
     }
     if (threadIdx.x == 0) {
@@ -380,6 +409,7 @@ small_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ 
       for (int k = threadIdx.x; k < K; k += ROW_THREADS) {
         float acc = 0.f;
         for (int j = 0; j < N; ++j) acc += dy[m * N + j] * __ldg(W + (long long)j * K + k);
+        if (drop.ctr) acc = drop_apply(acc, dseed, (uint32_t)(m * K + k), drop);
         float* d = dx + m * lddx + k;
         *d = accumulate_dx ? (*d + acc) : acc;
       }
@@ -390,20 +420,24 @@ small_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------ elementwise helpers
 // out = a * b (fusion_method "mul") or a + b ("sum"), f32 + bf16 copies (vilbert.py:1677-1682, 1236-1241)
 __global__ void fuse_pooled_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o32,
-                                       __nv_bfloat16* __restrict__ o16, long long n, int mul) {
+                                       __nv_bfloat16* __restrict__ o16, long long n, int mul, const DropCfg drop) {
   pdl_entry();
+  const uint32_t dseed = drop.ctr ? drop_seed(drop) : 0u;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = mul ? a[i] * b[i] : a[i] + b[i];
+    float v = mul ? a[i] * b[i] : a[i] + b[i];
+    if (drop.ctr) v = drop_apply(v, dseed, (uint32_t)i, drop);
     if (o32) o32[i] = v;
     if (o16) o16[i] = __float2bfloat16(v);
   }
 }
 // da += d * b, db += d * a (mul) or da += d, db += d (sum)
 __global__ void fuse_pooled_bwd_kernel(const float* __restrict__ d, const float* __restrict__ a, const float* __restrict__ b,
-                                       float* __restrict__ da, float* __restrict__ db, long long n, int mul) {
+                                       float* __restrict__ da, float* __restrict__ db, long long n, int mul, const DropCfg drop) {
   pdl_entry();
+  const uint32_t dseed = drop.ctr ? drop_seed(drop) : 0u;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float g = d[i];
+    float g = d[i];
+    if (drop.ctr) g = drop_apply(g, dseed, (uint32_t)i, drop);
     da[i] += mul ? g * b[i] : g;
     db[i] += mul ? g * a[i] : g;
   }
@@ -464,6 +498,21 @@ __global__ void mask_to_additive_kernel(const long long* __restrict__ m, float* 
   }
 }
 
+__global__ void step_bump_kernel(uint32_t* ctr) {
+  pdl_entry();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += 1u;
+}
+
+static inline DropCfg make_drop(const vb_dropout* d) {
+  DropCfg c;
+  const bool on = d && d->step && d->p > 0.f;
+  c.ctr = on ? d->step : nullptr;
+  c.site = d ? d->site : 0u;
+  c.thresh = on ? (uint32_t)((double)d->p * 4294967296.0) : 0u;
+  c.scale = on && d->p < 1.f ? 1.f / (1.f - d->p) : 1.f;
+  return c;
+}
+
 static inline int ew_grid(long long n, int threads = 256) {
   long long blocks = (n + threads - 1) / threads;
   long long cap = (long long)sm_count() * 8;
@@ -478,7 +527,8 @@ using namespace vb;
 #define ST(s) static_cast<cudaStream_t>(s)
 
 extern "C" vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* y_f32,
-                                      void* y_bf16, int64_t ldy, float* mean, float* rstd, int32_t M, int32_t H, void* stream) {
+                                      void* y_bf16, int64_t ldy, float* mean, float* rstd, int32_t M, int32_t H, const vb_dropout* out_dropout,
+                                      void* stream) {
   if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_layernorm_fwd: empty problem");
   if ((H & 3) || H > MAX_V4 * 128 || (ldx & 3) || (ldy & 3) || !al16(x) || !al16(gamma) || !al16(beta) || (y_f32 && !al16(y_f32)) ||
       (y_bf16 && (reinterpret_cast<uintptr_t>(y_bf16) & 7)))
@@ -486,7 +536,8 @@ extern "C" vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* 
   const int nv4 = (H / 4 + 31) / 32;
   const int grid = row_grid(M);
   __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
-#define LN_F(NV) launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), x, ldx, gamma, beta, eps, y_f32, y16, ldy, mean, rstd, M, H)
+  const DropCfg dc = make_drop(out_dropout);
+#define LN_F(NV) launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), x, ldx, gamma, beta, eps, y_f32, y16, ldy, mean, rstd, M, H, dc)
   if (nv4 <= 1) LN_F(1); else if (nv4 <= 2) LN_F(2); else if (nv4 <= 4) LN_F(4); else if (nv4 <= 6) LN_F(6);
   else if (nv4 <= 8) LN_F(8); else LN_F(16);
 #undef LN_F
@@ -495,17 +546,21 @@ extern "C" vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* 
 
 extern "C" vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma, const float* mean,
                                       const float* rstd, float* dx_f32, void* dx_bf16, int64_t lddx, const void* gelu_pre,
-                                      int64_t ld_pre, float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H, void* stream) {
+                                      int64_t ld_pre, float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H,
+                                      const vb_dropout* out_dropout, const vb_dropout* in_dropout, void* stream) {
   if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: empty problem");
   if ((H & 3) || H > MAX_V4 * 128 || (ldx & 3) || (lddy & 3) || (lddx & 3) || (gelu_pre && (ld_pre & 3)) || !al16(dy) || !al16(x) || !al16(gamma))
     return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: need H %% 4 == 0, H <= %d, ld %% 4 == 0, 16-byte aligned rows", MAX_V4 * 128);
+  const DropCfg dc_out = make_drop(out_dropout), dc_in = make_drop(in_dropout);
+  if ((dc_out.ctr || dc_in.ctr) && (ldx != H || lddy != H || lddx != H))
+    return set_error(VB_ERR_INVALID, "vb_layernorm_bwd: dropout masks are indexed row*H + col and need dense rows");
   const int nv = (H / 4 + 63) / 64;   // float4 chunks per lane of a 64-lane row team
   long long blocks = ((long long)M + 3) / 4;
   const int cap = sm_count() * 2;     // two resident CTAs per SM; fewer CTAs -> fewer dgamma/dbeta atomics
   int grid = (int)(blocks < cap || cap <= 0 ? (blocks > 0 ? blocks : 1) : cap);
   __nv_bfloat16* dx16 = static_cast<__nv_bfloat16*>(dx_bf16);
   const __nv_bfloat16* pre = static_cast<const __nv_bfloat16*>(gelu_pre);
-#define LN_B(NV) launch_pdl(ln_bwd_kernel<NV>, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), dy, lddy, x, ldx, gamma, mean, rstd, dx_f32, dx16, lddx, pre, ld_pre, dgamma, dbeta, dbias, M, H)
+#define LN_B(NV) launch_pdl(ln_bwd_kernel<NV>, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), dy, lddy, x, ldx, gamma, mean, rstd, dx_f32, dx16, lddx, pre, ld_pre, dgamma, dbeta, dbias, M, H, dc_out, dc_in)
   if (nv <= 1) LN_B(1); else if (nv <= 2) LN_B(2); else if (nv <= 3) LN_B(3); else if (nv <= 4) LN_B(4); else LN_B(8);
 #undef LN_B
   return check_launch("vb_layernorm_bwd");
@@ -578,29 +633,31 @@ extern "C" vb_status vb_colsum(const void* X, int32_t is_bf16, int64_t ld, float
 }
 
 extern "C" vb_status vb_small_linear_fwd(const float* x, int64_t ldx, const float* W, const float* b, const float* row_addend, float* y,
-                                         int32_t M, int32_t K, int32_t N, void* stream) {
+                                         int32_t M, int32_t K, int32_t N, const vb_dropout* in_dropout, void* stream) {
   if (M <= 0 || K <= 0 || N <= 0 || N > 8) return set_error(VB_ERR_INVALID, "vb_small_linear_fwd: bad shape (N <= 8)");
-  launch_pdl(small_linear_fwd_kernel, dim3(row_grid(M)), dim3(ROW_THREADS), (size_t)(0), ST(stream), x, ldx, W, b, row_addend, y, M, K, N);
+  launch_pdl(small_linear_fwd_kernel, dim3(row_grid(M)), dim3(ROW_THREADS), (size_t)(0), ST(stream), x, ldx, W, b, row_addend, y, M, K, N, make_drop(in_dropout));
   return check_launch("vb_small_linear_fwd");
 }
 
 extern "C" vb_status vb_small_linear_bwd(const float* dy, const float* x, int64_t ldx, const float* W, float* dx, int64_t lddx,
-                                         int32_t accumulate_dx, float* dW, float* db, int32_t M, int32_t K, int32_t N, void* stream) {
+                                         int32_t accumulate_dx, float* dW, float* db, int32_t M, int32_t K, int32_t N,
+                                         const vb_dropout* in_dropout, void* stream) {
   if (M <= 0 || K <= 0 || N <= 0 || N > 8) return set_error(VB_ERR_INVALID, "vb_small_linear_bwd: bad shape (N <= 8)");
   int grid = sm_count(); if (grid > M) grid = M; if (grid <= 0) grid = 1;
-  launch_pdl(small_linear_bwd_kernel, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), dy, x, ldx, W, dx, lddx, accumulate_dx, dW, db, M, K, N);
+  launch_pdl(small_linear_bwd_kernel, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), dy, x, ldx, W, dx, lddx, accumulate_dx, dW, db, M, K, N, make_drop(in_dropout));
   return check_launch("vb_small_linear_bwd");
 }
 
-extern "C" vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul, void* stream) {
+extern "C" vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul,
+                                        const vb_dropout* dropout, void* stream) {
   if (n <= 0) return VB_OK;
-  launch_pdl(fuse_pooled_fwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), a, b, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n, mul);
+  launch_pdl(fuse_pooled_fwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), a, b, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n, mul, make_drop(dropout));
   return check_launch("vb_fuse_pooled_fwd");
 }
 extern "C" vb_status vb_fuse_pooled_bwd(const float* d, const float* a, const float* b, float* da, float* db, int64_t n, int32_t mul,
-                                        void* stream) {
+                                        const vb_dropout* dropout, void* stream) {
   if (n <= 0) return VB_OK;
-  launch_pdl(fuse_pooled_bwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), d, a, b, da, db, n, mul);
+  launch_pdl(fuse_pooled_bwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), d, a, b, da, db, n, mul, make_drop(dropout));
   return check_launch("vb_fuse_pooled_bwd");
 }
 extern "C" vb_status vb_relu_bwd(const float* dy, const float* y, void* dx_bf16, float* dx_f32, int64_t n, void* stream) {
@@ -627,6 +684,12 @@ extern "C" vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_
   if (B <= 0 || N <= 0) return set_error(VB_ERR_INVALID, "vb_mask_to_additive: bad shape");
   launch_pdl(mask_to_additive_kernel, dim3(ew_grid((long long)B * (N + 1))), dim3(256), (size_t)(0), ST(stream), reinterpret_cast<const long long*>(mask), out, B, N, prepend_one ? 1 : 0);
   return check_launch("vb_mask_to_additive");
+}
+extern "C" vb_status vb_step_counter_bump(uint32_t* step, void* stream) {
+  if (!step) return set_error(VB_ERR_INVALID, "vb_step_counter_bump: null counter");
+  cudaError_t e = launch_pdl(step_bump_kernel, dim3(1), dim3(32), (size_t)0, ST(stream), step);
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_step_counter_bump: %s", cudaGetErrorString(e));
+  return VB_OK;
 }
 extern "C" vb_status vb_memset_zero(void* ptr, int64_t bytes, void* stream) {
   if (bytes <= 0) return VB_OK;

@@ -14,6 +14,7 @@ are fp32; bf16 copies of activations exist only as GEMM / attention operands.
 """
 import ctypes as C
 import math
+import zlib
 from collections import OrderedDict
 
 import torch
@@ -25,6 +26,11 @@ F32, BF16, I64 = torch.float32, torch.bfloat16, torch.int64
 
 def _pad8(n):
     return (n + 7) // 8 * 8
+
+
+def dropout_site_id(name):
+    """Stable 32-bit id of a dropout layer, shared with the oracle's mask generator (crc32 of its canonical name)."""
+    return zlib.crc32(name.encode()) & 0xFFFFFFFF
 
 
 # ------------------------------------------------------------------------------------------ parameters
@@ -158,7 +164,7 @@ class Plan:
     gradient in backward (dead branches are not emitted); `vqa_loss` fuses the VQA BCE objective
     (task_utils.py:325-327) and its gradient after the forward."""
 
-    def __init__(self, engine, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None):
+    def __init__(self, engine, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False):
         self.e, self.ps, self.cfg = engine, engine.ps, engine.cfg
         self.lib = L.lib()
         self.dev = engine.device
@@ -167,6 +173,8 @@ class Plan:
         self.Nt = Nt + (1 if self.has_task else 0)
         self.grad_outputs = frozenset(grad_outputs)
         self.vqa_loss = vqa_loss
+        self.train = bool(train)          # nn.Dropout layers active (model.train()); False = the reference's eval mode
+        self.head_dropout_prob = engine.head_dropout_prob
         self.heads = engine.ps.heads if heads is None else heads   # "vl" | "pretraining" | "none"
         self.fwd_id = 0
         self.fwd, self.bwd = [], []
@@ -232,8 +240,22 @@ class Plan:
             return None
         return t.data_ptr() if torch.is_tensor(t) else int(t)
 
+    def drop(self, name, p):
+        """ctypes byref of a vb_dropout for the dropout layer `name` with probability p, or None when inactive."""
+        if not self.train or p is None or p <= 0.0:
+            return None
+        d = L.Dropout()
+        d.step, d.site, d.p = self.e.drop_step.data_ptr(), dropout_site_id(name), float(p)
+        self._keep.append(d)
+        return d
+
+    @staticmethod
+    def _ref(d):
+        return C.byref(d) if d is not None else None
+
     def gemm(self, M, N, K, A, lda, B, ldb, a_mn=0, b_mn=0, bias=None, residual=None, ld_res=0, aux=None, ld_aux=0, act=0,
-             out_f32=None, ld_of=0, out_bf16=None, ld_ob=0, out_pre=None, ld_op=0, atomic=0, split_k=1, alpha=1.0, out_colsum=None):
+             out_f32=None, ld_of=0, out_bf16=None, ld_ob=0, out_pre=None, ld_op=0, atomic=0, split_k=1, alpha=1.0, out_colsum=None,
+             dropout=None):
         g = L.GemmArgs()
         g.M, g.N, g.K = M, N, K
         g.A, g.lda, g.a_mn_major = self._ptr(A), lda, a_mn
@@ -248,11 +270,13 @@ class Plan:
         g.out_pre, g.ld_out_pre = self._ptr(out_pre), ld_op
         g.atomic_out, g.split_k, g.block_n, g.max_ctas = atomic, split_k, 0, 0
         g.out_colsum = self._ptr(out_colsum)
+        if dropout is not None:
+            g.dropout = dropout
         self._keep.append(g)
         self.emit(self.lib.vb_gemm_bf16, C.byref(g))
 
     def attention(self, bwd, B, H, Nq, Nk, D, Q, ldq, K, ldk, V, ldv, mask, O, ldo, lse, dO=None, lddo=0, dQ=None, lddq=0,
-                  dK=None, lddk=0, dV=None, lddv=0, delta=None, dbq=None, dbk=None, dbv=None):
+                  dK=None, lddk=0, dV=None, lddv=0, delta=None, dbq=None, dbk=None, dbv=None, dropout=None):
         a = L.AttnArgs()
         a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
         a.Q, a.ldq, a.K, a.ldk, a.V, a.ldv = self._ptr(Q), ldq, self._ptr(K), ldk, self._ptr(V), ldv
@@ -261,21 +285,24 @@ class Plan:
         a.dO, a.lddo, a.dQ, a.lddq = self._ptr(dO), lddo, self._ptr(dQ), lddq
         a.dK, a.lddk, a.dV, a.lddv, a.delta = self._ptr(dK), lddk, self._ptr(dV), lddv, self._ptr(delta)
         a.dbias_q, a.dbias_k, a.dbias_v = self._ptr(dbq), self._ptr(dbk), self._ptr(dbv)
+        if dropout is not None:
+            a.dropout = dropout
         self._keep.append(a)
         self.emit(self.lib.vb_attention_bwd if bwd else self.lib.vb_attention_fwd, C.byref(a))
 
-    def ln_fwd(self, x, gamma, beta, M, H, want_f32=True):
+    def ln_fwd(self, x, gamma, beta, M, H, want_f32=True, out_drop=None):
         y32 = self.buf((M, H), F32) if want_f32 else None
         y16 = self.buf((M, H), BF16)
         mean, rstd = self.buf((M,), F32), self.buf((M,), F32)
         self.emit(self.lib.vb_layernorm_fwd, x.data_ptr(), H, gamma.data_ptr(), beta.data_ptr(), 1e-12, self._ptr(y32), y16.data_ptr(), H,
-                  mean.data_ptr(), rstd.data_ptr(), M, H)
+                  mean.data_ptr(), rstd.data_ptr(), M, H, self._ref(out_drop))
         return y32, y16, mean, rstd
 
-    def ln_bwd(self, dy, x, gamma, mean, rstd, dx32, dx16, M, H, ggamma, gbeta, pre=None, gbias=None):
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dx32, dx16, M, H, ggamma, gbeta, pre=None, gbias=None, out_drop=None, in_drop=None):
         """gbias: bias gradient of the Linear feeding this LayerNorm (column sums of dx), fused into the same pass."""
         self.emit(self.lib.vb_layernorm_bwd, dy.data_ptr(), H, x.data_ptr(), H, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                  self._ptr(dx32), self._ptr(dx16), H, self._ptr(pre), H, ggamma.data_ptr(), gbeta.data_ptr(), self._ptr(gbias), M, H)
+                  self._ptr(dx32), self._ptr(dx16), H, self._ptr(pre), H, ggamma.data_ptr(), gbeta.data_ptr(), self._ptr(gbias), M, H,
+                  self._ref(out_drop), self._ref(in_drop))
 
     def colsum(self, X, ld, out, M, N):
         self.emit(self.lib.vb_colsum, X.data_ptr(), 1 if X.dtype == BF16 else 0, ld, out.data_ptr(), M, N)
@@ -311,12 +338,12 @@ class Plan:
         self.emit(self.lib.vb_axpy_f32, src32.data_ptr(), g.data_ptr(), g.numel(), 1.0)
 
     # ------------------------------------------------------------------ blocks
-    def dense_res_ln(self, a16, K_in, res, wname, lnname, tag):
+    def dense_res_ln(self, a16, K_in, res, wname, lnname, tag, drop=None):
         """LN(dense(a) + residual)  — BertSelfOutput / BertOutput / BertBiOutput halves (vilbert.py:470-474, 513-517, 844-855)."""
         ps, M, H = self.ps, res.M, res.H
         y = self.buf((M, H), F32)
         self.gemm(M, H, K_in, a16, K_in, ps.w16(wname + ".weight"), K_in, bias=ps.p(wname + ".bias"), residual=res.f32, ld_res=H,
-                  out_f32=y, ld_of=H)
+                  out_f32=y, ld_of=H, dropout=drop)
         o32, o16, mean, rstd = self.ln_fwd(y, ps.p(lnname + ".weight"), ps.p(lnname + ".bias"), M, H)
         out = Act(o32, o16, M, H)
 
@@ -327,18 +354,18 @@ class Plan:
             dy32 = self.scratch(tag + ".dy32", (M, H), F32)
             dy16 = self.scratch(tag + ".dy16", (M, H), BF16)
             self.ln_bwd(out.g32, y, ps.p(lnname + ".weight"), mean, rstd, dy32, dy16, M, H, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"),
-                        gbias=ps.g(wname + ".bias"))
+                        gbias=ps.g(wname + ".bias"), in_drop=drop)
             self.linear_wgrad(dy16, H, None, 0, a16, K_in, M, H, K_in, wname)
             return dy16, dy32
         return out, bwd
 
-    def ffn(self, x, I, w1, w2, lnname, tag):
+    def ffn(self, x, I, w1, w2, lnname, tag, drop=None):
         """LN(dense2(gelu(dense1(x))) + x) — BertIntermediate + BertOutput (vilbert.py:500-503, 513-517)."""
         ps, M, H = self.ps, x.M, x.H
         pre16, f16 = self.buf((M, I), BF16), self.buf((M, I), BF16)
         self.gemm(M, I, H, x.b16, H, ps.w16(w1 + ".weight"), H, bias=ps.p(w1 + ".bias"), act=L.VB_ACT_GELU, out_bf16=f16, ld_ob=I,
                   out_pre=pre16, ld_op=I)
-        out, out_bwd = self.dense_res_ln(f16, I, x, w2, lnname, tag + ".o")
+        out, out_bwd = self.dense_res_ln(f16, I, x, w2, lnname, tag + ".o", drop=drop)
 
         def bwd():
             r = out_bwd()
@@ -354,7 +381,7 @@ class Plan:
         self.push_bwd(bwd)
         return out
 
-    def self_attention_block(self, x, B, N, nh, mask, prefix, tag):
+    def self_attention_block(self, x, B, N, nh, mask, prefix, tag, p_attn=0.0, p_hidden=0.0):
         """BertAttention (self-attention + output), text or image stream (vilbert.py:424-474, 571-633)."""
         ps, M, H = self.ps, x.M, x.H
         D = H // nh
@@ -363,8 +390,10 @@ class Plan:
         ctx = self.buf((M, H), BF16)
         lse = self.buf((B, nh, N), F32)
         q, k, v = qkv[:, 0:H], qkv[:, H:2 * H], qkv[:, 2 * H:]
-        self.attention(False, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse)
-        out, out_bwd = self.dense_res_ln(ctx, H, x, prefix + ".output.dense", prefix + ".output.LayerNorm", tag + ".ao")
+        adrop = self.drop(prefix + ".self.dropout", p_attn)
+        self.attention(False, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dropout=adrop)
+        out, out_bwd = self.dense_res_ln(ctx, H, x, prefix + ".output.dense", prefix + ".output.LayerNorm", tag + ".ao",
+                                         drop=self.drop(prefix + ".output.dropout", p_hidden))
 
         def bwd():
             r = out_bwd()
@@ -378,7 +407,7 @@ class Plan:
             gb = ps.g(prefix + ".self.qkv.bias")     # bias gradients = column sums of dQ|dK|dV, fused into the attention backward
             self.attention(True, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dO=dctx, lddo=H,
                            dQ=dqkv[:, 0:H], lddq=3 * H, dK=dqkv[:, H:2 * H], lddk=3 * H, dV=dqkv[:, 2 * H:], lddv=3 * H, delta=delta,
-                           dbq=gb[0:H], dbk=gb[H:2 * H], dbv=gb[2 * H:])
+                           dbq=gb[0:H], dbk=gb[H:2 * H], dbv=gb[2 * H:], dropout=adrop)
             self.linear_wgrad(dqkv, 3 * H, None, 0, x.b16, H, M, 3 * H, H, prefix + ".self.qkv")
             self.dgrad_into(x, dqkv, 3 * H, ps.w16(prefix + ".self.qkv.weight"), M, 3 * H, H, extra32=dy32)
         self.push_bwd(bwd)
@@ -402,13 +431,18 @@ class Plan:
         ctx1 = self.buf((Mt, Hb), BF16); lse1 = self.buf((B, nh, Nt), F32)   # text queries over vision keys/values
         ctx2 = self.buf((Mv, Hb), BF16); lse2 = self.buf((B, nh, Nv), F32)   # vision queries over text keys/values
         L3 = 3 * Hb
-        self.attention(False, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1)
+        # dropout1 acts on attention_probs1 (text queries over regions), dropout2 on attention_probs2 (vilbert.py:730, 738, 778, 800)
+        adrop1 = self.drop(p + ".biattention.dropout1", c.v_attention_probs_dropout_prob)
+        adrop2 = self.drop(p + ".biattention.dropout2", c.attention_probs_dropout_prob)
+        self.attention(False, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1, dropout=adrop1)
         with self.on(1):
-            self.attention(False, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2)
+            self.attention(False, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dropout=adrop2)
         # biOutput: ctx2 -> vision stream (dense1 / LayerNorm1), ctx1 -> text stream (dense2 / LayerNorm2) (:890-892)
         with self.on(1):
-            v1o, v1_bwd = self.dense_res_ln(ctx2, Hb, v, p + ".biOutput.dense1", p + ".biOutput.LayerNorm1", "c.v.bo")
-        t1o, t1_bwd = self.dense_res_ln(ctx1, Hb, t, p + ".biOutput.dense2", p + ".biOutput.LayerNorm2", "c.t.bo")
+            v1o, v1_bwd = self.dense_res_ln(ctx2, Hb, v, p + ".biOutput.dense1", p + ".biOutput.LayerNorm1", "c.v.bo",
+                                            drop=self.drop(p + ".biOutput.dropout1", c.v_hidden_dropout_prob))
+        t1o, t1_bwd = self.dense_res_ln(ctx1, Hb, t, p + ".biOutput.dense2", p + ".biOutput.LayerNorm2", "c.t.bo",
+                                        drop=self.drop(p + ".biOutput.dropout2", c.hidden_dropout_prob))
 
         def bwd():
             if not (v1o.gw or t1o.gw):
@@ -432,10 +466,10 @@ class Plan:
             d2 = self.scratch("c.delta2", (B, nh, Nv), F32)
             self.attention(True, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1, dO=dctx1, lddo=Hb,
                            dQ=dqkv2[:, 0:Hb], lddq=L3, dK=dqkv1[:, Hb:2 * Hb], lddk=L3, dV=dqkv1[:, 2 * Hb:], lddv=L3, delta=d1,
-                           dbq=gb2[0:Hb], dbk=gb1[Hb:2 * Hb], dbv=gb1[2 * Hb:])
+                           dbq=gb2[0:Hb], dbk=gb1[Hb:2 * Hb], dbv=gb1[2 * Hb:], dropout=adrop1)
             self.attention(True, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dO=dctx2, lddo=Hb,
                            dQ=dqkv1[:, 0:Hb], lddq=L3, dK=dqkv2[:, Hb:2 * Hb], lddk=L3, dV=dqkv2[:, 2 * Hb:], lddv=L3, delta=d2,
-                           dbq=gb1[0:Hb], dbk=gb2[Hb:2 * Hb], dbv=gb2[2 * Hb:])
+                           dbq=gb1[0:Hb], dbk=gb2[Hb:2 * Hb], dbv=gb2[2 * Hb:], dropout=adrop2)
             self.linear_wgrad(dqkv1, L3, None, 0, v.b16, Hv, Mv, L3, Hv, p + ".biattention.qkv1")
             self.linear_wgrad(dqkv2, L3, None, 0, t.b16, Ht, Mt, L3, Ht, p + ".biattention.qkv2")
             self.dgrad_into(v, dqkv1, L3, ps.w16(p + ".biattention.qkv1.weight"), Mv, L3, Hv, extra32=dyv32)
@@ -445,21 +479,27 @@ class Plan:
         self.push_bwd(bwd)
         self._bwd_emitters.append(None)
         with self.on(1):
-            v2o = self.ffn(v1o, c.v_intermediate_size, p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", "c.v.ffn")
-        t2o = self.ffn(t1o, c.intermediate_size, p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", "c.t.ffn")
+            v2o = self.ffn(v1o, c.v_intermediate_size, p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", "c.v.ffn",
+                           drop=self.drop(p + ".v_output.dropout", c.v_hidden_dropout_prob))
+        t2o = self.ffn(t1o, c.intermediate_size, p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", "c.t.ffn",
+                       drop=self.drop(p + ".t_output.dropout", c.hidden_dropout_prob))
         return v2o, t2o
 
     def text_layer(self, x, i):
         p = f"bert.encoder.layer.{i}"
         c = self.cfg
-        h1 = self.self_attention_block(x, self.B, self.Nt, c.num_attention_heads, self.mask_t, p + ".attention", "t")
-        return self.ffn(h1, c.intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "t.ffn")
+        h1 = self.self_attention_block(x, self.B, self.Nt, c.num_attention_heads, self.mask_t, p + ".attention", "t",
+                                       p_attn=c.attention_probs_dropout_prob, p_hidden=c.hidden_dropout_prob)
+        return self.ffn(h1, c.intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "t.ffn",
+                        drop=self.drop(p + ".output.dropout", c.hidden_dropout_prob))
 
     def image_layer(self, x, i):
         p = f"bert.encoder.v_layer.{i}"
         c = self.cfg
-        h1 = self.self_attention_block(x, self.B, self.Nv, c.v_num_attention_heads, self.mask_v, p + ".attention", "v")
-        return self.ffn(h1, c.v_intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "v.ffn")
+        h1 = self.self_attention_block(x, self.B, self.Nv, c.v_num_attention_heads, self.mask_v, p + ".attention", "v",
+                                       p_attn=c.v_attention_probs_dropout_prob, p_hidden=c.v_hidden_dropout_prob)
+        return self.ffn(h1, c.v_intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "v.ffn",
+                        drop=self.drop(p + ".output.dropout", c.v_hidden_dropout_prob))
 
     # ------------------------------------------------------------------ embeddings
     def embeddings(self):
@@ -485,13 +525,15 @@ class Plan:
         self.emit(lib.vb_embed_text_fwd, self.in_ids.data_ptr(), self.in_tt.data_ptr(), self._ptr(self.in_task), ps.p(e + ".word_embeddings.weight").data_ptr(),
                   ps.p(e + ".position_embeddings.weight").data_ptr(), ps.p(e + ".token_type_embeddings.weight").data_ptr(),
                   ps.p(e + ".task_embeddings.weight").data_ptr() if self.has_task else None, xe.data_ptr(), B, self.Nt_in, Ht)
-        t32, t16, tmean, trstd = self.ln_fwd(xe, ps.p(e + ".LayerNorm.weight"), ps.p(e + ".LayerNorm.bias"), Mt, Ht)
+        tdrop = self.drop(e + ".dropout", c.hidden_dropout_prob)
+        t32, t16, tmean, trstd = self.ln_fwd(xe, ps.p(e + ".LayerNorm.weight"), ps.p(e + ".LayerNorm.bias"), Mt, Ht, out_drop=tdrop)
         t = Act(t32, t16, Mt, Ht)
 
         def bwd_text():
             if t.gw:
                 dxe = self.scratch("emb.dxe", (Mt, Ht), F32)
-                self.ln_bwd(t.g32, xe, ps.p(e + ".LayerNorm.weight"), tmean, trstd, dxe, None, Mt, Ht, ps.g(e + ".LayerNorm.weight"), ps.g(e + ".LayerNorm.bias"))
+                self.ln_bwd(t.g32, xe, ps.p(e + ".LayerNorm.weight"), tmean, trstd, dxe, None, Mt, Ht, ps.g(e + ".LayerNorm.weight"), ps.g(e + ".LayerNorm.bias"),
+                            out_drop=tdrop)
                 self.emit(lib.vb_embed_text_bwd, dxe.data_ptr(), self.in_ids.data_ptr(), self.in_tt.data_ptr(), self._ptr(self.in_task),
                           ps.g(e + ".word_embeddings.weight").data_ptr(), ps.g(e + ".position_embeddings.weight").data_ptr(),
                           ps.g(e + ".token_type_embeddings.weight").data_ptr(),
@@ -508,7 +550,8 @@ class Plan:
             yv = self.buf((Mv, Hv), F32)
             self.gemm(Mv, Hv, Fv, feat16, Fv, ps.w16(ve + ".image_embeddings.weight"), Fv, bias=ps.p(ve + ".image_embeddings.bias"),
                       residual=locp, ld_res=Hv, out_f32=yv, ld_of=Hv)
-            v32, v16, vmean, vrstd = self.ln_fwd(yv, ps.p(ve + ".LayerNorm.weight"), ps.p(ve + ".LayerNorm.bias"), Mv, Hv)
+            vdrop = self.drop(ve + ".dropout", c.hidden_dropout_prob)     # BertImageEmbeddings uses hidden_dropout_prob (vilbert.py:1419)
+            v32, v16, vmean, vrstd = self.ln_fwd(yv, ps.p(ve + ".LayerNorm.weight"), ps.p(ve + ".LayerNorm.bias"), Mv, Hv, out_drop=vdrop)
             v = Act(v32, v16, Mv, Hv)
 
             def bwd_image():
@@ -516,7 +559,7 @@ class Plan:
                     dyv32 = self.scratch("emb.dyv32", (Mv, Hv), F32)
                     dyv16 = self.scratch("emb.dyv16", (Mv, Hv), BF16)
                     self.ln_bwd(v.g32, yv, ps.p(ve + ".LayerNorm.weight"), vmean, vrstd, dyv32, dyv16, Mv, Hv, ps.g(ve + ".LayerNorm.weight"), ps.g(ve + ".LayerNorm.bias"),
-                                gbias=ps.g(ve + ".image_embeddings.bias"))
+                                gbias=ps.g(ve + ".image_embeddings.bias"), out_drop=vdrop)
                     self.linear_wgrad(dyv16, Hv, None, 0, feat16, Fv, Mv, Hv, Fv, ve + ".image_embeddings")
                     self.emit(lib.vb_loc_proj_bwd, dyv32.data_ptr(), self.in_loc.data_ptr(), ps.g(ve + ".image_location_embeddings.weight").data_ptr(),
                               ps.g(ve + ".image_location_embeddings.bias").data_ptr(), Mv, Hv)
@@ -601,14 +644,14 @@ class Plan:
             self.dgrad_into(x, dpre16, Hh, ps.w16(wdense + ".weight"), M, Hh, K)
         return hn, bwd
 
-    def small_head(self, name, x, wname, N_out, addend=None, x32=None, M=None, K=None):
+    def small_head(self, name, x, wname, N_out, addend=None, x32=None, M=None, K=None, in_drop=None):
         ps = self.ps
         M = x.M if M is None else M
         K = x.H if K is None else K
         xin = x.f32 if x32 is None else x32
         y = self.buf((M, N_out), F32)
         self.emit(self.lib.vb_small_linear_fwd, xin.data_ptr(), K, ps.p(wname + ".weight").data_ptr(), ps.p(wname + ".bias").data_ptr(),
-                  self._ptr(addend), y.data_ptr(), M, K, N_out)
+                  self._ptr(addend), y.data_ptr(), M, K, N_out, self._ref(in_drop))
         self.outputs[name] = y
 
         def bwd():
@@ -619,7 +662,7 @@ class Plan:
             acc = 1 if x.gw else 0
             x.gw = True
             self.emit(self.lib.vb_small_linear_bwd, dy.data_ptr(), xin.data_ptr(), K, ps.p(wname + ".weight").data_ptr(), g.data_ptr(), K, acc,
-                      ps.g(wname + ".weight").data_ptr(), ps.g(wname + ".bias").data_ptr(), M, K, N_out)
+                      ps.g(wname + ".weight").data_ptr(), ps.g(wname + ".bias").data_ptr(), M, K, N_out, self._ref(in_drop))
         self.push_bwd(bwd)
 
     def build_heads(self, seq_t, seq_v, pooled_t, pooled_v):
@@ -628,21 +671,33 @@ class Plan:
         ps, c, B, lib = self.ps, self.cfg, self.B, self.lib
         Hb, Ht, Hv, Nt, Nv = c.bi_hidden_size, c.hidden_size, c.v_hidden_size, self.Nt, self.Nv
         mul = 1 if c.fusion_method == "mul" else 0
-        f32, f16 = self.buf((B, Hb), F32), self.buf((B, Hb), BF16)
-        self.emit(lib.vb_fuse_pooled_fwd, pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), f32.data_ptr(), f16.data_ptr(), B * Hb, mul)
-        fused = Act(f32, f16, B, Hb)
+        def fuse(drop):
+            f32, f16 = self.buf((B, Hb), F32), self.buf((B, Hb), BF16)
+            self.emit(lib.vb_fuse_pooled_fwd, pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), f32.data_ptr(), f16.data_ptr(), B * Hb, mul, self._ref(drop))
+            act = Act(f32, f16, B, Hb)
 
-        def fused_bwd():
-            if not fused.gw:
-                return
-            for a in (pooled_t, pooled_v):
-                g = self.grad_of(a)
-                if not a.gw:
-                    self.emit(lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
-                    a.gw = True
-            self.emit(lib.vb_fuse_pooled_bwd, fused.g32.data_ptr(), pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), pooled_t.g32.data_ptr(),
-                      pooled_v.g32.data_ptr(), B * Hb, mul)
-        self.push_bwd(fused_bwd)
+            def fuse_bwd():
+                if not act.gw:
+                    return
+                for a in (pooled_t, pooled_v):
+                    g = self.grad_of(a)
+                    if not a.gw:
+                        self.emit(lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
+                        a.gw = True
+                self.emit(lib.vb_fuse_pooled_bwd, act.g32.data_ptr(), pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), pooled_t.g32.data_ptr(),
+                          pooled_v.g32.data_ptr(), B * Hb, mul, self._ref(drop))
+            self.push_bwd(fuse_bwd)
+            return act
+        # VILBertForVLTasks.dropout on the fused vector (vilbert.py:1677-1682); BertPreTrainingHeads has its own nn.Dropout(0.1)
+        # on its own fused vector (:1233-1241) — a different mask, needed only where the alignment score is an output
+        fused = fuse(self.drop("dropout.pooled", self.head_dropout_prob)) if self.heads == "vl" else None
+        need_cls_fused = self.heads == "pretraining" or (B % 2 == 1)
+        cls_drop = self.drop("cls.dropout", 0.1)
+        if need_cls_fused:
+            fused_cls = fuse(cls_drop) if (cls_drop is not None or fused is None) else fused
+        else:
+            fused_cls = None
+        f32, f16 = (fused.f32, fused.b16) if fused is not None else (None, None)
 
         # --- cls: masked-LM head (decoder tied to the word embeddings), image-region head, alignment head
         ht, ht_bwd = self.transform(seq_t, "cls.predictions.transform.dense", "cls.predictions.transform.LayerNorm", "lm.tr")
@@ -668,7 +723,7 @@ class Plan:
 
         if self.heads == "pretraining":
             # BertForMultiModalPreTraining returns the alignment score of self.cls (vilbert.py:1497)
-            self.small_head("seq_relationship_score", fused, "cls.bi_seq_relationship", 2)
+            self.small_head("seq_relationship_score", fused_cls, "cls.bi_seq_relationship", 2)
             return
         if B % 2 == 0:
             # vil_binary_prediction pairs consecutive samples: pooled.view(-1, 2*Hb) (:1686-1689)
@@ -692,7 +747,7 @@ class Plan:
             self.small_head("vil_binary_prediction", hb, "vil_binary_prediction.logit_fc.3", 2)
         else:
             # odd batch: the reference returns the [B, 2] alignment output of self.cls here (:1673, 1686)
-            self.small_head("vil_binary_prediction", fused, "cls.bi_seq_relationship", 2)
+            self.small_head("vil_binary_prediction", fused_cls, "cls.bi_seq_relationship", 2)
 
         for nm, n_out in (("vil_prediction", 3129), ("vil_prediction_gqa", 1533)):
             hh, hh_bwd = self.transform(fused, nm + ".logit_fc.0", nm + ".logit_fc.2", nm + ".tr")
@@ -700,8 +755,8 @@ class Plan:
             self.push_bwd(wide_bwd(head_bwd, hh, hh_bwd, 2 * Hb, n_out))
         self.small_head("vil_logit", fused, "vil_logit", 1)
         self.small_head("vil_tri_prediction", fused, "vil_tri_prediction", 3)
-        self.small_head("vision_logit", seq_v, "vision_logit", 1, addend=self.mask_v)
-        self.small_head("linguisic_logit", seq_t, "linguisic_logit", 1)
+        self.small_head("vision_logit", seq_v, "vision_logit", 1, addend=self.mask_v, in_drop=self.drop("dropout.seq_v", self.head_dropout_prob))
+        self.small_head("linguisic_logit", seq_t, "linguisic_logit", 1, in_drop=self.drop("dropout.seq_t", self.head_dropout_prob))
 
     # ------------------------------------------------------------------ whole model
     def _build(self):
@@ -828,6 +883,8 @@ class Plan:
         weight shadow from the fp32 master parameters (what an optimizer step invalidates) before the forward."""
         ps, lib = self.ps, self.lib
         self.prologue = []
+        if self.train:
+            self.prologue.append((lib.vb_step_counter_bump, (self.e.drop_step.data_ptr(),), 0))
         if zero_grad:
             self.prologue.append((lib.vb_memset_zero, (ps.grad.data_ptr(), ps.grad.numel() * 4), 0))
         if refresh_weights:
@@ -888,12 +945,18 @@ class Engine:
         self.ps = ParamStore(cfg, self.device, heads)
         self.two_streams = two_streams   # text / vision segments on two CUDA streams (parallel graph branches)
         self.plans = {}
+        self.head_dropout_prob = 0.1     # VILBertForVLTasks(dropout_prob=0.1), vilbert.py:1601
+        self.drop_step = torch.zeros(1, dtype=torch.int32, device=self.device)   # dropout step counter (uint32 on the device)
 
-    def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None):
-        key = (B, Nt, Nv, frozenset(grad_outputs), vqa_loss, heads)
+    def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False):
+        key = (B, Nt, Nv, frozenset(grad_outputs), vqa_loss, heads, bool(train))
         if key not in self.plans:
-            self.plans[key] = Plan(self, B, Nt, Nv, grad_outputs, vqa_loss, heads)
+            self.plans[key] = Plan(self, B, Nt, Nv, grad_outputs, vqa_loss, heads, train)
         return self.plans[key]
+
+    def bump_dropout_step(self):
+        """New dropout masks for the next forward (plans with a training prologue do this inside their graph)."""
+        L.check(L.lib().vb_step_counter_bump(self.drop_step.data_ptr(), torch.cuda.current_stream().cuda_stream), "vb_step_counter_bump")
 
     def refresh_weights(self):
         self.ps.refresh_shadow(torch.cuda.current_stream().cuda_stream)

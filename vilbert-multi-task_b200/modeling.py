@@ -73,12 +73,15 @@ class _EngineFn(torch.autograd.Function):
     def forward(ctx, model, names, anchor, inputs):
         B, Nt = inputs["input_txt"].shape
         Nv = inputs["input_imgs"].shape[1]
-        hint = model._grad_hint.get((B, Nt, Nv, names), ())
-        plan = model.engine.plan(B, Nt, Nv, grad_outputs=hint, heads=model._heads_for(names))
+        train = bool(model.training)
+        hint = model._grad_hint.get((B, Nt, Nv, names, train), ())
+        plan = model.engine.plan(B, Nt, Nv, grad_outputs=hint, heads=model._heads_for(names), train=train)
         model._sync_weights()
+        if train:
+            model.engine.bump_dropout_step()      # fresh nn.Dropout masks for this forward
         plan.load_inputs(**inputs)
         plan.run_forward()
-        ctx.model, ctx.names, ctx.inputs, ctx.plan, ctx.fwd_id = model, names, inputs, plan, plan.fwd_id
+        ctx.model, ctx.names, ctx.inputs, ctx.plan, ctx.fwd_id, ctx.train = model, names, inputs, plan, plan.fwd_id, train
         ctx.set_materialize_grads(False)
         return tuple(plan.outputs[n].clone() for n in names)
 
@@ -90,8 +93,8 @@ class _EngineFn(torch.autograd.Function):
             B, Nt = inputs["input_txt"].shape
             Nv = inputs["input_imgs"].shape[1]
             if frozenset(live) != plan.grad_outputs or plan.fwd_id != ctx.fwd_id:
-                model._grad_hint[(B, Nt, Nv, names)] = live
-                plan = model.engine.plan(B, Nt, Nv, grad_outputs=live, heads=model._heads_for(names))
+                model._grad_hint[(B, Nt, Nv, names, ctx.train)] = live
+                plan = model.engine.plan(B, Nt, Nv, grad_outputs=live, heads=model._heads_for(names), train=ctx.train)
                 plan.load_inputs(**inputs)     # different plan (or overwritten activations): recompute the forward
                 plan.run_forward()
             for n, g in zip(names, grads):
@@ -221,6 +224,7 @@ class VILBertForVLTasks(BertPreTrainedModel):
         super().__init__(config, device)
         self.num_labels = num_labels
         self.dropout_prob = dropout_prob
+        self.engine.head_dropout_prob = dropout_prob
         self.fusion_method = config.fusion_method
 
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
