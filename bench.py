@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--regions", type=int, default=100)
     ap.add_argument("--tokens", type=int, default=36)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce after the whole backward instead of overlapping it")
     ap.add_argument("--eval-mode", action="store_true", help="disable the dropout layers (reference eval mode); default is train mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8)
@@ -203,15 +204,26 @@ def main():
     plan.load_inputs(*(host[0][k] for k in keys))
     plan.vqa_target.copy_(tgt_host)
     torch.cuda.synchronize()
-    if not a.no_graph:
-        plan.capture()
-
     from vilbert_b200.ddp import FlatGradAllReducer
     reducer = FlatGradAllReducer(eng.ps.grad, n_buckets=8)   # NCCL all-reduce (AVG) of the flat fp32 gradient buffer
+    overlapped = world > 1 and not a.no_graph and not a.no_overlap
+    if overlapped:
+        # data parallel: the step is captured as 8 graphs; after each one the finished tail range of the flat gradient
+        # buffer is all-reduced on a communication stream while the remaining backward pieces run
+        plan.capture_segments(8)
+        comm_stream = torch.cuda.Stream()
+    elif not a.no_graph:
+        plan.capture()
 
     def step():
-        plan.run_step()
-        reducer.allreduce()
+        if overlapped:
+            works = plan.run_step_overlapped(reducer.allreduce_range, comm_stream)
+            for w in works:
+                if w is not None:
+                    w.wait()          # the main stream waits for the collectives (the next step zeroes the buffer)
+        else:
+            plan.run_step()
+            reducer.allreduce()
 
     def timed(fn, steps):
         if world > 1:
@@ -340,6 +352,8 @@ def main():
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not a.no_graph,
+                   "allreduce": ("none (1 GPU)" if world == 1 else ("NCCL AVG of the flat fp32 gradient buffer, 8 tail ranges overlapped with backward" if overlapped
+                                 else "NCCL AVG of the flat fp32 gradient buffer after backward (8 buckets)")),
                    "l2": "working set (activations + weights + grads ~6 GB/step) exceeds the 126 MB L2; no explicit flush",
                    "streams": "text and vision segments on two CUDA streams (parallel graph branches)" if eng.two_streams else "single stream",
                    "numerics": "bf16 tensor-core operands, fp32 accumulate/residual/LayerNorm/softmax",

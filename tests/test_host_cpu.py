@@ -91,3 +91,24 @@ def test_plan_builds_on_cpu(golden_dir, task_tokens, B):
     assert tuple(full.outputs["vil_binary_prediction"].shape) == ((B // 2, 2) if B % 2 == 0 else (B, 2))
     bert_only = eng.plan(B, 9, 11, heads="none")
     assert set(bert_only.outputs) == set(O.BERT_OUT_NAMES)
+
+
+def test_ddp_segments_partition_the_gradient_buffer(golden_dir):
+    """Overlapped data-parallel step: backward pieces end at stream barriers and release tail ranges of the flat gradient
+    buffer that (a) tile it exactly and (b) are never written by a later backward op."""
+    cfgj = json.load(open(os.path.join(golden_dir, "tiny_b4.json")))["config"]
+    eng = Engine(BertConfig.from_dict(cfgj), "cpu", _build_only=True)
+    plan = eng.plan(4, 9, 11, grad_outputs=O.HEAD_NAMES, train=True)
+    for k in (1, 3, 8):
+        segs = plan.ddp_segments(k)
+        assert segs[0][0] == 0 and segs[-1][1] == len(plan.bwd) and segs[0][3] == eng.ps.numel and segs[-1][2] == 0
+        for (lo, hi, glo, ghi), nxt in zip(segs, segs[1:] + [None]):
+            assert lo < hi and glo <= ghi
+            assert hi == 0 or plan.bwd[hi - 1][0] is None or hi == len(plan.bwd)      # cut right after a barrier
+            if nxt is not None:
+                assert nxt[0] == hi and nxt[3] == glo
+            for (off, n), touch in plan.grad_touch.items():                              # released ranges are final
+                if off >= glo and off < ghi:
+                    assert touch < hi, (off, touch, hi)
+    # execution-order layout: the tied word-embedding table (written first AND last in backward) sits at offset 0
+    assert eng.ps.entries["bert.embeddings.word_embeddings.weight"][0] == 0

@@ -45,13 +45,13 @@ def test_layernorm_fwd_bwd(M, H):
     lib, dev = L.lib(), "cuda"
     x = torch.randn(M, H, device=dev) * 2 + 0.5; g = torch.randn(H, device=dev); b = torch.randn(H, device=dev)
     y32 = torch.empty(M, H, device=dev); y16 = torch.empty(M, H, device=dev, dtype=BF); mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
-    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, y32.data_ptr(), y16.data_ptr(), H, mean.data_ptr(), rstd.data_ptr(), M, H, S()))
+    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, y32.data_ptr(), y16.data_ptr(), H, mean.data_ptr(), rstd.data_ptr(), M, H, None, S()))
     xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
     yr = F.layer_norm(xr, (H,), gr, br, 1e-12)
     dy = torch.randn(M, H, device=dev); yr.backward(dy)
     dx32 = torch.empty(M, H, device=dev); dx16 = torch.empty(M, H, device=dev, dtype=BF); dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
     L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx32.data_ptr(), dx16.data_ptr(), H, None, 0,
-                                 dg.data_ptr(), db.data_ptr(), None, M, H, S()))
+                                 dg.data_ptr(), db.data_ptr(), None, M, H, None, None, S()))
     torch.cuda.synchronize()
     assert rel(y32, yr) < 1e-5 and rel(y16, yr) < 5e-3
     assert rel(dx32, xr.grad) < 1e-5 and rel(dx16, xr.grad) < 5e-3 and rel(dg, gr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
@@ -66,7 +66,7 @@ def test_layernorm_bwd_fused_gelu_grad():
     gp = pre.float()          # the buffer holds gelu'(pre-activation) as saved by the forward GEMM epilogue
     dx16 = torch.empty(M, H, device=dev, dtype=BF); dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
     L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, dx16.data_ptr(), H, pre.data_ptr(), H,
-                                 dg.data_ptr(), db.data_ptr(), None, M, H, S()))
+                                 dg.data_ptr(), db.data_ptr(), None, M, H, None, None, S()))
     torch.cuda.synchronize()
     assert rel(dx16, xr.grad * gp) < 5e-3
 
@@ -121,16 +121,16 @@ def test_misc_rowops():
     for (M, K, N) in [(64, 1024, 1), (64, 1024, 3), (32, 2048, 2), (6400, 1024, 1)]:
         x = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev); add = torch.randn(M, device=dev)
         y = torch.empty(M, N, device=dev)
-        L.check(lib.vb_small_linear_fwd(x.data_ptr(), K, W.data_ptr(), b.data_ptr(), add.data_ptr(), y.data_ptr(), M, K, N, S()))
+        L.check(lib.vb_small_linear_fwd(x.data_ptr(), K, W.data_ptr(), b.data_ptr(), add.data_ptr(), y.data_ptr(), M, K, N, None, S()))
         dy = torch.randn(M, N, device=dev); dx = torch.ones(M, K, device=dev); dW = torch.zeros(N, K, device=dev); db = torch.zeros(N, device=dev)
-        L.check(lib.vb_small_linear_bwd(dy.data_ptr(), x.data_ptr(), K, W.data_ptr(), dx.data_ptr(), K, 1, dW.data_ptr(), db.data_ptr(), M, K, N, S()))
+        L.check(lib.vb_small_linear_bwd(dy.data_ptr(), x.data_ptr(), K, W.data_ptr(), dx.data_ptr(), K, 1, dW.data_ptr(), db.data_ptr(), M, K, N, None, S()))
         torch.cuda.synchronize()
         assert rel(y, x @ W.t() + b + add[:, None]) < 1e-5 and rel(dx, 1 + dy @ W) < 1e-5 and rel(dW, dy.t() @ x) < 1e-5 and rel(db, dy.sum(0)) < 1e-5
     # pooled fusion, relu backward
     a = torch.randn(64, 1024, device=dev); b = torch.randn(64, 1024, device=dev); o32 = torch.empty_like(a); o16 = torch.empty(64, 1024, device=dev, dtype=BF)
-    L.check(lib.vb_fuse_pooled_fwd(a.data_ptr(), b.data_ptr(), o32.data_ptr(), o16.data_ptr(), a.numel(), 1, S()))
+    L.check(lib.vb_fuse_pooled_fwd(a.data_ptr(), b.data_ptr(), o32.data_ptr(), o16.data_ptr(), a.numel(), 1, None, S()))
     d = torch.randn_like(a); da = torch.ones_like(a); db = torch.ones_like(a)
-    L.check(lib.vb_fuse_pooled_bwd(d.data_ptr(), a.data_ptr(), b.data_ptr(), da.data_ptr(), db.data_ptr(), a.numel(), 1, S())); torch.cuda.synchronize()
+    L.check(lib.vb_fuse_pooled_bwd(d.data_ptr(), a.data_ptr(), b.data_ptr(), da.data_ptr(), db.data_ptr(), a.numel(), 1, None, S())); torch.cuda.synchronize()
     assert torch.equal(o32, a * b) and rel(da, 1 + d * b) < 1e-6 and rel(db, 1 + d * a) < 1e-6
     # VQA BCE objective (task_utils.py:325-327)
     z = torch.randn(64, 3129, device=dev) * 3; t = (torch.rand(64, 3129, device=dev) < 0.001).float() * 0.6

@@ -87,13 +87,13 @@ print("=== layernorm")
 for (M, H) in [(37, 64), (50, 96), (2304, 768), (6400, 1024), (33, 2048), (128, 128)]:
     x = torch.randn(M, H, device=dev) * 2 + 0.5; g = torch.randn(H, device=dev); b = torch.randn(H, device=dev)
     y32 = torch.empty(M, H, device=dev); y16 = torch.empty(M, H, device=dev, dtype=BF); mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
-    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, y32.data_ptr(), y16.data_ptr(), H, mean.data_ptr(), rstd.data_ptr(), M, H, ST()))
+    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, y32.data_ptr(), y16.data_ptr(), H, mean.data_ptr(), rstd.data_ptr(), M, H, None, ST()))
     xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
     yr = F.layer_norm(xr, (H,), gr, br, 1e-12)
     dy = torch.randn(M, H, device=dev); yr.backward(dy)
     dx32 = torch.empty(M, H, device=dev); dx16 = torch.empty(M, H, device=dev, dtype=BF); dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
     L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx32.data_ptr(), dx16.data_ptr(), H, None, 0,
-                                 dg.data_ptr(), db.data_ptr(), None, M, H, ST()))
+                                 dg.data_ptr(), db.data_ptr(), None, M, H, None, None, ST()))
     torch.cuda.synchronize()
     report(f"layernorm M{M} H{H}", dict(y=rel(y32, yr), y16=max(rel(y16, yr) - 4e-3, 0), dx=rel(dx32, xr.grad), dg=rel(dg, gr.grad), db=rel(db, br.grad)), 1e-4)
 # LN bwd with gelu' fusion
@@ -103,7 +103,7 @@ mean = x.mean(-1); rstd = 1 / torch.sqrt(x.var(-1, unbiased=False) + 1e-12); dy 
 xr = x.clone().requires_grad_(True); F.layer_norm(xr, (H,), g, b, 1e-12).backward(dy)
 gp = pre.float()
 dx16 = torch.empty(M, H, device=dev, dtype=BF); dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
-L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, dx16.data_ptr(), H, pre.data_ptr(), H, dg.data_ptr(), db.data_ptr(), None, M, H, ST()))
+L.check(lib.vb_layernorm_bwd(dy.data_ptr(), H, x.data_ptr(), H, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, dx16.data_ptr(), H, pre.data_ptr(), H, dg.data_ptr(), db.data_ptr(), None, M, H, None, None, ST()))
 torch.cuda.synchronize()
 report("layernorm bwd + gelu'", dict(dx16=max(rel(dx16, xr.grad * gp) - 4e-3, 0)), 1e-3)
 
@@ -152,15 +152,15 @@ for dt_ in (torch.float32, BF):
 for (M, K, N) in [(64, 1024, 1), (64, 1024, 3), (32, 2048, 2), (6400, 1024, 1)]:
     x = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev); add = torch.randn(M, device=dev)
     y = torch.empty(M, N, device=dev)
-    L.check(lib.vb_small_linear_fwd(x.data_ptr(), K, W.data_ptr(), b.data_ptr(), add.data_ptr(), y.data_ptr(), M, K, N, ST()))
+    L.check(lib.vb_small_linear_fwd(x.data_ptr(), K, W.data_ptr(), b.data_ptr(), add.data_ptr(), y.data_ptr(), M, K, N, None, ST()))
     dy = torch.randn(M, N, device=dev); dx = torch.ones(M, K, device=dev); dW = torch.zeros(N, K, device=dev); db = torch.zeros(N, device=dev)
-    L.check(lib.vb_small_linear_bwd(dy.data_ptr(), x.data_ptr(), K, W.data_ptr(), dx.data_ptr(), K, 1, dW.data_ptr(), db.data_ptr(), M, K, N, ST())); torch.cuda.synchronize()
+    L.check(lib.vb_small_linear_bwd(dy.data_ptr(), x.data_ptr(), K, W.data_ptr(), dx.data_ptr(), K, 1, dW.data_ptr(), db.data_ptr(), M, K, N, None, ST())); torch.cuda.synchronize()
     report(f"small_linear M{M} K{K} N{N}", dict(y=rel(y, x @ W.t() + b + add[:, None]), dx=rel(dx, 1 + dy @ W), dW=rel(dW, dy.t() @ x), db=rel(db, dy.sum(0))), 1e-5)
 # pooled fuse / relu / axpy / bce / mask
 a = torch.randn(64, 1024, device=dev); b = torch.randn(64, 1024, device=dev); o32 = torch.empty_like(a); o16 = torch.empty(64, 1024, device=dev, dtype=BF)
-L.check(lib.vb_fuse_pooled_fwd(a.data_ptr(), b.data_ptr(), o32.data_ptr(), o16.data_ptr(), a.numel(), 1, ST()))
+L.check(lib.vb_fuse_pooled_fwd(a.data_ptr(), b.data_ptr(), o32.data_ptr(), o16.data_ptr(), a.numel(), 1, None, ST()))
 d = torch.randn_like(a); da = torch.ones_like(a); db = torch.ones_like(a)
-L.check(lib.vb_fuse_pooled_bwd(d.data_ptr(), a.data_ptr(), b.data_ptr(), da.data_ptr(), db.data_ptr(), a.numel(), 1, ST())); torch.cuda.synchronize()
+L.check(lib.vb_fuse_pooled_bwd(d.data_ptr(), a.data_ptr(), b.data_ptr(), da.data_ptr(), db.data_ptr(), a.numel(), 1, None, ST())); torch.cuda.synchronize()
 report("fuse_pooled", dict(o=rel(o32, a * b), da=rel(da, 1 + d * b), db=rel(db, 1 + d * a)), 1e-6)
 y = torch.randn(64, 1024, device=dev); dy = torch.randn_like(y); dx16 = torch.empty(64, 1024, device=dev, dtype=BF); dx32 = torch.empty_like(y)
 L.check(lib.vb_relu_bwd(dy.data_ptr(), y.data_ptr(), dx16.data_ptr(), dx32.data_ptr(), y.numel(), ST())); torch.cuda.synchronize()

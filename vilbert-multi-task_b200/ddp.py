@@ -31,6 +31,18 @@ class FlatGradAllReducer:
                 dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group)
                 b.div_(self.world)
 
+    def allreduce_range(self, lo, hi, async_op=True):
+        """Averages flat[lo:hi] over all ranks; returns the async work handle (or None for world 1). Used by the
+        overlapped step: backward finishes the buffer from its end, ranges are reduced while backward continues."""
+        if self.world == 1 or hi <= lo:
+            return None
+        t = self.flat[lo:hi]
+        if self.use_avg:
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=False)
+        t.div_(self.world)
+        return w
+
     def broadcast_params(self, flat_params, src=0):
         """Rank-`src` parameters to every rank (what apex DDP does at wrap time)."""
         if self.world > 1:

@@ -66,14 +66,17 @@ class ParamStore:
         lin("bert.v_embeddings.image_embeddings", Hv, c.v_feature_size)
         lin("bert.v_embeddings.image_location_embeddings", Hv, 5)
         ln("bert.v_embeddings.LayerNorm", Hv)
-        for kind, n, H, I in (("layer", c.num_hidden_layers, Ht, It), ("v_layer", c.v_num_hidden_layers, Hv, Iv)):
-            for i in range(n):
-                p = f"bert.encoder.{kind}.{i}"
-                self._qkv(f"{p}.attention.self", ("query", "key", "value"), H, H)
-                lin(f"{p}.attention.output.dense", H, H); ln(f"{p}.attention.output.LayerNorm", H)
-                lin(f"{p}.intermediate.dense", I, H)
-                lin(f"{p}.output.dense", H, I); ln(f"{p}.output.LayerNorm", H)
-        for i in range(len(c.v_biattention_id)):
+        # Encoder parameters are laid out in EXECUTION order (the interleaving schedule of BertEncoder.forward,
+        # vilbert.py:960-1096): backward then finishes the flat gradient buffer from its end towards its start, so the
+        # data-parallel all-reduce can start on finished tail ranges while earlier layers are still in backward.
+        def block(kind, i, H, I):
+            p = f"bert.encoder.{kind}.{i}"
+            self._qkv(f"{p}.attention.self", ("query", "key", "value"), H, H)
+            lin(f"{p}.attention.output.dense", H, H); ln(f"{p}.attention.output.LayerNorm", H)
+            lin(f"{p}.intermediate.dense", I, H)
+            lin(f"{p}.output.dense", H, I); ln(f"{p}.output.LayerNorm", H)
+
+        def conn(i):
             p = f"bert.encoder.c_layer.{i}"
             self._qkv(f"{p}.biattention", ("query1", "key1", "value1"), Hb, Hv, fused="qkv1")
             self._qkv(f"{p}.biattention", ("query2", "key2", "value2"), Hb, Ht, fused="qkv2")
@@ -81,6 +84,19 @@ class ParamStore:
             lin(f"{p}.biOutput.dense2", Ht, Hb); ln(f"{p}.biOutput.LayerNorm2", Ht); lin(f"{p}.biOutput.q_dense2", Ht, Hb)
             lin(f"{p}.v_intermediate.dense", Iv, Hv); lin(f"{p}.v_output.dense", Hv, Iv); ln(f"{p}.v_output.LayerNorm", Hv)
             lin(f"{p}.t_intermediate.dense", It, Ht); lin(f"{p}.t_output.dense", Ht, It); ln(f"{p}.t_output.LayerNorm", Ht)
+
+        t_start = v_start = 0
+        for count, (v_end, t_end) in enumerate(zip(c.v_biattention_id, c.t_biattention_id)):
+            for i in range(t_start, t_end):
+                block("layer", i, Ht, It)
+            for i in range(v_start, v_end):
+                block("v_layer", i, Hv, Iv)
+            conn(count)
+            v_start, t_start = v_end, t_end
+        for i in range(v_start, c.v_num_hidden_layers):
+            block("v_layer", i, Hv, Iv)
+        for i in range(t_start, c.num_hidden_layers):
+            block("layer", i, Ht, It)
         lin("bert.t_pooler.dense", Hb, Ht); lin("bert.v_pooler.dense", Hb, Hv)
         if heads != "none":
             add("cls.predictions.bias", (c.vocab_size,))
@@ -145,6 +161,27 @@ class ParamStore:
 
 
 # ------------------------------------------------------------------------------------------ plan
+class _TrackedParams:
+    """ParamStore proxy used while a plan is emitted: remembers, for every gradient range handed out during the
+    backward emission, the index of the backward op about to write it (the last such index per range is kept)."""
+
+    def __init__(self, ps, plan):
+        self._ps, self._plan = ps, plan
+
+    def __getattr__(self, name):
+        return getattr(self._ps, name)
+
+    def g(self, name):
+        ps, plan = self._ps, self._plan
+        off, shape = ps.entries[name] if name in ps.entries else ps.fused[name]
+        n = 1
+        for d in shape:
+            n *= d
+        if plan.cur is plan.bwd:
+            plan.grad_touch[(off, n)] = len(plan.bwd)
+        return ps.g(name)
+
+
 class Act:
     """A residual-stream activation: fp32 values, bf16 operand copy, fp32 gradient (lazily allocated)."""
     __slots__ = ("f32", "b16", "g32", "gw", "M", "H")
@@ -165,7 +202,9 @@ class Plan:
     (task_utils.py:325-327) and its gradient after the forward."""
 
     def __init__(self, engine, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False):
-        self.e, self.ps, self.cfg = engine, engine.ps, engine.cfg
+        self.e, self.cfg = engine, engine.cfg
+        self.grad_touch = {}           # (flat offset, numel) -> index of the last backward op writing that gradient range
+        self.ps = _TrackedParams(engine.ps, self)
         self.lib = L.lib()
         self.dev = engine.device
         self.B, self.Nt_in, self.Nv = B, Nt, Nv
@@ -904,6 +943,76 @@ class Plan:
             self._run(self.prologue)
             self._run(self.fwd)
             self._run(self.bwd)
+
+    def ddp_segments(self, n_segments=4):
+        """Cuts the backward op list at stream barriers into `n_segments` pieces and returns
+        [(bwd_op_lo, bwd_op_hi, grad_lo, grad_hi)]: after piece i has run, the flat gradient range [grad_lo, grad_hi) is
+        final (no later op writes it) and may be all-reduced while the remaining pieces execute. The ranges tile the
+        whole flat buffer from its end (heads, last layers) to its start (embeddings)."""
+        n_ops = len(self.bwd)
+        barriers = [i + 1 for i, op in enumerate(self.bwd) if op[0] is None and 0 < i + 1 < n_ops]
+        cuts = []
+        for k in range(1, n_segments):
+            want = n_ops * k // n_segments
+            cand = [b for b in barriers if b not in cuts]
+            if not cand:
+                break
+            cuts.append(min(cand, key=lambda b: abs(b - want)))
+        cuts = sorted(set(cuts)) + [n_ops]
+        ranges = sorted(self.grad_touch.items())          # by flat offset
+        numel = self.e.ps.numel
+        segs, lo_op, hi_grad = [], 0, numel
+        for cut in cuts:
+            ready_lo = 0 if cut == n_ops else hi_grad
+            if cut != n_ops:
+                for (off, n), touch in reversed(ranges):
+                    if off >= hi_grad:
+                        continue
+                    if touch >= cut:
+                        break
+                    ready_lo = off
+            segs.append((lo_op, cut, ready_lo, hi_grad))
+            lo_op, hi_grad = cut, ready_lo
+        return segs
+
+    def capture_segments(self, n_segments=4):
+        """Captures the step as `n_segments` CUDA graphs (graph 0 = prologue + forward + first backward piece) for the
+        data-parallel step: see run_step_overlapped."""
+        self.segments = self.ddp_segments(n_segments)
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._run(self.prologue); self._run(self.fwd); self._run(self.bwd)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        barrier = [(None, (), 0)]
+        self.segment_graphs = []
+        for i, (lo, hi, _, _) in enumerate(self.segments):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if i == 0:
+                    self._run(self.prologue); self._run(self.fwd)
+                self._run(barrier + self.bwd[lo:hi] + barrier)
+            self.segment_graphs.append(g)
+        torch.cuda.synchronize()
+
+    def run_step_overlapped(self, allreduce_range, comm_stream):
+        """Replays the segment graphs; after each one the finished tail range of the flat gradient buffer is handed to
+        `allreduce_range(lo, hi)` (issued under `comm_stream`, which first waits for that segment) so the collective
+        overlaps the rest of the backward. Returns the list of whatever allreduce_range returned (async work handles)."""
+        self.fwd_id += 1
+        main = torch.cuda.current_stream()
+        works = []
+        for g, (_, _, lo, hi) in zip(self.segment_graphs, self.segments):
+            g.replay()
+            if hi > lo:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ev)
+                    works.append(allreduce_range(lo, hi))
+        return works
 
     def capture(self, separate=False):
         """Captures the plan into CUDA graphs (one for the whole step, or one per pass)."""
