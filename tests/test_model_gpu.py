@@ -160,6 +160,8 @@ def test_module_surface_autograd_and_state_dict(golden_dir):
     P = O.synth_params(cfg, seed=0, device="cuda")
     missing, unexpected = model.load_state_dict(P, strict=True)
     assert not missing and not unexpected
+    assert model.training           # a freshly constructed module is in train mode, like the reference's
+    model.eval()                    # parity protocol: eval mode (from_pretrained also returns eval, vilbert/utils.py:1022)
     assert model.state_dict()["cls.predictions.decoder.weight"].data_ptr() == model.state_dict()["bert.embeddings.word_embeddings.weight"].data_ptr()
     inp = O.synth_inputs(cfg, 4, 11, 9, seed=1234, device="cuda")
     tgt = O.synth_vqa_target(4, 3129, device="cuda")
@@ -182,6 +184,11 @@ def test_module_surface_autograd_and_state_dict(golden_dir):
     for k in ("bert.encoder.layer.0.attention.self.query.weight", "bert.v_embeddings.image_embeddings.weight", "vil_prediction.logit_fc.3.weight",
               "bert.encoder.c_layer.1.biOutput.dense2.weight", "bert.embeddings.word_embeddings.weight", "vil_logit.weight"):
         assert rel(named[k].grad, Pg[k].grad) < 3e-2, k
+    model.train()                   # dropout on: outputs change from call to call (new masks per forward)
+    o1 = model(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])[0]
+    o2 = model(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])[0]
+    assert not torch.equal(o1, o2) and torch.isfinite(o1).all()
+    model.eval()
     bert_out = model.bert(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
     assert len(bert_out) == 5 and tuple(bert_out[0].shape) == (4, 9, cfg["hidden_size"])
 
