@@ -28,24 +28,18 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle span of bf16
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
 constexpr int GEMM_THREADS = 192;
-// Epilogue staging tile per warp: 32 rows x 32 fp32, dense 128-byte rows whose 16-byte chunks are XOR-swizzled with the
-// row index (chunk ^ (row & 7)): thread-per-row 128-bit stores and row-wise 128-bit loads are both bank-conflict free
-// without padding (4 KB per warp, which lets two 128-wide CTAs share one SM).
-constexpr int STAGING_BYTES_PER_WARP = 32 * 32 * 4;
-__device__ __forceinline__ int stg_off(int row, int col) { return row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); }
+constexpr int STAGE_PAD = 36;    // fp32 staging row stride: 144 B rows keep 128-bit accesses aligned and conflict-free
+constexpr int STAGING_BYTES_PER_WARP = 32 * STAGE_PAD * 4;
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // BN = 128: 3 stages (96 KB) + staging -> 112.25 KB, two CTAs (2 x 256 TMEM columns) per SM: the epilogue / prologue
-  // of one CTA overlaps the main loop of its neighbour, and with PDL the next kernel's CTAs move in while this kernel
-  // drains. BN = 256: 4 stages (192 KB), one CTA per SM.
-  static constexpr int NUM_STAGES = (BN == 256) ? 4 : 3;
-  static constexpr int CTAS_PER_SM = (BN == 256) ? 1 : 2;
+  static constexpr int NUM_STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 4 * STAGING_BYTES_PER_WARP + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES =
+      1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + 4 * STAGING_BYTES_PER_WARP + 256 /*barriers*/;
 };
 
 struct GemmKernelParams {
@@ -106,7 +100,7 @@ __device__ __noinline__ void epi_generic_chunk(const GemmKernelParams& p, const 
     if (m >= p.M) break;
 #pragma unroll 1
     for (int j = 0; j < nv; ++j) {
-      float v = stg[stg_off(row, cc + j)] * p.alpha;
+      float v = stg[row * STAGE_PAD + cc + j] * p.alpha;
       if (p.bias) v += p.bias[n + j];
       if (p.act == VB_ACT_GELU) {
         float gg, dg;
@@ -143,7 +137,7 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
   for (int ps = 0; ps < 8; ++ps) {
     const int row = ps * 4 + rr;
     const long long m = m_base + row;
-    const float4 a4 = *reinterpret_cast<const float4*>(stg + stg_off(row, cc));
+    const float4 a4 = *reinterpret_cast<const float4*>(stg + row * STAGE_PAD + cc);
     float v0 = fmaf(a4.x, p.alpha, b4.x), v1 = fmaf(a4.y, p.alpha, b4.y), v2 = fmaf(a4.z, p.alpha, b4.z), v3 = fmaf(a4.w, p.alpha, b4.w);
     if (EPI == EPI_GELU) {
       float d0, d1, d2, d3;
@@ -190,16 +184,15 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, GemmCfg<BN>::CTAS_PER_SM)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int NUM_STAGES = Cfg::NUM_STAGES;
 
-  // SWIZZLE_128B tiles need 1024-byte alignment: the kernel has no static shared memory, so the dynamic window starts
-  // at the CTA's (1024-aligned) shared base; checked once below.
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_tiles = smem;
   float* staging = reinterpret_cast<float*>(smem + NUM_STAGES * Cfg::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * Cfg::STAGE_BYTES + 4 * STAGING_BYTES_PER_WARP);
@@ -327,7 +320,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // stores into a padded smem tile, (4) row-wise pass where a lane owns 4 consecutive columns of rows {rr, rr+4, ..}:
     // 128-bit smem reads, fused math, 128-bit coalesced global stores.
     const int lane_grp = warp_idx & 3;  // TMEM lanes [32*lane_grp, +32) are visible to this warp
-    float* stg = staging + (warp_idx - 2) * (32 * 32);
+    float* stg = staging + (warp_idx - 2) * (32 * STAGE_PAD);
     const int rr = lane >> 3;           // row within a 4-row group of the coalesced pass
     const int cc = (lane & 7) * 4;      // first of 4 columns handled by this lane
     int it = 0;
@@ -385,7 +378,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + stg_off(lane, j * 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            *reinterpret_cast<uint4*>(stg + lane * STAGE_PAD + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
         if (c == NC - 1) {
           // every TMEM read of this accumulator stage has landed in registers
@@ -463,8 +456,6 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   cudaError_t e = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmCfg<BN>::SMEM_BYTES, stream, ta, tb, p);
@@ -593,8 +584,7 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   if (st) return st;
 
   const long long total_tiles = (long long)num_m * num_n * split_k;
-  const long long slots = (long long)max_ctas * (bn == 128 ? 2 : 1);   // resident CTAs (two 128-wide CTAs per SM)
-  const int grid = (int)(total_tiles < slots ? total_tiles : slots);
+  const int grid = (int)(total_tiles < max_ctas ? total_tiles : max_ctas);
 
   // pick the epilogue specialisation; anything unusual runs the generic one
   int epi = EPI_GENERIC;
