@@ -918,21 +918,35 @@ class Plan:
             self._run(self.bwd)
 
     def enable_training_prologue(self, zero_grad=True, refresh_weights=True):
-        """Makes run_step a complete training-step body: zero the flat gradient buffer and refresh the bf16
-        weight shadow from the fp32 master parameters (what an optimizer step invalidates) before the forward."""
+        """Makes run_step a complete training-step body: bump the dropout step counter (train mode), zero the flat
+        gradient buffer and refresh the bf16 weight shadow from the fp32 master parameters (what an optimizer step
+        invalidates) before the forward. With two streams only the weights the first text layers need (everything laid out
+        before the first connection layer) are cast on the main stream; the rest of the cast and the gradient memset run on
+        the vision stream underneath those text layers (the vision stream's own first consumer, the image embedding, is
+        queued behind them and is not needed before the first connection layer)."""
         ps, lib = self.ps, self.lib
         self.prologue = []
         if self.train:
             self.prologue.append((lib.vb_step_counter_bump, (self.e.drop_step.data_ptr(),), 0))
+        n = ps.numel
+        first_c = [off for name, (off, _) in ps.entries.items() if ".c_layer." in name]
+        split = min(first_c) if (self.two_streams and first_c) else n
+        if refresh_weights and split > 0:
+            self.prologue.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr(), ps.shadow.data_ptr(), split), 0))
+        tail = []
         if zero_grad:
-            self.prologue.append((lib.vb_memset_zero, (ps.grad.data_ptr(), ps.grad.numel() * 4), 0))
-        if refresh_weights:
-            self.prologue.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr(), ps.shadow.data_ptr(), ps.numel), 0))
+            tail.append((lib.vb_memset_zero, (ps.grad.data_ptr(), ps.grad.numel() * 4), 1 if self.two_streams else 0))
+        if refresh_weights and split < n:
+            tail.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr() + 4 * split, ps.shadow.data_ptr() + 2 * split, n - split), 1))
+        if self.two_streams:
+            self.prologue += [(None, (), 0)] + tail       # barrier: the vision stream starts after the main-stream part
+        else:
+            self.prologue += tail
         self.graph_step = None
 
     @property
     def n_launches_step(self):
-        return len(self.prologue) + self.n_kernels_fwd + self.n_kernels_bwd
+        return sum(1 for op in self.prologue if op[0] is not None) + self.n_kernels_fwd + self.n_kernels_bwd
 
     def run_step(self):
         """(prologue) + forward + (loss) + backward; gradients accumulate into ParamStore.grad."""
