@@ -221,7 +221,10 @@ class Plan:
         self.cur = self.fwd
         self.sid = 0             # stream the next emitted op goes to: 0 = text/main stream, 1 = vision stream
         self.two_streams = engine.two_streams
-        self._aux = None
+        self.wgrad_streams = engine.wgrad_streams and engine.two_streams   # weight-gradient GEMMs off the critical chain
+        self._streams = None
+        self._n_events = 0
+        self._scratch_epoch = 0
         self._keep = []          # ctypes structs / tensors referenced by raw pointer
         self._scratch = {}
         self._bwd_emitters = []
@@ -236,7 +239,9 @@ class Plan:
         return t
 
     def scratch(self, tag, shape, dtype):
-        key = (tag, tuple(shape), dtype)
+        # with asynchronous weight-gradient streams a temporary may still be read after its layer's backward has moved on:
+        # temporaries are then unique per backward emitter instead of being recycled by the next layer
+        key = (tag, tuple(shape), dtype, self._scratch_epoch if self.wgrad_streams else 0)
         if key not in self._scratch:
             self._scratch[key] = self.buf(shape, dtype)
         return self._scratch[key]
@@ -352,11 +357,24 @@ class Plan:
         return act.g32
 
     # dW, db of y = x W^T + b given dy (bf16 operand copy + a source for the bias column sums)
-    def linear_wgrad(self, dy16, ld_dy, dy_bias, ld_dyb, x16, ld_x, M, N_out, K_in, wname):
+    def linear_wgrad(self, dy16, ld_dy, dy_bias, ld_dyb, x16, ld_x, M, N_out, K_in, wname, gw=None):
+        """dW += dy^T x (split-K, atomics). Nothing on the critical chain depends on it, so with wgrad_streams it is issued on
+        a side stream (2 = text chain, 3 = vision chain) right after an event marking that dy is ready; the side streams are
+        joined at the data-parallel segment cuts and at the end of the backward pass."""
         if dy_bias is not None:
             self.colsum(dy_bias, ld_dyb, self.ps.g(wname + ".bias"), M, N_out)
-        self.gemm(N_out, K_in, M, dy16, ld_dy, x16, ld_x, a_mn=1, b_mn=1, out_f32=self.ps.g(wname + ".weight"), ld_of=K_in, atomic=1,
-                  split_k=0)
+        out = gw if gw is not None else self.ps.g(wname + ".weight")
+        if not self.wgrad_streams:
+            self.gemm(N_out, K_in, M, dy16, ld_dy, x16, ld_x, a_mn=1, b_mn=1, out_f32=out, ld_of=K_in, atomic=1, split_k=0)
+            return
+        ev = self._n_events
+        self._n_events += 1
+        chain = self.sid
+        self.cur.append((None, ("rec", ev), chain))
+        self.sid = 2 + chain
+        self.cur.append((None, ("wait", ev), self.sid))
+        self.gemm(N_out, K_in, M, dy16, ld_dy, x16, ld_x, a_mn=1, b_mn=1, out_f32=out, ld_of=K_in, atomic=1, split_k=0)
+        self.sid = chain
 
     # act.g32 (+)= dy16 @ W (+ extra32)
     def dgrad_into(self, act, dy16, ld_dy, W16, M, N_out, K_in, extra32=None):
@@ -656,8 +674,7 @@ class Plan:
                 dl16 = self.scratch("head.dl16." + name, (M, ldp), BF16)
                 self.emit(self.lib.vb_cast2d_f32_to_bf16, dl32.data_ptr(), N_out, dl16.data_ptr(), ldp, M, N_out, 1.0)
             self.colsum(dl32, N_out, ps.g(bias_name), M, N_out)
-            gW = gw if gw is not None else ps.g(wname + ".weight")
-            self.gemm(N_out, K_in, M, dl16, ldp, x16, ld_x, a_mn=1, b_mn=1, out_f32=gW, ld_of=K_in, atomic=1, split_k=0)
+            self.linear_wgrad(dl16, ldp, None, 0, x16, ld_x, M, N_out, K_in, wname, gw=gw)
             return dl16, ldp, W16
         return bwd
 
@@ -858,9 +875,10 @@ class Plan:
                 self.sync_streams()
             else:
                 self.sid, emitter = entry
+                self._scratch_epoch += 1
                 emitter()
         self.sid = 0
-        self.sync_streams()
+        self.cur.append((None, ("all",), 0))     # join every stream (incl. the weight-gradient side streams)
         self.n_kernels_bwd = sum(1 for op in self.bwd if op[0] is not None)
         self.cur = self.fwd
 
@@ -889,18 +907,35 @@ class Plan:
             self.in_task.copy_(task_ids.reshape(-1), non_blocking=non_blocking)
 
     def _run(self, ops):
+        """Issues the ops on their streams. Markers: (None, ()) = barrier between the text and vision streams;
+        (None, ("all",)) = join of every stream; (None, ("rec"|"wait", id)) = event edge to a weight-gradient side stream."""
         main = torch.cuda.current_stream()
-        if self.two_streams and self._aux is None:
-            self._aux = torch.cuda.Stream(device=self.dev)
-        aux = self._aux if self.two_streams else main
-        handles = (main.cuda_stream, aux.cuda_stream)
+        if self._streams is None:
+            n = 4 if self.wgrad_streams else (2 if self.two_streams else 1)
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(n - 1)]
+        streams = [main] + self._streams
+        handles = [st.cuda_stream for st in streams]
         check = L.check
+        events = {}
         for fn, args, sid in ops:
-            if fn is None:      # barrier between the two streams
-                e1 = torch.cuda.Event(); e1.record(main); aux.wait_event(e1)
-                e2 = torch.cuda.Event(); e2.record(aux); main.wait_event(e2)
+            if fn is None:
+                if not args:                      # text <-> vision barrier
+                    if len(streams) > 1:
+                        aux = streams[1]
+                        e1 = torch.cuda.Event(); e1.record(main); aux.wait_event(e1)
+                        e2 = torch.cuda.Event(); e2.record(aux); main.wait_event(e2)
+                elif args[0] == "all":
+                    for st in streams[1:]:
+                        e = torch.cuda.Event(); e.record(st); main.wait_event(e)
+                    e = torch.cuda.Event(); e.record(main)
+                    for st in streams[1:]:
+                        st.wait_event(e)
+                elif args[0] == "rec":
+                    e = torch.cuda.Event(); e.record(streams[sid]); events[args[1]] = e
+                elif args[0] == "wait":
+                    streams[sid].wait_event(events[args[1]])
                 continue
-            st = fn(*args, handles[sid])
+            st = fn(*args, handles[sid] if sid < len(handles) else handles[0])
             if st:
                 check(st, fn.__name__)
 
@@ -964,7 +999,7 @@ class Plan:
         final (no later op writes it) and may be all-reduced while the remaining pieces execute. The ranges tile the
         whole flat buffer from its end (heads, last layers) to its start (embeddings)."""
         n_ops = len(self.bwd)
-        barriers = [i + 1 for i, op in enumerate(self.bwd) if op[0] is None and 0 < i + 1 < n_ops]
+        barriers = [i + 1 for i, op in enumerate(self.bwd) if op[0] is None and not op[1] and 0 < i + 1 < n_ops]
         cuts = []
         for k in range(1, n_segments):
             want = n_ops * k // n_segments
@@ -1000,7 +1035,7 @@ class Plan:
             self._run(self.prologue); self._run(self.fwd); self._run(self.bwd)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        barrier = [(None, (), 0)]
+        barrier = [(None, ("all",), 0)]
         self.segment_graphs = []
         for i, (lo, hi, _, _) in enumerate(self.segments):
             g = torch.cuda.CUDAGraph()
@@ -1057,7 +1092,7 @@ class Plan:
 class Engine:
     """Owns the parameters and the per-shape plans."""
 
-    def __init__(self, cfg, device="cuda", heads="vl", _build_only=False, two_streams=True):
+    def __init__(self, cfg, device="cuda", heads="vl", _build_only=False, two_streams=True, wgrad_streams=True):
         """_build_only=True (tests) allows a CPU device: plans can be constructed and inspected but never run."""
         cfg.check_supported()
         self.cfg = cfg
@@ -1067,6 +1102,7 @@ class Engine:
         L.lib()  # fail loudly now if the extension is missing
         self.ps = ParamStore(cfg, self.device, heads)
         self.two_streams = two_streams   # text / vision segments on two CUDA streams (parallel graph branches)
+        self.wgrad_streams = wgrad_streams   # weight-gradient GEMMs on two more side streams (off the backward critical chain)
         self.plans = {}
         self.head_dropout_prob = 0.1     # VILBertForVLTasks(dropout_prob=0.1), vilbert.py:1601
         self.drop_step = torch.zeros(1, dtype=torch.int32, device=self.device)   # dropout step counter (uint32 on the device)
