@@ -59,16 +59,19 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe). The sampler
+    is started before the warm-up (nvidia-smi needs a moment to come up); only samples whose timestamp falls inside the
+    marked window are used (all samples if none does)."""
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,21 +80,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        rows = [r for (ts, r) in self.rows if self.t0 is not None and self.t0 - 0.05 <= ts <= (self.t1 or ts) + 0.1]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for (_, r) in self.rows], "whole run (no sample fell inside the timed region)"
+        num = lambda x: x.replace(".", "", 1).isdigit()
+        sm = sorted(int(float(r[1])) for r in rows if len(r) > 1 and num(r[1]))
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 4 + i and r[4 + i].lower().startswith("active") for r in rows)]
+        mx = [int(float(r[2])) for r in rows if len(r) > 2 and num(r[2])]
+        pw = [float(r[3]) for r in rows if len(r) > 3 and num(r[3])]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None, "window": window}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
@@ -150,8 +164,8 @@ def run_cpu_oracle(cfgj, B, Nv, Nt, steps, warmup, budget_s=60.0, threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
     ap.add_argument("--regions", type=int, default=100)
@@ -267,12 +281,15 @@ def main():
         return ms
 
     # ---------------- device-resident throughput
-    for _ in range(W):
-        step()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    clocks.mark_begin()
     ms = timed(lambda i: step(), a.steps)
+    clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms / a.steps
     loss_val = plan.loss.item()
