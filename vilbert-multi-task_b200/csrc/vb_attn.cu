@@ -80,7 +80,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 // acc[nt][4] (16 x 64 block, 8 n-tiles) = A(16 x D from sA rows a_row0..) * B^T where B rows b_row0.. (64 rows) of sB.
 template <int D>
 __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16* sA, int a_row0, const __nv_bfloat16* sB,
-                                         int b_row0, int lane) {
+                                         int b_row0, int lane, int nb_valid) {   // B rows >= nb_valid are padding: skipped
   constexpr int LD = D + 8;
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk) {
@@ -88,6 +88,7 @@ __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16
     ldmatrix_x4(a, smem_u32(sA + (a_row0 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8));
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
+      if (b_row0 + np * 16 >= nb_valid) break;   // warp-uniform
       uint32_t b[4];
       const int mi = lane >> 3;
       ldmatrix_x4(b, smem_u32(sB + (b_row0 + np * 16 + (mi >> 1) * 8 + (lane & 7)) * LD + kk * 16 + (mi & 1) * 8));
@@ -100,10 +101,11 @@ __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16
 // acc[D/8][4] (16 x D) += P(16 x 64, given as C-fragments pf[8][4] converted to bf16) * B where B rows b_row0.. (64 rows, k index) of sB [row][D].
 template <int D>
 __device__ __forceinline__ void mma_p_b(float (&acc)[D / 8][4], const float (&pf)[8][4], const __nv_bfloat16* sB, int b_row0,
-                                        int lane) {
+                                        int lane, int nb_valid) {   // k-steps whose 16 B rows are all padding are skipped
   constexpr int LD = D + 8;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
+    if (b_row0 + kk * 16 >= nb_valid) break;   // warp-uniform
     uint32_t a[4];
     a[0] = pack_bf16(pf[2 * kk][0], pf[2 * kk][1]);
     a[1] = pack_bf16(pf[2 * kk][2], pf[2 * kk][3]);
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    mma_a_bt<D>(s, sQ, r0, sK, kb, lane);
+    mma_a_bt<D>(s, sQ, r0, sK, kb, lane, p.Nk);
     float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
         s[nt][2] *= drop_factor(dseed, e1 + nt * 8, p.drop); s[nt][3] *= drop_factor(dseed, e1 + nt * 8 + 1, p.drop);
       }
     }
-    mma_p_b<D>(o, s, sV, kb, lane);
+    mma_p_b<D>(o, s, sV, kb, lane, p.Nk);
   }
   l[0] = quad_sum(l[0]); l[1] = quad_sum(l[1]);
   const int rows_valid = p.Nq - q0;
@@ -308,8 +310,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
       s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
       dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
     }
-    mma_a_bt<D>(s, sQ, r0, sK, kb, lane);
-    mma_a_bt<D>(dp, sdO, r0, sV, kb, lane);
+    mma_a_bt<D>(s, sQ, r0, sK, kb, lane, p.Nk);
+    mma_a_bt<D>(dp, sdO, r0, sV, kb, lane, p.Nk);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const float mk0 = sMask[kb + nt * 8 + 2 * t], mk1 = sMask[kb + nt * 8 + 2 * t + 1];
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
       s[nt][0] = p0 * (dp[nt][0] - dl[0]); s[nt][1] = p1 * (dp[nt][1] - dl[0]);
       s[nt][2] = p2 * (dp[nt][2] - dl[1]); s[nt][3] = p3 * (dp[nt][3] - dl[1]);
     }
-    mma_p_b<D>(dq, s, sK, kb, lane);
+    mma_p_b<D>(dq, s, sK, kb, lane, p.Nk);
   }
   store_tile<D>(p.dQ + ((long long)b * p.Nq + q0) * p.lddq + h * D, p.lddq, dq, p.scale, p.scale, r0, rows_valid, lane,
                 p.dbq ? p.dbq + h * D : nullptr);
@@ -387,8 +389,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
       st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
       dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
     }
-    mma_a_bt<D>(st, sK, r0, sQ, qb, lane);     // S^T  = K Q^T   (rows = keys, cols = queries)
-    mma_a_bt<D>(dpt, sV, r0, sdO, qb, lane);   // dP^T = V dO^T
+    mma_a_bt<D>(st, sK, r0, sQ, qb, lane, p.Nq);     // S^T  = K Q^T   (rows = keys, cols = queries)
+    mma_a_bt<D>(dpt, sV, r0, sdO, qb, lane, p.Nq);   // dP^T = V dO^T
     // P^T, then dV += P^T dO ; overwrite st with dS^T afterwards
     float pt[8][4];
 #pragma unroll
@@ -409,8 +411,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
       st[nt][2] = pt[nt][2] * (dpt[nt][2] * f2 - d0); st[nt][3] = pt[nt][3] * (dpt[nt][3] * f3 - d1);
       pt[nt][0] *= f0; pt[nt][1] *= f1; pt[nt][2] *= f2; pt[nt][3] *= f3;   // dV = (mask/(1-p) P)^T dO
     }
-    mma_p_b<D>(dv, pt, sdO, qb, lane);
-    mma_p_b<D>(dk, st, sQ, qb, lane);
+    mma_p_b<D>(dv, pt, sdO, qb, lane, p.Nq);
+    mma_p_b<D>(dk, st, sQ, qb, lane, p.Nq);
   }
   store_tile<D>(p.dV + ((long long)b * p.Nk + k0) * p.lddv + h * D, p.lddv, dv, 1.f, 1.f, r0, rows_valid, lane, p.dbv ? p.dbv + h * D : nullptr);
   store_tile<D>(p.dK + ((long long)b * p.Nk + k0) * p.lddk + h * D, p.lddk, dk, p.scale, p.scale, r0, rows_valid, lane, p.dbk ? p.dbk + h * D : nullptr);

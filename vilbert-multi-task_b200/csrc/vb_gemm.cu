@@ -10,7 +10,8 @@
 //   warp 1      single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1), accumulators
 //               double-buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the
 //               main loop of tile i+1; tcgen05.commit releases smem stages / publishes accumulators;
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> padded smem transpose -> row-wise,
+//   warps 2..9  epilogue (two per TMEM lane quadrant, alternate 32-column chunks): tcgen05.ld (32 lanes x 32 columns)
+//               -> XOR-swizzled smem transpose -> row-wise,
 //               128-bit coalesced pass doing bias / erf-GELU / GELU' / residual / bf16 conversion.
 // Operands may be K-major (nn.Linear forward) or MN-major (dgrad / wgrad operands read in place, no
 // transposed copies); both use the canonical SWIZZLE_128B UMMA layouts written directly by TMA.
@@ -27,9 +28,13 @@ namespace vb {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle span of bf16
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
-constexpr int GEMM_THREADS = 192;
-constexpr int STAGE_PAD = 36;    // fp32 staging row stride: 144 B rows keep 128-bit accesses aligned and conflict-free
-constexpr int STAGING_BYTES_PER_WARP = 32 * STAGE_PAD * 4;
+constexpr int EPI_WARPS = 8;      // two epilogue warps per TMEM lane quadrant: twice the global-memory requests in flight
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+// Epilogue staging tile per warp: 32 rows x 32 fp32, dense 128-byte rows whose 16-byte chunks are XOR-swizzled with the
+// row index (chunk ^ (row & 7)): thread-per-row 128-bit stores and row-wise 128-bit loads are both bank-conflict free
+// without padding (4 KB per warp).
+constexpr int STAGING_BYTES_PER_WARP = 32 * 32 * 4;
+__device__ __forceinline__ int stg_off(int row, int col) { return row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); }
 
 template <int BN>
 struct GemmCfg {
@@ -38,8 +43,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NUM_STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES =
-      1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + 4 * STAGING_BYTES_PER_WARP + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES_PER_WARP + 256 /*barriers*/;
 };
 
 struct GemmKernelParams {
@@ -100,7 +104,7 @@ __device__ __noinline__ void epi_generic_chunk(const GemmKernelParams& p, const 
     if (m >= p.M) break;
 #pragma unroll 1
     for (int j = 0; j < nv; ++j) {
-      float v = stg[row * STAGE_PAD + cc + j] * p.alpha;
+      float v = stg[stg_off(row, cc + j)] * p.alpha;
       if (p.bias) v += p.bias[n + j];
       if (p.act == VB_ACT_GELU) {
         float gg, dg;
@@ -137,7 +141,7 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
   for (int ps = 0; ps < 8; ++ps) {
     const int row = ps * 4 + rr;
     const long long m = m_base + row;
-    const float4 a4 = *reinterpret_cast<const float4*>(stg + row * STAGE_PAD + cc);
+    const float4 a4 = *reinterpret_cast<const float4*>(stg + stg_off(row, cc));
     float v0 = fmaf(a4.x, p.alpha, b4.x), v1 = fmaf(a4.y, p.alpha, b4.y), v2 = fmaf(a4.z, p.alpha, b4.z), v3 = fmaf(a4.w, p.alpha, b4.w);
     if (EPI == EPI_GELU) {
       float d0, d1, d2, d3;
@@ -190,12 +194,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   using Cfg = GemmCfg<BN>;
   constexpr int NUM_STAGES = Cfg::NUM_STAGES;
 
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B tiles need 1024-byte alignment: the kernel has no static shared memory, so the dynamic window starts at
+  // the CTA's (1024-aligned) shared base; checked once below.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smem_tiles = smem;
   float* staging = reinterpret_cast<float*>(smem + NUM_STAGES * Cfg::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * Cfg::STAGE_BYTES + 4 * STAGING_BYTES_PER_WARP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * Cfg::STAGE_BYTES + EPI_WARPS * STAGING_BYTES_PER_WARP);
   uint64_t* full_bar = bars;                       // [NUM_STAGES]
   uint64_t* empty_bar = bars + NUM_STAGES;         // [NUM_STAGES]
   uint64_t* tmem_full_bar = bars + 2 * NUM_STAGES; // [2]
@@ -217,7 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_WARPS * 32);
     }
     fence_mbar_init();
   }
@@ -314,13 +319,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       __syncwarp();
     }
   } else {
-    // ================================================================ epilogue (warps 2..5)
+    // ================================================================ epilogue (warps 2..9)
     // Per 32-column chunk: (1) issue the global reads of this chunk (fp32 residual / bf16 GELU pre-activation) so their
     // latency overlaps the TMEM read, (2) tcgen05.ld 32 lanes x 32 columns -> registers (thread = row), (3) 128-bit
     // stores into a padded smem tile, (4) row-wise pass where a lane owns 4 consecutive columns of rows {rr, rr+4, ..}:
     // 128-bit smem reads, fused math, 128-bit coalesced global stores.
     const int lane_grp = warp_idx & 3;  // TMEM lanes [32*lane_grp, +32) are visible to this warp
-    float* stg = staging + (warp_idx - 2) * (32 * STAGE_PAD);
+    float* stg = staging + (warp_idx - 2) * (32 * 32);
+    const int half = (warp_idx - 2) >> 2;   // the two warps of a lane quadrant take alternate 32-column chunks
     const int rr = lane >> 3;           // row within a 4-row group of the coalesced pass
     const int cc = (lane & 7) * 4;      // first of 4 columns handled by this lane
     int it = 0;
@@ -378,10 +384,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * STAGE_PAD + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            *reinterpret_cast<uint4*>(stg + stg_off(lane, j * 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
-        if (c == NC - 1) {
-          // every TMEM read of this accumulator stage has landed in registers
+        if (c == NC - 2 + half) {
+          // every TMEM read this warp makes of the accumulator stage has landed in registers
           tc_fence_before();
           mbar_arrive(smem_u32(&tmem_empty_bar[as]));
         }
@@ -392,13 +398,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         else               epi_generic_chunk(p, stg, m_base, n_chunk + cc, rr, cc);
         __syncwarp();
       };
-      prefetch(0, res0, aux0, bia0);
+      prefetch(half, res0, aux0, bia0);
 #pragma unroll 1
-      for (int c = 0; c < NC; c += 2) {
-        prefetch(c + 1, res1, aux1, bia1);
+      for (int c = half; c < NC; c += 4) {
+        prefetch(c + 2, res1, aux1, bia1);
         process(c, res0, aux0, bia0);
-        prefetch(c + 2, res0, aux0, bia0);
-        process(c + 1, res1, aux1, bia1);
+        prefetch(c + 4, res0, aux0, bia0);
+        process(c + 2, res1, aux1, bia1);
       }
       if (tile == blockIdx.x && warp_idx == 2 && lane == 0) VB_DBG(6);
     }
