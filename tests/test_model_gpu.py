@@ -247,3 +247,93 @@ def test_full_size_config2_properties(golden_dir):
     p8.load_inputs(*(inp[k][:8] for k in ("input_txt", "input_imgs", "image_loc", "token_type_ids", "attention_mask", "image_attention_mask")))
     p8.run_forward(); torch.cuda.synchronize()
     assert ((p8.outputs["sequence_output_v"] - first).abs().max() / first.abs().max()).item() < 1e-5
+
+
+@pytest.mark.parametrize("B,Nv,Nt,task", [(2, 306, 256, True), (3, 200, 20, True), (2, 37, 36, False), (4, 101, 56, True)])
+def test_twelve_in_one_shapes_base_6layer(golden_dir, B, Nv, Nt, task):
+    """Shapes of the 12-in-1 mix (BASELINE.json configs[4]): the largest one (TASK17: 306 regions x 256
+    tokens + task token), Visual7w (200 x 20+1), Conceptual-Captions (36+1 x 36), Visual-Entailment (101 x 56+1) on
+    bert_base_6layer_6conect. Forward outputs vs the fp32 oracle and vs the bf16-operand oracle."""
+    from _gpu_util import model_case
+    cfgj = dict(_cfg(golden_dir, "base_6layer_6conect_b4"), task_specific_tokens=task)
+    r = model_case(cfgj, B, Nv, Nt, seed=5, grads=False)
+    for mode in ("out_fp32", "out_bf16"):
+        for n, e in r[mode].items():
+            assert e < (6e-2 if n in SMALL_HEADS else 1.5e-2), (mode, n, e)
+
+
+def test_bert_large_6layer_6conect_vcr_shape():
+    """BASELINE.json configs[3] architecture (24 text layers, 1024/4096, 16 heads) at the VCR shape (100 regions, 60 tokens),
+    small batch: forward + backward against the bf16-operand oracle."""
+    from _gpu_util import model_case
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfgj = json.load(open(os.path.join(root, "vilbert-multi-task_b200", "configs", "bert_large_6layer_6conect.json")))
+    r = model_case(cfgj, 4, 100, 60, seed=2, names=("vil_logit", "vil_prediction"))
+    for mode in ("out_fp32", "out_bf16"):
+        for n, e in r[mode].items():
+            assert e < (8e-2 if n in SMALL_HEADS else 2e-2), (mode, n, e)
+    l2 = sorted(v[1] for v in r["grad_bf16"].values())
+    assert l2[len(l2) // 2] < 3e-2 and l2[int(len(l2) * 0.9)] < 1e-1, (l2[len(l2) // 2], l2[int(len(l2) * 0.9)])
+
+
+def test_pretraining_model_losses_and_gradients(golden_dir):
+    """BertForMultiModalPreTraining (vilbert.py:1435-1597): masked-LM CE, masked-region KL and alignment CE through the
+    module surface, eval mode, vs the oracle; backward through the autograd bridge."""
+    import vilbert_b200
+    from _gpu_util import rel
+    cfgj = _cfg(golden_dir, "tiny_b4")
+    cfg = O.make_config(cfgj)
+    model = vilbert_b200.BertForMultiModalPreTraining(vilbert_b200.BertConfig.from_dict(cfgj))
+    P = O.synth_params(cfg, seed=3, device="cuda", with_task_heads=False)
+    model.load_state_dict(P, strict=True)
+    model.eval()
+    B, Nv, Nt = 4, 9, 8
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=77, device="cuda")
+    g = torch.Generator().manual_seed(5)
+    lm = torch.full((B, Nt), -1, dtype=torch.long)
+    sel = torch.rand(B, Nt, generator=g) < 0.15; sel[:, 1] = True
+    lm[sel] = torch.randint(0, cfg["vocab_size"], (int(sel.sum()),), generator=g)
+    il = torch.full((B, Nv - 1), -1, dtype=torch.long); il[torch.rand(B, Nv - 1, generator=g) < 0.15] = 1; il[:, 0] = 1
+    it = torch.softmax(torch.randn(B, Nv - 1, cfg["v_target_size"], generator=g), -1)
+    ns = torch.randint(0, 2, (B,), generator=g)
+    lm, il, it, ns = lm.cuda(), il.cuda(), it.cuda(), ns.cuda()
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], lm, il, it, ns)
+    losses = model(*args)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    ref = O.pretraining_losses(Pg, cfg, *args)
+    gold = json.load(open(os.path.join(golden_dir, "tiny_pretraining_losses.json")))["losses"]     # from the reference itself
+    for a, b, c in zip(losses, ref, gold):
+        assert a.shape == (1,) and abs(a.item() - b.item()) < 5e-3 * abs(b.item()) and abs(a.item() - c) < 5e-3 * abs(c)
+    model.zero_grad()
+    sum(losses).sum().backward()
+    sum(ref).backward()
+    named = dict(model.named_parameters())
+    for k in ("bert.encoder.layer.1.attention.self.value.weight", "cls.predictions.transform.dense.weight", "cls.imagePredictions.decoder.weight",
+              "cls.bi_seq_relationship.weight", "bert.embeddings.word_embeddings.weight", "bert.encoder.c_layer.0.biattention.key1.weight"):
+        assert rel(named[k].grad, Pg[k].grad) < 3e-2, k
+    # without labels the reference returns the three score tensors + attention-mask tuple (:1591-1597)
+    out = model(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+    assert len(out) == 4 and tuple(out[0].shape) == (B, Nt, cfg["vocab_size"]) and tuple(out[1].shape) == (B, Nv, cfg["v_target_size"]) and tuple(out[2].shape) == (B, 2)
+
+
+def test_from_pretrained_local_file_with_legacy_names(tmp_path, golden_dir):
+    """from_pretrained on a local checkpoint: gamma/beta -> weight/bias renaming, `module.` prefix stripping, base-model
+    checkpoint into a model with heads, eval mode on return (vilbert/utils.py:945-958, 1022)."""
+    import vilbert_b200
+    cfgj = _cfg(golden_dir, "tiny_b4")
+    cfg = O.make_config(cfgj)
+    P = O.synth_params(cfg, seed=9)
+    legacy = {}
+    for k, v in P.items():
+        k2 = "module." + k
+        if "LayerNorm.weight" in k: k2 = k2.replace("LayerNorm.weight", "LayerNorm.gamma")
+        if "LayerNorm.bias" in k: k2 = k2.replace("LayerNorm.bias", "LayerNorm.beta")
+        legacy[k2] = v
+    path = tmp_path / "pytorch_model.bin"
+    torch.save(legacy, str(path))
+    model = vilbert_b200.VILBertForVLTasks.from_pretrained(str(path), config=vilbert_b200.BertConfig.from_dict(cfgj), num_labels=1, default_gpu=True)
+    assert not model.training
+    sd = model.state_dict()
+    for k in ("bert.embeddings.LayerNorm.weight", "bert.encoder.c_layer.1.biOutput.LayerNorm2.bias", "vil_prediction.logit_fc.3.weight"):
+        assert torch.equal(sd[k].cpu(), P[k]), k

@@ -80,7 +80,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 // acc[nt][4] (16 x 64 block, 8 n-tiles) = A(16 x D from sA rows a_row0..) * B^T where B rows b_row0.. (64 rows) of sB.
 template <int D>
 __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16* sA, int a_row0, const __nv_bfloat16* sB,
-                                         int b_row0, int lane, int nb_valid) {   // B rows >= nb_valid are padding: skipped
+                                         int b_row0, int lane, int /*nb_valid*/) {
   constexpr int LD = D + 8;
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk) {
@@ -88,7 +88,6 @@ __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16
     ldmatrix_x4(a, smem_u32(sA + (a_row0 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8));
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
-      if (b_row0 + np * 16 >= nb_valid) break;   // warp-uniform
       uint32_t b[4];
       const int mi = lane >> 3;
       ldmatrix_x4(b, smem_u32(sB + (b_row0 + np * 16 + (mi >> 1) * 8 + (lane & 7)) * LD + kk * 16 + (mi & 1) * 8));
@@ -101,11 +100,10 @@ __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16
 // acc[D/8][4] (16 x D) += P(16 x 64, given as C-fragments pf[8][4] converted to bf16) * B where B rows b_row0.. (64 rows, k index) of sB [row][D].
 template <int D>
 __device__ __forceinline__ void mma_p_b(float (&acc)[D / 8][4], const float (&pf)[8][4], const __nv_bfloat16* sB, int b_row0,
-                                        int lane, int nb_valid) {   // k-steps whose 16 B rows are all padding are skipped
+                                        int lane, int /*nb_valid*/) {
   constexpr int LD = D + 8;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    if (b_row0 + kk * 16 >= nb_valid) break;   // warp-uniform
     uint32_t a[4];
     a[0] = pack_bf16(pf[2 * kk][0], pf[2 * kk][1]);
     a[1] = pack_bf16(pf[2 * kk][2], pf[2 * kk][3]);
