@@ -149,6 +149,22 @@ def run_pretraining_case(ref, name, cfg_json, B, Nv, Nt):
                        pin=dict(worst=max(errs), tolerance=TOL)), f)
 
 
+def check_all_encoded_layers(ref, cfg_json):
+    """output_all_encoded_layers=True: per-connection-layer states + poolers on the last connection layer's output."""
+    cfg = O.make_config(cfg_json)
+    model = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfg_json)), num_labels=1, default_gpu=False)
+    P = O.synth_params(cfg, seed=0)
+    model.load_state_dict(P, strict=False); model.tie_weights(); model.eval()
+    inp = O.synth_inputs(cfg, 4, 11, 9, seed=1234)
+    r = model.bert(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"],
+                   output_all_encoded_layers=True)
+    o = O.bert_model(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+                     inp["image_attention_mask"], output_all_encoded_layers=True)
+    errs = [rel(a, b) for a, b in zip(list(o[0]) + list(o[1]) + [o[2], o[3]], list(r[0]) + list(r[1]) + [r[2], r[3]])]
+    print(f"{'all_encoded_layers':28s} worst {max(errs):.2e}")
+    assert len(r[0]) == len(o[0]) and max(errs) < TOL
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
@@ -162,6 +178,7 @@ def main():
     run_case(ref, "base_6layer_6conect_b4", base66, B=4, Nv=100, Nt=36, seed=0)           # configs[1] shape, small B
     run_case(ref, "base_6layer_6conect_tasktok", base66, B=2, Nv=101, Nt=23, task_tokens=True, grads=False, seed=1)
     run_pretraining_case(ref, "tiny_pretraining_losses", TINY, B=4, Nv=9, Nt=8)
+    check_all_encoded_layers(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

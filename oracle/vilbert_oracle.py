@@ -241,6 +241,10 @@ def bert_model(P, cfg, input_txt, input_imgs, image_loc, token_type_ids=None, at
     t = text_embeddings(P, prefix + ".embeddings", cfg, input_txt, token_type_ids, task_ids, drop)
     v = image_embeddings(P, prefix + ".v_embeddings", input_imgs, image_loc, drop, cfg["hidden_dropout_prob"])
     t, v, all_t, all_v = encoder(P, prefix + ".encoder", cfg, t, v, mask_t, mask_v, drop)
+    if output_all_encoded_layers:
+        # :1098-1101 + :1388-1394 — in this mode the encoder returns only the per-connection-layer states and the poolers see
+        # encoded_layers[-1], i.e. the output of the LAST CONNECTION LAYER (the tail layers' result is dropped)
+        t, v = all_t[-1], all_v[-1]
     pooled_t = torch.relu(linear(P, prefix + ".t_pooler.dense", t[:, 0]))
     pooled_v = torch.relu(linear(P, prefix + ".v_pooler.dense", v[:, 0]))
     if output_all_encoded_layers:

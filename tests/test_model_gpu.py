@@ -343,3 +343,30 @@ def test_from_pretrained_local_file_with_legacy_names(tmp_path, golden_dir):
     sd = model.state_dict()
     for k in ("bert.embeddings.LayerNorm.weight", "bert.encoder.c_layer.1.biOutput.LayerNorm2.bias", "vil_prediction.logit_fc.3.weight"):
         assert torch.equal(sd[k].cpu(), P[k]), k
+
+
+def test_bert_model_surface_and_all_encoded_layers(golden_dir):
+    """BertModel(config).forward 5-tuple (bare state_dict names, default masks) and output_all_encoded_layers=True: one entry
+    per connection layer, pooled outputs taken from the last connection layer like the reference (vilbert.py:1388-1394)."""
+    import vilbert_b200
+    from _gpu_util import rel
+    cfgj = _cfg(golden_dir, "tiny_b4")
+    cfg = O.make_config(cfgj)
+    model = vilbert_b200.BertModel(vilbert_b200.BertConfig.from_dict(cfgj))
+    P = O.synth_params(cfg, seed=0, device="cuda")
+    bare = {k[len("bert."):]: v for k, v in P.items() if k.startswith("bert.")}
+    assert set(model.state_dict().keys()) == set(bare.keys())
+    model.load_state_dict(bare)
+    model.eval()
+    inp = O.synth_inputs(cfg, 4, 11, 9, seed=1234, device="cuda", ragged=False)
+    out = model(inp["input_txt"], inp["input_imgs"], inp["image_loc"])                 # all masks defaulted (:1322-1329)
+    ref = O.bert_model(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"])
+    assert len(out) == 5
+    for a, b in zip(out[:4], ref):
+        assert rel(a, b) < 1e-2
+    all_t, all_v, pt, pv, _ = model(inp["input_txt"], inp["input_imgs"], inp["image_loc"], output_all_encoded_layers=True)
+    r_t, r_v, r_pt, r_pv = O.bert_model(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], output_all_encoded_layers=True)
+    assert len(all_t) == len(r_t) == len(cfg["t_biattention_id"])
+    for a, b in zip(all_t + all_v, r_t + r_v):
+        assert rel(a, b) < 1e-2
+    assert rel(pt, r_pt) < 1e-2 and rel(pv, r_pv) < 1e-2

@@ -818,6 +818,7 @@ class Plan:
     def _build(self):
         c, B = self.cfg, self.B
         self.outputs, self.gout = OrderedDict(), {}
+        self.enc_t, self.enc_v = [], []
         t, v = self.embeddings()
         # BertEncoder.forward interleaving schedule (vilbert.py:960-1096)
         t_start = v_start = 0
@@ -830,6 +831,7 @@ class Plan:
             if c.with_coattention:
                 v, t = self.connection_layer(v, t, count)
             v_start, t_start = v_end, t_end
+            self.enc_t.append(t); self.enc_v.append(v)     # output_all_encoded_layers: one entry per connection layer (:1075-1077)
         with self.on(1):
             for i in range(v_start, c.v_num_hidden_layers):
                 v = self.image_layer(v, i)

@@ -25,11 +25,11 @@ class _BertNode(_Node):
 
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
-        if output_all_attention_masks or output_all_encoded_layers:
-            raise NotImplementedError("output_all_encoded_layers / output_all_attention_masks are not supported by the B200 engine")
+        if output_all_attention_masks:
+            raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
         owner = self.__dict__["_owner_ref"]()
-        o = owner._run(BERT_OUT_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
-        return (o["sequence_output_t"], o["sequence_output_v"], o["pooled_output_t"], o["pooled_output_v"], ([], [], []))
+        return owner._bert_forward(input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids,
+                                   output_all_encoded_layers)
 
 
 def _register_tree(root, store):
@@ -82,6 +82,7 @@ class _EngineFn(torch.autograd.Function):
         plan.load_inputs(**inputs)
         plan.run_forward()
         ctx.model, ctx.names, ctx.inputs, ctx.plan, ctx.fwd_id, ctx.train = model, names, inputs, plan, plan.fwd_id, train
+        model._last_plan = plan
         ctx.set_materialize_grads(False)
         return tuple(plan.outputs[n].clone() for n in names)
 
@@ -186,6 +187,25 @@ class BertPreTrainedModel(nn.Module):
         model.eval()
         return model
 
+    def _bert_forward(self, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids,
+                      output_all_encoded_layers):
+        """BertModel.forward outputs (vilbert.py:1388-1406). With output_all_encoded_layers the encoded-layer entries are lists with
+        one tensor per connection layer (:1075-1077); only the last entry is connected to autograd here."""
+        o = self._run(BERT_OUT_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
+        seq_t, seq_v = o["sequence_output_t"], o["sequence_output_v"]
+        if output_all_encoded_layers:
+            plan = self._last_plan
+            B = seq_t.shape[0]
+            enc_t = [a.f32.view(B, plan.Nt, -1).clone() for a in plan.enc_t]
+            enc_v = [a.f32.view(B, plan.Nv, -1).clone() for a in plan.enc_v]
+            # Reference quirk (:1098-1101, :1388-1394): in this mode the encoder returns ONLY the per-connection-layer states, and
+            # BertModel pools encoded_layers[-1], i.e. the output of the last connection layer, not of the tail layers. This
+            # inspection path (not the hot path) reproduces that with two tiny fp32 ops on the pooler parameters.
+            pt = F.relu(F.linear(enc_t[-1][:, 0], self._params["bert.t_pooler.dense.weight"], self._params["bert.t_pooler.dense.bias"]))
+            pv = F.relu(F.linear(enc_v[-1][:, 0], self._params["bert.v_pooler.dense.weight"], self._params["bert.v_pooler.dense.bias"]))
+            return (enc_t, enc_v, pt, pv, ([], [], []))
+        return (seq_t, seq_v, o["pooled_output_t"], o["pooled_output_v"], ([], [], []))
+
     # ---- shared forward machinery
     def _run(self, names, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids):
         inputs = dict(input_txt=input_txt, input_imgs=input_imgs, image_loc=image_loc, token_type_ids=token_type_ids,
@@ -209,10 +229,8 @@ class BertModel(BertPreTrainedModel):
                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
         if output_all_attention_masks:
             raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
-        if output_all_encoded_layers:
-            raise NotImplementedError("output_all_encoded_layers=True is not supported by the B200 engine yet")
-        o = self._run(BERT_OUT_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
-        return (o["sequence_output_t"], o["sequence_output_v"], o["pooled_output_t"], o["pooled_output_v"], ([], [], []))
+        return self._bert_forward(input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids,
+                                  output_all_encoded_layers)
 
 
 class VILBertForVLTasks(BertPreTrainedModel):
@@ -229,8 +247,10 @@ class VILBertForVLTasks(BertPreTrainedModel):
 
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
-        if output_all_attention_masks or output_all_encoded_layers:
-            raise NotImplementedError("output_all_encoded_layers / output_all_attention_masks are not supported by the B200 engine")
+        if output_all_attention_masks:
+            raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
+        if output_all_encoded_layers:
+            raise NotImplementedError("VILBertForVLTasks(output_all_encoded_layers=True) is not supported; use model.bert(..., output_all_encoded_layers=True)")
         if image_attention_mask is None:
             raise TypeError("image_attention_mask is required by VILBertForVLTasks.forward (vilbert.py:1693)")
         o = self._run(HEAD_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
