@@ -411,7 +411,30 @@ def main():
     if prof:
         gm = prof["vb_gemm_bf16"]
         ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
-        out["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all launches of one step)",
+        # dominant single kernel = the GEMM problem signature with the largest total time in one step
+        sigs = {}
+        for (fn, args, _sid), (s0, s1) in zip(ops, evs):
+            if fn.__name__ == "vb_gemm_bf16":
+                ga = args[0]._obj
+                key = (ga.M, ga.N, ga.K, int(ga.a_mn_major), int(ga.b_mn_major), ga.act, int(bool(ga.residual)), int(ga.atomic_out))
+                d = sigs.setdefault(key, [0, 0.0])
+                d[0] += 1; d[1] += s0.elapsed_time(s1)
+        dom, (dn, dms) = max(sigs.items(), key=lambda kv: kv[1][1])
+        dflops = 2.0 * dom[0] * dom[1] * dom[2]
+        dach = dflops / (dms / dn / 1e3) / 1e12
+        # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01_ncu_full_top_kernels_raw.csv), same signatures
+        NCU_DRAM_BYTES = {(1024, 1024, 6400, 1, 1, 0, 0, 1): 30.44e6, (6400, 1024, 1024, 0, 0, 0, 1, 0): 44.54e6,
+                          (6400, 3072, 1024, 0, 0, 0, 0, 0): 22.51e6, (2304, 3072, 768, 0, 1, 3, 0, 0): 22.49e6,
+                          (2304, 768, 768, 0, 0, 0, 1, 0): 11.83e6}
+        out["roofline"] = {"bound": "tensor",
+                           "kernel": f"gemm_tcgen05_kernel M={dom[0]} N={dom[1]} K={dom[2]} (a_mn={dom[3]} b_mn={dom[4]} act={dom[5]} residual={dom[6]} "
+                                     f"atomic={dom[7]}): the GEMM signature with the largest share of the step ({dn} launches, {dms:.3f} ms)",
+                           "achieved": dach, "peak": peak_sus, "unit": "TFLOP/s", "frac": dach / peak_sus,
+                           "traffic": NCU_DRAM_BYTES.get(dom), "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, cold cache)",
+                           "algorithmic_flops_per_launch": dflops, "avg_launch_us": dms / dn * 1e3,
+                           "peak_source": peak_src + ", sustained cuBLAS bf16",
+                           "how": "algorithmic 2MNK / mean CUDA-event duration of that launch in an eager single-stream replay of the step"}
+        out["roofline_all_gemm"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all launches of one step)",
                            "how": "sum of algorithmic 2MNK over the step's GEMM launches / sum of their CUDA-event durations in an eager single-stream replay "
                                   "(each launch bracketed by events, so launch gaps and event latency count against the kernel)",
                            "achieved": ach, "peak": peak_sus,

@@ -927,11 +927,13 @@ class Plan:
                         e1 = torch.cuda.Event(); e1.record(main); aux.wait_event(e1)
                         e2 = torch.cuda.Event(); e2.record(aux); main.wait_event(e2)
                 elif args[0] == "all":
-                    for st in streams[1:]:
-                        e = torch.cuda.Event(); e.record(st); main.wait_event(e)
+                    # full barrier over every stream. Fork first (main -> side streams), then join (side -> main): inside a
+                    # graph capture a side stream only belongs to the capture once it has waited on a captured event
                     e = torch.cuda.Event(); e.record(main)
                     for st in streams[1:]:
                         st.wait_event(e)
+                    for st in streams[1:]:
+                        e2 = torch.cuda.Event(); e2.record(st); main.wait_event(e2)
                 elif args[0] == "rec":
                     e = torch.cuda.Event(); e.record(streams[sid]); events[args[1]] = e
                 elif args[0] == "wait":
