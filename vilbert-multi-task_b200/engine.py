@@ -1012,6 +1012,13 @@ class Plan:
                 break
             cuts.append(min(cand, key=lambda b: abs(b - want)))
         cuts = sorted(set(cuts)) + [n_ops]
+        # every piece must contain at least one kernel (an empty CUDA graph is legal but pointless)
+        kept, prev = [], 0
+        for cpos in cuts:
+            if any(op[0] is not None for op in self.bwd[prev:cpos]) or cpos == n_ops:
+                kept.append(cpos)
+                prev = cpos
+        cuts = kept
         ranges = sorted(self.grad_touch.items())          # by flat offset
         numel = self.e.ps.numel
         segs, lo_op, hi_grad = [], 0, numel
