@@ -242,7 +242,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int total_tiles = tiles_mn * p.split_k;
 
   if (warp_idx == 0) {
-    // ================================================================ TMA producer (lane 0 issues; the warp stays converged)
+    // ================================================================ TMA producer (one elected lane issues; the warp stays converged).
+    // The guard must be elect.sync, not `lane == 0`: only then does ptxas know a single thread is active and emit the
+    // UTMALDG / UTCHMMA / UTCBAR once instead of inside a per-thread BRA.U.ANY serialisation loop (~80 cycles per MMA)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -253,7 +255,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int kb0 = split * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
       for (int kb = kb0; kb < kb1; ++kb) {
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
@@ -278,7 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else if (warp_idx == 1) {
-    // ================================================================ MMA issuer (lane 0 issues; the warp stays converged)
+    // ================================================================ MMA issuer (one elected lane issues; the warp stays converged)
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -289,13 +291,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const uint32_t tmem_d = tmem_base + as * BN;
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1);
         tc_fence_after();
       }
       __syncwarp();
       for (int kb = kb0; kb < kb1; ++kb) {
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           if (kb == kb0 && tile == blockIdx.x) VB_DBG(3);
@@ -312,7 +314,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         __syncwarp();
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) {
+      if (elect_one()) {
         umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete
         if (tile == blockIdx.x) VB_DBG(4);
       }
