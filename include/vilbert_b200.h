@@ -105,6 +105,7 @@ typedef struct vb_gemm_args {
   /* debug/test overrides for the smem matrix descriptors (0 = library default) */
   uint32_t dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b;
   void* dbg_timeline;    /* NULL, or u64 [grid][10]: per-CTA clock64 / globaltimer stamps (development only) */
+  int32_t cluster_m;     /* 0 = auto, 1 = no clusters, 2 = CTA pairs (tcgen05 cta_group::2) on adjacent row blocks */
 } vb_gemm_args;
 
 vb_status vb_gemm_bf16(const vb_gemm_args* args, void* stream);

@@ -26,7 +26,7 @@ def rel_l2(a, b):
 
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm_case(M, N, K, a_mn=False, b_mn=False, bias=False, res=False, act=0, out_bf16=False, atomic=False, split_k=1, block_n=0,
-              alpha=1.0, check=True, iters=0, seed=0, both_outputs=False):
+              alpha=1.0, check=True, iters=0, seed=0, both_outputs=False, cluster_m=0):
     """Returns (max relative error vs fp32 matmul of the bf16 operands, ms per launch or None)."""
     dev = torch.device("cuda")
     g_ = torch.Generator(device=dev).manual_seed(seed)
@@ -63,6 +63,7 @@ def gemm_case(M, N, K, a_mn=False, b_mn=False, bias=False, res=False, act=0, out
     g.out_bf16, g.ld_out_bf16 = (out16.data_ptr(), N) if out_bf16 and not atomic else (None, 0)
     g.out_pre, g.ld_out_pre = (pre16.data_ptr(), N) if pre16 is not None else (None, 0)
     g.atomic_out, g.split_k, g.block_n, g.max_ctas = int(atomic), split_k, block_n, 0
+    g.cluster_m = cluster_m
     L.check(lib.vb_gemm_bf16(C.byref(g), stream()), "vb_gemm_bf16")
     torch.cuda.synchronize()
     err = None

@@ -40,6 +40,23 @@ def test_mn_major_operands(a_mn, b_mn, M, N, K, bn):
     assert err < TOL
 
 
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("kw,shape", [
+    (dict(bias=True, res=True), (2304, 768, 768)),                       # even number of row blocks
+    (dict(bias=True, out_bf16=True), (6400, 3072, 1024)),                # several items per cluster, accumulator double buffering
+    (dict(bias=True, res=True), (333, 1601, 1024)),                      # 3 row blocks: the last pair has an idle half; ragged N
+    (dict(bias=True, act=L.VB_ACT_GELU, out_bf16=True), (1000, 520, 200)),
+    (dict(b_mn=True, res=True), (2304, 768, 3072)),                      # dgrad form: B read MN-major, its 64-column boxes split across the pair
+    (dict(a_mn=True, b_mn=True, atomic=True, split_k=0), (1024, 1024, 6400)),   # wgrad form with split-K
+    (dict(a_mn=True, b_mn=True, atomic=True, split_k=3), (768, 520, 2304)),
+])
+def test_cta_pairs(kw, shape, bn):
+    """cluster_m=2: CTA pairs (tcgen05 cta_group::2) on adjacent row blocks; the leader issues 256 x BN MMAs for both (vb_gemm.cu)."""
+    from _gpu_util import gemm_case
+    err, _ = gemm_case(*shape, block_n=bn, cluster_m=2, **kw)
+    assert err < 2e-3, err
+
+
 def test_invalid_arguments_are_rejected():
     import ctypes as C
     import torch

@@ -12,7 +12,7 @@ from vilbert_b200 import _lib as L
 lib = L.lib(); dev = "cuda"; BF = torch.bfloat16
 
 
-def feed(mt, nt, K, bn, a_mn=False, b_mn=False):
+def feed(mt, nt, K, bn, a_mn=False, b_mn=False, cl=1):
     M, N = 128 * mt, bn * nt
     A = (torch.randn(K, M, device=dev) if a_mn else torch.randn(M, K, device=dev)).to(BF)
     B = (torch.randn(K, N, device=dev) if b_mn else torch.randn(N, K, device=dev)).to(BF)
@@ -22,17 +22,19 @@ def feed(mt, nt, K, bn, a_mn=False, b_mn=False):
     g.A, g.lda, g.a_mn_major = A.data_ptr(), (M if a_mn else K), int(a_mn)
     g.B, g.ldb, g.b_mn_major = B.data_ptr(), (N if b_mn else K), int(b_mn)
     g.alpha, g.out_bf16, g.ld_out_bf16, g.split_k, g.block_n = 1.0, out.data_ptr(), N, 1, bn
+    g.cluster_m = cl
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     for _ in range(2): L.check(lib.vb_gemm_bf16(C.byref(g), st))
     torch.cuda.synchronize()
     g.dbg_timeline = dbg.data_ptr()
     L.check(lib.vb_gemm_bf16(C.byref(g), st)); torch.cuda.synchronize()
     full = dbg.view(148, 10).cpu(); full = full[full[:, 0] != 0]
-    loop = (full[:, 4] - full[:, 3]).float()          # first full_bar -> last MMA committed
+    lead = full[full[:, 4] != 0]                       # in pair mode only the leader CTA issues MMAs
+    loop = (lead[:, 4] - lead[:, 3]).float()          # first full_bar -> last MMA committed
     kb = K // 64
-    print(f"  tiles {mt:3d}x{nt}  bn{bn} a_mn{int(a_mn)} b_mn{int(b_mn)}: {len(full):3d} CTAs, cycles per k-block median {loop.median().item()/kb:6.0f} "
-          f"max {loop.max().item()/kb:6.0f}  ({(16384 + bn * 128) / (loop.median().item()/kb):5.1f} B/clk/SM, "
-          f"{(16384 + bn * 128) * len(full) / (loop.median().item()/kb):7.0f} B/clk chip)", flush=True)
+    print(f"  tiles {mt:3d}x{nt}  bn{bn} a_mn{int(a_mn)} b_mn{int(b_mn)} cluster{cl}: {len(full):3d} CTAs, cycles per k-block median {loop.median().item()/kb:6.0f} "
+          f"max {loop.max().item()/kb:6.0f}  ({(16384 + bn * 128 // cl) / (loop.median().item()/kb):5.1f} B/clk/SM, "
+          f"{(16384 + bn * 128 // cl) * len(full) / (loop.median().item()/kb):7.0f} B/clk chip)", flush=True)
 
 
 print("=== main-loop feed: one tile per CTA, K = 8192")
@@ -40,6 +42,12 @@ for bn in (128, 256):
     for (mt, nt) in [(1, 1), (8, 1), (37, 1), (74, 1), (148, 1), (37, 4), (74, 2), (18, 8), (4, 37)]:
         if mt * nt <= 148:
             feed(mt, nt, 8192, bn)
+print("=== CTA pairs, tcgen05 cta_group::2 (cluster_m=2): tiles are 256 x bn per pair")
+for bn in (128, 256):
+    for (mt, nt) in [(2, 1), (8, 1), (74, 1), (148, 1), (36, 4), (74, 2), (18, 8), (4, 37)]:
+        feed(mt, nt, 8192, bn, cl=2)
+    feed(36, 4, 8192, bn, a_mn=True, b_mn=True, cl=2)
+    feed(36, 4, 8192, bn, b_mn=True, cl=2)
 print("=== MN-major operands (wgrad form)")
 for bn in (128, 256):
     feed(37, 4, 8192, bn, a_mn=True, b_mn=True)

@@ -39,7 +39,7 @@ class GemmArgs(C.Structure):
         ("out_pre", C.c_void_p), ("ld_out_pre", C.c_int64),
         ("atomic_out", C.c_int32), ("out_colsum", C.c_void_p), ("dropout", Dropout), ("split_k", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
         ("dbg_lbo_a", C.c_uint32), ("dbg_sbo_a", C.c_uint32), ("dbg_lbo_b", C.c_uint32), ("dbg_sbo_b", C.c_uint32),
-        ("dbg_timeline", C.c_void_p),
+        ("dbg_timeline", C.c_void_p), ("cluster_m", C.c_int32),
     ]
 
 

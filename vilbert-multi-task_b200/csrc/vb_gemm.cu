@@ -36,12 +36,14 @@ constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int STAGING_BYTES_PER_WARP = 32 * 32 * 4;
 __device__ __forceinline__ int stg_off(int row, int col) { return row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); }
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile. CG = 2: CTA pairs (tcgen05 cta_group::2) on a 256 x BN tile; each CTA stages its 128
+// rows of A and its BN/2 rows of B, so a stage is smaller and the ring deeper (192 KB of operand stages either way).
+template <int BN, int CG>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NUM_STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int NUM_STAGES = (192 * 1024) / STAGE_BYTES;   // 6 / 4 (CG 1), 8 / 6 (CG 2)
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES_PER_WARP + 256 /*barriers*/;
 };
@@ -71,6 +73,10 @@ struct GemmKernelParams {
   uint32_t idesc;
   DropCfg drop;              // dropout on the epilogue value before the residual add (EPI_F32 / generic)
   int a_mn, b_mn;            // operand majors (runtime: only the TMA producer cares)
+  int cluster;               // 1, or 2 = CTA pairs (tcgen05 cta_group::2): the two CTAs take adjacent row blocks of one column
+                             // block; the leader issues 256 x BN MMAs for both, each CTA stages its 128 rows of A and its
+                             // half of the B tile -> per-SM operand traffic (L2 -> smem and smem -> tensor core) drops by 25-33 %
+  int num_m_groups;          // ceil(num_m_blocks / cluster)
   int fast_ok;               // every buffer the specialised epilogue touches allows 128/64-bit accesses
   unsigned long long* dbg;   // optional per-CTA timeline [grid][10] (8 x clock64 + 2 x globaltimer ns), NULL in production
 };
@@ -187,11 +193,12 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
+  constexpr bool pair = (CG == 2);
   constexpr int NUM_STAGES = Cfg::NUM_STAGES;
 
   // SWIZZLE_128B tiles need 1024-byte alignment: the kernel has no static shared memory, so the dynamic window starts at
@@ -222,24 +229,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_WARPS * 32);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_WARPS * CG);   // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   __syncwarp();
   if (warp_idx == 1) {
-    tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (pair) { tmem_alloc_pair(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+    else                { tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // the barriers of both CTAs of a pair must exist before the peer's TMA / commits / arrives reach them
+  if constexpr (pair) cluster_sync_all();
   pdl_entry();   // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel's tail
   if (threadIdx.x == 0) VB_DBG(1);
 
-  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
-  const int total_tiles = tiles_mn * p.split_k;
+  // work items = (row-block group, column block, k split); the CTAs of a pair walk the same items in lockstep, CTA
+  // `crank` takes row block group * cluster + crank (possibly past the matrix: it then loads zero rows and stores
+  // nothing, but still stages its half of B)
+  const int crank = pair ? (int)cluster_ctarank() : 0;
+  const int group = blockIdx.x / CG;
+  const int num_groups = gridDim.x / CG;
+  const int total_work = p.num_m_groups * p.num_n_blocks * p.split_k;
+  const bool leader = (crank == 0);
 
   if (warp_idx == 0) {
     // ================================================================ TMA producer (one elected lane issues; the warp stays converged).
@@ -247,33 +262,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // UTMALDG / UTCHMMA / UTCBAR once instead of inside a per-thread BRA.U.ANY serialisation loop (~80 cycles per MMA)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int split = tile % p.split_k;
-      const int t2 = tile / p.split_k;
-      const int m_blk = t2 % p.num_m_blocks;
-      const int n_blk = t2 / p.num_m_blocks;
+    for (int w = group; w < total_work; w += num_groups) {
+      const int split = w % p.split_k;
+      const int t2 = w / p.split_k;
+      const int m_blk = (t2 % p.num_m_groups) * CG + crank;
+      const int n_blk = t2 / p.num_m_groups;
       const int kb0 = split * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
       for (int kb = kb0; kb < kb1; ++kb) {
         if (elect_one()) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
           const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
-          if (p.a_mn) {
+          if constexpr (!pair) {
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+            if (p.a_mn) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, fb);
-          } else {
-            tma_load_2d(sa, &tmap_a, kb * BK, m_blk * BM, fb);
-          }
-          if (p.b_mn) {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, fb);
+            } else {
+              tma_load_2d(sa, &tmap_a, kb * BK, m_blk * BM, fb);
+            }
+            if (p.b_mn) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmap_b, n_blk * BN + j * 64, kb * BK, fb);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmap_b, n_blk * BN + j * 64, kb * BK, fb);
+            } else {
+              tma_load_2d(sb, &tmap_b, kb * BK, n_blk * BN, fb);
+            }
           } else {
-            tma_load_2d(sb, &tmap_b, kb * BK, n_blk * BN, fb);
+            // both CTAs complete their bytes on the LEADER's full barrier (the leader issues the MMAs for the pair);
+            // this CTA stages its 128 rows of A and columns [crank * BN/2, +BN/2) of the B tile
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
+            if (p.a_mn) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, fb);
+            } else {
+              tma_load_2d_pair(sa, &tmap_a, kb * BK, m_blk * BM, fb);
+            }
+            const int n0 = n_blk * BN + crank * (BN / 2);
+            if (p.b_mn) {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * (BK * 128), &tmap_b, n0 + j * 64, kb * BK, fb);
+            } else {
+              tma_load_2d_pair(sb, &tmap_b, kb * BK, n0, fb);   // tensor-map box = BN/2 rows
+            }
           }
-          if (kb == kb0 && tile == blockIdx.x) VB_DBG(2);
+          if (kb == kb0 && w == group) VB_DBG(2);
         }
         __syncwarp();
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
@@ -284,8 +319,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int split = tile % p.split_k;
+    for (int w = group; w < total_work && leader; w += num_groups, ++it) {   // in a pair only the leader issues
+      const int split = w % p.split_k;
       const int kb0 = split * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
       const int as = it & 1;
@@ -300,23 +335,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (elect_one()) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
-          if (kb == kb0 && tile == blockIdx.x) VB_DBG(3);
+          if (kb == kb0 && w == group) VB_DBG(3);
           const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = umma_desc_at(p.desc_base_a, sa + k * p.kadv_a);
             const uint64_t db = umma_desc_at(p.desc_base_b, sb + k * p.kadv_b);
-            umma_bf16(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (pair) umma_bf16_pair(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else                umma_bf16(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty_bar[stage]));  // smem slot free once these MMAs retire
+          // smem slot free once these MMAs retire (in both CTAs of a pair)
+          if constexpr (pair) umma_commit_pair(smem_u32(&empty_bar[stage]), 0x3);
+          else                umma_commit(smem_u32(&empty_bar[stage]));
         }
         __syncwarp();
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       }
       if (elect_one()) {
-        umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete
-        if (tile == blockIdx.x) VB_DBG(4);
+        if constexpr (pair) umma_commit_pair(smem_u32(&tmem_full_bar[as]), 0x3);   // accumulator complete (both halves)
+        else                umma_commit(smem_u32(&tmem_full_bar[as]));
+        if (w == group) VB_DBG(4);
       }
       __syncwarp();
     }
@@ -332,10 +371,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int rr = lane >> 3;           // row within a 4-row group of the coalesced pass
     const int cc = (lane & 7) * 4;      // first of 4 columns handled by this lane
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int t2 = tile / p.split_k;
-      const int m_blk = t2 % p.num_m_blocks;
-      const int n_blk = t2 / p.num_m_blocks;
+    for (int w = group; w < total_work; w += num_groups, ++it) {
+      const int t2 = w / p.split_k;
+      const int m_blk = (t2 % p.num_m_groups) * CG + crank;
+      const int n_blk = t2 / p.num_m_groups;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m_base = m_blk * BM + lane_grp * 32;
@@ -377,7 +416,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
           tc_fence_after();
           waited = true;
-          if (tile == blockIdx.x && warp_idx == 2 && lane == 0) VB_DBG(5);
+          if (w == group && warp_idx == 2 && lane == 0) VB_DBG(5);
         }
         // TMEM -> registers -> padded smem tile (row = lane)
         if (chunk_live) {
@@ -391,7 +430,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (c == NC - 2 + half) {
           // every TMEM read this warp makes of the accumulator stage has landed in registers
           tc_fence_before();
-          mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (pair) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[as]), 0));   // the leader's MMA warp waits for both CTAs
+            else                mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+          }
         }
         if (!chunk_live) return;
         __syncwarp();
@@ -408,17 +451,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         prefetch(c + 4, res0, aux0, bia0);
         process(c + 2, res1, aux1, bia1);
       }
-      if (tile == blockIdx.x && warp_idx == 2 && lane == 0) VB_DBG(6);
+      if (w == group && warp_idx == 2 && lane == 0) VB_DBG(6);
     }
   }
 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  // the peer may still arrive on this CTA's barriers / the leader's MMAs may still write the peer's TMEM until both are done
+  if constexpr (pair) cluster_sync_all();
   if (threadIdx.x == 0) { VB_DBG(7); VB_DBG_NS(9); }
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (pair) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else                tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -456,34 +502,66 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
   return VB_OK;
 }
 
-template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
+template <int BN, int EPI, int CG>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmKernelParams& p, long long total_work, int max_ctas,
                        cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BN, EPI>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, CG>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CG>::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmCfg<BN>::SMEM_BYTES, stream, ta, tb, p);
+  // persistent grid: one CTA per SM; with clusters, as many clusters as the device can keep resident at once (a GPC
+  // with an odd number of free SMs cannot host a pair there) so that no cluster waits for a second wave
+  int groups_cap = max_ctas;
+  if (CG > 1) {
+    static int max_clusters = -1;   // per template instantiation; cluster size is 2 whenever it is not 1
+    if (max_clusters < 0) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * 148); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GemmCfg<BN, CG>::SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      cudaError_t eo = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      if (eo != cudaSuccess || n <= 0) return set_error(VB_ERR_CUDA, "cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(eo));
+      max_clusters = n;
+    }
+    groups_cap = max_ctas / CG < max_clusters ? max_ctas / CG : max_clusters;
+  }
+  const int groups = (int)(total_work < groups_cap ? total_work : groups_cap);
+  const int grid = groups * CG;
+  cudaError_t e = launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmCfg<BN, CG>::SMEM_BYTES, stream, CG, ta, tb, p);
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return VB_OK;
 }
 
-template <int BN>
-static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid, cudaStream_t stream) {
+template <int BN, int CG>
+static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, GemmKernelParams& p, long long work, int max_ctas,
+                           cudaStream_t stream) {
   switch (epi) {
-    case EPI_F32: return launch_gemm<BN, EPI_F32>(ta, tb, p, grid, stream);
-    case EPI_BF16: return launch_gemm<BN, EPI_BF16>(ta, tb, p, grid, stream);
-    case EPI_GELU: return launch_gemm<BN, EPI_GELU>(ta, tb, p, grid, stream);
-    case EPI_DGELU: return launch_gemm<BN, EPI_DGELU>(ta, tb, p, grid, stream);
-    case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC>(ta, tb, p, grid, stream);
-    default: return launch_gemm<BN, EPI_GENERIC>(ta, tb, p, grid, stream);
+    case EPI_F32: return launch_gemm<BN, EPI_F32, CG>(ta, tb, p, work, max_ctas, stream);
+    case EPI_BF16: return launch_gemm<BN, EPI_BF16, CG>(ta, tb, p, work, max_ctas, stream);
+    case EPI_GELU: return launch_gemm<BN, EPI_GELU, CG>(ta, tb, p, work, max_ctas, stream);
+    case EPI_DGELU: return launch_gemm<BN, EPI_DGELU, CG>(ta, tb, p, work, max_ctas, stream);
+    case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC, CG>(ta, tb, p, work, max_ctas, stream);
+    default: return launch_gemm<BN, EPI_GENERIC, CG>(ta, tb, p, work, max_ctas, stream);
   }
 }
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// cluster_m = 0 resolves to this (env VB_GEMM_CLUSTER=1|2 overrides, for experiments)
+static int default_cluster() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VB_GEMM_CLUSTER");
+    v = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 1;
+  }
+  return v;
+}
 
 }  // namespace vb
 
@@ -541,6 +619,12 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   int kps = (num_k + split_k - 1) / split_k;
   split_k = (num_k + kps - 1) / kps;  // no empty splits
 
+  // CTA pairs (tcgen05 cta_group::2) on adjacent row blocks
+  int cluster = a->cluster_m;
+  if (cluster == 0) cluster = default_cluster();
+  if (cluster != 1 && cluster != 2) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: cluster_m must be 0, 1 or 2");
+  if (num_m < 2 || max_ctas < 2) cluster = 1;
+
   GemmKernelParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_m_blocks = num_m; p.num_n_blocks = num_n; p.num_k_blocks = num_k;
@@ -572,10 +656,12 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   p.desc_base_b = umma_desc_base(lbo_b, sbo_b);
   p.kadv_a = a->a_mn_major ? 2 * 1024 : UK * 2;
   p.kadv_b = a->b_mn_major ? 2 * 1024 : UK * 2;
-  p.idesc = umma_idesc_bf16(BM, bn, a->a_mn_major ? 1 : 0, a->b_mn_major ? 1 : 0);
+  p.idesc = umma_idesc_bf16(BM * cluster, bn, a->a_mn_major ? 1 : 0, a->b_mn_major ? 1 : 0);   // pairs: 256 x bn MMAs
   p.dbg = reinterpret_cast<unsigned long long*>(a->dbg_timeline);
   p.a_mn = a->a_mn_major ? 1 : 0;
   p.b_mn = a->b_mn_major ? 1 : 0;
+  p.cluster = cluster;
+  p.num_m_groups = (num_m + cluster - 1) / cluster;
   p.fast_ok = 0;
   p.drop.ctr = (a->dropout.step && a->dropout.p > 0.f) ? a->dropout.step : nullptr;
   p.drop.site = a->dropout.site;
@@ -588,11 +674,10 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   else               st = make_tmap(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
   if (st) return st;
   if (a->b_mn_major) st = make_tmap(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
-  else               st = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)bn);
+  else               st = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)(bn / cluster));   // a pair CTA stages half the tile
   if (st) return st;
 
-  const long long total_tiles = (long long)num_m * num_n * split_k;
-  const int grid = (int)(total_tiles < max_ctas ? total_tiles : max_ctas);
+  const long long total_work = (long long)p.num_m_groups * num_n * split_k;
 
   // pick the epilogue specialisation; anything unusual runs the generic one
   int epi = EPI_GENERIC;
@@ -610,6 +695,10 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
     if (a->out_f32 && !a->out_bf16 && no_extra) { epi = EPI_F32; p.fast_ok = 1; }   // unaligned pitches use 32-bit accesses
     else if (a->out_bf16 && !a->out_f32 && !a->residual && no_extra && !has_drop) { epi = EPI_BF16; p.fast_ok = p.vec_bf16; }
   }
-  if (bn == 256) return launch_gemm_epi<256>(epi, ta, tb, p, grid, stream);
-  return launch_gemm_epi<128>(epi, ta, tb, p, grid, stream);
+  if (cluster == 2) {
+    if (bn == 256) return launch_gemm_epi<256, 2>(epi, ta, tb, p, total_work, max_ctas, stream);
+    return launch_gemm_epi<128, 2>(epi, ta, tb, p, total_work, max_ctas, stream);
+  }
+  if (bn == 256) return launch_gemm_epi<256, 1>(epi, ta, tb, p, total_work, max_ctas, stream);
+  return launch_gemm_epi<128, 1>(epi, ta, tb, p, total_work, max_ctas, stream);
 }
