@@ -553,12 +553,12 @@ static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-// cluster_m = 0 resolves to this (env VB_GEMM_CLUSTER=1|2 overrides, for experiments)
+// cluster_m = 0 resolves to this (env VB_GEMM_CLUSTER=1|2 forces one mode, for experiments)
 static int default_cluster() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VB_GEMM_CLUSTER");
-    v = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 1;
+    v = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;   // 0 = chosen per problem by the cost model
   }
   return v;
 }
@@ -587,43 +587,55 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   const int num_k = (a->K + BK - 1) / BK;
   int max_ctas = a->max_ctas > 0 ? a->max_ctas : dev_sms;
 
-  // tile width: minimise the modelled per-CTA time (cycles, from the clock64 timelines in profiles/): a 128x128 k-block
-  // costs ~580 cycles (bound by L2 -> smem operand traffic), a 128x256 one ~640; the epilogue of a tile (~4.5k / ~8.5k
-  // cycles) overlaps the next tile's main loop, the last one is exposed.
-  int bn = a->block_n;
-  if (bn == 0) {
-    auto cost = [&](int w) {
-      const long long tiles = (long long)num_m * ((a->N + w - 1) / w);
-      const long long rounds = (tiles + max_ctas - 1) / max_ctas;
-      const long long ml = (long long)num_k * (w == 256 ? 640 : 580);
-      const long long epi = (w == 256 ? 8500 : 4500);
-      return 2500 + rounds * (ml > epi ? ml : epi) + epi;
-    };
-    bn = (a->N > 128 && cost(256) < cost(128)) ? 256 : 128;
-  }
-  if (bn != 128 && bn != 256) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: block_n must be 0, 128 or 256");
-  const int num_n = (a->N + bn - 1) / bn;
-
-  int split_k = a->split_k;
-  if (split_k <= 0) {
-    split_k = 1;
-    if (a->atomic_out) {
-      const int tiles = num_m * num_n;
-      if (tiles * 2 <= max_ctas) split_k = max_ctas / tiles;
-      if (split_k > num_k) split_k = num_k;
-      if (split_k < 1) split_k = 1;
-    }
-  }
-  if (split_k > 1 && (!a->atomic_out || a->act != VB_ACT_NONE || a->bias || a->residual || a->out_colsum))
+  // Tile configuration = (tile width bn, CTAs per tile group cg, k splits): minimise the modelled time of the busiest CTA,
+  // in SM cycles, with constants measured on B200 (clock64 timelines / feed probes in profiles/):
+  //   main loop per 64-deep k-block: 128x128 ~430 (bound by the SM's operand ingest, ~98 B/clk of TMA writes competing with
+  //   the tensor core's smem reads), 128x256 ~650 (L2 -> SM bandwidth with all SMs pulling), CTA pair 256x128 ~400,
+  //   CTA pair 256x256 ~505 (= the tcgen05 floor); the epilogue of a tile overlaps the next tile's main loop, the last one
+  //   is exposed; ~3k cycles of prologue + first-load latency per launch.
+  if (a->block_n != 0 && a->block_n != 128 && a->block_n != 256) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: block_n must be 0, 128 or 256");
+  int cluster_req = a->cluster_m ? a->cluster_m : default_cluster();
+  if (cluster_req != 0 && cluster_req != 1 && cluster_req != 2) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: cluster_m must be 0, 1 or 2");
+  if (a->split_k > 1 && (!a->atomic_out || a->act != VB_ACT_NONE || a->bias || a->residual || a->out_colsum))
     return set_error(VB_ERR_INVALID, "vb_gemm_bf16: split_k > 1 needs atomic_out and a plain epilogue");
-  int kps = (num_k + split_k - 1) / split_k;
-  split_k = (num_k + kps - 1) / kps;  // no empty splits
-
-  // CTA pairs (tcgen05 cta_group::2) on adjacent row blocks
-  int cluster = a->cluster_m;
-  if (cluster == 0) cluster = default_cluster();
-  if (cluster != 1 && cluster != 2) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: cluster_m must be 0, 1 or 2");
-  if (num_m < 2 || max_ctas < 2) cluster = 1;
+  const bool can_split = a->atomic_out && a->act == VB_ACT_NONE && !a->bias && !a->residual && !a->out_colsum;
+  long long epi_base = 9000;   // generic epilogue
+  if (a->atomic_out) epi_base = 3000;
+  else if (a->act == VB_ACT_GELU || a->act == VB_ACT_DGELU) epi_base = 4200;
+  else if (a->act == VB_ACT_NONE && a->out_f32 && !a->out_bf16) epi_base = a->residual ? 4800 : 3000;
+  else if (a->act == VB_ACT_NONE && a->out_bf16 && !a->out_f32) epi_base = 3000;
+  int bn = 128, cluster = 1, split_k = 1;
+  {
+    long long best = -1;
+    static const int split_cand[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
+    for (int w = 128; w <= 256; w += 128) {
+      if (a->block_n && a->block_n != w) continue;
+      if (!a->block_n && w == 256 && a->N <= 128) continue;
+      for (int cg = 1; cg <= 2; ++cg) {
+        if (cluster_req && cluster_req != cg && !(cluster_req == 2 && cg == 1 && (num_m < 2 || max_ctas < 2))) continue;
+        if (cg == 2 && (num_m < 2 || max_ctas < 2)) continue;
+        const long long t_kb = (w == 128) ? (cg == 1 ? 430 : 400) : (cg == 1 ? 650 : 505);
+        const long long epi = epi_base * (w / 128);
+        const long long groups = (cg == 1) ? max_ctas : max_ctas / 2;
+        const long long tiles = (long long)((num_m + cg - 1) / cg) * ((a->N + w - 1) / w);
+        for (int sc : split_cand) {
+          if (a->split_k > 0 && sc != 1) break;
+          int sp = a->split_k > 0 ? a->split_k : sc;
+          if (sp > 1 && !can_split) break;
+          if (sp > num_k) { if (a->split_k > 0) sp = num_k; else break; }
+          const long long kps_ = (num_k + sp - 1) / sp;
+          sp = (int)((num_k + kps_ - 1) / kps_);   // no empty splits
+          const long long rounds = (tiles * sp + groups - 1) / groups;
+          const long long ml = kps_ * t_kb;
+          const long long c = 3000 + (cg == 2 ? 600 : 0) + rounds * (ml > epi ? ml : epi) + epi;
+          if (best < 0 || c < best) { best = c; bn = w; cluster = cg; split_k = sp; }
+        }
+      }
+    }
+    if (best < 0) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: no tile configuration for block_n=%d cluster_m=%d split_k=%d", a->block_n, a->cluster_m, a->split_k);
+  }
+  const int num_n = (a->N + bn - 1) / bn;
+  const int kps = (num_k + split_k - 1) / split_k;
 
   GemmKernelParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
