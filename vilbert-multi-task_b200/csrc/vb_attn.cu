@@ -50,12 +50,12 @@ struct AttnParams {
 // Copies `rows_valid` rows of D bf16 (row stride ld) into smem rows of stride D+8 with cp.async (16-byte LDGSTS, no
 // register staging: every request of the panel is in flight at once); rows beyond rows_valid are zero-filled
 // (src-size 0). Completion: cp_async_wait_all() + __syncthreads().
-template <int D>
+template <int D, int NTHREADS = ATT_THREADS>
 __device__ __forceinline__ void load_panel(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows_valid,
                                            int rows_total) {
   constexpr int LD = D + 8;
   constexpr int CH = D / 8;  // 16-byte chunks per row
-  for (int idx = threadIdx.x; idx < rows_total * CH; idx += ATT_THREADS) {
+  for (int idx = threadIdx.x; idx < rows_total * CH; idx += NTHREADS) {
     const int r = idx / CH, c = idx % CH;
     const bool ok = r < rows_valid;
     const __nv_bfloat16* g = src + (long long)(ok ? r : 0) * ld + c * 8;
@@ -416,6 +416,152 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
   store_tile<D>(p.dK + ((long long)b * p.Nk + k0) * p.lddk + h * D, p.lddk, dk, p.scale, p.scale, r0, rows_valid, lane, p.dbk ? p.dbk + h * D : nullptr);
 }
 
+
+// ------------------------------------------------------------------------------------------ backward: single pass (short sequences)
+// acc (16 x D) += A^T B with A^T[m][k] = sA[k0 + k][m0 + m] (sA row-major [k][m], pitch lda elements: the 16 x 16 A fragment
+// is fetched with ldmatrix.trans) and B = sB rows k0.. ([k][D], pitch D + 8).
+template <int D>
+__device__ __forceinline__ void mma_at_b(float (&acc)[D / 8][4], const __nv_bfloat16* sA, int lda, int m0,
+                                         const __nv_bfloat16* sB, int k0, int lane) {
+  constexpr int LD = D + 8;
+  const int mi = lane >> 3;
+  uint32_t a[4];
+  ldmatrix_x4_trans(a, smem_u32(sA + (k0 + (mi >> 1) * 8 + (lane & 7)) * lda + m0 + (mi & 1) * 8));
+#pragma unroll
+  for (int dp = 0; dp < D / 16; ++dp) {
+    uint32_t b[4];
+    ldmatrix_x4_trans(b, smem_u32(sB + (k0 + (mi & 1) * 8 + (lane & 7)) * LD + dp * 16 + (mi >> 1) * 8));
+    mma_bf16_16816(acc[2 * dp], a, b[0], b[1]);
+    mma_bf16_16816(acc[2 * dp + 1], a, b[2], b[3]);
+  }
+}
+
+// One CTA per (batch, head) when Nq, Nk <= 128 (every attention of ViLBERT: 36-38 tokens, 100-101 regions): Q, dO, K, V of the
+// head live in shared memory, S and dP are computed ONCE. Phase 1: warp w owns query rows [16w, 16w+16): P, dS per 64-key
+// block from registers, dQ += dS K, and P (with the dropout factor) / dS are parked as bf16 [query][key] tiles in shared
+// memory. Phase 2: warp w owns key rows [16w, 16w+16): dV = P^T dO and dK = dS^T Q over all queries (A fragments by
+// ldmatrix.trans). No recompute, no atomics, deterministic; the two-kernel path below remains for longer sequences.
+constexpr int ATT1_THREADS = 256;
+template <int D>
+__global__ void __launch_bounds__(ATT1_THREADS) attn_bwd_fused_kernel(const AttnParams p) {
+  constexpr int LD = D + 8;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  pdl_entry();
+  const int nqp = (p.Nq + 15) / 16 * 16;        // query rows staged (16-row warp tiles)
+  const int nkp = (p.Nk + KB - 1) / KB * KB;    // key rows staged (64-key blocks)
+  const int LDP = nkp + 8;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sdO = sQ + nqp * LD;
+  __nv_bfloat16* sK = sdO + nqp * LD;
+  __nv_bfloat16* sV = sK + nkp * LD;
+  __nv_bfloat16* sP = sV + nkp * LD;
+  __nv_bfloat16* sdS = sP + nqp * LDP;
+  float* sMask = reinterpret_cast<float*>(sdS + nqp * LDP);
+
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  load_panel<D, ATT1_THREADS>(sQ, p.Q + (long long)b * p.Nq * p.ldq + h * D, p.ldq, p.Nq, nqp);
+  load_panel<D, ATT1_THREADS>(sdO, p.dO + (long long)b * p.Nq * p.lddo + h * D, p.lddo, p.Nq, nqp);
+  load_panel<D, ATT1_THREADS>(sK, p.K + (long long)b * p.Nk * p.ldk + h * D, p.ldk, p.Nk, nkp);
+  load_panel<D, ATT1_THREADS>(sV, p.V + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
+  for (int j = threadIdx.x; j < nkp; j += ATT1_THREADS)
+    sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
+  cp_async_wait_all();
+  __syncthreads();
+
+  const float c = p.scale * LOG2E;
+  const uint32_t dseed = p.drop.ctr ? drop_seed(p.drop) : 0u;
+  const int r0 = warp * 16;
+  if (r0 < nqp) {
+    // ---- phase 1: this warp's 16 query rows
+    float dl[2] = {0.f, 0.f};   // delta = rowsum(dO o O)
+    {
+      const __nv_bfloat16* Og = p.O + (long long)b * p.Nq * p.ldo + h * D;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = r0 + g + hh * 8;
+        if (r < p.Nq) {
+          float acc = 0.f;
+          for (int cidx = t * 8; cidx < D; cidx += 32) {
+            const uint4 ov = __ldg(reinterpret_cast<const uint4*>(Og + (long long)r * p.ldo + cidx));
+            const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * LD + cidx);
+            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+            const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 of = __bfloat1622float2(o2[i]), df = __bfloat1622float2(d2[i]);
+              acc += of.x * df.x + of.y * df.y;
+            }
+          }
+          dl[hh] = acc;
+        }
+      }
+      dl[0] = quad_sum(dl[0]); dl[1] = quad_sum(dl[1]);
+    }
+    float ls[2] = {CUDART_INF_F, CUDART_INF_F};   // +inf -> P = 0 on padded query rows (their tiles must be zero for phase 2)
+    {
+      const float* lse = p.lse + ((long long)b * p.H + h) * p.Nq;
+      if (r0 + g < p.Nq) ls[0] = lse[r0 + g];
+      if (r0 + g + 8 < p.Nq) ls[1] = lse[r0 + g + 8];
+    }
+    float dq[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    for (int kb = 0; kb < nkp; kb += KB) {
+      float s[8][4], dp[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+      }
+      mma_a_bt<D>(s, sQ, r0, sK, kb, lane, p.Nk);
+      mma_a_bt<D>(dp, sdO, r0, sV, kb, lane, p.Nk);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = kb + nt * 8 + 2 * t;
+        const float mk0 = sMask[col], mk1 = sMask[col + 1];
+        float p0 = exp2f(s[nt][0] * c + mk0 - ls[0]), p1 = exp2f(s[nt][1] * c + mk1 - ls[0]);
+        float p2 = exp2f(s[nt][2] * c + mk0 - ls[1]), p3 = exp2f(s[nt][3] * c + mk1 - ls[1]);
+        float f0 = 1.f, f1 = 1.f, f2 = 1.f, f3 = 1.f;
+        if (p.drop.ctr) {   // element index of the reference's dropout on the probabilities: ((b*H + h)*Nq + q)*Nk + k
+          const uint32_t e0 = (uint32_t)((((long long)b * p.H + h) * p.Nq + r0 + g) * p.Nk + col);
+          const uint32_t e1 = e0 + 8u * (uint32_t)p.Nk;
+          f0 = drop_factor(dseed, e0, p.drop); f1 = drop_factor(dseed, e0 + 1, p.drop);
+          f2 = drop_factor(dseed, e1, p.drop); f3 = drop_factor(dseed, e1 + 1, p.drop);
+        }
+        // dS = P o (mask/(1-p) o dP - delta); the tile kept for dV is mask/(1-p) o P
+        s[nt][0] = p0 * (dp[nt][0] * f0 - dl[0]); s[nt][1] = p1 * (dp[nt][1] * f1 - dl[0]);
+        s[nt][2] = p2 * (dp[nt][2] * f2 - dl[1]); s[nt][3] = p3 * (dp[nt][3] * f3 - dl[1]);
+        *reinterpret_cast<uint32_t*>(sP + (r0 + g) * LDP + col) = pack_bf16(p0 * f0, p1 * f1);
+        *reinterpret_cast<uint32_t*>(sP + (r0 + g + 8) * LDP + col) = pack_bf16(p2 * f2, p3 * f3);
+        *reinterpret_cast<uint32_t*>(sdS + (r0 + g) * LDP + col) = pack_bf16(s[nt][0], s[nt][1]);
+        *reinterpret_cast<uint32_t*>(sdS + (r0 + g + 8) * LDP + col) = pack_bf16(s[nt][2], s[nt][3]);
+      }
+      mma_p_b<D>(dq, s, sK, kb, lane, p.Nk);
+    }
+    store_tile<D>(p.dQ + (long long)b * p.Nq * p.lddq + h * D, p.lddq, dq, p.scale, p.scale, r0, p.Nq, lane,
+                  p.dbq ? p.dbq + h * D : nullptr);
+  }
+  __syncthreads();
+  // ---- phase 2: this warp's 16 key rows
+  if (r0 < p.Nk) {
+    float dk[D / 8][4], dv[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    for (int q = 0; q < nqp; q += 16) {
+      mma_at_b<D>(dv, sP, LDP, r0, sdO, q, lane);
+      mma_at_b<D>(dk, sdS, LDP, r0, sQ, q, lane);
+    }
+    store_tile<D>(p.dV + (long long)b * p.Nk * p.lddv + h * D, p.lddv, dv, 1.f, 1.f, r0, p.Nk, lane, p.dbv ? p.dbv + h * D : nullptr);
+    store_tile<D>(p.dK + (long long)b * p.Nk * p.lddk + h * D, p.lddk, dk, p.scale, p.scale, r0, p.Nk, lane, p.dbk ? p.dbk + h * D : nullptr);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -456,13 +602,13 @@ static AttnParams to_params(const vb_attn_args* a) {
 }
 
 template <typename Kern>
-static int launch_att(Kern kern, dim3 grid, size_t smem, const AttnParams& p, cudaStream_t s, const char* what) {
+static int launch_att(Kern kern, dim3 grid, size_t smem, const AttnParams& p, cudaStream_t s, const char* what, int threads = ATT_THREADS) {
   if (smem > 227 * 1024) return set_error(VB_ERR_UNSUPPORTED, "%s: sequence too long for the smem-resident panel (%zu bytes)", what, smem);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   }
-  cudaError_t e = launch_pdl(kern, grid, dim3(ATT_THREADS), smem, s, p);
+  cudaError_t e = launch_pdl(kern, grid, dim3(threads), smem, s, p);
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return VB_OK;
 }
@@ -491,6 +637,19 @@ extern "C" vb_status vb_attention_bwd(const vb_attn_args* a, void* stream) {
   const AttnParams p = to_params(a);
   cudaStream_t st = (cudaStream_t)stream;
   const int nkp = (a->Nk + KB - 1) / KB * KB, nqp = (a->Nq + KB - 1) / KB * KB;
+  // short sequences (all of ViLBERT's): one CTA per (batch, head) computes dQ, dK and dV in a single pass
+  if (a->Nq <= 128 && a->Nk <= 128 && a->D >= 32 && !getenv("VB_ATTN_BWD_TWO_KERNELS")) {
+    const int nq16 = (a->Nq + 15) / 16 * 16;
+    const size_t smem_f = (size_t)(2 * nq16 + 2 * nkp) * (a->D + 8) * 2 + (size_t)2 * nq16 * (nkp + 8) * 2 + (size_t)nkp * 4;
+    if (smem_f <= 227 * 1024) {
+      dim3 gf(a->H, a->B);
+      switch (a->D) {
+        case 32: return launch_att(attn_bwd_fused_kernel<32>, gf, smem_f, p, st, "vb_attention_bwd(fused)", ATT1_THREADS);
+        case 64: return launch_att(attn_bwd_fused_kernel<64>, gf, smem_f, p, st, "vb_attention_bwd(fused)", ATT1_THREADS);
+        default: return launch_att(attn_bwd_fused_kernel<128>, gf, smem_f, p, st, "vb_attention_bwd(fused)", ATT1_THREADS);
+      }
+    }
+  }
   const size_t smem_q = (size_t)(2 * TQ + 2 * nkp) * (a->D + 8) * 2 + (size_t)nkp * 4;
   const size_t smem_k = (size_t)(2 * TQ + 2 * nqp) * (a->D + 8) * 2 + (size_t)nqp * 8;
   dim3 gq((a->Nq + TQ - 1) / TQ, a->H, a->B), gk((a->Nk + TQ - 1) / TQ, a->H, a->B);
