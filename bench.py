@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=36)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce after the whole backward instead of overlapping it")
+    ap.add_argument("--segments", type=int, default=12, help="N > 1: number of backward pieces whose gradient ranges are all-reduced while the rest runs")
     ap.add_argument("--eval-mode", action="store_true", help="disable the dropout layers (reference eval mode); default is train mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8)
@@ -248,7 +249,7 @@ def main():
     if overlapped:
         # data parallel: the step is captured as 12 graphs; after each one the finished tail range of the flat gradient
         # buffer is all-reduced on a communication stream while the remaining backward pieces run
-        plan.capture_segments(12)
+        plan.capture_segments(a.segments)
         comm_stream = torch.cuda.Stream()
     elif not a.no_graph:
         plan.capture()
@@ -393,7 +394,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not a.no_graph,
-                   "allreduce": ("none (1 GPU)" if world == 1 else ("NCCL AVG of the flat fp32 gradient buffer, 12 tail ranges overlapped with backward" if overlapped
+                   "allreduce": ("none (1 GPU)" if world == 1 else (f"NCCL AVG of the flat fp32 gradient buffer, {a.segments} tail ranges overlapped with backward" if overlapped
                                  else "NCCL AVG of the flat fp32 gradient buffer after backward (8 buckets)")),
                    "l2": "working set (activations + weights + grads ~6 GB/step) exceeds the 126 MB L2; no explicit flush",
                    "streams": "text and vision segments on two CUDA streams (parallel graph branches)" if eng.two_streams else "single stream",

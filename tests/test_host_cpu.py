@@ -94,8 +94,9 @@ def test_plan_builds_on_cpu(golden_dir, task_tokens, B):
 
 
 def test_ddp_segments_partition_the_gradient_buffer(golden_dir):
-    """Overlapped data-parallel step: backward pieces end at stream barriers and release tail ranges of the flat gradient
-    buffer that (a) tile it exactly and (b) are never written by a later backward op."""
+    """Overlapped data-parallel step: backward pieces (each with at least one kernel, no side-stream event recorded in one
+    piece and waited for in a later one) release tail ranges of the flat gradient buffer that (a) tile it exactly and (b)
+    are never written by a later backward op."""
     cfgj = json.load(open(os.path.join(golden_dir, "tiny_b4.json")))["config"]
     eng = Engine(BertConfig.from_dict(cfgj), "cpu", _build_only=True)
     plan = eng.plan(4, 9, 11, grad_outputs=O.HEAD_NAMES, train=True)
@@ -104,7 +105,10 @@ def test_ddp_segments_partition_the_gradient_buffer(golden_dir):
         assert segs[0][0] == 0 and segs[-1][1] == len(plan.bwd) and segs[0][3] == eng.ps.numel and segs[-1][2] == 0
         for (lo, hi, glo, ghi), nxt in zip(segs, segs[1:] + [None]):
             assert lo < hi and glo <= ghi
-            assert hi == 0 or plan.bwd[hi - 1][0] is None or hi == len(plan.bwd)      # cut right after a barrier
+            assert any(op[0] is not None for op in plan.bwd[lo:hi])                          # no kernel-less piece
+            recs = {op[1][1] for op in plan.bwd[:hi] if op[0] is None and len(op[1]) == 2 and op[1][0] == "rec"}
+            late = {op[1][1] for op in plan.bwd[hi:] if op[0] is None and len(op[1]) == 2 and op[1][0] == "wait"}
+            assert not (recs & late)                                                          # no event crosses the cut
             if nxt is not None:
                 assert nxt[0] == hi and nxt[3] == glo
             for (off, n), touch in plan.grad_touch.items():                              # released ranges are final

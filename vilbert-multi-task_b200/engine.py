@@ -1003,21 +1003,39 @@ class Plan:
         final (no later op writes it) and may be all-reduced while the remaining pieces execute. The ranges tile the
         whole flat buffer from its end (heads, last layers) to its start (embeddings)."""
         n_ops = len(self.bwd)
-        barriers = [i + 1 for i, op in enumerate(self.bwd) if op[0] is None and not op[1] and 0 < i + 1 < n_ops]
+        # legal cut positions: a piece ends with a join of every stream and the next one starts with a fork, so any position
+        # works as long as no event recorded in one piece is waited for in a later one (rec/wait markers of the side streams)
+        rec_pos, last_wait = {}, {}
+        for i, op in enumerate(self.bwd):
+            if op[0] is None and len(op[1]) == 2:
+                if op[1][0] == "rec": rec_pos[op[1][1]] = i
+                elif op[1][0] == "wait": last_wait[op[1][1]] = i
+        straddle = [0] * (n_ops + 1)
+        for ev, r in rec_pos.items():
+            for i in range(r + 1, last_wait.get(ev, r) + 1):
+                straddle[i] += 1
+        n_kern = [0] * (n_ops + 1)                      # kernels in bwd[:i]
+        for i, op in enumerate(self.bwd):
+            n_kern[i + 1] = n_kern[i] + (op[0] is not None)
+        cand = [i for i in range(1, n_ops) if straddle[i] == 0 and self.bwd[i - 1][0] is not None or
+                (straddle[i] == 0 and self.bwd[i - 1][0] is None and not self.bwd[i - 1][1])]
         cuts = []
         for k in range(1, n_segments):
-            want = n_ops * k // n_segments
-            cand = [b for b in barriers if b not in cuts]
-            if not cand:
+            want = n_kern[n_ops] * k // n_segments     # equal kernel counts per piece
+            free = [c for c in cand if c not in cuts]
+            if not free:
                 break
-            cuts.append(min(cand, key=lambda b: abs(b - want)))
+            cuts.append(min(free, key=lambda c: abs(n_kern[c] - want)))
         cuts = sorted(set(cuts)) + [n_ops]
         # every piece must contain at least one kernel (an empty CUDA graph is legal but pointless)
         kept, prev = [], 0
         for cpos in cuts:
-            if any(op[0] is not None for op in self.bwd[prev:cpos]) or cpos == n_ops:
+            if n_kern[cpos] > n_kern[prev]:
                 kept.append(cpos)
                 prev = cpos
+        if not kept or kept[-1] != n_ops:               # trailing markers join the last piece that has kernels
+            if kept: kept[-1] = n_ops
+            else: kept = [n_ops]
         cuts = kept
         ranges = sorted(self.grad_touch.items())          # by flat offset
         numel = self.e.ps.numel
