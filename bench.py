@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=36)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce after the whole backward instead of overlapping it")
-    ap.add_argument("--segments", type=int, default=12, help="N > 1: number of backward pieces whose gradient ranges are all-reduced while the rest runs")
+    ap.add_argument("--segments", type=int, default=8, help="N > 1: number of backward pieces whose gradient ranges are all-reduced while the rest runs")
     ap.add_argument("--eval-mode", action="store_true", help="disable the dropout layers (reference eval mode); default is train mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8)
@@ -423,10 +423,10 @@ def main():
         dom, (dn, dms) = max(sigs.items(), key=lambda kv: kv[1][1])
         dflops = 2.0 * dom[0] * dom[1] * dom[2]
         dach = dflops / (dms / dn / 1e3) / 1e12
-        # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01_ncu_full_top_kernels_raw.csv), same signatures
-        NCU_DRAM_BYTES = {(1024, 1024, 6400, 1, 1, 0, 0, 1): 30.44e6, (6400, 1024, 1024, 0, 0, 0, 1, 0): 44.54e6,
-                          (6400, 3072, 1024, 0, 0, 0, 0, 0): 22.51e6, (2304, 3072, 768, 0, 1, 3, 0, 0): 22.49e6,
-                          (2304, 768, 768, 0, 0, 0, 1, 0): 11.83e6}
+        # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01_ncu_full_top_kernels_v2_pairs_raw.csv), same signatures
+        NCU_DRAM_BYTES = {(1024, 1024, 6400, 1, 1, 0, 0, 1): 30.48e6, (6400, 1024, 1024, 0, 0, 0, 1, 0): 47.75e6,
+                          (6400, 3072, 1024, 0, 0, 0, 0, 0): 25.04e6, (2304, 3072, 768, 0, 1, 3, 0, 0): 22.67e6,
+                          (2304, 768, 768, 0, 0, 0, 1, 0): 11.87e6}
         out["roofline"] = {"bound": "tensor",
                            "kernel": f"gemm_tcgen05_kernel M={dom[0]} N={dom[1]} K={dom[2]} (a_mn={dom[3]} b_mn={dom[4]} act={dom[5]} residual={dom[6]} "
                                      f"atomic={dom[7]}): the GEMM signature with the largest share of the step ({dn} launches, {dms:.3f} ms)",
