@@ -110,6 +110,11 @@ typedef struct vb_gemm_args {
 
 vb_status vb_gemm_bf16(const vb_gemm_args* args, void* stream);
 
+/* Host-only query: the tile configuration vb_gemm_bf16 would use for `args` (fields block_n / cluster_m / split_k that are
+   non-zero in `args` are honoured) on a device with `sm_count` SMs (0 = the current CUDA device). No GPU work, no device
+   needed when sm_count > 0; only the shape, layout, epilogue and output fields of `args` are read. */
+vb_status vb_gemm_plan(const vb_gemm_args* args, int32_t sm_count, int32_t* block_n, int32_t* cluster_m, int32_t* split_k);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused attention:  P = softmax(Q K^T * scale + mask[b, key]),  O = P V, heads merged in the output.
  * Replaces BertSelfAttention.forward (vilbert.py:424-460), BertImageSelfAttention.forward (:571-619,

@@ -64,6 +64,7 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 _SIGNATURES = {
     "vb_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "vb_gemm_bf16": [C.POINTER(GemmArgs), _P],
+    "vb_gemm_plan": [C.POINTER(GemmArgs), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "vb_attention_fwd": [C.POINTER(AttnArgs), _P],
     "vb_attention_bwd": [C.POINTER(AttnArgs), _P],
     "vb_layernorm_fwd": [_P, _I64, _P, _P, _F, _P, _P, _I64, _P, _P, _I32, _I32, _P, _P],

@@ -563,30 +563,10 @@ static int default_cluster() {
   return v;
 }
 
-}  // namespace vb
-
-extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
-  using namespace vb;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!a) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: null args");
-  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: empty problem %dx%dx%d", a->M, a->N, a->K);
-  if (!a->A || !a->B) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: null operand");
-  if ((a->lda % 8) || (a->ldb % 8) || !aligned(a->A, 16) || !aligned(a->B, 16))
-    return set_error(VB_ERR_INVALID, "vb_gemm_bf16: operands need ld %% 8 == 0 and 16-byte aligned bases (lda=%lld ldb=%lld)",
-                     (long long)a->lda, (long long)a->ldb);
-  if (!a->out_f32 && !a->out_bf16) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: no output");
-  if (a->act == VB_ACT_DGELU && !a->aux) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: DGELU needs aux");
-  if (a->bias && !aligned(a->bias, 16)) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: bias must be 16-byte aligned");
-  if (a->atomic_out && (!a->out_f32 || a->out_bf16 || a->out_pre))
-    return set_error(VB_ERR_INVALID, "vb_gemm_bf16: atomic_out supports only out_f32");
-  int dev_sms = 0, cc = 0;
-  if (int s = vb_device_info(&dev_sms, &cc)) return s;
-  if (cc / 10 != 10) return set_error(VB_ERR_UNSUPPORTED, "vb_gemm_bf16: needs an sm_100 device (found sm_%d)", cc);
-
+// Chooses (tile width, CTAs per tile group, k splits) for a problem; honours the values the caller fixed. Pure host code.
+static int choose_config(const vb_gemm_args* a, int max_ctas, int* bn_out, int* cluster_out, int* split_out) {
   const int num_m = (a->M + BM - 1) / BM;
   const int num_k = (a->K + BK - 1) / BK;
-  int max_ctas = a->max_ctas > 0 ? a->max_ctas : dev_sms;
-
   // Tile configuration = (tile width bn, CTAs per tile group cg, k splits): minimise the modelled time of the busiest CTA,
   // in SM cycles, with constants measured on B200 (clock64 timelines / feed probes in profiles/):
   //   main loop per 64-deep k-block: 128x128 ~430 (bound by the SM's operand ingest, ~98 B/clk of TMA writes competing with
@@ -634,6 +614,36 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
     }
     if (best < 0) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: no tile configuration for block_n=%d cluster_m=%d split_k=%d", a->block_n, a->cluster_m, a->split_k);
   }
+  *bn_out = bn; *cluster_out = cluster; *split_out = split_k;
+  return VB_OK;
+}
+
+}  // namespace vb
+
+extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
+  using namespace vb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: null args");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: empty problem %dx%dx%d", a->M, a->N, a->K);
+  if (!a->A || !a->B) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: null operand");
+  if ((a->lda % 8) || (a->ldb % 8) || !aligned(a->A, 16) || !aligned(a->B, 16))
+    return set_error(VB_ERR_INVALID, "vb_gemm_bf16: operands need ld %% 8 == 0 and 16-byte aligned bases (lda=%lld ldb=%lld)",
+                     (long long)a->lda, (long long)a->ldb);
+  if (!a->out_f32 && !a->out_bf16) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: no output");
+  if (a->act == VB_ACT_DGELU && !a->aux) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: DGELU needs aux");
+  if (a->bias && !aligned(a->bias, 16)) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: bias must be 16-byte aligned");
+  if (a->atomic_out && (!a->out_f32 || a->out_bf16 || a->out_pre))
+    return set_error(VB_ERR_INVALID, "vb_gemm_bf16: atomic_out supports only out_f32");
+  int dev_sms = 0, cc = 0;
+  if (int s = vb_device_info(&dev_sms, &cc)) return s;
+  if (cc / 10 != 10) return set_error(VB_ERR_UNSUPPORTED, "vb_gemm_bf16: needs an sm_100 device (found sm_%d)", cc);
+
+  const int num_m = (a->M + BM - 1) / BM;
+  const int num_k = (a->K + BK - 1) / BK;
+  int max_ctas = a->max_ctas > 0 ? a->max_ctas : dev_sms;
+
+  int bn = 128, cluster = 1, split_k = 1;
+  if (int st = choose_config(a, max_ctas, &bn, &cluster, &split_k)) return st;
   const int num_n = (a->N + bn - 1) / bn;
   const int kps = (num_k + split_k - 1) / split_k;
 
@@ -713,4 +723,20 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   }
   if (bn == 256) return launch_gemm_epi<256, 1>(epi, ta, tb, p, total_work, max_ctas, stream);
   return launch_gemm_epi<128, 1>(epi, ta, tb, p, total_work, max_ctas, stream);
+}
+
+extern "C" vb_status vb_gemm_plan(const vb_gemm_args* a, int32_t sm_count_, int32_t* block_n, int32_t* cluster_m, int32_t* split_k) {
+  using namespace vb;
+  if (!a || !block_n || !cluster_m || !split_k) return set_error(VB_ERR_INVALID, "vb_gemm_plan: null argument");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(VB_ERR_INVALID, "vb_gemm_plan: empty problem %dx%dx%d", a->M, a->N, a->K);
+  int sms = sm_count_;
+  if (sms <= 0) {
+    int cc = 0;
+    if (int s = vb_device_info(&sms, &cc)) return s;
+  }
+  const int max_ctas = a->max_ctas > 0 ? a->max_ctas : sms;
+  int bn, cl, sp;
+  if (int s = choose_config(a, max_ctas, &bn, &cl, &sp)) return s;
+  *block_n = bn; *cluster_m = cl; *split_k = sp;
+  return VB_OK;
 }

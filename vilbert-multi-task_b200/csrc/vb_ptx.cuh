@@ -274,21 +274,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// erf(x) by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level): 1 rcp + 1 ex2 + 6 FMA instead of the
-// ~40-instruction libdevice erff. Keeps the fused GELU epilogues small enough for the instruction cache.
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float y = 1.0f - poly * t * __expf(-ax * ax);
-  return copysignf(y, x);
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  return x * 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f));
-}
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level): 1 rcp + 1 ex2 + 6 FMA instead of the ~40-instruction
+// libdevice erff. Keeps the fused GELU epilogues small enough for the instruction cache.
 // GELU and its derivative d/dx [x * Phi(x)] = Phi(x) + x * phi(x) in one go: erf(x/sqrt2) and phi(x) share exp(-x^2/2).
 __device__ __forceinline__ void gelu_erf_and_grad(float x, float& g, float& dg) {
   const float z = fabsf(x) * 0.70710678118654752440f;
@@ -302,11 +289,6 @@ __device__ __forceinline__ void gelu_erf_and_grad(float x, float& g, float& dg) 
   const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
   g = x * cdf;
   dg = fmaf(x * 0.39894228040143267794f, e, cdf);
-}
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  float g, dg;
-  gelu_erf_and_grad(x, g, dg);
-  return dg;
 }
 
 }  // namespace vb
