@@ -563,6 +563,20 @@ static int default_cluster() {
   return v;
 }
 
+// Modelled fixed cost of running a problem as CTA pairs. In isolation a pair launch costs only ~600 cycles more (cluster
+// sync, leader-only issue), but inside the two-stream step a pair needs both SMs of a TPC free at once while kernels of the
+// other stream hold SMs: sweeping this constant on the full training step (profiles/r01_bench_v15_pair_penalty_sweep.txt:
+// 600 -> 11.24 ms, 2500 -> 11.15, 6000 -> 11.07, 10000 -> 11.11, 16000 -> 11.17, 30000 -> 11.18) puts the optimum at ~6000,
+// i.e. pairs only where they save at least ~3 us.
+static long long pair_penalty() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("VB_GEMM_PAIR_PENALTY");   // cycles; development override
+    v = e ? atoll(e) : 6000;
+  }
+  return v;
+}
+
 // Chooses (tile width, CTAs per tile group, k splits) for a problem; honours the values the caller fixed. Pure host code.
 static int choose_config(const vb_gemm_args* a, int max_ctas, int* bn_out, int* cluster_out, int* split_out) {
   const int num_m = (a->M + BM - 1) / BM;
@@ -607,7 +621,7 @@ static int choose_config(const vb_gemm_args* a, int max_ctas, int* bn_out, int* 
           sp = (int)((num_k + kps_ - 1) / kps_);   // no empty splits
           const long long rounds = (tiles * sp + groups - 1) / groups;
           const long long ml = kps_ * t_kb;
-          const long long c = 3000 + (cg == 2 ? 600 : 0) + rounds * (ml > epi ? ml : epi) + epi;
+          const long long c = 3000 + (cg == 2 ? pair_penalty() : 0) + rounds * (ml > epi ? ml : epi) + epi;
           if (best < 0 || c < best) { best = c; bn = w; cluster = cg; split_k = sp; }
         }
       }
