@@ -190,10 +190,11 @@ def main():
             return
         W = max(min(a.warmup, 2), 1)
         r = run_cpu_oracle(cfgj, a.cpu_batch, Nv, Nt, min(a.steps, 5), W, budget_s=90.0)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": 0, "steps": r["steps_timed"], "warmup": W,
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": a.gpus, "steps": r["steps_timed"], "warmup": W,
                           "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "config": {"workload": workload, "sample_batch": r["sample_batch"],
-                                     "note": "CPU arm: bounded sample of the workload per step (per-sample cost is batch-independent on CPU at this size)"},
+                                     "note": "CPU arm on the host cores of rank 0 (no GPU work whatever --gpus says): bounded sample of the workload per step "
+                                             "(per-sample cost is batch-independent on CPU at this size)"},
                           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                           "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
