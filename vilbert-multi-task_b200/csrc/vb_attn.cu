@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "vb_internal.h"
 #include "vb_ptx.cuh"
@@ -638,7 +639,8 @@ extern "C" vb_status vb_attention_bwd(const vb_attn_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nkp = (a->Nk + KB - 1) / KB * KB, nqp = (a->Nq + KB - 1) / KB * KB;
   // short sequences (all of ViLBERT's): one CTA per (batch, head) computes dQ, dK and dV in a single pass
-  if (a->Nq <= 128 && a->Nk <= 128 && a->D >= 32 && !getenv("VB_ATTN_BWD_TWO_KERNELS")) {
+  static const bool two_kernels_forced = getenv("VB_ATTN_BWD_TWO_KERNELS") != nullptr;   // development switch (tools/attn_probe.py)
+  if (a->Nq <= 128 && a->Nk <= 128 && a->D >= 32 && !two_kernels_forced) {
     const int nq16 = (a->Nq + 15) / 16 * 16;
     const size_t smem_f = (size_t)(2 * nq16 + 2 * nkp) * (a->D + 8) * 2 + (size_t)2 * nq16 * (nkp + 8) * 2 + (size_t)nkp * 4;
     if (smem_f <= 227 * 1024) {
