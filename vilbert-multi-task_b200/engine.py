@@ -997,11 +997,12 @@ class Plan:
             self._run(self.fwd)
             self._run(self.bwd)
 
-    def ddp_segments(self, n_segments=4):
+    def ddp_segments(self, n_segments=4, tail_cut=True):
         """Cuts the backward op list at stream barriers into `n_segments` pieces and returns
         [(bwd_op_lo, bwd_op_hi, grad_lo, grad_hi)]: after piece i has run, the flat gradient range [grad_lo, grad_hi) is
         final (no later op writes it) and may be all-reduced while the remaining pieces execute. The ranges tile the
-        whole flat buffer from its end (heads, last layers) to its start (embeddings)."""
+        whole flat buffer from its end (heads, last layers) to its start (embeddings). With `tail_cut` one extra piece holds
+        only the last few kernels, so up to n_segments + 1 pieces are returned."""
         n_ops = len(self.bwd)
         # legal cut positions: a piece ends with a join of every stream and the next one starts with a fork, so any position
         # works as long as no event recorded in one piece is waited for in a later one (rec/wait markers of the side streams)
@@ -1026,6 +1027,12 @@ class Plan:
             if not free:
                 break
             cuts.append(min(free, key=lambda c: abs(n_kern[c] - want)))
+        if tail_cut and cand:
+            # one more cut just before the last kernels (the embedding backward): everything except the embedding tables, whose
+            # gradients only the very last kernels produce, leaves the exposed final all-reduce
+            late = [c for c in cand if n_kern[n_ops] - n_kern[c] >= 3]
+            if late and (not cuts or late[-1] > max(cuts)):
+                cuts.append(late[-1])
         cuts = sorted(set(cuts)) + [n_ops]
         # every piece must contain at least one kernel (an empty CUDA graph is legal but pointless)
         kept, prev = [], 0
