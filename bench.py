@@ -248,11 +248,23 @@ def main():
     reducer = FlatGradAllReducer(eng.ps.grad, n_buckets=8)   # NCCL all-reduce (AVG) of the flat fp32 gradient buffer
     overlapped = world > 1 and not a.no_graph and not a.no_overlap
     if overlapped:
-        # data parallel: the step is captured as 12 graphs; after each one the finished tail range of the flat gradient
-        # buffer is all-reduced on a communication stream while the remaining backward pieces run
-        plan.capture_segments(a.segments)
+        # data parallel: the step is captured as one graph per backward piece; after each one the finished tail range of the
+        # flat gradient buffer is all-reduced on a communication stream while the remaining backward pieces run. If a capture
+        # is refused the bench degrades (loudly, and the JSON says which mode ran) rather than losing the measurement.
+        for tail_cut in (True, False):
+            try:
+                plan.capture_segments(a.segments, tail_cut=tail_cut)
+                break
+            except Exception as e:   # noqa: BLE001
+                print(f"[bench] rank {rank}: capture_segments({a.segments}, tail_cut={tail_cut}) failed: {e}", file=sys.stderr)
+                try:
+                    torch.cuda.synchronize()
+                except Exception:    # noqa: BLE001
+                    pass
+        else:
+            overlapped = False
         comm_stream = torch.cuda.Stream()
-    elif not a.no_graph:
+    if not overlapped and not a.no_graph:
         plan.capture()
 
     def step():
@@ -395,7 +407,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not a.no_graph,
-                   "allreduce": ("none (1 GPU)" if world == 1 else (f"NCCL AVG of the flat fp32 gradient buffer, {a.segments} tail ranges overlapped with backward" if overlapped
+                   "allreduce": ("none (1 GPU)" if world == 1 else (f"NCCL AVG of the flat fp32 gradient buffer, {len(plan.segments)} tail ranges overlapped with backward" if overlapped
                                  else "NCCL AVG of the flat fp32 gradient buffer after backward (8 buckets)")),
                    "l2": "working set (activations + weights + grads ~6 GB/step) exceeds the 126 MB L2; no explicit flush",
                    "streams": "text and vision segments on two CUDA streams (parallel graph branches)" if eng.two_streams else "single stream",

@@ -1060,10 +1060,10 @@ class Plan:
             lo_op, hi_grad = cut, ready_lo
         return segs
 
-    def capture_segments(self, n_segments=4):
-        """Captures the step as `n_segments` CUDA graphs (graph 0 = prologue + forward + first backward piece) for the
-        data-parallel step: see run_step_overlapped."""
-        self.segments = self.ddp_segments(n_segments)
+    def capture_segments(self, n_segments=4, tail_cut=True):
+        """Captures the step as CUDA graphs, one per backward piece of ddp_segments (graph 0 = prologue + forward + first
+        backward piece), for the data-parallel step: see run_step_overlapped."""
+        self.segments = self.ddp_segments(n_segments, tail_cut=tail_cut)
         torch.cuda.synchronize()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
