@@ -106,6 +106,22 @@ typedef struct vb_gemm_args {
   uint32_t dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b;
   void* dbg_timeline;    /* NULL, or u64 [grid][10]: per-CTA clock64 / globaltimer stamps (development only) */
   int32_t cluster_m;     /* 0 = auto, 1 = no clusters, 2 = CTA pairs (tcgen05 cta_group::2) on adjacent row blocks */
+  /* ---- ABI v2: 16-bit operand formats and split precision -------------------------------------------------
+   * Forward operands (activations, weights) are IEEE fp16 (11 significant bits; the reference's own reduced
+   * precision mode is fp16, train_concap.py:504-505), gradient operands are bf16 (range). a_fp16 / b_fp16 / out_fp16:
+   * 0 = bf16, 1 = fp16 (out_fp16 is the format of out_bf16 and out_lo). A and B must have the SAME format: tcgen05
+   * kind::f16 encodes them separately but B200 raises an illegal-instruction fault on fp16 x bf16 (measured, round 2),
+   * so the backward contractions (dy bf16) read bf16 copies of the forward operands: out_b16 (same ld as out_bf16) is an
+   * additional, always-bf16 copy of the 16-bit output, written by the forward GEMM for the weight-gradient GEMM.
+   * Split precision ("fp32 parity mode", 1e-3): an operand x is stored as hi = fp16(x), lo = fp16(x - hi); with
+   * A_lo and/or B_lo given the contraction is A.B + A_lo.B + A.B_lo (three passes over K into the same TMEM
+   * accumulator; the lo.lo term, 2^-22 relative, is dropped). A_lo / B_lo use lda / ldb and the major of A / B.
+   * out_lo (same ld as out_bf16) receives the low part of the value written to out_bf16. */
+  int32_t a_fp16, b_fp16, out_fp16;
+  const void* A_lo;
+  const void* B_lo;
+  void* out_lo;
+  void* out_b16;
 } vb_gemm_args;
 
 vb_status vb_gemm_bf16(const vb_gemm_args* args, void* stream);
@@ -144,6 +160,14 @@ typedef struct vb_attn_args {
   /* optional (backward): += column sums of dQ / dK / dV, f32 [H*D] each — the bias gradients of the projections */
   float* dbias_q; float* dbias_k; float* dbias_v;
   vb_dropout dropout;   /* on the probabilities; element index ((b*H + h)*Nq + q)*Nk + k */
+  /* ---- ABI v2. qkv_fp16: Q, K, V and O are fp16 (forward operands) instead of bf16; dO / dQ / dK / dV are always bf16
+   * (the backward converts its Q / K / V panels to bf16 in shared memory). Split precision (forward only): with Q_lo,
+   * K_lo, V_lo given (same ld and indexing as Q / K / V) S = Q K^T + Q_lo K^T + Q K_lo^T and O = P V + P_lo V + P V_lo
+   * with P split in registers; O_lo (same ld as O) receives the low part of O. */
+  int32_t qkv_fp16;
+  const void* Q_lo; const void* K_lo; const void* V_lo;
+  void* O_lo;
+  void* O_b16;   /* forward: optional always-bf16 copy of O (same ldo): the operand of the out-projection's weight gradient */
 } vb_attn_args;
 
 vb_status vb_attention_fwd(const vb_attn_args* args, void* stream);
@@ -159,7 +183,9 @@ vb_status vb_attention_bwd(const vb_attn_args* args, void* stream);
 vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
                            float* y_f32, void* y_bf16, int64_t ldy, float* mean, float* rstd,
                            int32_t M, int32_t H, const vb_dropout* out_dropout /* may be NULL: dropout(LN(x)), embeddings */,
-                           void* stream);
+                           int32_t y_fp16 /* format of y_bf16 / y_lo: 0 = bf16, 1 = fp16 */,
+                           void* y_lo /* NULL, or the split-precision low part of y_bf16 (same ldy) */,
+                           void* y_b16 /* NULL, or an always-bf16 copy of y (same ldy): weight-gradient operand */, void* stream);
 /* Autograd of the above. dx as f32 and/or bf16; dgamma/dbeta are ACCUMULATED (atomics) and may be NULL.
  * If gelu_pre (bf16 [M,H], the GELU derivative saved by the forward GEMM) is given, dx_bf16 is multiplied by it — the
  * Linear -> GELU -> LayerNorm head transforms (vilbert.py:1152-1156, 1172-1176, 1714-1718).
@@ -173,9 +199,11 @@ vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_
                            const vb_dropout* in_dropout  /* NULL or the mask applied to the dense output feeding this LN: dx_bf16 / dbias are masked */,
                            void* stream);
 
-/* fp32 -> bf16 casts: flat (weights shadow, region-feature ingest) and 2-D with independent leading
+/* fp32 -> 16-bit casts: flat (weights shadow, region-feature ingest; bf16 or fp16, optionally hi + lo) and 2-D with independent leading
  * dimensions and a scale (pads operands whose row length is not a multiple of 8). */
-vb_status vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+vb_status vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, int32_t fp16 /* 0 = bf16, 1 = fp16 */,
+                              void* dst_lo /* NULL or split-precision low part */, void* dst_b16 /* NULL or always-bf16 copy */,
+                              void* stream);
 vb_status vb_cast2d_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows, int32_t cols,
                                 float scale, void* stream);
 
@@ -212,7 +240,9 @@ vb_status vb_small_linear_bwd(const float* dy, const float* x, int64_t ldx, cons
 /* pooled_output = pooled_t (*|+) pooled_v (fusion_method, vilbert.py:1677-1682, 1236-1241); backward
  * ACCUMULATES into da / db. */
 vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul,
-                             const vb_dropout* dropout /* NULL or dropout on the fused vector (index i) */, void* stream);
+                             const vb_dropout* dropout /* NULL or dropout on the fused vector (index i) */,
+                             int32_t out_fp16, void* out_lo /* format / split-precision low part of out_bf16 */,
+                             void* out_b16 /* NULL or always-bf16 copy */, void* stream);
 vb_status vb_fuse_pooled_bwd(const float* d, const float* a, const float* b, float* da, float* db, int64_t n, int32_t mul,
                              const vb_dropout* dropout, void* stream);
 /* ReLU backward of the poolers (vilbert.py:1121,1136): dx = dy * (y > 0). */
@@ -225,6 +255,23 @@ vb_status vb_axpy_f32(const float* x, float* y, int64_t n, float alpha, void* st
 vb_status vb_bce_logits_loss(const float* logits, const float* target, float* loss, float* dlogits_f32, void* dlogits_bf16,
                              int64_t ld_dlogits_bf16, int32_t rows, int32_t cols, float grad_scale, void* stream);
 
+/* Softmax cross-entropy, reduction = mean over the rows whose label != ignore_index (F.cross_entropy / nn.CrossEntropyLoss as
+ * used at vilbert.py:1578-1590 for the masked-LM (30522-way, ignore_index -1) and alignment objectives and at
+ * task_utils.py:339-343, 366-374 for the VL-logit / binary / tri heads). *loss (device scalar) = the mean (+= when
+ * accumulate_loss); dlogits = grad_scale * d loss / d logits as f32 and/or bf16 (the operand of the head's backward GEMMs),
+ * zero on ignored rows. No rows to average -> loss = NaN like torch, gradients 0. */
+vb_status vb_ce_loss(const float* logits, int64_t ld_logits, const int64_t* labels, int64_t ignore_index, float* loss,
+                     float* dlogits_f32, int64_t ld_d32, void* dlogits_bf16, int64_t ld_d16, int32_t rows, int32_t cols,
+                     float grad_scale, int32_t accumulate_loss, void* stream);
+
+/* Masked-region KL objective of BertForMultiModalPreTraining (visual_target == 0, vilbert.py:1506-1525):
+ *   loss = sum_{b,r: label[b,r]==1} sum_c t_c (log t_c - log_softmax(scores[b, r+1, :])_c) / max(#(label == 1), 0)
+ * scores f32 [B, Nv, C] (region 0 = the global feature is skipped, :1506), target f32 [B, Nv-1, C], label int64 [B, Nv-1].
+ * dscores (f32 [B,Nv,C] and/or bf16 with row pitch ld_d16) = grad_scale * d loss / d scores, zero on unmasked rows. */
+vb_status vb_kl_masked_loss(const float* scores, const float* target, const int64_t* label, float* loss, float* dscores_f32,
+                            void* dscores_bf16, int64_t ld_d16, int32_t B, int32_t Nv, int32_t C, float grad_scale,
+                            int32_t accumulate_loss, void* stream);
+
 /* Additive attention masks of BertModel.forward (vilbert.py:1341-1362): out[b,j] = (1 - mask[b,j]) * -10000,
  * mask int64 0/1 [B,N]; prepend_one != 0 emits N+1 entries per row with a leading 0 (task-token mask
  * extension, :1331-1334). */
@@ -234,6 +281,26 @@ vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_t B, int32_
 vb_status vb_step_counter_bump(uint32_t* step, void* stream);
 
 vb_status vb_memset_zero(void* ptr, int64_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-tensor AdamW on flat buffers. Replaces pytorch_transformers==1.0.0 AdamW as the reference
+ * builds it (train_tasks.py:401-426: one param group per tensor with its own lr / weight_decay, correct_bias=False),
+ * optimizer.step() + model.zero_grad() (train_tasks.py:550-551), and the engine's own weight-shadow cast:
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= step_size m / (sqrt(v) + eps);  p -= lr wd p   (decay after, on the new p)
+ *   step_size = lr, or lr sqrt(1-b2^t)/(1-b1^t) when correct_bias (t = *step, a device int32 the caller advances)
+ * p / g / m / v: flat f32 buffers with one layout. Work list: chunk c covers elements [chunk_start[c], +chunk_count[c]) of one
+ * tensor (starts multiples of 4) and uses groups[chunk_group[c]] (a DEVICE array, rewritten by the host when a scheduler
+ * changes an lr). g is multiplied by grad_scale on read (gradient accumulation / loss scaling) and zeroed when zero_grad.
+ * p16 (may be NULL): the 16-bit operand copy of the updated weights (bf16, or fp16 when p16_fp16), p16_lo its
+ * split-precision low part (may be NULL), p16_b an always-bf16 copy for the backward (may be NULL). */
+typedef struct vb_adamw_group {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t correct_bias;
+} vb_adamw_group;
+
+vb_status vb_adamw_step(float* p, float* g, float* m, float* v, void* p16, void* p16_lo, void* p16_b, int32_t p16_fp16,
+                        const int64_t* chunk_start, const int32_t* chunk_count, const int32_t* chunk_group, int32_t n_chunks,
+                        const vb_adamw_group* groups, const int32_t* step, float grad_scale, int32_t zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -444,7 +444,24 @@ def synth_vqa_target(B, n_ans=3129, seed=99, device="cpu"):
     return tgt.to(device)
 
 
-# --------------------------------------------------------------------------- bf16-operand mode
+# --------------------------------------------------------------------------- reduced-precision operand modes
+# The reference algorithm under the arithmetic contract of the engine's tensor-core modes: every F.linear / torch.matmul
+# rounds its OPERANDS (fp32 accumulation, fp32 everything else), forward and backward. Forward operands (activations,
+# weights) use _FWD_DT, gradient operands (dy, dS) use _GRAD_DT. Linear backward reads W and x in the forward format (the
+# engine's dgrad / wgrad read them in place); the attention backward rounds Q/K/V/P to the gradient format like the
+# engine's attention backward (its panels are converted to bf16 in shared memory). Separates the error inherent to the
+# operand formats from implementation error; not used for fp32 parity.
+_FWD_DT, _GRAD_DT = torch.bfloat16, torch.bfloat16
+
+
+def _rf(t):
+    return t.to(_FWD_DT).to(torch.float32)
+
+
+def _rg(t):
+    return t.to(_GRAD_DT).to(torch.float32)
+
+
 class _LinearBF16(torch.autograd.Function):
     """y = r(x) r(W)^T + b with fp32 accumulation; backward also rounds its matmul operands (dy, x, W)."""
 
@@ -452,15 +469,15 @@ class _LinearBF16(torch.autograd.Function):
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
-        y = _r(x) @ _r(w).t()
+        y = _rf(x) @ _rf(w).t()
         return y + b if b is not None else y
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        dyr = _r(dy)
-        dx = dyr @ _r(w)
-        dw = dyr.reshape(-1, dyr.shape[-1]).t() @ _r(x).reshape(-1, x.shape[-1])
+        dyr = _rg(dy)
+        dx = dyr @ _rf(w)
+        dw = dyr.reshape(-1, dyr.shape[-1]).t() @ _rf(x).reshape(-1, x.shape[-1])
         return dx, dw, (dy.reshape(-1, dy.shape[-1]).sum(0) if ctx.has_bias else None)
 
 
@@ -468,30 +485,35 @@ class _MatmulBF16(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
         ctx.save_for_backward(a, b)
-        return _r(a) @ _r(b)
+        return _rf(a) @ _rf(b)
 
     @staticmethod
     def backward(ctx, dy):
         a, b = ctx.saved_tensors
-        return _r(dy) @ _r(b).transpose(-1, -2), _r(a).transpose(-1, -2) @ _r(dy)
+        return _rg(dy) @ _rg(b).transpose(-1, -2), _rg(a).transpose(-1, -2) @ _rg(dy)
 
 
-def _r(t):
-    return t.to(torch.bfloat16).to(torch.float32)
+class operand_mode:
+    """Context manager: F.linear / torch.matmul of this oracle round their operands (see above).
+    operand_mode() = the engine's default "fp16" precision (fp16 forward operands, bf16 gradient operands)."""
 
-
-class bf16_operand_mode:
-    """Context manager: inside it every F.linear / torch.matmul of this oracle rounds its operands to bf16
-    (fp32 accumulation, fp32 everything else), forward AND backward. This is the reference algorithm under
-    the arithmetic contract of the engine's "bf16 mode" (north_star tolerance 1e-2): it separates the error
-    inherent to bf16 tensor-core operands from implementation error. Not used for fp32 parity."""
+    def __init__(self, fwd=torch.float16, grad=torch.bfloat16):
+        self.fwd, self.grad = fwd, grad
 
     def __enter__(self):
-        self._lin, self._mm = F.linear, torch.matmul
+        global _FWD_DT, _GRAD_DT
+        self._saved = (F.linear, torch.matmul, _FWD_DT, _GRAD_DT)
+        _FWD_DT, _GRAD_DT = self.fwd, self.grad
         F.linear = lambda x, w, b=None: _LinearBF16.apply(x, w, b)
         torch.matmul = lambda a, b: _MatmulBF16.apply(a, b)
         return self
 
     def __exit__(self, *exc):
-        F.linear, torch.matmul = self._lin, self._mm
+        global _FWD_DT, _GRAD_DT
+        F.linear, torch.matmul, _FWD_DT, _GRAD_DT = self._saved
         return False
+
+
+def bf16_operand_mode():
+    """Every operand bf16 (the engine's "bf16" precision; round-1 arithmetic)."""
+    return operand_mode(torch.bfloat16, torch.bfloat16)

@@ -26,27 +26,35 @@ def rel_l2(a, b):
 
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm_case(M, N, K, a_mn=False, b_mn=False, bias=False, res=False, act=0, out_bf16=False, atomic=False, split_k=1, block_n=0,
-              alpha=1.0, check=True, iters=0, seed=0, both_outputs=False, cluster_m=0):
-    """Returns (max relative error vs fp32 matmul of the bf16 operands, ms per launch or None)."""
+              alpha=1.0, check=True, iters=0, seed=0, both_outputs=False, cluster_m=0, a_fp16=False, b_fp16=False, out_fp16=False,
+              split=False):
+    """Returns (max relative error vs fp32 matmul of the 16-bit operands, ms per launch or None). a_fp16 / b_fp16 / out_fp16
+    pick fp16 instead of bf16 per operand (mixed formats = the dgrad / wgrad configuration). split=True stores A and B as
+    hi + lo (split precision, three passes) and compares with the float64 product of the fp32 operands."""
     dev = torch.device("cuda")
     g_ = torch.Generator(device=dev).manual_seed(seed)
     lib = L.lib()
-    A = (torch.randn(M, K, device=dev, generator=g_) * 0.5).to(BF)
-    B = (torch.randn(N, K, device=dev, generator=g_) * 0.5).to(BF)
+    dA, dB, dO = (torch.float16 if a_fp16 else BF), (torch.float16 if b_fp16 else BF), (torch.float16 if out_fp16 else BF)
+    A32 = torch.randn(M, K, device=dev, generator=g_) * 0.5
+    B32 = torch.randn(N, K, device=dev, generator=g_) * 0.5
+    A, B = A32.to(dA), B32.to(dB)
     pad8 = lambda x: (x + 7) // 8 * 8
-    if a_mn:
-        A_st = torch.zeros(K, pad8(M), device=dev, dtype=BF); A_st[:, :M] = A.t(); lda = pad8(M)
-    else:
-        A_st = torch.zeros(M, pad8(K), device=dev, dtype=BF); A_st[:, :K] = A; lda = pad8(K)
-    if b_mn:
-        B_st = torch.zeros(K, pad8(N), device=dev, dtype=BF); B_st[:, :N] = B.t(); ldb = pad8(N)
-    else:
-        B_st = torch.zeros(N, pad8(K), device=dev, dtype=BF); B_st[:, :K] = B; ldb = pad8(K)
+    def store(X, rows, cols, mn, dt):
+        if mn:
+            st = torch.zeros(cols, pad8(rows), device=dev, dtype=dt); st[:, :rows] = X.t(); return st, pad8(rows)
+        st = torch.zeros(rows, pad8(cols), device=dev, dtype=dt); st[:, :cols] = X; return st, pad8(cols)
+    A_st, lda = store(A, M, K, a_mn, dA)
+    B_st, ldb = store(B, N, K, b_mn, dB)
+    if split:
+        Al_st, _ = store((A32 - A.float()).to(dA), M, K, a_mn, dA)
+        Bl_st, _ = store((B32 - B.float()).to(dB), N, K, b_mn, dB)
     bias_t = torch.randn(N, device=dev, generator=g_) if bias else None
     res_t = torch.randn(M, N, device=dev, generator=g_) if res else None
     aux_t = torch.randn(M, N, device=dev, generator=g_).to(BF) if act == L.VB_ACT_DGELU else None
     out32 = torch.full((M, N), 0.0 if atomic else float("nan"), device=dev)
-    out16 = torch.empty(M, N, device=dev, dtype=BF) if out_bf16 else None
+    out16 = torch.empty(M, N, device=dev, dtype=dO) if out_bf16 else None
+    outlo = torch.empty(M, N, device=dev, dtype=dO) if (out_bf16 and split) else None
+    outb = torch.empty(M, N, device=dev, dtype=BF) if (out_bf16 and out_fp16 and not atomic) else None   # bf16 copy for the backward
     pre16 = torch.empty(M, N, device=dev, dtype=BF) if (act == L.VB_ACT_GELU and out_bf16 and N % 8 == 0) else None
     g = L.GemmArgs()
     g.M, g.N, g.K = M, N, K
@@ -64,11 +72,16 @@ def gemm_case(M, N, K, a_mn=False, b_mn=False, bias=False, res=False, act=0, out
     g.out_pre, g.ld_out_pre = (pre16.data_ptr(), N) if pre16 is not None else (None, 0)
     g.atomic_out, g.split_k, g.block_n, g.max_ctas = int(atomic), split_k, block_n, 0
     g.cluster_m = cluster_m
+    g.a_fp16, g.b_fp16, g.out_fp16 = int(a_fp16), int(b_fp16), int(out_fp16)
+    if split:
+        g.A_lo, g.B_lo = Al_st.data_ptr(), Bl_st.data_ptr()
+        if outlo is not None and not atomic: g.out_lo = outlo.data_ptr()
+    if outb is not None: g.out_b16 = outb.data_ptr()
     L.check(lib.vb_gemm_bf16(C.byref(g), stream()), "vb_gemm_bf16")
     torch.cuda.synchronize()
     err = None
     if check:
-        ref = alpha * (A.float() @ B.float().t())
+        ref = alpha * ((A32.double() @ B32.double().t()).float() if split else (A.float() @ B.float().t()))
         if bias: ref = ref + bias_t
         if act == L.VB_ACT_GELU:
             x_ = ref.clone(); ref = O.gelu(ref)
@@ -81,7 +94,12 @@ def gemm_case(M, N, K, a_mn=False, b_mn=False, bias=False, res=False, act=0, out
         scale = ref.abs().max().item() + 1e-9
         err = ((out32 - ref).abs().max() / scale).item() if want_f32 else 0.0
         if out16 is not None and not atomic:
-            err = max(err, ((out16.float() - ref).abs().max() / scale).item() - 4e-3)   # bf16 output rounding
+            if outlo is not None:   # hi + lo reconstructs the fp32 epilogue value
+                err = max(err, (((out16.float() + outlo.float()) - ref).abs().max() / scale).item())
+            else:
+                err = max(err, ((out16.float() - ref).abs().max() / scale).item() - (5e-4 if out_fp16 else 4e-3))   # output rounding
+        if outb is not None:
+            err = max(err, ((outb.float() - ref).abs().max() / scale).item() - 4e-3)
         if pre16 is not None:
             err = max(err, ((pre16.float() - pre_ref).abs().max() / (pre_ref.abs().max() + 1e-9)).item() - 4e-3)
         if err != err: err = float("inf")
@@ -100,21 +118,30 @@ def gemm_case(M, N, K, a_mn=False, b_mn=False, bias=False, res=False, act=0, out
 
 
 # ------------------------------------------------------------------------------------------ attention
-def attn_case(B, H, Nq, Nk, D, cross, peaked=1.0, iters=0, seed=0):
-    """Returns (dict of relative errors of O, dQ, dK, dV, lse vs fp32 torch on the same bf16 inputs, timing str)."""
+def attn_case(B, H, Nq, Nk, D, cross, peaked=1.0, iters=0, seed=0, fp16=False, split=False):
+    """Returns (dict of relative errors of O, dQ, dK, dV, lse vs fp32 torch on the same 16-bit inputs, timing str).
+    fp16: Q/K/V/O are fp16 (gradients stay bf16). split: Q/K/V given as hi + lo, O checked as hi + lo against the
+    fp32 inputs (forward only carries the low parts)."""
     dev = torch.device("cuda"); lib = L.lib()
     g_ = torch.Generator(device=dev).manual_seed(seed)
     Hd = H * D
+    DT = torch.float16 if fp16 else BF
     if cross:
-        qsrc = (torch.randn(B * Nq, 3 * Hd, device=dev, generator=g_) * peaked).to(BF)
-        ksrc = (torch.randn(B * Nk, 3 * Hd, device=dev, generator=g_) * peaked).to(BF)
+        q32 = torch.randn(B * Nq, 3 * Hd, device=dev, generator=g_) * peaked
+        k32 = torch.randn(B * Nk, 3 * Hd, device=dev, generator=g_) * peaked
+        qsrc, ksrc = q32.to(DT), k32.to(DT)
     else:
-        qsrc = ksrc = (torch.randn(B * Nq, 3 * Hd, device=dev, generator=g_) * peaked).to(BF)
+        q32 = k32 = torch.randn(B * Nq, 3 * Hd, device=dev, generator=g_) * peaked
+        qsrc = ksrc = q32.to(DT)
     q, k, v = qsrc[:, :Hd], ksrc[:, Hd:2 * Hd], ksrc[:, 2 * Hd:]
+    if split:
+        qlo_src, klo_src = (q32 - qsrc.float()).to(DT), (k32 - ksrc.float()).to(DT)
     lens = torch.randint(1, Nk + 1, (B,), device=dev, generator=g_); lens[0] = Nk
     if B > 1: lens[1] = 1                                                 # a row with a single valid key
     mask = ((torch.arange(Nk, device=dev)[None] >= lens[:, None]).float() * -10000.0).contiguous()
-    Ot = torch.zeros(B * Nq, Hd, device=dev, dtype=BF); lse = torch.zeros(B, H, Nq, device=dev)
+    Ot = torch.zeros(B * Nq, Hd, device=dev, dtype=DT); lse = torch.zeros(B, H, Nq, device=dev)
+    Olo = torch.zeros(B * Nq, Hd, device=dev, dtype=DT) if split else None
+    Ob = torch.zeros(B * Nq, Hd, device=dev, dtype=BF) if fp16 else None
     dO = torch.randn(B * Nq, Hd, device=dev, generator=g_).to(BF)
     dqb = torch.zeros(B * Nq, 3 * Hd, device=dev, dtype=BF); dkb = torch.zeros(B * Nk, 3 * Hd, device=dev, dtype=BF)
     delta = torch.zeros(B, H, Nq, device=dev)
@@ -128,6 +155,12 @@ def attn_case(B, H, Nq, Nk, D, cross, peaked=1.0, iters=0, seed=0):
     a.dK, a.lddk = dkb[:, Hd:2 * Hd].data_ptr(), 3 * Hd
     a.dV, a.lddv = dkb[:, 2 * Hd:].data_ptr(), 3 * Hd
     a.delta = delta.data_ptr()
+    a.qkv_fp16 = int(fp16)
+    if split:
+        a.Q_lo, a.K_lo, a.V_lo = qlo_src[:, :Hd].data_ptr(), klo_src[:, Hd:2 * Hd].data_ptr(), klo_src[:, 2 * Hd:].data_ptr()
+        a.O_lo = Olo.data_ptr()
+    if Ob is not None:
+        a.O_b16 = Ob.data_ptr()
     L.check(lib.vb_attention_fwd(C.byref(a), stream()), "vb_attention_fwd")
     L.check(lib.vb_attention_bwd(C.byref(a), stream()), "vb_attention_bwd")
     torch.cuda.synchronize()
@@ -138,10 +171,21 @@ def attn_case(B, H, Nq, Nk, D, cross, peaked=1.0, iters=0, seed=0):
     p = torch.softmax(s, -1)
     o = (p @ vf).permute(0, 2, 1, 3).reshape(B * Nq, Hd)
     o.backward(dO.float())
+    if split:
+        # forward against the fp32 (hi + lo) inputs; the backward of split precision contracts the hi parts only
+        qs = q32[:, :Hd].view(B, Nq, H, D).permute(0, 2, 1, 3); ks = k32[:, Hd:2 * Hd].view(B, Nk, H, D).permute(0, 2, 1, 3)
+        vs = k32[:, 2 * Hd:].view(B, Nk, H, D).permute(0, 2, 1, 3)
+        s32 = qs.double() @ ks.double().transpose(-1, -2) / math.sqrt(D) + mask[:, None, None, :].double()
+        o32 = (torch.softmax(s32, -1) @ vs.double()).permute(0, 2, 1, 3).reshape(B * Nq, Hd).float()
+        o_split = rel(Ot.float() + Olo.float(), o32)
     errs = dict(O=rel(Ot, o), dQ=rel(dqb[:, :Hd].view(B, Nq, H, D).permute(0, 2, 1, 3), qf.grad),
                 dK=rel(dkb[:, Hd:2 * Hd].view(B, Nk, H, D).permute(0, 2, 1, 3), kf.grad),
                 dV=rel(dkb[:, 2 * Hd:].view(B, Nk, H, D).permute(0, 2, 1, 3), vf.grad),
                 lse=rel(lse * math.log(2.0), torch.logsumexp(s, -1)))
+    if split:
+        errs["O_split"] = o_split
+    if Ob is not None:
+        errs["O_b16"] = max(rel(Ob, o) - 4e-3, 0.0)
     timing = ""
     if iters:
         for fn, nm in ((lib.vb_attention_fwd, "fwd"), (lib.vb_attention_bwd, "bwd")):
@@ -157,10 +201,10 @@ def attn_case(B, H, Nq, Nk, D, cross, peaked=1.0, iters=0, seed=0):
 
 
 # ------------------------------------------------------------------------------------------ full model
-def build_engine(cfgj, P, device):
+def build_engine(cfgj, P, device, precision="fp16"):
     from vilbert_b200.config import BertConfig
     from vilbert_b200.engine import Engine
-    eng = Engine(BertConfig.from_dict(cfgj), device)
+    eng = Engine(BertConfig.from_dict(cfgj), device, precision=precision)
     for k in eng.ps.entries:
         eng.ps.p(k).copy_(P[k])
     eng.refresh_weights()
@@ -181,8 +225,10 @@ def probe_loss(heads, names, tgt):
     return l
 
 
-def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, device="cuda", train_step=None):
-    """Engine vs the oracle in fp32 and in bf16-operand mode. Returns dict(out_fp32, out_bf16, grad_fp32, grad_bf16, ...)
+def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, device="cuda", train_step=None, precision="fp16",
+               oracle_modes=("fp32", "op")):
+    """Engine vs the oracle in fp32 and in the engine's operand-rounding mode ("op": fp16 forward / bf16 gradient operands for
+    precision "fp16" and "fp32", all-bf16 for "bf16"). Returns dict(out_fp32, out_op, grad_fp32, grad_op, ...)
     where each is {tensor name: error}; gradient errors are (max-rel with floor, rel-L2).
     train_step=k runs the engine in TRAIN mode (every nn.Dropout of the reference active, dropout step counter = k) against
     the oracle with the same stateless masks (oracle.DropMasks(k))."""
@@ -191,7 +237,7 @@ def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, de
     names = O.HEAD_NAMES if names is None else names
     P = O.synth_params(cfg, seed=seed, device=dev, qk_scale=qk_scale)
     inp = O.synth_inputs(cfg, B, Nv, Nt, seed=1234 + seed, device=dev)
-    eng = build_engine(cfgj, P, dev)
+    eng = build_engine(cfgj, P, dev, precision)
     drop = None
     if train_step is not None:
         eng.drop_step.fill_(int(train_step))
@@ -213,11 +259,11 @@ def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, de
         plan.run_backward()
         torch.cuda.synchronize()
         result["loss"] = lm.item()
-    for mode in ("fp32", "bf16"):
+    for mode in oracle_modes:
         Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
         Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
-        if mode == "bf16":
-            with O.bf16_operand_mode():
+        if mode == "op":
+            with (O.bf16_operand_mode() if precision == "bf16" else O.operand_mode()):
                 bert_o, heads_o = O.vilbert_for_vl_tasks(Pg, cfg, *oracle_args(inp), drop=drop)
                 if grads:
                     lo = probe_loss(heads_o, names, tgt); lo.backward()

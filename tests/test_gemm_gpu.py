@@ -57,6 +57,54 @@ def test_cta_pairs(kw, shape, bn):
     assert err < 2e-3, err
 
 
+@pytest.mark.parametrize("kw,shape", [
+    (dict(bias=True, res=True), (2304, 768, 768)),
+    (dict(bias=True, out_bf16=True, out_fp16=True), (6400, 3072, 1024)),
+    (dict(bias=True, act=L.VB_ACT_GELU, out_bf16=True, out_fp16=True), (300, 200, 136)),
+    (dict(b_mn=True, res=True), (2304, 768, 3072)),
+    (dict(a_mn=True, b_mn=True, atomic=True, split_k=0), (1024, 1024, 6400)),
+    (dict(b_mn=True, out_bf16=True), (333, 1601, 1024)),
+    (dict(bias=True, out_bf16=True, out_fp16=True, cluster_m=2, block_n=256), (1000, 520, 200)),
+])
+def test_fp16_operands(kw, shape):
+    """fp16 x fp16 (the forward operand format of the default precision), fp16 16-bit outputs, every operand major."""
+    from _gpu_util import gemm_case
+    err, _ = gemm_case(*shape, a_fp16=True, b_fp16=True, **kw)
+    assert err < TOL, err
+
+
+def test_mixed_operand_formats_are_rejected():
+    """tcgen05 kind::f16 encodes the A and B formats separately, but fp16 x bf16 raises an illegal-instruction fault on B200
+    (measured in round 2): the library refuses the combination instead of launching it."""
+    import ctypes as C
+    import torch
+    lib = L.lib()
+    x = torch.zeros(128, 64, device="cuda", dtype=torch.float16); w = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)
+    o = torch.zeros(128, 128, device="cuda")
+    g = L.GemmArgs()
+    g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb = 128, 128, 64, x.data_ptr(), 64, w.data_ptr(), 64
+    g.out_f32, g.ld_out_f32, g.alpha, g.split_k, g.a_fp16, g.b_fp16 = o.data_ptr(), 128, 1.0, 1, 1, 0
+    assert lib.vb_gemm_bf16(C.byref(g), None) == 2 and b"same 16-bit format" in lib.vb_last_error()
+
+
+@pytest.mark.parametrize("kw,shape", [
+    (dict(bias=True, res=True), (2304, 768, 768)),
+    (dict(bias=True, out_bf16=True), (6400, 3072, 1024)),
+    (dict(bias=True, out_bf16=True, cluster_m=1, block_n=128), (1000, 520, 200)),
+    (dict(bias=True, act=L.VB_ACT_GELU, out_bf16=True), (300, 200, 136)),
+    (dict(bias=True, act=L.VB_ACT_RELU, out_bf16=True, both_outputs=True), (64, 1024, 768)),
+    (dict(bias=True), (130, 30522, 768)),
+    (dict(bias=True, res=True, cluster_m=2), (6400, 1024, 4096)),
+])
+def test_split_precision(kw, shape):
+    """fp32 parity mode: operands as fp16 hi + lo, three passes (hi.hi + lo.hi + hi.lo) into one TMEM accumulator; the
+    16-bit output is written as hi + lo too. Compared with the float64 product of the fp32 operands: 2e-5 of max|ref|
+    (single-pass fp16 operands give ~5e-4, bf16 ~4e-3)."""
+    from _gpu_util import gemm_case
+    err, _ = gemm_case(*shape, a_fp16=True, b_fp16=True, out_fp16=True, split=True, **kw)
+    assert err < 2e-5, err
+
+
 def test_invalid_arguments_are_rejected():
     import ctypes as C
     import torch

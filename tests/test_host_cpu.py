@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/vilbert_b200.h but not exported"
     assert set(L._SIGNATURES) <= set(declared)
-    assert lib.vb_version() == 1
+    assert lib.vb_version() == 2
     assert ctypes.sizeof(L.GemmArgs) >= 160 and ctypes.sizeof(L.AttnArgs) >= 150
 
 

@@ -25,6 +25,29 @@ def test_attention_fwd_bwd(B, H, Nq, Nk, D, cross):
     assert max(errs.values()) < 2e-2, errs
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk,D,cross", [
+    (3, 3, 11, 11, 32, False), (4, 12, 36, 36, 64, False), (4, 8, 100, 100, 128, False), (4, 8, 36, 100, 128, True),
+    (4, 8, 100, 36, 128, True), (2, 8, 257, 306, 128, True), (2, 2, 7, 12, 16, True)])
+def test_attention_fp16_operands(B, H, Nq, Nk, D, cross):
+    """The engine's default arithmetic: Q/K/V/O fp16 (forward operands), dO/dQ/dK/dV bf16. The forward is checked at fp16
+    accuracy; the backward converts its Q/K/V panels to bf16 (dS and dO are bf16 MMA operands): same 2e-2 bound as bf16."""
+    from _gpu_util import attn_case
+    errs, _ = attn_case(B, H, Nq, Nk, D, cross, fp16=True)
+    assert errs["lse"] < 1e-5 and errs["O"] < 2e-3, errs
+    assert max(errs.values()) < 2e-2, errs
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,D,cross", [
+    (3, 3, 11, 11, 32, False), (4, 12, 36, 36, 64, False), (4, 8, 100, 100, 128, False), (4, 8, 36, 100, 128, True),
+    (2, 8, 257, 306, 128, True)])
+def test_attention_split_precision_forward(B, H, Nq, Nk, D, cross):
+    """fp32 parity mode: Q/K/V as fp16 hi + lo, three MMA passes for QK^T and for PV (P split in registers), O written as
+    hi + lo. Checked against a float64 attention of the fp32 inputs: 2e-5 (north_star fp32 tolerance is 1e-3)."""
+    from _gpu_util import attn_case
+    errs, _ = attn_case(B, H, Nq, Nk, D, cross, fp16=True, split=True)
+    assert errs["O_split"] < 2e-5, errs
+
+
 def test_attention_peaked_softmax():
     from _gpu_util import attn_case
     for args in [(4, 8, 100, 100, 128, False), (4, 12, 36, 36, 64, False)]:
@@ -45,7 +68,11 @@ def test_layernorm_fwd_bwd(M, H):
     lib, dev = L.lib(), "cuda"
     x = torch.randn(M, H, device=dev) * 2 + 0.5; g = torch.randn(H, device=dev); b = torch.randn(H, device=dev)
     y32 = torch.empty(M, H, device=dev); y16 = torch.empty(M, H, device=dev, dtype=BF); mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
-    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, y32.data_ptr(), y16.data_ptr(), H, mean.data_ptr(), rstd.data_ptr(), M, H, None, S()))
+    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, y32.data_ptr(), y16.data_ptr(), H, mean.data_ptr(), rstd.data_ptr(), M, H, None, 0, None, None, S()))
+    # fp16 operand copy as hi + lo (split precision): hi + lo reconstructs the fp32 output to ~2^-22
+    yh = torch.empty(M, H, device=dev, dtype=torch.float16); yl = torch.empty(M, H, device=dev, dtype=torch.float16)
+    yb = torch.empty(M, H, device=dev, dtype=BF)
+    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, None, yh.data_ptr(), H, None, None, M, H, None, 1, yl.data_ptr(), yb.data_ptr(), S()))
     xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
     yr = F.layer_norm(xr, (H,), gr, br, 1e-12)
     dy = torch.randn(M, H, device=dev); yr.backward(dy)
@@ -54,6 +81,7 @@ def test_layernorm_fwd_bwd(M, H):
                                  dg.data_ptr(), db.data_ptr(), None, M, H, None, None, S()))
     torch.cuda.synchronize()
     assert rel(y32, yr) < 1e-5 and rel(y16, yr) < 5e-3
+    assert torch.equal(yh, y32.to(torch.float16)) and rel(yh.float() + yl.float(), y32) < 2e-6 and torch.equal(yb, y16)
     assert rel(dx32, xr.grad) < 1e-5 and rel(dx16, xr.grad) < 5e-3 and rel(dg, gr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
 
 
@@ -100,8 +128,12 @@ def test_misc_rowops():
     lib, dev = L.lib(), "cuda"
     # casts
     x = torch.randn(1000003, device=dev); y = torch.empty(1000003, device=dev, dtype=BF)
-    L.check(lib.vb_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), S())); torch.cuda.synchronize()
+    L.check(lib.vb_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), 0, None, None, S())); torch.cuda.synchronize()
     assert torch.equal(y, x.to(BF))
+    yh = torch.empty(1000003, device=dev, dtype=torch.float16); yl = torch.empty_like(yh)
+    yb = torch.empty(1000003, device=dev, dtype=BF)
+    L.check(lib.vb_cast_f32_to_bf16(x.data_ptr(), yh.data_ptr(), x.numel(), 1, yl.data_ptr(), yb.data_ptr(), S())); torch.cuda.synchronize()
+    assert torch.equal(yh, x.to(torch.float16)) and torch.equal(yl, (x - yh.float()).to(torch.float16)) and torch.equal(yb, x.to(BF))
     x = torch.randn(77, 3129, device=dev); y = torch.zeros(77, 3136, device=dev, dtype=BF)
     L.check(lib.vb_cast2d_f32_to_bf16(x.data_ptr(), 3129, y.data_ptr(), 3136, 77, 3129, 0.5, S())); torch.cuda.synchronize()
     assert torch.equal(y[:, :3129], (x * 0.5).to(BF)) and y[:, 3129:].abs().max().item() == 0
@@ -128,7 +160,7 @@ def test_misc_rowops():
         assert rel(y, x @ W.t() + b + add[:, None]) < 1e-5 and rel(dx, 1 + dy @ W) < 1e-5 and rel(dW, dy.t() @ x) < 1e-5 and rel(db, dy.sum(0)) < 1e-5
     # pooled fusion, relu backward
     a = torch.randn(64, 1024, device=dev); b = torch.randn(64, 1024, device=dev); o32 = torch.empty_like(a); o16 = torch.empty(64, 1024, device=dev, dtype=BF)
-    L.check(lib.vb_fuse_pooled_fwd(a.data_ptr(), b.data_ptr(), o32.data_ptr(), o16.data_ptr(), a.numel(), 1, None, S()))
+    L.check(lib.vb_fuse_pooled_fwd(a.data_ptr(), b.data_ptr(), o32.data_ptr(), o16.data_ptr(), a.numel(), 1, None, 0, None, None, S()))
     d = torch.randn_like(a); da = torch.ones_like(a); db = torch.ones_like(a)
     L.check(lib.vb_fuse_pooled_bwd(d.data_ptr(), a.data_ptr(), b.data_ptr(), da.data_ptr(), db.data_ptr(), a.numel(), 1, None, S())); torch.cuda.synchronize()
     assert torch.equal(o32, a * b) and rel(da, 1 + d * b) < 1e-6 and rel(db, 1 + d * a) < 1e-6

@@ -87,7 +87,7 @@ print("=== layernorm")
 for (M, H) in [(37, 64), (50, 96), (2304, 768), (6400, 1024), (33, 2048), (128, 128)]:
     x = torch.randn(M, H, device=dev) * 2 + 0.5; g = torch.randn(H, device=dev); b = torch.randn(H, device=dev)
     y32 = torch.empty(M, H, device=dev); y16 = torch.empty(M, H, device=dev, dtype=BF); mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
-    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, y32.data_ptr(), y16.data_ptr(), H, mean.data_ptr(), rstd.data_ptr(), M, H, None, ST()))
+    L.check(lib.vb_layernorm_fwd(x.data_ptr(), H, g.data_ptr(), b.data_ptr(), 1e-12, y32.data_ptr(), y16.data_ptr(), H, mean.data_ptr(), rstd.data_ptr(), M, H, None, 0, None, None, ST()))
     xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
     yr = F.layer_norm(xr, (H,), gr, br, 1e-12)
     dy = torch.randn(M, H, device=dev); yr.backward(dy)
@@ -110,7 +110,7 @@ report("layernorm bwd + gelu'", dict(dx16=max(rel(dx16, xr.grad * gp) - 4e-3, 0)
 print("=== misc rowops")
 # casts
 x = torch.randn(1000003, device=dev); y = torch.empty(1000003, device=dev, dtype=BF)
-L.check(lib.vb_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), ST())); torch.cuda.synchronize()
+L.check(lib.vb_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), 0, None, None, ST())); torch.cuda.synchronize()
 report("cast flat", dict(e=(y.float() - x.to(BF).float()).abs().max().item()), 1e-9)
 x = torch.randn(77, 3129, device=dev); y = torch.zeros(77, 3136, device=dev, dtype=BF)
 L.check(lib.vb_cast2d_f32_to_bf16(x.data_ptr(), 3129, y.data_ptr(), 3136, 77, 3129, 0.5, ST())); torch.cuda.synchronize()
@@ -158,7 +158,7 @@ for (M, K, N) in [(64, 1024, 1), (64, 1024, 3), (32, 2048, 2), (6400, 1024, 1)]:
     report(f"small_linear M{M} K{K} N{N}", dict(y=rel(y, x @ W.t() + b + add[:, None]), dx=rel(dx, 1 + dy @ W), dW=rel(dW, dy.t() @ x), db=rel(db, dy.sum(0))), 1e-5)
 # pooled fuse / relu / axpy / bce / mask
 a = torch.randn(64, 1024, device=dev); b = torch.randn(64, 1024, device=dev); o32 = torch.empty_like(a); o16 = torch.empty(64, 1024, device=dev, dtype=BF)
-L.check(lib.vb_fuse_pooled_fwd(a.data_ptr(), b.data_ptr(), o32.data_ptr(), o16.data_ptr(), a.numel(), 1, None, ST()))
+L.check(lib.vb_fuse_pooled_fwd(a.data_ptr(), b.data_ptr(), o32.data_ptr(), o16.data_ptr(), a.numel(), 1, None, 0, None, None, ST()))
 d = torch.randn_like(a); da = torch.ones_like(a); db = torch.ones_like(a)
 L.check(lib.vb_fuse_pooled_bwd(d.data_ptr(), a.data_ptr(), b.data_ptr(), da.data_ptr(), db.data_ptr(), a.numel(), 1, None, ST())); torch.cuda.synchronize()
 report("fuse_pooled", dict(o=rel(o32, a * b), da=rel(da, 1 + d * b), db=rel(db, 1 + d * a)), 1e-6)

@@ -40,6 +40,8 @@ class GemmArgs(C.Structure):
         ("atomic_out", C.c_int32), ("out_colsum", C.c_void_p), ("dropout", Dropout), ("split_k", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
         ("dbg_lbo_a", C.c_uint32), ("dbg_sbo_a", C.c_uint32), ("dbg_lbo_b", C.c_uint32), ("dbg_sbo_b", C.c_uint32),
         ("dbg_timeline", C.c_void_p), ("cluster_m", C.c_int32),
+        ("a_fp16", C.c_int32), ("b_fp16", C.c_int32), ("out_fp16", C.c_int32),
+        ("A_lo", C.c_void_p), ("B_lo", C.c_void_p), ("out_lo", C.c_void_p), ("out_b16", C.c_void_p),
     ]
 
 
@@ -56,7 +58,16 @@ class AttnArgs(C.Structure):
         ("delta", C.c_void_p),
         ("dbias_q", C.c_void_p), ("dbias_k", C.c_void_p), ("dbias_v", C.c_void_p),
         ("dropout", Dropout),
+        ("qkv_fp16", C.c_int32), ("Q_lo", C.c_void_p), ("K_lo", C.c_void_p), ("V_lo", C.c_void_p), ("O_lo", C.c_void_p),
+        ("O_b16", C.c_void_p),
     ]
+
+
+class AdamWGroup(C.Structure):
+    """Mirror of ``struct vb_adamw_group``."""
+
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("correct_bias", C.c_int32)]
 
 
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -67,9 +78,9 @@ _SIGNATURES = {
     "vb_gemm_plan": [C.POINTER(GemmArgs), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "vb_attention_fwd": [C.POINTER(AttnArgs), _P],
     "vb_attention_bwd": [C.POINTER(AttnArgs), _P],
-    "vb_layernorm_fwd": [_P, _I64, _P, _P, _F, _P, _P, _I64, _P, _P, _I32, _I32, _P, _P],
+    "vb_layernorm_fwd": [_P, _I64, _P, _P, _F, _P, _P, _I64, _P, _P, _I32, _I32, _P, _I32, _P, _P, _P],
     "vb_layernorm_bwd": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I32, _I32, _P, _P, _P],
-    "vb_cast_f32_to_bf16": [_P, _P, _I64, _P],
+    "vb_cast_f32_to_bf16": [_P, _P, _I64, _I32, _P, _P, _P],
     "vb_cast2d_f32_to_bf16": [_P, _I64, _P, _I64, _I32, _I32, _F, _P],
     "vb_embed_text_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
     "vb_embed_text_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
@@ -78,7 +89,7 @@ _SIGNATURES = {
     "vb_colsum": [_P, _I32, _I64, _P, _I32, _I32, _P],
     "vb_small_linear_fwd": [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P],
     "vb_small_linear_bwd": [_P, _P, _I64, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P],
-    "vb_fuse_pooled_fwd": [_P, _P, _P, _P, _I64, _I32, _P, _P],
+    "vb_fuse_pooled_fwd": [_P, _P, _P, _P, _I64, _I32, _P, _I32, _P, _P, _P],
     "vb_fuse_pooled_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _P, _P],
     "vb_step_counter_bump": [_P, _P],
     "vb_relu_bwd": [_P, _P, _P, _P, _I64, _P],
@@ -86,6 +97,9 @@ _SIGNATURES = {
     "vb_bce_logits_loss": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
     "vb_mask_to_additive": [_P, _P, _I32, _I32, _I32, _P],
     "vb_memset_zero": [_P, _I64, _P],
+    "vb_ce_loss": [_P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _F, _I32, _P],
+    "vb_kl_masked_loss": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _I32, _P],
+    "vb_adamw_step": [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _I32, _P, _P, _F, _I32, _P],
 }
 
 _lib = None

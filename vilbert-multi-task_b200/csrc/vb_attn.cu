@@ -46,7 +46,27 @@ struct AttnParams {
   float* delta;  // [B,H,Nq]
   DropCfg drop;            // dropout on the attention probabilities (element index ((b*H + h)*Nq + q)*Nk + k)
   float *dbq, *dbk, *dbv;  // optional bias gradients [H*D] of the Q / K / V projections (+= column sums of dQ / dK / dV)
+  int qkv_fp16;            // Q, K, V, O are fp16 (forward operands); gradients are always bf16
+  const __nv_bfloat16 *Ql, *Kl, *Vl;   // split precision (forward): low parts of Q / K / V, or NULL
+  __nv_bfloat16* Ol;                   // low part of O, or NULL
+  __nv_bfloat16* Ob;                   // always-bf16 copy of O, or NULL
 };
+
+// In-place fp16 -> bf16 conversion of a staged panel (rows x D at pitch D + 8): the backward kernels run their products in
+// bf16 because dO / dS are bf16 (gradient range), while Q / K / V arrive as fp16 forward operands.
+template <int D, int NTHREADS>
+__device__ __forceinline__ void panel_f16_to_bf16(__nv_bfloat16* panel, int rows) {
+  constexpr int LD = D + 8;
+  constexpr int CH = D / 8;
+  for (int idx = threadIdx.x; idx < rows * CH; idx += NTHREADS) {
+    uint4* ptr = reinterpret_cast<uint4*>(panel + (idx / CH) * LD + (idx % CH) * 8);
+    uint4 v = *ptr;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = unpack16(w[i], 1); w[i] = pack_bf16(f.x, f.y); }
+    *ptr = v;
+  }
+}
 
 // Copies `rows_valid` rows of D bf16 (row stride ld) into smem rows of stride D+8 with cp.async (16-byte LDGSTS, no
 // register staging: every request of the panel is in flight at once); rows beyond rows_valid are zero-filled
@@ -79,7 +99,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 // acc[nt][4] (16 x 64 block, 8 n-tiles) = A(16 x D from sA rows a_row0..) * B^T where B rows b_row0.. (64 rows) of sB.
-template <int D>
+template <int D, bool FP16 = false>
 __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16* sA, int a_row0, const __nv_bfloat16* sB,
                                          int b_row0, int lane, int /*nb_valid*/) {
   constexpr int LD = D + 8;
@@ -92,31 +112,47 @@ __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const __nv_bfloat16
       uint32_t b[4];
       const int mi = lane >> 3;
       ldmatrix_x4(b, smem_u32(sB + (b_row0 + np * 16 + (mi >> 1) * 8 + (lane & 7)) * LD + kk * 16 + (mi & 1) * 8));
-      mma_bf16_16816(acc[2 * np], a, b[0], b[1]);
-      mma_bf16_16816(acc[2 * np + 1], a, b[2], b[3]);
+      mma_16816<FP16>(acc[2 * np], a, b[0], b[1]);
+      mma_16816<FP16>(acc[2 * np + 1], a, b[2], b[3]);
     }
   }
 }
 
 // acc[D/8][4] (16 x D) += P(16 x 64, given as C-fragments pf[8][4] converted to bf16) * B where B rows b_row0.. (64 rows, k index) of sB [row][D].
-template <int D>
+// FP16: operand format. SPLIT: P is split into hi + lo in registers and sBl holds the low part of B: acc += Ph B + Pl B + Ph Bl.
+template <int D, bool FP16 = false, bool SPLIT = false>
 __device__ __forceinline__ void mma_p_b(float (&acc)[D / 8][4], const float (&pf)[8][4], const __nv_bfloat16* sB, int b_row0,
-                                        int lane, int /*nb_valid*/) {
+                                        int lane, int /*nb_valid*/, const __nv_bfloat16* sBl = nullptr) {
   constexpr int LD = D + 8;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    uint32_t a[4];
-    a[0] = pack_bf16(pf[2 * kk][0], pf[2 * kk][1]);
-    a[1] = pack_bf16(pf[2 * kk][2], pf[2 * kk][3]);
-    a[2] = pack_bf16(pf[2 * kk + 1][0], pf[2 * kk + 1][1]);
-    a[3] = pack_bf16(pf[2 * kk + 1][2], pf[2 * kk + 1][3]);
+    uint32_t a[4], al[4];
+    if constexpr (SPLIT) {
+      a[0] = pack16_split(pf[2 * kk][0], pf[2 * kk][1], FP16, al[0]);
+      a[1] = pack16_split(pf[2 * kk][2], pf[2 * kk][3], FP16, al[1]);
+      a[2] = pack16_split(pf[2 * kk + 1][0], pf[2 * kk + 1][1], FP16, al[2]);
+      a[3] = pack16_split(pf[2 * kk + 1][2], pf[2 * kk + 1][3], FP16, al[3]);
+    } else {
+      a[0] = pack16(pf[2 * kk][0], pf[2 * kk][1], FP16);
+      a[1] = pack16(pf[2 * kk][2], pf[2 * kk][3], FP16);
+      a[2] = pack16(pf[2 * kk + 1][0], pf[2 * kk + 1][1], FP16);
+      a[3] = pack16(pf[2 * kk + 1][2], pf[2 * kk + 1][3], FP16);
+    }
 #pragma unroll
     for (int dp = 0; dp < D / 16; ++dp) {
       uint32_t b[4];
       const int mi = lane >> 3;
-      ldmatrix_x4_trans(b, smem_u32(sB + (b_row0 + kk * 16 + (mi & 1) * 8 + (lane & 7)) * LD + dp * 16 + (mi >> 1) * 8));
-      mma_bf16_16816(acc[2 * dp], a, b[0], b[1]);
-      mma_bf16_16816(acc[2 * dp + 1], a, b[2], b[3]);
+      const int off = (b_row0 + kk * 16 + (mi & 1) * 8 + (lane & 7)) * LD + dp * 16 + (mi >> 1) * 8;
+      ldmatrix_x4_trans(b, smem_u32(sB + off));
+      mma_16816<FP16>(acc[2 * dp], a, b[0], b[1]);
+      mma_16816<FP16>(acc[2 * dp + 1], a, b[2], b[3]);
+      if constexpr (SPLIT) {
+        mma_16816<FP16>(acc[2 * dp], al, b[0], b[1]);
+        mma_16816<FP16>(acc[2 * dp + 1], al, b[2], b[3]);
+        ldmatrix_x4_trans(b, smem_u32(sBl + off));
+        mma_16816<FP16>(acc[2 * dp], a, b[0], b[1]);
+        mma_16816<FP16>(acc[2 * dp + 1], a, b[2], b[3]);
+      }
     }
   }
 }
@@ -125,15 +161,23 @@ __device__ __forceinline__ void mma_p_b(float (&acc)[D / 8][4], const float (&pf
 // column sums of the stored (valid, scaled) values are accumulated there (bias gradient of the projection).
 template <int D>
 __device__ __forceinline__ void store_tile(__nv_bfloat16* dst, long long ld, const float (&acc)[D / 8][4], float s0, float s1,
-                                           int row0, int rows_valid, int lane, float* colsum = nullptr) {
+                                           int row0, int rows_valid, int lane, float* colsum = nullptr, int fp16 = 0,
+                                           __nv_bfloat16* dst_lo = nullptr) {
   const int g = lane >> 2, t = lane & 3;
   const bool v0 = row0 + g < rows_valid, v1 = row0 + g + 8 < rows_valid;
 #pragma unroll
   for (int nt = 0; nt < D / 8; ++nt) {
     const int col = nt * 8 + 2 * t;
     const float a0 = acc[nt][0] * s0, a1 = acc[nt][1] * s0, a2 = acc[nt][2] * s1, a3 = acc[nt][3] * s1;
-    if (v0) *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g) * ld + col) = pack_bf16(a0, a1);
-    if (v1) *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g + 8) * ld + col) = pack_bf16(a2, a3);
+    uint32_t l01 = 0, l23 = 0;
+    const uint32_t h01 = dst_lo ? pack16_split(a0, a1, fp16, l01) : pack16(a0, a1, fp16);
+    const uint32_t h23 = dst_lo ? pack16_split(a2, a3, fp16, l23) : pack16(a2, a3, fp16);
+    if (v0) *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g) * ld + col) = h01;
+    if (v1) *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g + 8) * ld + col) = h23;
+    if (dst_lo) {
+      if (v0) *reinterpret_cast<uint32_t*>(dst_lo + (long long)(row0 + g) * ld + col) = l01;
+      if (v1) *reinterpret_cast<uint32_t*>(dst_lo + (long long)(row0 + g + 8) * ld + col) = l23;
+    }
     if (colsum) {
       float c0 = (v0 ? a0 : 0.f) + (v1 ? a2 : 0.f), c1 = (v0 ? a1 : 0.f) + (v1 ? a3 : 0.f);
 #pragma unroll
@@ -147,7 +191,7 @@ __device__ __forceinline__ void store_tile(__nv_bfloat16* dst, long long ld, con
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <int D>
+template <int D, bool FP16, bool SPLIT>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams p) {
   constexpr int LD = D + 8;
   extern __shared__ __align__(16) uint8_t smem_att[];
@@ -156,7 +200,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
   __nv_bfloat16* sK = sQ + TQ * LD;
   __nv_bfloat16* sV = sK + nkp * LD;
-  float* sMask = reinterpret_cast<float*>(sV + nkp * LD);
+  // split precision: low-part panels behind the hi ones
+  __nv_bfloat16* sQl = sV + nkp * LD;
+  __nv_bfloat16* sKl = sQl + (SPLIT ? TQ * LD : 0);
+  __nv_bfloat16* sVl = sKl + (SPLIT ? nkp * LD : 0);
+  float* sMask = reinterpret_cast<float*>(sVl + (SPLIT ? nkp * LD : 0));
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,6 +213,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
   load_panel<D>(sQ, p.Q + ((long long)b * p.Nq + q0) * p.ldq + h * D, p.ldq, min(TQ, p.Nq - q0), TQ);
   load_panel<D>(sK, p.K + (long long)b * p.Nk * p.ldk + h * D, p.ldk, p.Nk, nkp);
   load_panel<D>(sV, p.V + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
+  if constexpr (SPLIT) {
+    load_panel<D>(sQl, p.Ql + ((long long)b * p.Nq + q0) * p.ldq + h * D, p.ldq, min(TQ, p.Nq - q0), TQ);
+    load_panel<D>(sKl, p.Kl + (long long)b * p.Nk * p.ldk + h * D, p.ldk, p.Nk, nkp);
+    load_panel<D>(sVl, p.Vl + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
+  }
   for (int j = threadIdx.x; j < nkp; j += ATT_THREADS)
     sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
   cp_async_wait_all();
@@ -184,7 +237,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    mma_a_bt<D>(s, sQ, r0, sK, kb, lane, p.Nk);
+    mma_a_bt<D, FP16>(s, sQ, r0, sK, kb, lane, p.Nk);
+    if constexpr (SPLIT) {   // S = Q K^T + Q_lo K^T + Q K_lo^T
+      mma_a_bt<D, FP16>(s, sQl, r0, sK, kb, lane, p.Nk);
+      mma_a_bt<D, FP16>(s, sQ, r0, sKl, kb, lane, p.Nk);
+    }
     float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -217,11 +274,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
         s[nt][2] *= drop_factor(dseed, e1 + nt * 8, p.drop); s[nt][3] *= drop_factor(dseed, e1 + nt * 8 + 1, p.drop);
       }
     }
-    mma_p_b<D>(o, s, sV, kb, lane, p.Nk);
+    mma_p_b<D, FP16, SPLIT>(o, s, sV, kb, lane, p.Nk, sVl);
   }
   l[0] = quad_sum(l[0]); l[1] = quad_sum(l[1]);
   const int rows_valid = p.Nq - q0;
-  store_tile<D>(p.O + ((long long)b * p.Nq + q0) * p.ldo + h * D, p.ldo, o, 1.f / l[0], 1.f / l[1], r0, rows_valid, lane);
+  store_tile<D>(p.O + ((long long)b * p.Nq + q0) * p.ldo + h * D, p.ldo, o, 1.f / l[0], 1.f / l[1], r0, rows_valid, lane, nullptr,
+                FP16 ? 1 : 0, (SPLIT && p.Ol) ? p.Ol + ((long long)b * p.Nq + q0) * p.ldo + h * D : nullptr);
+  if (p.Ob) store_tile<D>(p.Ob + ((long long)b * p.Nq + q0) * p.ldo + h * D, p.ldo, o, 1.f / l[0], 1.f / l[1], r0, rows_valid, lane);
   if (p.lse && t == 0) {
     float* lse = p.lse + ((long long)b * p.H + h) * p.Nq + q0;
     if (r0 + g < rows_valid) lse[r0 + g] = m[0] + log2f(l[0]);
@@ -255,6 +314,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
     sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
   cp_async_wait_all();
   __syncthreads();
+  if (p.qkv_fp16) {
+    panel_f16_to_bf16<D, ATT_THREADS>(sQ, TQ); panel_f16_to_bf16<D, ATT_THREADS>(sK, nkp); panel_f16_to_bf16<D, ATT_THREADS>(sV, nkp);
+    __syncthreads();
+  }
 
   const int r0 = warp * 16;
   if (r0 >= rows_valid) return;
@@ -271,11 +334,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
         for (int cidx = t * 8; cidx < D; cidx += 32) {
           const uint4 ov = __ldg(reinterpret_cast<const uint4*>(Og + (long long)r * p.ldo + cidx));
           const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * LD + cidx);
-          const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+          const uint32_t* o2 = reinterpret_cast<const uint32_t*>(&ov);
           const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float2 of = __bfloat1622float2(o2[i]), df = __bfloat1622float2(d2[i]);
+            const float2 of = unpack16(o2[i], p.qkv_fp16), df = __bfloat1622float2(d2[i]);
             acc += of.x * df.x + of.y * df.y;
           }
         }
@@ -364,6 +427,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
   }
   cp_async_wait_all();
   __syncthreads();
+  if (p.qkv_fp16) {
+    panel_f16_to_bf16<D, ATT_THREADS>(sK, TQ); panel_f16_to_bf16<D, ATT_THREADS>(sV, TQ); panel_f16_to_bf16<D, ATT_THREADS>(sQ, nqp);
+    __syncthreads();
+  }
 
   const int r0 = warp * 16;
   if (r0 >= rows_valid) return;
@@ -471,6 +538,10 @@ __global__ void __launch_bounds__(ATT1_THREADS) attn_bwd_fused_kernel(const Attn
     sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
   cp_async_wait_all();
   __syncthreads();
+  if (p.qkv_fp16) {
+    panel_f16_to_bf16<D, ATT1_THREADS>(sQ, nqp); panel_f16_to_bf16<D, ATT1_THREADS>(sK, nkp); panel_f16_to_bf16<D, ATT1_THREADS>(sV, nkp);
+    __syncthreads();
+  }
 
   const float c = p.scale * LOG2E;
   const uint32_t dseed = p.drop.ctr ? drop_seed(p.drop) : 0u;
@@ -488,11 +559,11 @@ __global__ void __launch_bounds__(ATT1_THREADS) attn_bwd_fused_kernel(const Attn
           for (int cidx = t * 8; cidx < D; cidx += 32) {
             const uint4 ov = __ldg(reinterpret_cast<const uint4*>(Og + (long long)r * p.ldo + cidx));
             const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * LD + cidx);
-            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+            const uint32_t* o2 = reinterpret_cast<const uint32_t*>(&ov);
             const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float2 of = __bfloat1622float2(o2[i]), df = __bfloat1622float2(d2[i]);
+              const float2 of = unpack16(o2[i], p.qkv_fp16), df = __bfloat1622float2(d2[i]);
               acc += of.x * df.x + of.y * df.y;
             }
           }
@@ -599,6 +670,10 @@ static AttnParams to_params(const vb_attn_args* a) {
   p.drop.site = a->dropout.site;
   p.drop.thresh = on ? (uint32_t)((double)a->dropout.p * 4294967296.0) : 0u;
   p.drop.scale = on && a->dropout.p < 1.f ? 1.f / (1.f - a->dropout.p) : 1.f;
+  p.qkv_fp16 = a->qkv_fp16 ? 1 : 0;
+  p.Ql = (const __nv_bfloat16*)a->Q_lo; p.Kl = (const __nv_bfloat16*)a->K_lo; p.Vl = (const __nv_bfloat16*)a->V_lo;
+  p.Ol = (__nv_bfloat16*)a->O_lo;
+  p.Ob = (__nv_bfloat16*)a->O_b16;
   return p;
 }
 
@@ -621,15 +696,25 @@ extern "C" vb_status vb_attention_fwd(const vb_attn_args* a, void* stream) {
   if (int s = validate(a, false)) return s;
   const AttnParams p = to_params(a);
   const int nkp = (a->Nk + KB - 1) / KB * KB;
-  const size_t smem = (size_t)(TQ + 2 * nkp) * (a->D + 8) * 2 + (size_t)nkp * 4;
+  const bool split = a->Q_lo || a->K_lo || a->V_lo;
+  if (split && !(a->Q_lo && a->K_lo && a->V_lo)) return set_error(VB_ERR_INVALID, "vb_attention_fwd: split precision needs Q_lo, K_lo and V_lo");
+  if (split && (!al16(a->Q_lo) || !al16(a->K_lo) || !al16(a->V_lo) || (a->O_lo && !al16(a->O_lo))))
+    return set_error(VB_ERR_INVALID, "vb_attention_fwd: low-part tensors need 16-byte aligned bases");
+  const size_t smem = (size_t)(TQ + 2 * nkp) * (a->D + 8) * 2 * (split ? 2 : 1) + (size_t)nkp * 4;
   dim3 grid((a->Nq + TQ - 1) / TQ, a->H, a->B);
   cudaStream_t st = (cudaStream_t)stream;
+#define VB_FWD(DD)                                                                                                     \
+  if (split) return a->qkv_fp16 ? launch_att(attn_fwd_kernel<DD, true, true>, grid, smem, p, st, "vb_attention_fwd")   \
+                                : launch_att(attn_fwd_kernel<DD, false, true>, grid, smem, p, st, "vb_attention_fwd"); \
+  return a->qkv_fp16 ? launch_att(attn_fwd_kernel<DD, true, false>, grid, smem, p, st, "vb_attention_fwd")             \
+                     : launch_att(attn_fwd_kernel<DD, false, false>, grid, smem, p, st, "vb_attention_fwd");
   switch (a->D) {
-    case 16: return launch_att(attn_fwd_kernel<16>, grid, smem, p, st, "vb_attention_fwd");
-    case 32: return launch_att(attn_fwd_kernel<32>, grid, smem, p, st, "vb_attention_fwd");
-    case 64: return launch_att(attn_fwd_kernel<64>, grid, smem, p, st, "vb_attention_fwd");
-    default: return launch_att(attn_fwd_kernel<128>, grid, smem, p, st, "vb_attention_fwd");
+    case 16: VB_FWD(16)
+    case 32: VB_FWD(32)
+    case 64: VB_FWD(64)
+    default: VB_FWD(128)
   }
+#undef VB_FWD
 }
 
 extern "C" vb_status vb_attention_bwd(const vb_attn_args* a, void* stream) {

@@ -50,7 +50,13 @@ struct GemmCfg {
 
 struct GemmKernelParams {
   int M, N, K;
-  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int num_m_blocks, num_n_blocks, num_k_blocks;   // num_k_blocks counts VIRTUAL k-blocks: npass x real_k_blocks
+  int real_k_blocks;         // ceil(K / 64)
+  int npass;                 // 1, or 2..3 in split precision: pass_sel[i] bit 0 = A_lo, bit 1 = B_lo
+  int pass_sel[3];
+  int out_fp16;              // format of out_bf16 / out_lo: 0 = bf16, 1 = fp16
+  __nv_bfloat16* out_lo;     // split precision: low part of the value written to out_bf16 (same pitch), or NULL
+  __nv_bfloat16* out_b16;    // always-bf16 copy of the value written to out_bf16 (same pitch), or NULL
   int split_k, k_blocks_per_split;
   float alpha;
   const float* bias;
@@ -129,13 +135,31 @@ __device__ __noinline__ void epi_generic_chunk(const GemmKernelParams& p, const 
         if (p.atomic_out) atomicAdd(p.out_f32 + m * p.ld_of + n + j, v);
         else p.out_f32[m * p.ld_of + n + j] = v;
       }
-      if (p.out_bf16) p.out_bf16[m * p.ld_ob + n + j] = __float2bfloat16(v);
+      if (p.out_bf16) {
+        const uint16_t hi = cvt16(v, p.out_fp16);
+        reinterpret_cast<uint16_t*>(p.out_bf16)[m * p.ld_ob + n + j] = hi;
+        if (p.out_lo) reinterpret_cast<uint16_t*>(p.out_lo)[m * p.ld_ob + n + j] = cvt16(v - cvt16_to_f32(hi, p.out_fp16), p.out_fp16);
+        if (p.out_b16) p.out_b16[m * p.ld_ob + n + j] = __float2bfloat16(v);
+      }
     }
   }
   if (p.out_colsum) {
 #pragma unroll 1
     for (int j = 0; j < nv; ++j) atomicAdd(p.out_colsum + n + j, cs[j]);
   }
+}
+
+// 4 consecutive values -> out_bf16 (bf16 or fp16 per p.out_fp16) and, in split precision, their low parts -> out_lo
+__device__ __forceinline__ void store16x4(const GemmKernelParams& p, long long off, float v0, float v1, float v2, float v3) {
+  if (p.out_lo) {
+    uint32_t l01, l23;
+    const uint32_t h01 = pack16_split(v0, v1, p.out_fp16, l01), h23 = pack16_split(v2, v3, p.out_fp16, l23);
+    *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(p.out_lo + off) = make_uint2(l01, l23);
+  } else {
+    *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack16(v0, v1, p.out_fp16), pack16(v2, v3, p.out_fp16));
+  }
+  if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
 }
 
 template <int EPI>
@@ -154,13 +178,13 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
       gelu_erf_and_grad(v0, v0, d0); gelu_erf_and_grad(v1, v1, d1); gelu_erf_and_grad(v2, v2, d2); gelu_erf_and_grad(v3, v3, d3);
       *reinterpret_cast<uint2*>(p.out_pre + m * p.ld_op + n) = make_uint2(pack_bf16(d0, d1), pack_bf16(d2, d3));   // gelu'(pre) for backward
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_of + n) = make_float4(v0, v1, v2, v3);
-      if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+      if (p.out_bf16) store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);
     } else if (EPI == EPI_DGELU) {
       const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].x));
       const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].y));
       v0 *= x01.x; v1 *= x01.y; v2 *= x23.x; v3 *= x23.y;   // aux = gelu'(pre) saved by the forward epilogue
       cs0 += v0; cs1 += v1; cs2 += v2; cs3 += v3;
-      *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+      store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);
     } else if (EPI == EPI_F32) {
       if (p.drop.ctr) {   // LN(dropout(dense(x)) + residual): mask the dense output, element index m*N + n
         const uint32_t e0 = (uint32_t)(m * p.N + n);
@@ -175,7 +199,7 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
         dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
       }
     } else if (EPI == EPI_BF16) {
-      *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_ob + n) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+      store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);
     } else if (EPI == EPI_ATOMIC) {
       asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p.out_f32 + m * p.ld_of + n), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
     }
@@ -195,8 +219,9 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
 
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
+                    const GemmKernelParams p) {
   using Cfg = GemmCfg<BN, CG>;
   constexpr bool pair = (CG == 2);
   constexpr int NUM_STAGES = Cfg::NUM_STAGES;
@@ -223,6 +248,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.npass > 1) { tma_prefetch_desc(&tmap_a_lo); tma_prefetch_desc(&tmap_b_lo); }
     for (int s = 0; s < NUM_STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -269,8 +295,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = t2 / p.num_m_groups;
       const int kb0 = split * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kbv = kb0; kbv < kb1; ++kbv) {
         if (elect_one()) {
+          // virtual k-block -> (pass, real k-block): split precision walks K once per pass with the hi / lo tensor maps
+          int kb = kbv, sel = 0;
+          if (p.npass > 1) { const int ps = kbv / p.real_k_blocks; kb = kbv - ps * p.real_k_blocks; sel = p.pass_sel[ps]; }
+          const CUtensorMap* tma_a = (sel & 1) ? &tmap_a_lo : &tmap_a;
+          const CUtensorMap* tma_b = (sel & 2) ? &tmap_b_lo : &tmap_b;
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -279,15 +310,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
             if (p.a_mn) {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, fb);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), tma_a, m_blk * BM + j * 64, kb * BK, fb);
             } else {
-              tma_load_2d(sa, &tmap_a, kb * BK, m_blk * BM, fb);
+              tma_load_2d(sa, tma_a, kb * BK, m_blk * BM, fb);
             }
             if (p.b_mn) {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmap_b, n_blk * BN + j * 64, kb * BK, fb);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), tma_b, n_blk * BN + j * 64, kb * BK, fb);
             } else {
-              tma_load_2d(sb, &tmap_b, kb * BK, n_blk * BN, fb);
+              tma_load_2d(sb, tma_b, kb * BK, n_blk * BN, fb);
             }
           } else {
             // both CTAs complete their bytes on the LEADER's full barrier (the leader issues the MMAs for the pair);
@@ -296,19 +327,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
             if (p.a_mn) {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, fb);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * (BK * 128), tma_a, m_blk * BM + j * 64, kb * BK, fb);
             } else {
-              tma_load_2d_pair(sa, &tmap_a, kb * BK, m_blk * BM, fb);
+              tma_load_2d_pair(sa, tma_a, kb * BK, m_blk * BM, fb);
             }
             const int n0 = n_blk * BN + crank * (BN / 2);
             if (p.b_mn) {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * (BK * 128), &tmap_b, n0 + j * 64, kb * BK, fb);
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * (BK * 128), tma_b, n0 + j * 64, kb * BK, fb);
             } else {
-              tma_load_2d_pair(sb, &tmap_b, kb * BK, n0, fb);   // tensor-map box = BN/2 rows
+              tma_load_2d_pair(sb, tma_b, kb * BK, n0, fb);   // tensor-map box = BN/2 rows
             }
           }
-          if (kb == kb0 && w == group) VB_DBG(2);
+          if (kbv == kb0 && w == group) VB_DBG(2);
         }
         __syncwarp();
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
@@ -503,7 +534,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
 }
 
 template <int BN, int EPI, int CG>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmKernelParams& p, long long total_work, int max_ctas,
+static int launch_gemm(const CUtensorMap* tm, GemmKernelParams& p, long long total_work, int max_ctas,
                        cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<BN, EPI, CG>;
   static bool attr_set = false;  // per template instantiation
@@ -533,21 +564,21 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmKernelP
   }
   const int groups = (int)(total_work < groups_cap ? total_work : groups_cap);
   const int grid = groups * CG;
-  cudaError_t e = launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmCfg<BN, CG>::SMEM_BYTES, stream, CG, ta, tb, p);
+  cudaError_t e = launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmCfg<BN, CG>::SMEM_BYTES, stream, CG, tm[0], tm[1], tm[2], tm[3], p);
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return VB_OK;
 }
 
 template <int BN, int CG>
-static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, GemmKernelParams& p, long long work, int max_ctas,
+static int launch_gemm_epi(int epi, const CUtensorMap* tm, GemmKernelParams& p, long long work, int max_ctas,
                            cudaStream_t stream) {
   switch (epi) {
-    case EPI_F32: return launch_gemm<BN, EPI_F32, CG>(ta, tb, p, work, max_ctas, stream);
-    case EPI_BF16: return launch_gemm<BN, EPI_BF16, CG>(ta, tb, p, work, max_ctas, stream);
-    case EPI_GELU: return launch_gemm<BN, EPI_GELU, CG>(ta, tb, p, work, max_ctas, stream);
-    case EPI_DGELU: return launch_gemm<BN, EPI_DGELU, CG>(ta, tb, p, work, max_ctas, stream);
-    case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC, CG>(ta, tb, p, work, max_ctas, stream);
-    default: return launch_gemm<BN, EPI_GENERIC, CG>(ta, tb, p, work, max_ctas, stream);
+    case EPI_F32: return launch_gemm<BN, EPI_F32, CG>(tm, p, work, max_ctas, stream);
+    case EPI_BF16: return launch_gemm<BN, EPI_BF16, CG>(tm, p, work, max_ctas, stream);
+    case EPI_GELU: return launch_gemm<BN, EPI_GELU, CG>(tm, p, work, max_ctas, stream);
+    case EPI_DGELU: return launch_gemm<BN, EPI_DGELU, CG>(tm, p, work, max_ctas, stream);
+    case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC, CG>(tm, p, work, max_ctas, stream);
+    default: return launch_gemm<BN, EPI_GENERIC, CG>(tm, p, work, max_ctas, stream);
   }
 }
 
@@ -580,7 +611,7 @@ static long long pair_penalty() {
 // Chooses (tile width, CTAs per tile group, k splits) for a problem; honours the values the caller fixed. Pure host code.
 static int choose_config(const vb_gemm_args* a, int max_ctas, int* bn_out, int* cluster_out, int* split_out) {
   const int num_m = (a->M + BM - 1) / BM;
-  const int num_k = (a->K + BK - 1) / BK;
+  const int num_k = (a->K + BK - 1) / BK * (1 + (a->A_lo ? 1 : 0) + (a->B_lo ? 1 : 0));   // virtual k-blocks (split precision passes)
   // Tile configuration = (tile width bn, CTAs per tile group cg, k splits): minimise the modelled time of the busiest CTA,
   // in SM cycles, with constants measured on B200 (clock64 timelines / feed probes in profiles/):
   //   main loop per 64-deep k-block: 128x128 ~430 (bound by the SM's operand ingest, ~98 B/clk of TMA writes competing with
@@ -648,12 +679,19 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   if (a->bias && !aligned(a->bias, 16)) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: bias must be 16-byte aligned");
   if (a->atomic_out && (!a->out_f32 || a->out_bf16 || a->out_pre))
     return set_error(VB_ERR_INVALID, "vb_gemm_bf16: atomic_out supports only out_f32");
+  if ((a->A_lo && !aligned(a->A_lo, 16)) || (a->B_lo && !aligned(a->B_lo, 16)))
+    return set_error(VB_ERR_INVALID, "vb_gemm_bf16: A_lo / B_lo must be 16-byte aligned");
+  if ((a->out_lo || a->out_b16) && !a->out_bf16) return set_error(VB_ERR_INVALID, "vb_gemm_bf16: out_lo / out_b16 need out_bf16");
+  if ((a->a_fp16 != 0) != (a->b_fp16 != 0))
+    return set_error(VB_ERR_UNSUPPORTED, "vb_gemm_bf16: A and B must have the same 16-bit format (fp16 x bf16 faults on sm_100)");
   int dev_sms = 0, cc = 0;
   if (int s = vb_device_info(&dev_sms, &cc)) return s;
   if (cc / 10 != 10) return set_error(VB_ERR_UNSUPPORTED, "vb_gemm_bf16: needs an sm_100 device (found sm_%d)", cc);
 
   const int num_m = (a->M + BM - 1) / BM;
-  const int num_k = (a->K + BK - 1) / BK;
+  const int real_k = (a->K + BK - 1) / BK;
+  const int npass = 1 + (a->A_lo ? 1 : 0) + (a->B_lo ? 1 : 0);
+  const int num_k = real_k * npass;   // virtual k-blocks (split precision: K is walked once per pass)
   int max_ctas = a->max_ctas > 0 ? a->max_ctas : dev_sms;
 
   int bn = 128, cluster = 1, split_k = 1;
@@ -664,6 +702,11 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   GemmKernelParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_m_blocks = num_m; p.num_n_blocks = num_n; p.num_k_blocks = num_k;
+  p.real_k_blocks = real_k; p.npass = npass;
+  p.pass_sel[0] = 0; p.pass_sel[1] = a->A_lo ? 1 : 2; p.pass_sel[2] = 2;
+  p.out_fp16 = a->out_fp16 ? 1 : 0;
+  p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);
+  p.out_b16 = static_cast<__nv_bfloat16*>(a->out_b16);
   p.split_k = split_k; p.k_blocks_per_split = kps;
   p.alpha = a->alpha;
   p.bias = a->bias;
@@ -676,7 +719,8 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   p.atomic_out = a->atomic_out;
   p.out_colsum = a->out_colsum;
   p.vec_f32 = a->out_f32 && aligned(a->out_f32, 16) && (a->ld_out_f32 % 4 == 0);
-  p.vec_bf16 = a->out_bf16 && aligned(a->out_bf16, 8) && (a->ld_out_bf16 % 4 == 0);
+  p.vec_bf16 = a->out_bf16 && aligned(a->out_bf16, 8) && (a->ld_out_bf16 % 4 == 0) && (!a->out_lo || aligned(a->out_lo, 8)) &&
+               (!a->out_b16 || aligned(a->out_b16, 8));
   p.vec_pre = a->out_pre && aligned(a->out_pre, 8) && (a->ld_out_pre % 4 == 0);
   p.vec_res = a->residual && aligned(a->residual, 16) && (a->ld_res % 4 == 0);
   p.vec_aux = a->aux && aligned(a->aux, 8) && (a->ld_aux % 4 == 0);
@@ -692,7 +736,7 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   p.desc_base_b = umma_desc_base(lbo_b, sbo_b);
   p.kadv_a = a->a_mn_major ? 2 * 1024 : UK * 2;
   p.kadv_b = a->b_mn_major ? 2 * 1024 : UK * 2;
-  p.idesc = umma_idesc_bf16(BM * cluster, bn, a->a_mn_major ? 1 : 0, a->b_mn_major ? 1 : 0);   // pairs: 256 x bn MMAs
+  p.idesc = umma_idesc_bf16(BM * cluster, bn, a->a_mn_major ? 1 : 0, a->b_mn_major ? 1 : 0, a->a_fp16, a->b_fp16);   // pairs: 256 x bn MMAs
   p.dbg = reinterpret_cast<unsigned long long*>(a->dbg_timeline);
   p.a_mn = a->a_mn_major ? 1 : 0;
   p.b_mn = a->b_mn_major ? 1 : 0;
@@ -704,14 +748,21 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   p.drop.thresh = (uint32_t)((double)a->dropout.p * 4294967296.0);
   p.drop.scale = a->dropout.p < 1.f ? 1.f / (1.f - a->dropout.p) : 0.f;
 
-  CUtensorMap ta, tb;
+  CUtensorMap tm[4];   // A, B, A_lo, B_lo (the lo maps alias the hi ones when a low part is absent)
   int st;
-  if (a->a_mn_major) st = make_tmap(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
-  else               st = make_tmap(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
-  if (st) return st;
-  if (a->b_mn_major) st = make_tmap(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
-  else               st = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)(bn / cluster));   // a pair CTA stages half the tile
-  if (st) return st;
+  for (int i = 0; i < 4; ++i) {
+    const bool is_a = (i & 1) == 0;
+    const void* ptr = is_a ? (i < 2 ? a->A : a->A_lo) : (i < 2 ? a->B : a->B_lo);
+    if (!ptr) { tm[i] = tm[i - 2]; continue; }
+    if (is_a) {
+      if (a->a_mn_major) st = make_tmap(&tm[i], ptr, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
+      else               st = make_tmap(&tm[i], ptr, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
+    } else {
+      if (a->b_mn_major) st = make_tmap(&tm[i], ptr, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
+      else               st = make_tmap(&tm[i], ptr, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)(bn / cluster));   // a pair CTA stages half the tile
+    }
+    if (st) return st;
+  }
 
   const long long total_work = (long long)p.num_m_groups * num_n * split_k;
 
@@ -732,11 +783,11 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
     else if (a->out_bf16 && !a->out_f32 && !a->residual && no_extra && !has_drop) { epi = EPI_BF16; p.fast_ok = p.vec_bf16; }
   }
   if (cluster == 2) {
-    if (bn == 256) return launch_gemm_epi<256, 2>(epi, ta, tb, p, total_work, max_ctas, stream);
-    return launch_gemm_epi<128, 2>(epi, ta, tb, p, total_work, max_ctas, stream);
+    if (bn == 256) return launch_gemm_epi<256, 2>(epi, tm, p, total_work, max_ctas, stream);
+    return launch_gemm_epi<128, 2>(epi, tm, p, total_work, max_ctas, stream);
   }
-  if (bn == 256) return launch_gemm_epi<256, 1>(epi, ta, tb, p, total_work, max_ctas, stream);
-  return launch_gemm_epi<128, 1>(epi, ta, tb, p, total_work, max_ctas, stream);
+  if (bn == 256) return launch_gemm_epi<256, 1>(epi, tm, p, total_work, max_ctas, stream);
+  return launch_gemm_epi<128, 1>(epi, tm, p, total_work, max_ctas, stream);
 }
 
 extern "C" vb_status vb_gemm_plan(const vb_gemm_args* a, int32_t sm_count_, int32_t* block_n, int32_t* cluster_m, int32_t* split_k) {

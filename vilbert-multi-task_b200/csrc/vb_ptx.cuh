@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace vb {
@@ -234,13 +235,13 @@ __host__ __device__ __forceinline__ uint64_t umma_desc_base(uint32_t lbo_bytes, 
 __device__ __forceinline__ uint64_t umma_desc_at(uint64_t base, uint32_t smem_addr) {
   return base | (uint64_t)((smem_addr & 0x3FFFF) >> 4);
 }
-// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
+// Instruction descriptor for kind::f16: A and B independently fp16 (format 0) or bf16 (format 1), fp32 accumulate.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major,
-                                                             int b_mn_major) {
+                                                             int b_mn_major, int a_fp16 = 0, int b_fp16 = 0) {
   uint32_t d = 0;
   d |= 1u << 4;                         // C format: F32
-  d |= 1u << 7;                         // A format: BF16
-  d |= 1u << 10;                        // B format: BF16
+  d |= (a_fp16 ? 0u : 1u) << 7;         // A format: F16 = 0, BF16 = 1
+  d |= (b_fp16 ? 0u : 1u) << 10;        // B format
   d |= (uint32_t)(a_mn_major & 1) << 15;
   d |= (uint32_t)(b_mn_major & 1) << 16;
   d |= (uint32_t)(N >> 3) << 17;
@@ -269,9 +270,47 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// same with fp16 inputs (forward attention operands)
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                              uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool FP16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (FP16) mma_f16_16816(d, a, b0, b1); else mma_bf16_16816(d, a, b0, b1);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 16-bit operand formats: fmt 0 = bf16 (gradient operands), 1 = IEEE fp16 (forward operands).
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) { return fp16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+__device__ __forceinline__ float2 unpack16(uint32_t v, int fp16) {
+  return fp16 ? __half22float2(*reinterpret_cast<const __half2*>(&v)) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+__device__ __forceinline__ uint16_t cvt16(float v, int fp16) {
+  if (fp16) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 b = __float2bfloat16(v); return *reinterpret_cast<uint16_t*>(&b);
+}
+__device__ __forceinline__ float cvt16_to_f32(uint16_t v, int fp16) {
+  return fp16 ? __half2float(*reinterpret_cast<const __half*>(&v)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&v));
+}
+// Split precision: hi = round16(x) (returned), lo = round16(x - hi): hi + lo carries ~2x the significand bits.
+__device__ __forceinline__ uint32_t pack16_split(float a, float b, int fp16, uint32_t& lo) {
+  const uint32_t hi = pack16(a, b, fp16);
+  const float2 h = unpack16(hi, fp16);
+  lo = pack16(a - h.x, b - h.y, fp16);
+  return hi;
 }
 
 // erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level): 1 rcp + 1 ex2 + 6 FMA instead of the ~40-instruction

@@ -33,7 +33,8 @@ template <int NV4>
 __global__ void __launch_bounds__(ROW_THREADS)
 ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
               float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, long long ldy, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, int M, int H, const DropCfg drop) {
+              float* __restrict__ rstd_out, int M, int H, const DropCfg drop, int y_fp16, __nv_bfloat16* __restrict__ y_lo,
+              __nv_bfloat16* __restrict__ y_b16) {
   pdl_entry();
   const int lane = threadIdx.x & 31;
   const int n4 = H >> 2;
@@ -81,7 +82,17 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
           o.z = drop_apply(o.z, dseed, e0 + 2, drop); o.w = drop_apply(o.w, dseed, e0 + 3, drop);
         }
         if (y32) reinterpret_cast<float4*>(y32 + row * ldy)[c] = o;
-        if (y16) reinterpret_cast<uint2*>(y16 + row * ldy)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        if (y16) {
+          if (y_lo) {   // split precision: operand copy as hi + lo
+            uint32_t l01, l23;
+            const uint32_t h01 = pack16_split(o.x, o.y, y_fp16, l01), h23 = pack16_split(o.z, o.w, y_fp16, l23);
+            reinterpret_cast<uint2*>(y16 + row * ldy)[c] = make_uint2(h01, h23);
+            reinterpret_cast<uint2*>(y_lo + row * ldy)[c] = make_uint2(l01, l23);
+          } else {
+            reinterpret_cast<uint2*>(y16 + row * ldy)[c] = make_uint2(pack16(o.x, o.y, y_fp16), pack16(o.z, o.w, y_fp16));
+          }
+        }
+        if (y_b16) reinterpret_cast<uint2*>(y_b16 + row * ldy)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       }
     }
   }
@@ -201,16 +212,28 @@ ln_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------ casts
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4, long long n) {
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4, long long n, int fp16,
+                                     __nv_bfloat16* __restrict__ dst_lo, __nv_bfloat16* __restrict__ dst_b) {
   pdl_entry();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
-    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    if (dst_lo) {
+      uint32_t l01, l23;
+      const uint32_t h01 = pack16_split(v.x, v.y, fp16, l01), h23 = pack16_split(v.z, v.w, fp16, l23);
+      reinterpret_cast<uint2*>(dst)[i] = make_uint2(h01, h23);
+      reinterpret_cast<uint2*>(dst_lo)[i] = make_uint2(l01, l23);
+    } else {
+      reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack16(v.x, v.y, fp16), pack16(v.z, v.w, fp16));
+    }
+    if (dst_b) reinterpret_cast<uint2*>(dst_b)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
-    dst[i] = __float2bfloat16(src[i]);
+    const uint16_t hi = cvt16(src[i], fp16);
+    reinterpret_cast<uint16_t*>(dst)[i] = hi;
+    if (dst_lo) reinterpret_cast<uint16_t*>(dst_lo)[i] = cvt16(src[i] - cvt16_to_f32(hi, fp16), fp16);
+    if (dst_b) dst_b[i] = __float2bfloat16(src[i]);
   }
 }
 
@@ -420,14 +443,20 @@ small_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------ elementwise helpers
 // out = a * b (fusion_method "mul") or a + b ("sum"), f32 + bf16 copies (vilbert.py:1677-1682, 1236-1241)
 __global__ void fuse_pooled_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o32,
-                                       __nv_bfloat16* __restrict__ o16, long long n, int mul, const DropCfg drop) {
+                                       __nv_bfloat16* __restrict__ o16, long long n, int mul, const DropCfg drop, int fp16,
+                                       __nv_bfloat16* __restrict__ o_lo, __nv_bfloat16* __restrict__ o_b) {
   pdl_entry();
   const uint32_t dseed = drop.ctr ? drop_seed(drop) : 0u;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = mul ? a[i] * b[i] : a[i] + b[i];
     if (drop.ctr) v = drop_apply(v, dseed, (uint32_t)i, drop);
     if (o32) o32[i] = v;
-    if (o16) o16[i] = __float2bfloat16(v);
+    if (o16) {
+      const uint16_t hi = cvt16(v, fp16);
+      reinterpret_cast<uint16_t*>(o16)[i] = hi;
+      if (o_lo) reinterpret_cast<uint16_t*>(o_lo)[i] = cvt16(v - cvt16_to_f32(hi, fp16), fp16);
+    }
+    if (o_b) o_b[i] = __float2bfloat16(v);
   }
 }
 // da += d * b, db += d * a (mul) or da += d, db += d (sum)
@@ -528,16 +557,17 @@ using namespace vb;
 
 extern "C" vb_status vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* y_f32,
                                       void* y_bf16, int64_t ldy, float* mean, float* rstd, int32_t M, int32_t H, const vb_dropout* out_dropout,
-                                      void* stream) {
+                                      int32_t y_fp16, void* y_lo, void* y_b16, void* stream) {
   if (M <= 0 || H <= 0) return set_error(VB_ERR_INVALID, "vb_layernorm_fwd: empty problem");
   if ((H & 3) || H > MAX_V4 * 128 || (ldx & 3) || (ldy & 3) || !al16(x) || !al16(gamma) || !al16(beta) || (y_f32 && !al16(y_f32)) ||
-      (y_bf16 && (reinterpret_cast<uintptr_t>(y_bf16) & 7)))
+      (y_bf16 && (reinterpret_cast<uintptr_t>(y_bf16) & 7)) || (y_lo && ((reinterpret_cast<uintptr_t>(y_lo) & 7) || !y_bf16)) ||
+      (reinterpret_cast<uintptr_t>(y_b16) & 7))
     return set_error(VB_ERR_INVALID, "vb_layernorm_fwd: need H %% 4 == 0, H <= %d, ld %% 4 == 0, 16-byte aligned rows", MAX_V4 * 128);
   const int nv4 = (H / 4 + 31) / 32;
   const int grid = row_grid(M);
   __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
   const DropCfg dc = make_drop(out_dropout);
-#define LN_F(NV) launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), x, ldx, gamma, beta, eps, y_f32, y16, ldy, mean, rstd, M, H, dc)
+#define LN_F(NV) launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(ROW_THREADS), (size_t)(0), ST(stream), x, ldx, gamma, beta, eps, y_f32, y16, ldy, mean, rstd, M, H, dc, (int)(y_fp16 ? 1 : 0), static_cast<__nv_bfloat16*>(y_lo), static_cast<__nv_bfloat16*>(y_b16))
   if (nv4 <= 1) LN_F(1); else if (nv4 <= 2) LN_F(2); else if (nv4 <= 4) LN_F(4); else if (nv4 <= 6) LN_F(6);
   else if (nv4 <= 8) LN_F(8); else LN_F(16);
 #undef LN_F
@@ -566,10 +596,12 @@ extern "C" vb_status vb_layernorm_bwd(const float* dy, int64_t lddy, const float
   return check_launch("vb_layernorm_bwd");
 }
 
-extern "C" vb_status vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+extern "C" vb_status vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, int32_t fp16, void* dst_lo, void* dst_b16, void* stream) {
   if (n <= 0) return VB_OK;
-  if (!al16(src) || (reinterpret_cast<uintptr_t>(dst) & 7)) return set_error(VB_ERR_INVALID, "vb_cast_f32_to_bf16: misaligned buffers");
-  launch_pdl(cast_f32_bf16_kernel, dim3(ew_grid(n / 4 + 1)), dim3(256), (size_t)(0), ST(stream), src, static_cast<__nv_bfloat16*>(dst), n / 4, n);
+  if (!al16(src) || (reinterpret_cast<uintptr_t>(dst) & 7) || (reinterpret_cast<uintptr_t>(dst_lo) & 7) || (reinterpret_cast<uintptr_t>(dst_b16) & 7))
+    return set_error(VB_ERR_INVALID, "vb_cast_f32_to_bf16: misaligned buffers");
+  launch_pdl(cast_f32_bf16_kernel, dim3(ew_grid(n / 4 + 1)), dim3(256), (size_t)(0), ST(stream), src, static_cast<__nv_bfloat16*>(dst), n / 4, n,
+             (int)(fp16 ? 1 : 0), static_cast<__nv_bfloat16*>(dst_lo), static_cast<__nv_bfloat16*>(dst_b16));
   return check_launch("vb_cast_f32_to_bf16");
 }
 
@@ -649,9 +681,10 @@ extern "C" vb_status vb_small_linear_bwd(const float* dy, const float* x, int64_
 }
 
 extern "C" vb_status vb_fuse_pooled_fwd(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t n, int32_t mul,
-                                        const vb_dropout* dropout, void* stream) {
+                                        const vb_dropout* dropout, int32_t out_fp16, void* out_lo, void* out_b16, void* stream) {
   if (n <= 0) return VB_OK;
-  launch_pdl(fuse_pooled_fwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), a, b, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n, mul, make_drop(dropout));
+  launch_pdl(fuse_pooled_fwd_kernel, dim3(ew_grid(n)), dim3(256), (size_t)(0), ST(stream), a, b, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n, mul, make_drop(dropout),
+             (int)(out_fp16 ? 1 : 0), static_cast<__nv_bfloat16*>(out_lo), static_cast<__nv_bfloat16*>(out_b16));
   return check_launch("vb_fuse_pooled_fwd");
 }
 extern "C" vb_status vb_fuse_pooled_bwd(const float* d, const float* a, const float* b, float* da, float* db, int64_t n, int32_t mul,

@@ -8,9 +8,17 @@ become flat lists of C-ABI calls into libvilbert_b200.so (tcgen05 GEMMs, fused a
 kernels). A plan can be replayed eagerly (a tight loop of ctypes calls) or captured into one CUDA
 graph per pass. PyTorch is used for device memory, streams and (optionally) graph capture only.
 
-Numerics ("bf16 mode"): GEMM operands bf16, accumulation fp32 (TMEM); the residual
-stream, LayerNorm statistics/outputs, softmax statistics, biases and every gradient accumulation
-are fp32; bf16 copies of activations exist only as GEMM / attention operands.
+Numerics. Accumulation is always fp32 (TMEM / registers); the residual stream, LayerNorm
+statistics and outputs, softmax statistics, biases and every gradient accumulation are fp32; 16-bit copies of
+activations and weights exist only as tensor-core operands. Three operand precisions (Engine(precision=...)):
+  "fp16" (default)  forward operands (activations, weights) fp16 — 11 significant bits, the reference's own reduced
+                    precision (model.half(), train_concap.py:504-505) — gradient operands (dy, dS, ...) bf16 for range.
+                    tcgen05 faults on fp16 x bf16 (measured), so every forward operand the backward contracts with a
+                    gradient (weights for dgrad, saved activations for wgrad) also has a bf16 copy, written by the kernel
+                    that produces it (Act.bw, ParamStore.shadow_b);
+  "fp32"            split precision: every forward operand is stored as fp16 hi + lo and every forward contraction
+                    runs as three tensor-core passes (hi.hi + lo.hi + hi.lo), ~fp32 accuracy (north_star 1e-3);
+  "bf16"            every operand bf16 (round-1 arithmetic; kept for A/B measurements).
 """
 import ctypes as C
 import math
@@ -21,7 +29,8 @@ import torch
 
 from . import _lib as L
 
-F32, BF16, I64 = torch.float32, torch.bfloat16, torch.int64
+F32, BF16, F16, I64 = torch.float32, torch.bfloat16, torch.float16, torch.int64
+PRECISIONS = ("fp16", "fp32", "bf16")
 
 
 def _pad8(n):
@@ -40,10 +49,12 @@ class ParamStore:
     bf16 shadow used as GEMM operands. query/key/value weights of one attention are allocated contiguously
     so that the fused [3H, H] QKV GEMM reads them in place."""
 
-    def __init__(self, cfg, device, heads="vl"):
+    def __init__(self, cfg, device, heads="vl", op_dtype=F16, split=False):
         """heads: "vl" = pre-training heads + the 7 task heads (VILBertForVLTasks), "pretraining" = cls.* only
-        (BertForMultiModalPreTraining), "none" = bare BertModel."""
+        (BertForMultiModalPreTraining), "none" = bare BertModel. op_dtype: format of the 16-bit weight shadow;
+        split: also keep the low parts (shadow_lo) for the split-precision mode."""
         assert heads in ("vl", "pretraining", "none")
+        self.op_dtype, self.split = op_dtype, split
         self.heads = heads
         with_task_heads = heads == "vl"
         self.cfg = cfg
@@ -112,7 +123,10 @@ class ParamStore:
         self.numel = self._off
         self.flat = torch.zeros(self.numel, dtype=F32, device=device)
         self.grad = torch.zeros(self.numel, dtype=F32, device=device)
-        self.shadow = torch.zeros(self.numel, dtype=BF16, device=device)
+        self.shadow = torch.zeros(self.numel, dtype=op_dtype, device=device)
+        self.shadow_lo = torch.zeros(self.numel, dtype=op_dtype, device=device) if split else None
+        # bf16 copy for the backward (dgrad: dy bf16 x W): the shadow itself when the operand format is already bf16
+        self.shadow_b = self.shadow if op_dtype == BF16 else torch.zeros(self.numel, dtype=BF16, device=device)
         self.shadow_version = None
 
     def _add(self, name, shape):
@@ -155,9 +169,18 @@ class ParamStore:
     def w16(self, name):
         return self._view(self.shadow, name)
 
+    def w16lo(self, name):
+        return self._view(self.shadow_lo, name) if self.split else None
+
+    def w16b(self, name):
+        return self._view(self.shadow_b, name)
+
     def refresh_shadow(self, stream):
-        """bf16 copy of every parameter in one launch (belongs with the optimizer step in training)."""
-        L.check(L.lib().vb_cast_f32_to_bf16(self.flat.data_ptr(), self.shadow.data_ptr(), self.numel, stream), "vb_cast_f32_to_bf16")
+        """16-bit operand copy (hi, and lo in split precision) of every parameter in one launch (belongs with the
+        optimizer step in training)."""
+        L.check(L.lib().vb_cast_f32_to_bf16(self.flat.data_ptr(), self.shadow.data_ptr(), self.numel, 1 if self.op_dtype == F16 else 0,
+                                            self.shadow_lo.data_ptr() if self.split else None,
+                                            self.shadow_b.data_ptr() if self.shadow_b is not self.shadow else None, stream), "vb_cast_f32_to_bf16")
 
 
 # ------------------------------------------------------------------------------------------ plan
@@ -183,11 +206,14 @@ class _TrackedParams:
 
 
 class Act:
-    """A residual-stream activation: fp32 values, bf16 operand copy, fp32 gradient (lazily allocated)."""
-    __slots__ = ("f32", "b16", "g32", "gw", "M", "H")
+    """A residual-stream activation: fp32 values, 16-bit operand copy (b16; lo = its split-precision low part or None),
+    fp32 gradient (lazily allocated)."""
+    __slots__ = ("f32", "b16", "lo", "bw", "g32", "gw", "M", "H")
 
-    def __init__(self, f32, b16, M, H):
-        self.f32, self.b16, self.M, self.H = f32, b16, M, H
+    def __init__(self, f32, b16, M, H, lo=None, bw=None):
+        """bw: bf16 copy of the operand for the backward's weight-gradient GEMM (== b16 when the operand format is bf16)."""
+        self.f32, self.b16, self.lo, self.M, self.H = f32, b16, lo, M, H
+        self.bw = b16 if bw is None else bw
         self.g32, self.gw = None, False
 
 
@@ -213,11 +239,14 @@ class Plan:
         self.grad_outputs = frozenset(grad_outputs)
         self.vqa_loss = vqa_loss
         self.train = bool(train)          # nn.Dropout layers active (model.train()); False = the reference's eval mode
+        self.op_fp16 = 1 if engine.op_dtype == F16 else 0   # format of the forward operands (activations, weights)
+        self.op_dtype, self.split = engine.op_dtype, engine.split
         self.head_dropout_prob = engine.head_dropout_prob
         self.heads = engine.ps.heads if heads is None else heads   # "vl" | "pretraining" | "none"
         self.fwd_id = 0
         self.fwd, self.bwd = [], []
         self.prologue = []       # optional per-step ops run before the forward (see enable_training_prologue)
+        self.epilogue = []       # optional per-step ops run after the backward (the fused optimizer: enable_optimizer)
         self.cur = self.fwd
         self.sid = 0             # stream the next emitted op goes to: 0 = text/main stream, 1 = vision stream
         self.two_streams = engine.two_streams
@@ -237,6 +266,19 @@ class Plan:
         t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
         self._keep.append(t)
         return t
+
+    def buf16(self, shape, bw=True):
+        """Forward-operand buffer in the engine's operand format: (hi, lo, bw) with lo = None unless split precision and
+        bw = the bf16 copy the backward's weight-gradient GEMM reads (hi itself when the format is bf16, None if not wanted)."""
+        hi = self.buf(shape, self.op_dtype)
+        lo = self.buf(shape, self.op_dtype) if self.split else None
+        b = None if not bw else (hi if self.op_dtype == BF16 else self.buf(shape, BF16))
+        return hi, lo, b
+
+    @staticmethod
+    def _extra(bw, hi):
+        """Pointer for a kernel's optional bf16-copy output: None when the copy IS the primary output."""
+        return None if (bw is None or bw is hi) else bw
 
     def scratch(self, tag, shape, dtype):
         # with asynchronous weight-gradient streams a temporary may still be read after its layer's backward has moved on:
@@ -299,8 +341,18 @@ class Plan:
 
     def gemm(self, M, N, K, A, lda, B, ldb, a_mn=0, b_mn=0, bias=None, residual=None, ld_res=0, aux=None, ld_aux=0, act=0,
              out_f32=None, ld_of=0, out_bf16=None, ld_ob=0, out_pre=None, ld_op=0, atomic=0, split_k=1, alpha=1.0, out_colsum=None,
-             dropout=None):
+             dropout=None, a_lo=None, b_lo=None, out_lo=None, out_b16=None):
+        """Operand formats follow the pass being emitted: in the forward pass A, B and the 16-bit output are forward
+        operands (engine format, + low parts in split precision; out_b16 = optional bf16 copy of the output for the
+        backward); in the backward pass everything is bf16: A is a gradient operand, B the bf16 copy of a weight (dgrad) or
+        of a saved activation (wgrad), 16-bit outputs are gradients."""
         g = L.GemmArgs()
+        fwd = self.cur is self.fwd
+        g.a_fp16 = g.b_fp16 = g.out_fp16 = self.op_fp16 if fwd else 0
+        if fwd:
+            g.out_b16 = self._ptr(out_b16)
+        if fwd and self.split:
+            g.A_lo, g.B_lo, g.out_lo = self._ptr(a_lo), self._ptr(b_lo), self._ptr(out_lo)
         g.M, g.N, g.K = M, N, K
         g.A, g.lda, g.a_mn_major = self._ptr(A), lda, a_mn
         g.B, g.ldb, g.b_mn_major = self._ptr(B), ldb, b_mn
@@ -320,8 +372,14 @@ class Plan:
         self.emit(self.lib.vb_gemm_bf16, C.byref(g))
 
     def attention(self, bwd, B, H, Nq, Nk, D, Q, ldq, K, ldk, V, ldv, mask, O, ldo, lse, dO=None, lddo=0, dQ=None, lddq=0,
-                  dK=None, lddk=0, dV=None, lddv=0, delta=None, dbq=None, dbk=None, dbv=None, dropout=None):
+                  dK=None, lddk=0, dV=None, lddv=0, delta=None, dbq=None, dbk=None, dbv=None, dropout=None, q_lo=None, k_lo=None,
+                  v_lo=None, o_lo=None, o_b16=None):
         a = L.AttnArgs()
+        a.qkv_fp16 = self.op_fp16
+        if not bwd:
+            a.O_b16 = self._ptr(o_b16)
+        if not bwd and self.split:
+            a.Q_lo, a.K_lo, a.V_lo, a.O_lo = self._ptr(q_lo), self._ptr(k_lo), self._ptr(v_lo), self._ptr(o_lo)
         a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
         a.Q, a.ldq, a.K, a.ldk, a.V, a.ldv = self._ptr(Q), ldq, self._ptr(K), ldk, self._ptr(V), ldv
         a.mask, a.scale = self._ptr(mask), 1.0 / math.sqrt(D)
@@ -336,11 +394,11 @@ class Plan:
 
     def ln_fwd(self, x, gamma, beta, M, H, want_f32=True, out_drop=None):
         y32 = self.buf((M, H), F32) if want_f32 else None
-        y16 = self.buf((M, H), BF16)
+        y16, ylo, ybw = self.buf16((M, H))
         mean, rstd = self.buf((M,), F32), self.buf((M,), F32)
         self.emit(self.lib.vb_layernorm_fwd, x.data_ptr(), H, gamma.data_ptr(), beta.data_ptr(), 1e-12, self._ptr(y32), y16.data_ptr(), H,
-                  mean.data_ptr(), rstd.data_ptr(), M, H, self._ref(out_drop))
-        return y32, y16, mean, rstd
+                  mean.data_ptr(), rstd.data_ptr(), M, H, self._ref(out_drop), self.op_fp16, self._ptr(ylo), self._ptr(self._extra(ybw, y16)))
+        return y32, y16, mean, rstd, ylo, ybw
 
     def ln_bwd(self, dy, x, gamma, mean, rstd, dx32, dx16, M, H, ggamma, gbeta, pre=None, gbias=None, out_drop=None, in_drop=None):
         """gbias: bias gradient of the Linear feeding this LayerNorm (column sums of dx), fused into the same pass."""
@@ -395,14 +453,15 @@ class Plan:
         self.emit(self.lib.vb_axpy_f32, src32.data_ptr(), g.data_ptr(), g.numel(), 1.0)
 
     # ------------------------------------------------------------------ blocks
-    def dense_res_ln(self, a16, K_in, res, wname, lnname, tag, drop=None):
+    def dense_res_ln(self, a16, K_in, res, wname, lnname, tag, drop=None, a_lo=None, a_bw=None):
         """LN(dense(a) + residual)  — BertSelfOutput / BertOutput / BertBiOutput halves (vilbert.py:470-474, 513-517, 844-855)."""
         ps, M, H = self.ps, res.M, res.H
         y = self.buf((M, H), F32)
         self.gemm(M, H, K_in, a16, K_in, ps.w16(wname + ".weight"), K_in, bias=ps.p(wname + ".bias"), residual=res.f32, ld_res=H,
-                  out_f32=y, ld_of=H, dropout=drop)
-        o32, o16, mean, rstd = self.ln_fwd(y, ps.p(lnname + ".weight"), ps.p(lnname + ".bias"), M, H)
-        out = Act(o32, o16, M, H)
+                  out_f32=y, ld_of=H, dropout=drop, a_lo=a_lo, b_lo=ps.w16lo(wname + ".weight"))
+        o32, o16, mean, rstd, olo, obw = self.ln_fwd(y, ps.p(lnname + ".weight"), ps.p(lnname + ".bias"), M, H)
+        out = Act(o32, o16, M, H, lo=olo, bw=obw)
+        a_bw = a16 if a_bw is None else a_bw
 
         def bwd():
             """returns (dy16, dy32) of the dense output (== grad of the LN input); adds dy32 to res."""
@@ -412,17 +471,18 @@ class Plan:
             dy16 = self.scratch(tag + ".dy16", (M, H), BF16)
             self.ln_bwd(out.g32, y, ps.p(lnname + ".weight"), mean, rstd, dy32, dy16, M, H, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"),
                         gbias=ps.g(wname + ".bias"), in_drop=drop)
-            self.linear_wgrad(dy16, H, None, 0, a16, K_in, M, H, K_in, wname)
+            self.linear_wgrad(dy16, H, None, 0, a_bw, K_in, M, H, K_in, wname)
             return dy16, dy32
         return out, bwd
 
     def ffn(self, x, I, w1, w2, lnname, tag, drop=None):
         """LN(dense2(gelu(dense1(x))) + x) — BertIntermediate + BertOutput (vilbert.py:500-503, 513-517)."""
         ps, M, H = self.ps, x.M, x.H
-        pre16, f16 = self.buf((M, I), BF16), self.buf((M, I), BF16)
+        pre16 = self.buf((M, I), BF16)          # gelu'(pre), bf16 in every mode (only the backward reads it)
+        f16, flo, fbw = self.buf16((M, I))
         self.gemm(M, I, H, x.b16, H, ps.w16(w1 + ".weight"), H, bias=ps.p(w1 + ".bias"), act=L.VB_ACT_GELU, out_bf16=f16, ld_ob=I,
-                  out_pre=pre16, ld_op=I)
-        out, out_bwd = self.dense_res_ln(f16, I, x, w2, lnname, tag + ".o", drop=drop)
+                  out_pre=pre16, ld_op=I, a_lo=x.lo, b_lo=ps.w16lo(w1 + ".weight"), out_lo=flo, out_b16=self._extra(fbw, f16))
+        out, out_bwd = self.dense_res_ln(f16, I, x, w2, lnname, tag + ".o", drop=drop, a_lo=flo, a_bw=fbw)
 
         def bwd():
             r = out_bwd()
@@ -431,10 +491,10 @@ class Plan:
             dy16, dy32 = r
             dpre16 = self.scratch(tag + ".dpre16", (M, I), BF16)
             # d pre = (dy W2) * gelu'(pre)
-            self.gemm(M, I, H, dy16, H, ps.w16(w2 + ".weight"), I, b_mn=1, aux=pre16, ld_aux=I, act=L.VB_ACT_DGELU, out_bf16=dpre16, ld_ob=I,
+            self.gemm(M, I, H, dy16, H, ps.w16b(w2 + ".weight"), I, b_mn=1, aux=pre16, ld_aux=I, act=L.VB_ACT_DGELU, out_bf16=dpre16, ld_ob=I,
                       out_colsum=ps.g(w1 + ".bias"))
-            self.linear_wgrad(dpre16, I, None, 0, x.b16, H, M, I, H, w1)
-            self.dgrad_into(x, dpre16, I, ps.w16(w1 + ".weight"), M, I, H, extra32=dy32)
+            self.linear_wgrad(dpre16, I, None, 0, x.bw, H, M, I, H, w1)
+            self.dgrad_into(x, dpre16, I, ps.w16b(w1 + ".weight"), M, I, H, extra32=dy32)
         self.push_bwd(bwd)
         return out
 
@@ -442,15 +502,18 @@ class Plan:
         """BertAttention (self-attention + output), text or image stream (vilbert.py:424-474, 571-633)."""
         ps, M, H = self.ps, x.M, x.H
         D = H // nh
-        qkv = self.buf((M, 3 * H), BF16)
-        self.gemm(M, 3 * H, H, x.b16, H, ps.w16(prefix + ".self.qkv.weight"), H, bias=ps.p(prefix + ".self.qkv.bias"), out_bf16=qkv, ld_ob=3 * H)
-        ctx = self.buf((M, H), BF16)
+        qkv, qkvl, _ = self.buf16((M, 3 * H), bw=False)     # the attention backward converts its Q/K/V panels in shared memory
+        self.gemm(M, 3 * H, H, x.b16, H, ps.w16(prefix + ".self.qkv.weight"), H, bias=ps.p(prefix + ".self.qkv.bias"), out_bf16=qkv, ld_ob=3 * H,
+                  a_lo=x.lo, b_lo=ps.w16lo(prefix + ".self.qkv.weight"), out_lo=qkvl)
+        ctx, ctxl, ctxb = self.buf16((M, H))
         lse = self.buf((B, nh, N), F32)
         q, k, v = qkv[:, 0:H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+        ql, kl, vl = (qkvl[:, 0:H], qkvl[:, H:2 * H], qkvl[:, 2 * H:]) if self.split else (None, None, None)
         adrop = self.drop(prefix + ".self.dropout", p_attn)
-        self.attention(False, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dropout=adrop)
+        self.attention(False, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dropout=adrop, q_lo=ql, k_lo=kl, v_lo=vl, o_lo=ctxl,
+                       o_b16=self._extra(ctxb, ctx))
         out, out_bwd = self.dense_res_ln(ctx, H, x, prefix + ".output.dense", prefix + ".output.LayerNorm", tag + ".ao",
-                                         drop=self.drop(prefix + ".output.dropout", p_hidden))
+                                         drop=self.drop(prefix + ".output.dropout", p_hidden), a_lo=ctxl, a_bw=ctxb)
 
         def bwd():
             r = out_bwd()
@@ -458,15 +521,15 @@ class Plan:
                 return
             dy16, dy32 = r
             dctx = self.scratch(tag + ".dctx", (M, H), BF16)
-            self.gemm(M, H, H, dy16, H, ps.w16(prefix + ".output.dense.weight"), H, b_mn=1, out_bf16=dctx, ld_ob=H)
+            self.gemm(M, H, H, dy16, H, ps.w16b(prefix + ".output.dense.weight"), H, b_mn=1, out_bf16=dctx, ld_ob=H)
             dqkv = self.scratch(tag + ".dqkv", (M, 3 * H), BF16)
             delta = self.scratch(tag + ".delta", (B, nh, N), F32)
             gb = ps.g(prefix + ".self.qkv.bias")     # bias gradients = column sums of dQ|dK|dV, fused into the attention backward
             self.attention(True, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dO=dctx, lddo=H,
                            dQ=dqkv[:, 0:H], lddq=3 * H, dK=dqkv[:, H:2 * H], lddk=3 * H, dV=dqkv[:, 2 * H:], lddv=3 * H, delta=delta,
                            dbq=gb[0:H], dbk=gb[H:2 * H], dbv=gb[2 * H:], dropout=adrop)
-            self.linear_wgrad(dqkv, 3 * H, None, 0, x.b16, H, M, 3 * H, H, prefix + ".self.qkv")
-            self.dgrad_into(x, dqkv, 3 * H, ps.w16(prefix + ".self.qkv.weight"), M, 3 * H, H, extra32=dy32)
+            self.linear_wgrad(dqkv, 3 * H, None, 0, x.bw, H, M, 3 * H, H, prefix + ".self.qkv")
+            self.dgrad_into(x, dqkv, 3 * H, ps.w16b(prefix + ".self.qkv.weight"), M, 3 * H, H, extra32=dy32)
         self.push_bwd(bwd)
         return out
 
@@ -477,29 +540,38 @@ class Plan:
         Hb, nh = c.bi_hidden_size, c.bi_num_attention_heads
         D = Hb // nh
         Mv, Mt, Hv, Ht, Nv, Nt = v.M, t.M, v.H, t.H, self.Nv, self.Nt
-        qkv1 = self.buf((Mv, 3 * Hb), BF16)
-        qkv2 = self.buf((Mt, 3 * Hb), BF16)
+        qkv1, qkv1l, _ = self.buf16((Mv, 3 * Hb), bw=False)
+        qkv2, qkv2l, _ = self.buf16((Mt, 3 * Hb), bw=False)
         with self.on(1):
-            self.gemm(Mv, 3 * Hb, Hv, v.b16, Hv, ps.w16(p + ".biattention.qkv1.weight"), Hv, bias=ps.p(p + ".biattention.qkv1.bias"), out_bf16=qkv1, ld_ob=3 * Hb)
-        self.gemm(Mt, 3 * Hb, Ht, t.b16, Ht, ps.w16(p + ".biattention.qkv2.weight"), Ht, bias=ps.p(p + ".biattention.qkv2.bias"), out_bf16=qkv2, ld_ob=3 * Hb)
+            self.gemm(Mv, 3 * Hb, Hv, v.b16, Hv, ps.w16(p + ".biattention.qkv1.weight"), Hv, bias=ps.p(p + ".biattention.qkv1.bias"), out_bf16=qkv1, ld_ob=3 * Hb,
+                      a_lo=v.lo, b_lo=ps.w16lo(p + ".biattention.qkv1.weight"), out_lo=qkv1l)
+        self.gemm(Mt, 3 * Hb, Ht, t.b16, Ht, ps.w16(p + ".biattention.qkv2.weight"), Ht, bias=ps.p(p + ".biattention.qkv2.bias"), out_bf16=qkv2, ld_ob=3 * Hb,
+                  a_lo=t.lo, b_lo=ps.w16lo(p + ".biattention.qkv2.weight"), out_lo=qkv2l)
         self.sync_streams()      # each direction needs the other stream's keys / values
         q1, k1, v1 = qkv1[:, 0:Hb], qkv1[:, Hb:2 * Hb], qkv1[:, 2 * Hb:]
         q2, k2, v2 = qkv2[:, 0:Hb], qkv2[:, Hb:2 * Hb], qkv2[:, 2 * Hb:]
-        ctx1 = self.buf((Mt, Hb), BF16); lse1 = self.buf((B, nh, Nt), F32)   # text queries over vision keys/values
-        ctx2 = self.buf((Mv, Hb), BF16); lse2 = self.buf((B, nh, Nv), F32)   # vision queries over text keys/values
+        ctx1, ctx1l, ctx1b = self.buf16((Mt, Hb)); lse1 = self.buf((B, nh, Nt), F32)   # text queries over vision keys/values
+        ctx2, ctx2l, ctx2b = self.buf16((Mv, Hb)); lse2 = self.buf((B, nh, Nv), F32)   # vision queries over text keys/values
         L3 = 3 * Hb
+        if self.split:
+            q1l, k1l, v1l = qkv1l[:, 0:Hb], qkv1l[:, Hb:2 * Hb], qkv1l[:, 2 * Hb:]
+            q2l, k2l, v2l = qkv2l[:, 0:Hb], qkv2l[:, Hb:2 * Hb], qkv2l[:, 2 * Hb:]
+        else:
+            q1l = k1l = v1l = q2l = k2l = v2l = None
         # dropout1 acts on attention_probs1 (text queries over regions), dropout2 on attention_probs2 (vilbert.py:730, 738, 778, 800)
         adrop1 = self.drop(p + ".biattention.dropout1", c.v_attention_probs_dropout_prob)
         adrop2 = self.drop(p + ".biattention.dropout2", c.attention_probs_dropout_prob)
-        self.attention(False, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1, dropout=adrop1)
+        self.attention(False, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1, dropout=adrop1,
+                       q_lo=q2l, k_lo=k1l, v_lo=v1l, o_lo=ctx1l, o_b16=self._extra(ctx1b, ctx1))
         with self.on(1):
-            self.attention(False, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dropout=adrop2)
+            self.attention(False, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dropout=adrop2,
+                           q_lo=q1l, k_lo=k2l, v_lo=v2l, o_lo=ctx2l, o_b16=self._extra(ctx2b, ctx2))
         # biOutput: ctx2 -> vision stream (dense1 / LayerNorm1), ctx1 -> text stream (dense2 / LayerNorm2) (:890-892)
         with self.on(1):
             v1o, v1_bwd = self.dense_res_ln(ctx2, Hb, v, p + ".biOutput.dense1", p + ".biOutput.LayerNorm1", "c.v.bo",
-                                            drop=self.drop(p + ".biOutput.dropout1", c.v_hidden_dropout_prob))
+                                            drop=self.drop(p + ".biOutput.dropout1", c.v_hidden_dropout_prob), a_lo=ctx2l, a_bw=ctx2b)
         t1o, t1_bwd = self.dense_res_ln(ctx1, Hb, t, p + ".biOutput.dense2", p + ".biOutput.LayerNorm2", "c.t.bo",
-                                        drop=self.drop(p + ".biOutput.dropout2", c.hidden_dropout_prob))
+                                        drop=self.drop(p + ".biOutput.dropout2", c.hidden_dropout_prob), a_lo=ctx1l, a_bw=ctx1b)
 
         def bwd():
             if not (v1o.gw or t1o.gw):
@@ -516,8 +588,8 @@ class Plan:
             dctx1 = self.scratch("c.dctx1", (Mt, Hb), BF16)
             dyv16, dyv32 = rv
             dyt16, dyt32 = rt
-            self.gemm(Mv, Hb, Hv, dyv16, Hv, ps.w16(p + ".biOutput.dense1.weight"), Hb, b_mn=1, out_bf16=dctx2, ld_ob=Hb)
-            self.gemm(Mt, Hb, Ht, dyt16, Ht, ps.w16(p + ".biOutput.dense2.weight"), Hb, b_mn=1, out_bf16=dctx1, ld_ob=Hb)
+            self.gemm(Mv, Hb, Hv, dyv16, Hv, ps.w16b(p + ".biOutput.dense1.weight"), Hb, b_mn=1, out_bf16=dctx2, ld_ob=Hb)
+            self.gemm(Mt, Hb, Ht, dyt16, Ht, ps.w16b(p + ".biOutput.dense2.weight"), Hb, b_mn=1, out_bf16=dctx1, ld_ob=Hb)
             gb1, gb2 = ps.g(p + ".biattention.qkv1.bias"), ps.g(p + ".biattention.qkv2.bias")
             d1 = self.scratch("c.delta1", (B, nh, Nt), F32)
             d2 = self.scratch("c.delta2", (B, nh, Nv), F32)
@@ -527,10 +599,10 @@ class Plan:
             self.attention(True, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dO=dctx2, lddo=Hb,
                            dQ=dqkv1[:, 0:Hb], lddq=L3, dK=dqkv2[:, Hb:2 * Hb], lddk=L3, dV=dqkv2[:, 2 * Hb:], lddv=L3, delta=d2,
                            dbq=gb1[0:Hb], dbk=gb2[Hb:2 * Hb], dbv=gb2[2 * Hb:], dropout=adrop2)
-            self.linear_wgrad(dqkv1, L3, None, 0, v.b16, Hv, Mv, L3, Hv, p + ".biattention.qkv1")
-            self.linear_wgrad(dqkv2, L3, None, 0, t.b16, Ht, Mt, L3, Ht, p + ".biattention.qkv2")
-            self.dgrad_into(v, dqkv1, L3, ps.w16(p + ".biattention.qkv1.weight"), Mv, L3, Hv, extra32=dyv32)
-            self.dgrad_into(t, dqkv2, L3, ps.w16(p + ".biattention.qkv2.weight"), Mt, L3, Ht, extra32=dyt32)
+            self.linear_wgrad(dqkv1, L3, None, 0, v.bw, Hv, Mv, L3, Hv, p + ".biattention.qkv1")
+            self.linear_wgrad(dqkv2, L3, None, 0, t.bw, Ht, Mt, L3, Ht, p + ".biattention.qkv2")
+            self.dgrad_into(v, dqkv1, L3, ps.w16b(p + ".biattention.qkv1.weight"), Mv, L3, Hv, extra32=dyv32)
+            self.dgrad_into(t, dqkv2, L3, ps.w16b(p + ".biattention.qkv2.weight"), Mt, L3, Ht, extra32=dyt32)
         # the cross-modal backward touches both streams' tensors: it runs on the main stream between two barriers
         self._bwd_emitters.append(None)
         self.push_bwd(bwd)
@@ -583,8 +655,8 @@ class Plan:
                   ps.p(e + ".position_embeddings.weight").data_ptr(), ps.p(e + ".token_type_embeddings.weight").data_ptr(),
                   ps.p(e + ".task_embeddings.weight").data_ptr() if self.has_task else None, xe.data_ptr(), B, self.Nt_in, Ht)
         tdrop = self.drop(e + ".dropout", c.hidden_dropout_prob)
-        t32, t16, tmean, trstd = self.ln_fwd(xe, ps.p(e + ".LayerNorm.weight"), ps.p(e + ".LayerNorm.bias"), Mt, Ht, out_drop=tdrop)
-        t = Act(t32, t16, Mt, Ht)
+        t32, t16, tmean, trstd, tlo, tbw = self.ln_fwd(xe, ps.p(e + ".LayerNorm.weight"), ps.p(e + ".LayerNorm.bias"), Mt, Ht, out_drop=tdrop)
+        t = Act(t32, t16, Mt, Ht, lo=tlo, bw=tbw)
 
         def bwd_text():
             if t.gw:
@@ -599,17 +671,18 @@ class Plan:
         # image: region features fp32 -> bf16 ingest, 2048 -> Hv GEMM with the 5 -> Hv box projection as residual, LayerNorm (:1421-1432)
         ve = "bert.v_embeddings"
         with self.on(1):
-            feat16 = self.buf((Mv, Fv), BF16)
-            self.emit(lib.vb_cast_f32_to_bf16, self.in_feat.data_ptr(), feat16.data_ptr(), Mv * Fv)
+            feat16, featl, featb = self.buf16((Mv, Fv))
+            self.emit(lib.vb_cast_f32_to_bf16, self.in_feat.data_ptr(), feat16.data_ptr(), Mv * Fv, self.op_fp16, self._ptr(featl),
+                      self._ptr(self._extra(featb, feat16)))
             locp = self.buf((Mv, Hv), F32)
             self.emit(lib.vb_loc_proj_fwd, self.in_loc.data_ptr(), ps.p(ve + ".image_location_embeddings.weight").data_ptr(),
                       ps.p(ve + ".image_location_embeddings.bias").data_ptr(), locp.data_ptr(), Mv, Hv)
             yv = self.buf((Mv, Hv), F32)
             self.gemm(Mv, Hv, Fv, feat16, Fv, ps.w16(ve + ".image_embeddings.weight"), Fv, bias=ps.p(ve + ".image_embeddings.bias"),
-                      residual=locp, ld_res=Hv, out_f32=yv, ld_of=Hv)
+                      residual=locp, ld_res=Hv, out_f32=yv, ld_of=Hv, a_lo=featl, b_lo=ps.w16lo(ve + ".image_embeddings.weight"))
             vdrop = self.drop(ve + ".dropout", c.hidden_dropout_prob)     # BertImageEmbeddings uses hidden_dropout_prob (vilbert.py:1419)
-            v32, v16, vmean, vrstd = self.ln_fwd(yv, ps.p(ve + ".LayerNorm.weight"), ps.p(ve + ".LayerNorm.bias"), Mv, Hv, out_drop=vdrop)
-            v = Act(v32, v16, Mv, Hv)
+            v32, v16, vmean, vrstd, vlo, vbw = self.ln_fwd(yv, ps.p(ve + ".LayerNorm.weight"), ps.p(ve + ".LayerNorm.bias"), Mv, Hv, out_drop=vdrop)
+            v = Act(v32, v16, Mv, Hv, lo=vlo, bw=vbw)
 
             def bwd_image():
                 if v.gw:
@@ -617,7 +690,7 @@ class Plan:
                     dyv16 = self.scratch("emb.dyv16", (Mv, Hv), BF16)
                     self.ln_bwd(v.g32, yv, ps.p(ve + ".LayerNorm.weight"), vmean, vrstd, dyv32, dyv16, Mv, Hv, ps.g(ve + ".LayerNorm.weight"), ps.g(ve + ".LayerNorm.bias"),
                                 gbias=ps.g(ve + ".image_embeddings.bias"), out_drop=vdrop)
-                    self.linear_wgrad(dyv16, Hv, None, 0, feat16, Fv, Mv, Hv, Fv, ve + ".image_embeddings")
+                    self.linear_wgrad(dyv16, Hv, None, 0, featb, Fv, Mv, Hv, Fv, ve + ".image_embeddings")
                     self.emit(lib.vb_loc_proj_bwd, dyv32.data_ptr(), self.in_loc.data_ptr(), ps.g(ve + ".image_location_embeddings.weight").data_ptr(),
                               ps.g(ve + ".image_location_embeddings.bias").data_ptr(), Mv, Hv)
             self.push_bwd(bwd_image)
@@ -627,10 +700,11 @@ class Plan:
     def pooler(self, seq, N, wname):
         """Linear + ReLU on token 0 (vilbert.py:1116-1122, 1131-1137); A is read with row pitch N*H."""
         ps, B, H, Hb = self.ps, self.B, seq.H, self.cfg.bi_hidden_size
-        p32, p16 = self.buf((B, Hb), F32), self.buf((B, Hb), BF16)
+        p32 = self.buf((B, Hb), F32)
+        p16, plo, _ = self.buf16((B, Hb), bw=False)
         self.gemm(B, Hb, H, seq.b16, N * H, ps.w16(wname + ".weight"), H, bias=ps.p(wname + ".bias"), act=L.VB_ACT_RELU, out_f32=p32, ld_of=Hb,
-                  out_bf16=p16, ld_ob=Hb)
-        pooled = Act(p32, p16, B, Hb)
+                  out_bf16=p16, ld_ob=Hb, a_lo=seq.lo, b_lo=ps.w16lo(wname + ".weight"), out_lo=plo)
+        pooled = Act(p32, p16, B, Hb, lo=plo)
 
         def bwd():
             if not pooled.gw:
@@ -638,13 +712,13 @@ class Plan:
             dpre = self.scratch("pool.dpre", (B, Hb), BF16)
             dpre32 = self.scratch("pool.dpre32", (B, Hb), F32)
             self.emit(self.lib.vb_relu_bwd, pooled.g32.data_ptr(), p32.data_ptr(), dpre.data_ptr(), dpre32.data_ptr(), B * Hb)
-            self.linear_wgrad(dpre, Hb, dpre32, Hb, seq.b16, N * H, B, Hb, H, wname)
+            self.linear_wgrad(dpre, Hb, dpre32, Hb, seq.bw, N * H, B, Hb, H, wname)
             g = self.grad_of(seq)
             if not seq.gw:
                 self.emit(self.lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
                 seq.gw = True
             # rows b*N of the sequence gradient += dpre @ W
-            self.gemm(B, H, Hb, dpre, Hb, ps.w16(wname + ".weight"), H, b_mn=1, residual=g, ld_res=N * H, out_f32=g, ld_of=N * H)
+            self.gemm(B, H, Hb, dpre, Hb, ps.w16b(wname + ".weight"), H, b_mn=1, residual=g, ld_res=N * H, out_f32=g, ld_of=N * H)
         self.push_bwd(bwd)
         return pooled
 
@@ -654,13 +728,15 @@ class Plan:
             self.gout[name] = self.buf(shape, F32, zero=True)
         return self.gout[name]
 
-    def big_head(self, name, x16, ld_x, x_act, M, K_in, N_out, wname, bias_name, w16=None, gw=None):
+    def big_head(self, name, x16, ld_x, x_act, M, K_in, N_out, wname, bias_name, w16=None, gw=None, w16lo=None, w16b=None):
         """Wide linear head (N_out in the thousands): logits = x W^T + b as fp32 [M, N_out]; backward from a
         caller-supplied fp32 d(logits) (cast to a bf16 operand with an 8-padded row pitch)."""
         ps = self.ps
         W16 = w16 if w16 is not None else ps.w16(wname + ".weight")
+        W16lo = w16lo if w16 is not None else ps.w16lo(wname + ".weight")
+        W16b = w16b if w16 is not None else ps.w16b(wname + ".weight")
         logits = self.buf((M, N_out), F32)
-        self.gemm(M, N_out, K_in, x16, ld_x, W16, K_in, bias=ps.p(bias_name), out_f32=logits, ld_of=N_out)
+        self.gemm(M, N_out, K_in, x16, ld_x, W16, K_in, bias=ps.p(bias_name), out_f32=logits, ld_of=N_out, a_lo=x_act.lo, b_lo=W16lo)
         self.outputs[name] = logits
 
         def bwd():
@@ -674,8 +750,8 @@ class Plan:
                 dl16 = self.scratch("head.dl16." + name, (M, ldp), BF16)
                 self.emit(self.lib.vb_cast2d_f32_to_bf16, dl32.data_ptr(), N_out, dl16.data_ptr(), ldp, M, N_out, 1.0)
             self.colsum(dl32, N_out, ps.g(bias_name), M, N_out)
-            self.linear_wgrad(dl16, ldp, None, 0, x16, ld_x, M, N_out, K_in, wname, gw=gw)
-            return dl16, ldp, W16
+            self.linear_wgrad(dl16, ldp, None, 0, x_act.bw, ld_x, M, N_out, K_in, wname, gw=gw)
+            return dl16, ldp, W16b
         return bwd
 
     def transform(self, x, wdense, lnname, tag):
@@ -686,9 +762,9 @@ class Plan:
         Hh = ps.p(wdense + ".weight").shape[0]
         g32, pre16 = self.buf((M, Hh), F32), self.buf((M, Hh), BF16)
         self.gemm(M, Hh, K, x.b16, K, ps.w16(wdense + ".weight"), K, bias=ps.p(wdense + ".bias"), act=L.VB_ACT_GELU, out_f32=g32, ld_of=Hh,
-                  out_pre=pre16, ld_op=Hh)
-        _, h16, mean, rstd = self.ln_fwd(g32, ps.p(lnname + ".weight"), ps.p(lnname + ".bias"), M, Hh, want_f32=False)
-        hn = Act(None, h16, M, Hh)
+                  out_pre=pre16, ld_op=Hh, a_lo=x.lo, b_lo=ps.w16lo(wdense + ".weight"))
+        _, h16, mean, rstd, hlo, hbw = self.ln_fwd(g32, ps.p(lnname + ".weight"), ps.p(lnname + ".bias"), M, Hh, want_f32=False)
+        hn = Act(None, h16, M, Hh, lo=hlo, bw=hbw)
 
         def bwd():
             if not hn.gw:
@@ -696,8 +772,8 @@ class Plan:
             dpre16 = self.scratch(tag + ".dpre16", (M, Hh), BF16)
             self.ln_bwd(hn.g32, g32, ps.p(lnname + ".weight"), mean, rstd, None, dpre16, M, Hh, ps.g(lnname + ".weight"), ps.g(lnname + ".bias"), pre=pre16,
                         gbias=ps.g(wdense + ".bias"))
-            self.linear_wgrad(dpre16, Hh, None, 0, x.b16, K, M, Hh, K, wdense)
-            self.dgrad_into(x, dpre16, Hh, ps.w16(wdense + ".weight"), M, Hh, K)
+            self.linear_wgrad(dpre16, Hh, None, 0, x.bw, K, M, Hh, K, wdense)
+            self.dgrad_into(x, dpre16, Hh, ps.w16b(wdense + ".weight"), M, Hh, K)
         return hn, bwd
 
     def small_head(self, name, x, wname, N_out, addend=None, x32=None, M=None, K=None, in_drop=None):
@@ -728,9 +804,11 @@ class Plan:
         Hb, Ht, Hv, Nt, Nv = c.bi_hidden_size, c.hidden_size, c.v_hidden_size, self.Nt, self.Nv
         mul = 1 if c.fusion_method == "mul" else 0
         def fuse(drop):
-            f32, f16 = self.buf((B, Hb), F32), self.buf((B, Hb), BF16)
-            self.emit(lib.vb_fuse_pooled_fwd, pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), f32.data_ptr(), f16.data_ptr(), B * Hb, mul, self._ref(drop))
-            act = Act(f32, f16, B, Hb)
+            f32 = self.buf((B, Hb), F32)
+            f16, flo, fbw = self.buf16((B, Hb))
+            self.emit(lib.vb_fuse_pooled_fwd, pooled_t.f32.data_ptr(), pooled_v.f32.data_ptr(), f32.data_ptr(), f16.data_ptr(), B * Hb, mul, self._ref(drop),
+                      self.op_fp16, self._ptr(flo), self._ptr(self._extra(fbw, f16)))
+            act = Act(f32, f16, B, Hb, lo=flo, bw=fbw)
 
             def fuse_bwd():
                 if not act.gw:
@@ -753,12 +831,13 @@ class Plan:
             fused_cls = fuse(cls_drop) if (cls_drop is not None or fused is None) else fused
         else:
             fused_cls = None
-        f32, f16 = (fused.f32, fused.b16) if fused is not None else (None, None)
+        f32, f16, f16lo, f16bw = (fused.f32, fused.b16, fused.lo, fused.bw) if fused is not None else (None, None, None, None)
 
         # --- cls: masked-LM head (decoder tied to the word embeddings), image-region head, alignment head
         ht, ht_bwd = self.transform(seq_t, "cls.predictions.transform.dense", "cls.predictions.transform.LayerNorm", "lm.tr")
         lm_bwd = self.big_head("linguisic_prediction", ht.b16, Ht, ht, B * Nt, Ht, c.vocab_size, None, "cls.predictions.bias",
-                               w16=ps.w16("bert.embeddings.word_embeddings.weight"), gw=ps.g("bert.embeddings.word_embeddings.weight"))
+                               w16=ps.w16("bert.embeddings.word_embeddings.weight"), gw=ps.g("bert.embeddings.word_embeddings.weight"),
+                               w16lo=ps.w16lo("bert.embeddings.word_embeddings.weight"), w16b=ps.w16b("bert.embeddings.word_embeddings.weight"))
         hv, hv_bwd = self.transform(seq_v, "cls.imagePredictions.transform.dense", "cls.imagePredictions.transform.LayerNorm", "im.tr")
         im_bwd = self.big_head("vision_prediction", hv.b16, Hv, hv, B * Nv, Hv, c.v_target_size, "cls.imagePredictions.decoder",
                                "cls.imagePredictions.decoder.bias")
@@ -783,7 +862,7 @@ class Plan:
             return
         if B % 2 == 0:
             # vil_binary_prediction pairs consecutive samples: pooled.view(-1, 2*Hb) (:1686-1689)
-            pair = Act(f32.view(B // 2, 2 * Hb), f16.view(B // 2, 2 * Hb), B // 2, 2 * Hb)
+            pair = Act(f32.view(B // 2, 2 * Hb), f16.view(B // 2, 2 * Hb), B // 2, 2 * Hb, lo=f16lo.view(B // 2, 2 * Hb) if f16lo is not None else None, bw=f16bw.view(B // 2, 2 * Hb))
             hb, hb_bwd = self.transform(pair, "vil_binary_prediction.logit_fc.0", "vil_binary_prediction.logit_fc.2", "bin.tr")
             # LayerNorm output is needed in fp32 for the 2-way linear: recompute it from the bf16 copy is lossy, so run the small
             # linear on an fp32 LayerNorm output
@@ -951,6 +1030,7 @@ class Plan:
             self._run(self.fwd)
 
     def run_backward(self):
+        self.e.grad_clean = False
         if self.graph_bwd is not None:
             self.graph_bwd.replay()
         else:
@@ -971,31 +1051,49 @@ class Plan:
         first_c = [off for name, (off, _) in ps.entries.items() if ".c_layer." in name]
         split = min(first_c) if (self.two_streams and first_c) else n
         if refresh_weights and split > 0:
-            self.prologue.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr(), ps.shadow.data_ptr(), split), 0))
+            sb = ps.shadow_b if ps.shadow_b is not ps.shadow else None
+            self.prologue.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr(), ps.shadow.data_ptr(), split, self.op_fp16,
+                                                            ps.shadow_lo.data_ptr() if self.split else None, sb.data_ptr() if sb is not None else None), 0))
         tail = []
         if zero_grad:
             tail.append((lib.vb_memset_zero, (ps.grad.data_ptr(), ps.grad.numel() * 4), 1 if self.two_streams else 0))
         if refresh_weights and split < n:
-            tail.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr() + 4 * split, ps.shadow.data_ptr() + 2 * split, n - split), 1))
+            tail.append((lib.vb_cast_f32_to_bf16, (ps.flat.data_ptr() + 4 * split, ps.shadow.data_ptr() + 2 * split, n - split, self.op_fp16,
+                                                   ps.shadow_lo.data_ptr() + 2 * split if self.split else None,
+                                                   ps.shadow_b.data_ptr() + 2 * split if ps.shadow_b is not ps.shadow else None), 1))
         if self.two_streams:
             self.prologue += [(None, (), 0)] + tail       # barrier: the vision stream starts after the main-stream part
         else:
             self.prologue += tail
         self.graph_step = None
 
+    def enable_optimizer(self, opt, dropout_bump=True):
+        """Training step with the fused optimizer (optim.FusedAdamW): the step body becomes [dropout step bump] + forward + loss +
+        backward + ONE AdamW launch that also rewrites the 16-bit weight copy and zeroes the gradients — no weight cast and no
+        gradient memset in the step. (The host-side lr table of `opt` is refreshed by opt.step(); here the launch alone is
+        replayed, e.g. inside the step graph, with the table currently on the device.)"""
+        self.prologue = []
+        if self.train and dropout_bump:
+            self.prologue.append((self.lib.vb_step_counter_bump, (self.e.drop_step.data_ptr(),), 0))
+        fn, args = opt.op()
+        self.epilogue = [(fn, args, 0)]
+        self.graph_step = None
+
     @property
     def n_launches_step(self):
-        return sum(1 for op in self.prologue if op[0] is not None) + self.n_kernels_fwd + self.n_kernels_bwd
+        return sum(1 for op in self.prologue + self.epilogue if op[0] is not None) + self.n_kernels_fwd + self.n_kernels_bwd
 
     def run_step(self):
-        """(prologue) + forward + (loss) + backward; gradients accumulate into ParamStore.grad."""
+        """(prologue) + forward + (loss) + backward (+ epilogue); gradients accumulate into ParamStore.grad."""
         self.fwd_id += 1
+        self.e.grad_clean = False
         if self.graph_step is not None:
             self.graph_step.replay()
         else:
             self._run(self.prologue)
             self._run(self.fwd)
             self._run(self.bwd)
+            self._run(self.epilogue)
 
     def ddp_segments(self, n_segments=4, tail_cut=True):
         """Cuts the backward op list at stream barriers into `n_segments` pieces and returns
@@ -1087,6 +1185,7 @@ class Plan:
         `allreduce_range(lo, hi)` (issued under `comm_stream`, which first waits for that segment) so the collective
         overlaps the rest of the backward. Returns the list of whatever allreduce_range returned (async work handles)."""
         self.fwd_id += 1
+        self.e.grad_clean = False
         main = torch.cuda.current_stream()
         works = []
         for g, (_, _, lo, hi) in zip(self.segment_graphs, self.segments):
@@ -1108,6 +1207,7 @@ class Plan:
             self._run(self.prologue)
             self._run(self.fwd)
             self._run(self.bwd)
+            self._run(self.epilogue)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if separate:
@@ -1122,39 +1222,69 @@ class Plan:
                 self._run(self.prologue)
                 self._run(self.fwd)
                 self._run(self.bwd)
+                self._run(self.epilogue)
         torch.cuda.synchronize()
 
 
 class Engine:
     """Owns the parameters and the per-shape plans."""
 
-    def __init__(self, cfg, device="cuda", heads="vl", _build_only=False, two_streams=True, wgrad_streams=True):
-        """_build_only=True (tests) allows a CPU device: plans can be constructed and inspected but never run."""
+    def __init__(self, cfg, device="cuda", heads="vl", _build_only=False, two_streams=True, wgrad_streams=True, precision="fp16"):
+        """_build_only=True (tests) allows a CPU device: plans can be constructed and inspected but never run.
+        precision: "fp16" | "fp32" | "bf16" (module docstring)."""
         cfg.check_supported()
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        self.precision = precision
+        self.op_dtype = BF16 if precision == "bf16" else F16
+        self.split = precision == "fp32"
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda" and not _build_only:
             raise L.VBError("vilbert_b200 runs on sm_100a GPUs only; there is no CPU path (device=%s)" % device)
         L.lib()  # fail loudly now if the extension is missing
-        self.ps = ParamStore(cfg, self.device, heads)
+        self.ps = ParamStore(cfg, self.device, heads, self.op_dtype, self.split)
         self.two_streams = two_streams   # text / vision segments on two CUDA streams (parallel graph branches)
         self.wgrad_streams = wgrad_streams   # weight-gradient GEMMs on two more side streams (off the backward critical chain)
-        self.plans = {}
+        self.plans = OrderedDict()       # LRU cache of per-shape plans (each owns its activation buffers)
+        self.max_plans = 16              # a 12-in-1 mix has ~12 shapes x {train} x one gradient set in steady state
         self.head_dropout_prob = 0.1     # VILBertForVLTasks(dropout_prob=0.1), vilbert.py:1601
         self.drop_step = torch.zeros(1, dtype=torch.int32, device=self.device)   # dropout step counter (uint32 on the device)
+        self.drop_step_host = 0          # host mirror of the counter for the eager module path (bump / set below)
+        self.shadow_clean = False        # the 16-bit weight copy matches the fp32 master parameters
+        self.shadow_trusted = False      # True while the engine's own fused optimizer is the only writer of the parameters
+        self.grad_clean = False          # the flat gradient buffer is all zeros (set by zero_grad / the fused optimizer)
 
     def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False):
         key = (B, Nt, Nv, frozenset(grad_outputs), vqa_loss, heads, bool(train))
-        if key not in self.plans:
-            self.plans[key] = Plan(self, B, Nt, Nv, grad_outputs, vqa_loss, heads, train)
+        if key in self.plans:
+            self.plans.move_to_end(key)
+            return self.plans[key]
+        while len(self.plans) >= self.max_plans:   # evict the least recently used plan: its buffers go back to the allocator
+            self.plans.popitem(last=False)
+        self.plans[key] = Plan(self, B, Nt, Nv, grad_outputs, vqa_loss, heads, train)
         return self.plans[key]
+
+    def release_plans(self):
+        """Drops every cached plan (and its activation / scratch buffers)."""
+        self.plans.clear()
 
     def bump_dropout_step(self):
         """New dropout masks for the next forward (plans with a training prologue do this inside their graph)."""
         L.check(L.lib().vb_step_counter_bump(self.drop_step.data_ptr(), torch.cuda.current_stream().cuda_stream), "vb_step_counter_bump")
+        self.drop_step_host = (self.drop_step_host + 1) & 0xFFFFFFFF
+
+    def set_dropout_step(self, step):
+        self.drop_step_host = int(step) & 0xFFFFFFFF
+        self.drop_step.fill_(self.drop_step_host if self.drop_step_host < 2 ** 31 else self.drop_step_host - 2 ** 32)
 
     def refresh_weights(self):
         self.ps.refresh_shadow(torch.cuda.current_stream().cuda_stream)
+        self.shadow_clean = True
 
-    def zero_grad(self):
+    def zero_grad(self, force=False):
+        """Zeroes the flat gradient buffer unless it is known to be clean (the fused optimizer zeroes it in its own pass)."""
+        if self.grad_clean and not force:
+            return
         L.check(L.lib().vb_memset_zero(self.ps.grad.data_ptr(), self.ps.grad.numel() * 4, torch.cuda.current_stream().cuda_stream))
+        self.grad_clean = True

@@ -15,6 +15,21 @@ from .config import BertConfig
 from .engine import BERT_OUT_NAMES, HEAD_NAMES, Engine
 
 
+# Any torch.optim.Optimizer.step() (pytorch_transformers.AdamW and the reference's RAdam subclass it) may have rewritten
+# parameters through p.data: bump a global epoch that every model compares with the epoch its 16-bit weight copy was made at.
+_OPT_EPOCH = [0]
+
+
+def _on_optimizer_step(optimizer, args, kwargs):
+    _OPT_EPOCH[0] += 1
+
+
+try:
+    torch.optim.optimizer.register_optimizer_step_post_hook(_on_optimizer_step)
+except AttributeError:      # very old torch: train-mode forwards refresh unconditionally anyway
+    pass
+
+
 class _Node(nn.Module):
     """Container whose children / parameters are registered under the reference's dotted names."""
 
@@ -82,6 +97,7 @@ class _EngineFn(torch.autograd.Function):
         plan.load_inputs(**inputs)
         plan.run_forward()
         ctx.model, ctx.names, ctx.inputs, ctx.plan, ctx.fwd_id, ctx.train = model, names, inputs, plan, plan.fwd_id, train
+        ctx.drop_step = int(model.engine.drop_step_host)     # the masks this forward used (needed if it has to be recomputed)
         model._last_plan = plan
         ctx.set_materialize_grads(False)
         return tuple(plan.outputs[n].clone() for n in names)
@@ -96,8 +112,16 @@ class _EngineFn(torch.autograd.Function):
             if frozenset(live) != plan.grad_outputs or plan.fwd_id != ctx.fwd_id:
                 model._grad_hint[(B, Nt, Nv, names, ctx.train)] = live
                 plan = model.engine.plan(B, Nt, Nv, grad_outputs=live, heads=model._heads_for(names), train=ctx.train)
-                plan.load_inputs(**inputs)     # different plan (or overwritten activations): recompute the forward
-                plan.run_forward()
+                plan.load_inputs(**inputs)     # different plan (or overwritten activations): recompute the forward ...
+                eng = model.engine
+                now = int(eng.drop_step_host)
+                if ctx.train and now != ctx.drop_step:
+                    eng.set_dropout_step(ctx.drop_step)   # ... with the dropout masks of the forward the loss was computed on
+                    plan.run_forward()
+                    eng.set_dropout_step(now)
+                else:
+                    plan.run_forward()
+            model._attach_grads()
             for n, g in zip(names, grads):
                 if g is not None:
                     plan.gout[n].copy_(g.reshape(plan.gout[n].shape))
@@ -112,19 +136,25 @@ class BertPreTrainedModel(nn.Module):
     config_class = BertConfig
     _heads = "vl"          # which heads own parameters: "vl" | "pretraining" | "none"
 
-    def __init__(self, config, device=None):
+    def __init__(self, config, device=None, precision=None):
+        """precision: "fp16" (default: fp16 forward operands, bf16 gradient operands, fp32 accumulation / residual stream),
+        "fp32" (split precision, matches the reference's fp32 outputs to 1e-3) or "bf16"; default from
+        $VILBERT_B200_PRECISION. The reference's constructors have no such argument: it selects what `model.half()` /
+        default fp32 select there."""
         super().__init__()
         if not isinstance(config, BertConfig):
             raise ValueError("Parameter config should be an instance of class `BertConfig`.")
         self.config = config
+        precision = precision or os.environ.get("VILBERT_B200_PRECISION", "fp16")
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         if dev.type != "cuda" or not torch.cuda.is_available():
             raise L.VBError("vilbert_b200 models run on sm_100a GPUs only; there is no CPU path")
-        self.engine = Engine(config, dev, heads=self._heads)
+        self.engine = Engine(config, dev, heads=self._heads, precision=precision)
         self._params = _register_tree(self, self.engine.ps)
         self._grad_hint = {}
         self._anchor = torch.zeros((), device=dev, requires_grad=True)
         self._shadow_version = None
+        self._opt_epoch = -1
         self.init_weights()
 
     # ---- reference init (vilbert.py:1274-1285): N(0, initializer_range) for Linear/Embedding weights, zero bias, LN 1/0
@@ -147,13 +177,52 @@ class BertPreTrainedModel(nn.Module):
         return "none" if all(n in BERT_OUT_NAMES for n in names) else self._heads
 
     def _sync_weights(self):
-        v = self.engine.ps.flat._version
-        if v != self._shadow_version:
-            self.engine.refresh_weights()
-            self._shadow_version = v
+        """Refreshes the 16-bit operand copy of the weights from the fp32 master parameters. Optimizers write parameters
+        through `p.data` (pytorch_transformers.AdamW: p.data.addcdiv_, vilbert/optimization.py RAdam: p.data.copy_), which no
+        tensor version counter sees, so in train mode the copy is refreshed before EVERY forward (one cast kernel) unless the
+        engine's own fused optimizer produced it (engine.shadow_trusted). In eval mode the version counter of the flat buffer,
+        load_state_dict() and a global post-hook on every torch.optim.Optimizer.step() mark it stale; after writing parameters
+        by hand through .data in eval mode call `model.engine.shadow_clean = False`."""
+        eng = self.engine
+        v = eng.ps.flat._version
+        stale = (not eng.shadow_clean) or v != self._shadow_version
+        if not eng.shadow_trusted and (self.training or _OPT_EPOCH[0] != self._opt_epoch):
+            stale = True
+        if stale:
+            eng.refresh_weights()
+        self._shadow_version, self._opt_epoch = v, _OPT_EPOCH[0]
+
+    def load_state_dict(self, state_dict, strict=True):
+        """strict is honoured (missing / unexpected keys raise like nn.Module). The tied decoder weight is one Parameter
+        registered under two names: a checkpoint carrying only one of them is complete."""
+        sd = dict(state_dict)
+        w, d = "bert.embeddings.word_embeddings.weight", "cls.predictions.decoder.weight"
+        if w in sd and d not in sd:
+            sd[d] = sd[w]
+        elif d in sd and w not in sd:
+            sd[w] = sd[d]
+        r = super().load_state_dict(sd, strict=strict)
+        self.engine.shadow_clean = False
+        return r
 
     def zero_grad(self, set_to_none=False):
+        """Zeroes the flat gradient buffer. The Parameters' .grad stay views of it (set_to_none is accepted and ignored: the
+        engine accumulates into the flat buffer, dropping the views would only hide the gradients from the optimizer)."""
         self.engine.zero_grad()
+        self._attach_grads(zero_if_detached=False)
+
+    def _attach_grads(self, zero_if_detached=True):
+        """torch.optim.Optimizer.zero_grad() defaults to set_to_none=True and detaches every .grad from the flat buffer.
+        Before a backward the views are re-attached; if they had been dropped since the last backward the flat buffer (which
+        the engine kept accumulating into) is zeroed first, which is what the caller asked for."""
+        ps = self.engine.ps
+        detached = [name for name, prm in self._params.items() if prm.grad is None]
+        if not detached:
+            return
+        if zero_if_detached:
+            self.engine.zero_grad()
+        for name in detached:
+            self._params[name].grad = ps.g(name)
 
     def _apply(self, fn, recurse=True):
         raise L.VBError("vilbert_b200 models own flat CUDA parameter buffers; .to()/.cuda()/.half() are not supported "
@@ -183,7 +252,15 @@ class BertPreTrainedModel(nn.Module):
         own = model.state_dict()
         if not any(k.startswith("bert.") for k in renamed) and any(("bert." + k) in own for k in renamed):
             renamed = {"bert." + k: v for k, v in renamed.items()}   # base-model checkpoint into a model with heads
+        # like the reference's loader (vilbert/utils.py:960-1012) missing and unexpected keys are tolerated but REPORTED
+        missing = sorted(k for k in own if k not in renamed and k != "cls.predictions.decoder.weight")
+        unexpected = sorted(k for k in renamed if k not in own)
         model.load_state_dict({k: v for k, v in renamed.items() if k in own}, strict=False)
+        model.loading_info = {"missing_keys": missing, "unexpected_keys": unexpected}
+        if missing or unexpected:
+            import logging
+            logging.getLogger(__name__).warning("from_pretrained(%s): %d missing keys (kept at their initial values): %s; %d unexpected keys (ignored): %s",
+                                                pretrained_model_name_or_path, len(missing), missing[:8], len(unexpected), unexpected[:8])
         model.eval()
         return model
 
@@ -223,7 +300,7 @@ class BertModel(BertPreTrainedModel):
         return type(sd)((key[len("bert."):], v) for key, v in sd.items() if key.startswith("bert."))
 
     def load_state_dict(self, state_dict, strict=True):
-        return super().load_state_dict({"bert." + k: v for k, v in state_dict.items()}, strict=False)
+        return super().load_state_dict({"bert." + k: v for k, v in state_dict.items()}, strict=strict)
 
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
@@ -238,8 +315,8 @@ class VILBertForVLTasks(BertPreTrainedModel):
     (:1697-1708). co_attention_mask is accepted and ignored exactly like the reference (:774-775, 796-797)."""
     _heads = "vl"
 
-    def __init__(self, config, num_labels=1, dropout_prob=0.1, default_gpu=True, device=None):
-        super().__init__(config, device)
+    def __init__(self, config, num_labels=1, dropout_prob=0.1, default_gpu=True, device=None, precision=None):
+        super().__init__(config, device, precision)
         self.num_labels = num_labels
         self.dropout_prob = dropout_prob
         self.engine.head_dropout_prob = dropout_prob
@@ -263,8 +340,8 @@ class BertForMultiModalPreTraining(BertPreTrainedModel):
     exactly as the reference does (:1506-1590) and their gradients re-enter the engine through autograd."""
     _heads = "pretraining"
 
-    def __init__(self, config, device=None):
-        super().__init__(config, device)
+    def __init__(self, config, device=None, precision=None):
+        super().__init__(config, device, precision)
         self.visual_target = config.visual_target
         if self.visual_target != 0:
             raise NotImplementedError("only visual_target == 0 (KLDiv) is supported")
