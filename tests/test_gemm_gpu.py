@@ -98,11 +98,11 @@ def test_mixed_operand_formats_are_rejected():
 ])
 def test_split_precision(kw, shape):
     """fp32 parity mode: operands as fp16 hi + lo, three passes (hi.hi + lo.hi + hi.lo) into one TMEM accumulator; the
-    16-bit output is written as hi + lo too. Compared with the float64 product of the fp32 operands: 2e-5 of max|ref|
+    16-bit output is written as hi + lo too. Compared with the float64 product of the fp32 operands: 5e-5 of max|ref|
     (single-pass fp16 operands give ~5e-4, bf16 ~4e-3)."""
     from _gpu_util import gemm_case
     err, _ = gemm_case(*shape, a_fp16=True, b_fp16=True, out_fp16=True, split=True, **kw)
-    assert err < 2e-5, err
+    assert err < 5e-5, err
 
 
 def test_invalid_arguments_are_rejected():

@@ -1,15 +1,14 @@
 """Whole-path parity of the CUDA engine (through the C ABI) against the oracle and the reference's golden tensors.
 
-Arithmetic contract under test = the engine's "bf16 mode": bf16 tensor-core operands, fp32 accumulation, fp32
-residual stream / LayerNorm / softmax statistics. Tolerances (all `max|a-b| / max|ref|` per tensor unless noted):
-  * vs the fp32 oracle (== the reference, bit-exact on CPU): 1e-2 for sequence/pooled outputs and the wide heads
-    (north_star bf16 tolerance); 3e-2 for the 1-3-logit pooled-path heads, which the survey's precision budget
-     shows are ill-conditioned under ANY bf16-operand arithmetic at small batch;
-  * vs the oracle in bf16-operand mode (the reference algorithm with the same operand rounding, forward and
-    backward): gradients within 2e-2 max-rel / 1e-2 rel-L2 on the shallow config (8e-2 / 4e-2 worst tensor and 2e-2
-    median on the 24-sublayer configs, where two bf16 implementations decorrelate) — this isolates implementation
-    error from the error inherent to bf16 operands, which tools/bf16_budget_cpu.py measures at 3.6e-2 (median
-    gradient error vs fp32) for base-6-6.
+Numerical contract (BASELINE.json north_star: outputs "within 1e-3 rel fp32 / 1e-2 bf16" of the reference), checked as
+`max|a-b| / max|ref|` per tensor against the fp32 oracle (== the reference, bit-exact on CPU), on EVERY one of the 13 outputs
+(sequence_output_t/v, pooled_output_t/v and the nine task-head outputs) with no per-head allowance:
+  * default precision "fp16" (fp16 forward operands, bf16 gradient operands, fp32 accumulate): 1e-2 — measured 0.8-3.6e-3 at
+    config 2 (B=64), 5.2e-3 worst on bert_large (profiles/r02_model_probe_precisions_v1.log);
+  * precision "fp32" (split precision, fp16 hi+lo operands, 3 tensor-core passes): 1e-3 — measured <= 7.5e-5 (base), 1.7e-4 (large).
+Gradients are not part of the north_star contract; they are bounded against the fp32 oracle by rel-L2 per tensor (worst and
+median over all parameter tensors) with the measured values (median 5e-3, worst 8e-3 on base-6-6; 9e-3 / 2.3e-2 on
+bert_large) plus margin, and against the oracle run under the engine's operand rounding ("op" mode).
 """
 import json
 import os
@@ -20,27 +19,28 @@ import torch
 from oracle import vilbert_oracle as O
 
 pytestmark = pytest.mark.gpu
-SMALL_HEADS = ("vil_logit", "vil_binary_prediction", "vil_tri_prediction", "vil_prediction_gqa", "vil_prediction")
+OUT_TOL = {"fp16": 1e-2, "fp32": 1e-3, "bf16": 3e-2}
 
 
 def _cfg(golden_dir, name):
     return json.load(open(os.path.join(golden_dir, name + ".json")))["config"]
 
 
-def _check(r, out_tol=1e-2, small_tol=3e-2, grad_max=2e-2, grad_l2=1e-2, grad_fp32_l2=None):
-    for n, e in r["out_fp32"].items():
-        assert e < (small_tol if n in SMALL_HEADS else out_tol), ("fp32-oracle output", n, e)
-    for n, e in r["out_bf16"].items():
-        assert e < (small_tol if n in SMALL_HEADS else out_tol), ("bf16-oracle output", n, e)
-    if "grad_bf16" in r:
-        assert abs(r["loss"] - r["loss_fp32"]) < 2e-3 * abs(r["loss_fp32"])
-        bad = {k: v for k, v in r["grad_bf16"].items() if not (v[0] < grad_max and v[1] < grad_l2)}
-        assert not bad, ("gradients vs bf16-operand oracle", dict(list(bad.items())[:8]))
-        l2 = sorted(v[1] for v in r["grad_bf16"].values())
-        assert l2[len(l2) // 2] < grad_l2 / 2, ("median rel-L2 vs bf16-operand oracle", l2[len(l2) // 2])
-        if grad_fp32_l2 is not None:
-            l2 = sorted(v[1] for v in r["grad_fp32"].values())
-            assert l2[len(l2) // 2] < grad_fp32_l2
+def _check(r, precision="fp16", grad_worst=2e-2, grad_median=1e-2, modes=("fp32", "op")):
+    tol = OUT_TOL[precision]
+    for mode in modes:
+        if "out_" + mode not in r:
+            continue
+        for n, e in r["out_" + mode].items():
+            assert e < tol, (mode + "-oracle output", n, e)
+    if "grad_fp32" in r:
+        assert abs(r["loss"] - r["loss_fp32"]) < 1e-3 * abs(r["loss_fp32"])
+        for mode in modes:
+            if "grad_" + mode not in r:
+                continue
+            l2 = sorted((v[1], k) for k, v in r["grad_" + mode].items())
+            assert l2[-1][0] < grad_worst, ("worst gradient rel-L2 vs " + mode + " oracle", l2[-3:])
+            assert l2[len(l2) // 2][0] < grad_median, ("median gradient rel-L2 vs " + mode + " oracle", l2[len(l2) // 2])
 
 
 @pytest.mark.parametrize("B,Nv,Nt,seed,task", [(4, 11, 9, 0, False), (3, 7, 12, 1, True), (2, 37, 21, 2, False), (6, 33, 24, 4, True)])
@@ -50,7 +50,16 @@ def test_tiny_config_outputs_and_gradients(golden_dir, B, Nv, Nt, seed, task):
     from _gpu_util import model_case
     cfgj = dict(_cfg(golden_dir, "tiny_b4"), task_specific_tokens=task)
     r = model_case(cfgj, B, Nv, Nt, seed=seed)
-    _check(r, grad_fp32_l2=2e-2)
+    _check(r)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_tiny_config_other_precisions(golden_dir, precision):
+    """The split-precision (fp32 parity) mode and the legacy all-bf16 mode on the tiny config, outputs and gradients."""
+    from _gpu_util import model_case
+    cfgj = dict(_cfg(golden_dir, "tiny_b4"), task_specific_tokens=True)
+    r = model_case(cfgj, 6, 33, 24, seed=4, precision=precision)
+    _check(r, precision, modes=("fp32",), grad_worst=5e-2 if precision == "bf16" else 2e-2, grad_median=2e-2 if precision == "bf16" else 1e-2)
 
 
 @pytest.mark.parametrize("B,Nv,Nt,seed,task,step", [(4, 11, 9, 0, False, 3), (3, 7, 12, 1, True, 11), (6, 33, 24, 4, False, 123456)])
@@ -62,7 +71,7 @@ def test_train_mode_dropout_matches_oracle_masks(golden_dir, B, Nv, Nt, seed, ta
     from _gpu_util import model_case
     cfgj = dict(_cfg(golden_dir, "tiny_b4"), task_specific_tokens=task)
     r = model_case(cfgj, B, Nv, Nt, seed=seed, train_step=step)
-    _check(r, grad_fp32_l2=2e-2)
+    _check(r)
     r_eval = model_case(cfgj, B, Nv, Nt, seed=seed)
     # sanity: train and eval outputs really differ (dropout is on)
     assert (r["plan"].outputs["sequence_output_t"] - r_eval["plan"].outputs["sequence_output_t"]).abs().max().item() > 1e-2
@@ -104,14 +113,11 @@ def test_tiny_against_reference_golden_tensors(golden_dir):
 
 
 def test_peaked_attention_tiny(golden_dir):
-    """query/key weights x8 (SURVEY.md §8c adversarial case i): compared with the bf16-operand oracle, since peaked
-    softmax amplifies operand rounding itself (scores error ~ |S| * 2^-9)."""
+    """query/key weights x8 (SURVEY.md §8c adversarial case i): a peaked softmax amplifies operand rounding of the scores
+    (error ~ |S| * 2^-11); still inside the 1e-2 contract in the default precision and 1e-3 in split precision."""
     from _gpu_util import model_case
-    r = model_case(_cfg(golden_dir, "tiny_b4"), 2, 37, 21, seed=2, qk_scale=8.0)
-    for n, e in r["out_bf16"].items():
-        assert e < 2e-2, (n, e)
-    l2 = sorted(v[1] for v in r["grad_bf16"].values())
-    assert l2[len(l2) // 2] < 1e-2 and l2[-1] < 5e-2
+    _check(model_case(_cfg(golden_dir, "tiny_b4"), 2, 37, 21, seed=2, qk_scale=8.0))
+    _check(model_case(_cfg(golden_dir, "tiny_b4"), 2, 37, 21, seed=2, qk_scale=8.0, precision="fp32", grads=False), "fp32")
 
 
 def test_vqa_only_gradient_set_skips_dead_heads(golden_dir):
@@ -126,25 +132,71 @@ def test_vqa_only_gradient_set_skips_dead_heads(golden_dir):
 
 
 def test_base_2layer_2conect_config1(golden_dir):
-    """BASELINE.json configs[0] (forward, B=2, 36 regions, 20 tokens) on the real 2-connection-layer config. With two
-    samples the pooled path is ill-conditioned (vil_binary_prediction is ONE row of two logits; a single ReLU flip in a
-    pooler moves whole gradient rows), so gradients are bounded statistically here and per-tensor in the B=32 test."""
+    """BASELINE.json configs[0] (B=2, 36 regions, 20 tokens) on the real 2-connection-layer config: all 13 outputs inside the
+    contract in both precisions. With two samples the pooled path is ill-conditioned for GRADIENTS (vil_binary_prediction is ONE
+    row of two logits; a single ReLU flip in a pooler moves whole gradient rows), so gradients are bounded against the oracle
+    under the same operand rounding here and against fp32 in the full-size tests."""
     from _gpu_util import model_case
     r = model_case(_cfg(golden_dir, "base_2layer_2conect_cfg1"), 2, 36, 20)
-    for mode in ("out_fp32", "out_bf16"):
-        for n, e in r[mode].items():
-            assert e < (6e-2 if n in SMALL_HEADS else 1e-2), (mode, n, e)
-    assert abs(r["loss"] - r["loss_fp32"]) < 2e-3 * abs(r["loss_fp32"])
-    l2 = sorted(v[1] for v in r["grad_bf16"].values())
-    assert l2[len(l2) // 2] < 4e-2 and l2[int(len(l2) * 0.9)] < 1e-1, (l2[len(l2) // 2], l2[int(len(l2) * 0.9)])
+    _check(r, modes=("op",), grad_worst=3e-2, grad_median=1.5e-2)
+    for n, e in r["out_fp32"].items():
+        assert e < 1e-2, ("fp32-oracle output", n, e)
+    r = model_case(_cfg(golden_dir, "base_2layer_2conect_cfg1"), 2, 36, 20, precision="fp32", grads=False)
+    _check(r, "fp32")
 
 
-def test_base_6layer_6conect_vqa_shape(golden_dir):
-    """BASELINE.json configs[1] architecture at the VQA shape (100 regions, 36 tokens), B=32 (measure
-    tolerances on >= 32-sample batches)."""
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_config2_full_size_parity(golden_dir, precision):
+    """BASELINE.json configs[1] at its stated size: bert_base_6layer_6conect, B=64, 100 regions, 36 tokens — all 13 outputs and
+    every parameter gradient vs the fp32 oracle (1e-2 default precision, 1e-3 split precision)."""
     from _gpu_util import model_case
-    r = model_case(_cfg(golden_dir, "base_6layer_6conect_b4"), 32, 100, 36)
-    _check(r, grad_max=8e-2, grad_l2=4e-2)
+    r = model_case(_cfg(golden_dir, "base_6layer_6conect_b4"), 64, 100, 36, precision=precision, oracle_modes=("fp32",))
+    _check(r, precision, modes=("fp32",))
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_config3_cc_shape_full_size_parity(golden_dir, precision):
+    """BASELINE.json configs[2] per-GPU share: B=64 (global 512 / 8), 36 + 1 regions, 36 tokens, outputs and gradients."""
+    from _gpu_util import model_case
+    r = model_case(_cfg(golden_dir, "base_6layer_6conect_b4"), 64, 37, 36, seed=3, precision=precision, oracle_modes=("fp32",))
+    _check(r, precision, modes=("fp32",))
+
+
+def test_config3_pretraining_objective_fused_losses(golden_dir):
+    """The three-loss pre-training objective (vilbert.py:1578-1590) fused into the plan (masked-LM CE over 30522, masked-region
+    KL over 1601, alignment CE; csrc/vb_loss.cu) at the CC shape: loss value and every parameter gradient vs the oracle."""
+    from _gpu_util import build_engine, rel_l2
+    from vilbert_b200.engine import LOSS_HEADS
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import synth_loss_inputs
+    cfgj = _cfg(golden_dir, "base_6layer_6conect_b4")
+    cfg = O.make_config(cfgj)
+    B, Nv, Nt = 16, 37, 36
+    P = O.synth_params(cfg, seed=0, device="cuda", with_task_heads=False)
+    from vilbert_b200.config import BertConfig
+    from vilbert_b200.engine import Engine
+    eng = Engine(BertConfig.from_dict(cfgj), "cuda", heads="pretraining")
+    for k in eng.ps.entries:
+        eng.ps.p(k).copy_(P[k])
+    eng.refresh_weights()
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=11, device="cuda")
+    plan = eng.plan(B, Nt, Nv, grad_outputs=LOSS_HEADS["pretraining"], loss="pretraining")
+    plan.load_inputs(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+    li = synth_loss_inputs(plan, "pretraining", 5, torch)
+    for k, v in li.items():
+        plan.loss_inputs[k].copy_(v.reshape(plan.loss_inputs[k].shape))
+    eng.zero_grad(); plan.run_step(); torch.cuda.synchronize()
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    lt, lv, ln = O.pretraining_losses(Pg, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+                                      inp["image_attention_mask"], li["masked_lm_labels"].view(B, Nt).cuda(), li["image_label"].cuda(),
+                                      li["image_target"].cuda(), li["next_sentence_label"].cuda())
+    ref = lt + lv + ln
+    ref.backward()
+    assert abs(plan.loss.item() - ref.item()) < 2e-3 * abs(ref.item()), (plan.loss.item(), ref.item())
+    l2 = sorted((rel_l2(eng.ps.g(k), Pg[k].grad), k) for k in eng.ps.entries if Pg[k].grad is not None and Pg[k].grad.abs().max() > 0)
+    assert l2[-1][0] < 3e-2 and l2[len(l2) // 2][0] < 1e-2, l2[-3:]
 
 
 def test_module_surface_autograd_and_state_dict(golden_dir):
@@ -249,37 +301,38 @@ def test_full_size_config2_properties(golden_dir):
     assert ((p8.outputs["sequence_output_v"] - first).abs().max() / first.abs().max()).item() < 1e-5
 
 
-@pytest.mark.parametrize("B,Nv,Nt,task", [(2, 306, 256, True), (3, 200, 20, True), (2, 37, 36, False), (4, 101, 56, True)])
-def test_twelve_in_one_shapes_base_6layer(golden_dir, B, Nv, Nt, task):
-    """Shapes of the 12-in-1 mix (BASELINE.json configs[4]): the largest one (TASK17: 306 regions x 256
-    tokens + task token), Visual7w (200 x 20+1), Conceptual-Captions (36+1 x 36), Visual-Entailment (101 x 56+1) on
-    bert_base_6layer_6conect. Forward outputs vs the fp32 oracle and vs the bf16-operand oracle."""
+# the 8 distinct shapes of the 12 tasks (regions, tokens before the task token) at their per-GPU batch (vilbert_tasks.yml / 8)
+TWELVE_IN_ONE = [(16, 101, 23), (16, 101, 26), (32, 200, 20), (64, 101, 30), (32, 101, 20), (16, 101, 40), (32, 101, 56), (8, 306, 256)]
+
+
+@pytest.mark.parametrize("B,Nv,Nt", TWELVE_IN_ONE)
+def test_config5_twelve_in_one_shapes(golden_dir, B, Nv, Nt):
+    """BASELINE.json configs[4]: every shape of the 12-in-1 mix (tasks 1-2-4-7-8-9-10-11-12-13-15-17, task tokens on) at its
+    per-GPU batch on bert_base_6layer_6conect, outputs AND gradients vs the fp32 oracle; the largest is TASK17 (306 regions x
+    256 + 1 tokens)."""
     from _gpu_util import model_case
-    cfgj = dict(_cfg(golden_dir, "base_6layer_6conect_b4"), task_specific_tokens=task)
-    r = model_case(cfgj, B, Nv, Nt, seed=5, grads=False)
-    for mode in ("out_fp32", "out_bf16"):
-        for n, e in r[mode].items():
-            assert e < (6e-2 if n in SMALL_HEADS else 1.5e-2), (mode, n, e)
+    cfgj = dict(_cfg(golden_dir, "base_6layer_6conect_b4"), task_specific_tokens=True)
+    r = model_case(cfgj, B, Nv, Nt, seed=5, oracle_modes=("fp32",))
+    _check(r, modes=("fp32",))
 
 
-def test_bert_large_6layer_6conect_vcr_shape():
-    """BASELINE.json configs[3] architecture (24 text layers, 1024/4096, 16 heads) at the VCR shape (100 regions, 60 tokens),
-    small batch: forward + backward against the bf16-operand oracle."""
+@pytest.mark.parametrize("B,Nv,Nt", [(8, 306, 256), (32, 200, 20)])
+def test_config5_split_precision_forward(golden_dir, B, Nv, Nt):
+    from _gpu_util import model_case
+    cfgj = dict(_cfg(golden_dir, "base_6layer_6conect_b4"), task_specific_tokens=True)
+    _check(model_case(cfgj, B, Nv, Nt, seed=5, precision="fp32", grads=False, oracle_modes=("fp32",)), "fp32", modes=("fp32",))
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_config4_bert_large_vcr_shape_full_size(precision):
+    """BASELINE.json configs[3] per-GPU share: bert_large_6layer_6conect (24 text layers, 1024/4096, 16 heads), B=32 (global 256
+    / 8), 100 regions, 60 tokens; all 13 outputs inside the contract, gradients of the VL-logit + VQA heads' paths bounded
+    (36 sub-layers deep: measured median 9e-3, worst 2.3e-2 rel-L2 in the default precision)."""
     from _gpu_util import model_case
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cfgj = json.load(open(os.path.join(root, "vilbert-multi-task_b200", "configs", "bert_large_6layer_6conect.json")))
-    r = model_case(cfgj, 4, 100, 60, seed=2, names=("vil_logit", "vil_prediction"))
-    for mode in ("out_fp32", "out_bf16"):
-        for n, e in r[mode].items():
-            assert e < (8e-2 if n in SMALL_HEADS else 2e-2), (mode, n, e)
-    # 24 + 6 + 6 blocks at B = 4: two bf16-operand implementations (different accumulation orders, bf16 rounding points that
-    # flip on 1-ulp differences) decorrelate with depth; the engine must stay as close to the bf16-operand oracle as that
-    # oracle is to fp32 (measured ~6e-2 median rel-L2 for this depth and batch)
-    l2 = sorted(v[1] for v in r["grad_bf16"].values())
-    l2f = sorted(v[1] for v in r["grad_fp32"].values())
-    assert l2[len(l2) // 2] < 1e-1 and l2[int(len(l2) * 0.9)] < 2e-1, (l2[len(l2) // 2], l2[int(len(l2) * 0.9)])
-    assert l2f[len(l2f) // 2] < 1.5e-1, l2f[len(l2f) // 2]
-    assert abs(r["loss"] - r["loss_fp32"]) < 5e-3 * abs(r["loss_fp32"])
+    r = model_case(cfgj, 32, 100, 60, seed=2, names=("vil_logit", "vil_prediction"), precision=precision, oracle_modes=("fp32",))
+    _check(r, precision, modes=("fp32",), grad_worst=5e-2, grad_median=2e-2)
 
 
 def test_pretraining_model_losses_and_gradients(golden_dir):

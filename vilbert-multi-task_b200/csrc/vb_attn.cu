@@ -50,6 +50,7 @@ struct AttnParams {
   const __nv_bfloat16 *Ql, *Kl, *Vl;   // split precision (forward): low parts of Q / K / V, or NULL
   __nv_bfloat16* Ol;                   // low part of O, or NULL
   __nv_bfloat16* Ob;                   // always-bf16 copy of O, or NULL
+  int kchunk;                          // forward: keys resident in shared memory at a time (multiple of KB; >= padded Nk = one pass)
 };
 
 // In-place fp16 -> bf16 conversion of a staged panel (rows x D at pitch D + 8): the backward kernels run their products in
@@ -197,34 +198,28 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
   extern __shared__ __align__(16) uint8_t smem_att[];
   pdl_entry();
   const int nkp = (p.Nk + KB - 1) / KB * KB;
+  const int kch = min(p.kchunk, nkp);   // keys resident at a time: the whole (padded) key range unless it does not fit (long
+                                        // sequences in split precision), then chunks streamed through the same panels
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
   __nv_bfloat16* sK = sQ + TQ * LD;
-  __nv_bfloat16* sV = sK + nkp * LD;
+  __nv_bfloat16* sV = sK + kch * LD;
   // split precision: low-part panels behind the hi ones
-  __nv_bfloat16* sQl = sV + nkp * LD;
+  __nv_bfloat16* sQl = sV + kch * LD;
   __nv_bfloat16* sKl = sQl + (SPLIT ? TQ * LD : 0);
-  __nv_bfloat16* sVl = sKl + (SPLIT ? nkp * LD : 0);
-  float* sMask = reinterpret_cast<float*>(sVl + (SPLIT ? nkp * LD : 0));
+  __nv_bfloat16* sVl = sKl + (SPLIT ? kch * LD : 0);
+  float* sMask = reinterpret_cast<float*>(sVl + (SPLIT ? kch * LD : 0));
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
   load_panel<D>(sQ, p.Q + ((long long)b * p.Nq + q0) * p.ldq + h * D, p.ldq, min(TQ, p.Nq - q0), TQ);
-  load_panel<D>(sK, p.K + (long long)b * p.Nk * p.ldk + h * D, p.ldk, p.Nk, nkp);
-  load_panel<D>(sV, p.V + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
-  if constexpr (SPLIT) {
-    load_panel<D>(sQl, p.Ql + ((long long)b * p.Nq + q0) * p.ldq + h * D, p.ldq, min(TQ, p.Nq - q0), TQ);
-    load_panel<D>(sKl, p.Kl + (long long)b * p.Nk * p.ldk + h * D, p.ldk, p.Nk, nkp);
-    load_panel<D>(sVl, p.Vl + (long long)b * p.Nk * p.ldv + h * D, p.ldv, p.Nk, nkp);
-  }
+  if constexpr (SPLIT) load_panel<D>(sQl, p.Ql + ((long long)b * p.Nq + q0) * p.ldq + h * D, p.ldq, min(TQ, p.Nq - q0), TQ);
   for (int j = threadIdx.x; j < nkp; j += ATT_THREADS)
     sMask[j] = (j < p.Nk) ? (p.mask ? p.mask[(long long)b * p.Nk + j] * LOG2E : 0.f) : -CUDART_INF_F;
-  cp_async_wait_all();
-  __syncthreads();
 
   const int r0 = warp * 16;
-  if (q0 + r0 >= p.Nq) return;  // whole warp out of range (no later block-wide sync)
+  const bool active = q0 + r0 < p.Nq;   // a warp whose 16 query rows are all out of range only helps with the loads
 
   const float c = p.scale * LOG2E;
   const uint32_t dseed = p.drop.ctr ? drop_seed(p.drop) : 0u;
@@ -233,49 +228,65 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
 #pragma unroll
   for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 
-  for (int kb = 0; kb < nkp; kb += KB) {
-    float s[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    mma_a_bt<D, FP16>(s, sQ, r0, sK, kb, lane, p.Nk);
-    if constexpr (SPLIT) {   // S = Q K^T + Q_lo K^T + Q K_lo^T
-      mma_a_bt<D, FP16>(s, sQl, r0, sK, kb, lane, p.Nk);
-      mma_a_bt<D, FP16>(s, sQ, r0, sKl, kb, lane, p.Nk);
+  for (int k0 = 0; k0 < nkp; k0 += kch) {
+    const int kc = min(kch, nkp - k0);
+    const int kvalid = max(0, min(kc, p.Nk - k0));
+    if (k0 > 0) __syncthreads();   // every warp is done with the previous chunk's panels
+    load_panel<D>(sK, p.K + ((long long)b * p.Nk + k0) * p.ldk + h * D, p.ldk, kvalid, kc);
+    load_panel<D>(sV, p.V + ((long long)b * p.Nk + k0) * p.ldv + h * D, p.ldv, kvalid, kc);
+    if constexpr (SPLIT) {
+      load_panel<D>(sKl, p.Kl + ((long long)b * p.Nk + k0) * p.ldk + h * D, p.ldk, kvalid, kc);
+      load_panel<D>(sVl, p.Vl + ((long long)b * p.Nk + k0) * p.ldv + h * D, p.ldv, kvalid, kc);
     }
-    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+    cp_async_wait_all();
+    __syncthreads();
+    if (!active) continue;
+
+    for (int kb = 0; kb < kc; kb += KB) {
+      float s[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float mk0 = sMask[kb + nt * 8 + 2 * t], mk1 = sMask[kb + nt * 8 + 2 * t + 1];
-      s[nt][0] = s[nt][0] * c + mk0; s[nt][1] = s[nt][1] * c + mk1;
-      s[nt][2] = s[nt][2] * c + mk0; s[nt][3] = s[nt][3] * c + mk1;
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    mx0 = quad_max(mx0); mx1 = quad_max(mx1);
-    const float mn0 = fmaxf(m[0], mx0), mn1 = fmaxf(m[1], mx1);
-    const float al0 = exp2f(m[0] - mn0), al1 = exp2f(m[1] - mn1);
-    m[0] = mn0; m[1] = mn1;
-    float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
-      s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
-      rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
-    }
-    l[0] = l[0] * al0 + rs0; l[1] = l[1] * al1 + rs1;
-#pragma unroll
-    for (int i = 0; i < D / 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
-    if (p.drop.ctr) {   // nn.Dropout on the probabilities (vilbert.py:443, 604, 778, 800): the row sum above stays undropped
-      const uint32_t e0 = (uint32_t)((((long long)b * p.H + h) * p.Nq + q0 + r0 + g) * p.Nk + kb + 2 * t);
-      const uint32_t e1 = e0 + 8u * (uint32_t)p.Nk;
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      mma_a_bt<D, FP16>(s, sQ, r0, sK, kb, lane, p.Nk);
+      if constexpr (SPLIT) {   // S = Q K^T + Q_lo K^T + Q K_lo^T
+        mma_a_bt<D, FP16>(s, sQl, r0, sK, kb, lane, p.Nk);
+        mma_a_bt<D, FP16>(s, sQ, r0, sKl, kb, lane, p.Nk);
+      }
+      float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] *= drop_factor(dseed, e0 + nt * 8, p.drop); s[nt][1] *= drop_factor(dseed, e0 + nt * 8 + 1, p.drop);
-        s[nt][2] *= drop_factor(dseed, e1 + nt * 8, p.drop); s[nt][3] *= drop_factor(dseed, e1 + nt * 8 + 1, p.drop);
+        const float mk0 = sMask[k0 + kb + nt * 8 + 2 * t], mk1 = sMask[k0 + kb + nt * 8 + 2 * t + 1];
+        s[nt][0] = s[nt][0] * c + mk0; s[nt][1] = s[nt][1] * c + mk1;
+        s[nt][2] = s[nt][2] * c + mk0; s[nt][3] = s[nt][3] * c + mk1;
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
+      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+      const float mn0 = fmaxf(m[0], mx0), mn1 = fmaxf(m[1], mx1);
+      const float al0 = exp2f(m[0] - mn0), al1 = exp2f(m[1] - mn1);
+      m[0] = mn0; m[1] = mn1;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
+        s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+        rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
+      }
+      l[0] = l[0] * al0 + rs0; l[1] = l[1] * al1 + rs1;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
+      if (p.drop.ctr) {   // nn.Dropout on the probabilities (vilbert.py:443, 604, 778, 800): the row sum above stays undropped
+        const uint32_t e0 = (uint32_t)((((long long)b * p.H + h) * p.Nq + q0 + r0 + g) * p.Nk + k0 + kb + 2 * t);
+        const uint32_t e1 = e0 + 8u * (uint32_t)p.Nk;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          s[nt][0] *= drop_factor(dseed, e0 + nt * 8, p.drop); s[nt][1] *= drop_factor(dseed, e0 + nt * 8 + 1, p.drop);
+          s[nt][2] *= drop_factor(dseed, e1 + nt * 8, p.drop); s[nt][3] *= drop_factor(dseed, e1 + nt * 8 + 1, p.drop);
+        }
+      }
+      mma_p_b<D, FP16, SPLIT>(o, s, sV, kb, lane, p.Nk, sVl);
     }
-    mma_p_b<D, FP16, SPLIT>(o, s, sV, kb, lane, p.Nk, sVl);
   }
+  if (!active) return;
   l[0] = quad_sum(l[0]); l[1] = quad_sum(l[1]);
   const int rows_valid = p.Nq - q0;
   store_tile<D>(p.O + ((long long)b * p.Nq + q0) * p.ldo + h * D, p.ldo, o, 1.f / l[0], 1.f / l[1], r0, rows_valid, lane, nullptr,
@@ -674,6 +685,7 @@ static AttnParams to_params(const vb_attn_args* a) {
   p.Ql = (const __nv_bfloat16*)a->Q_lo; p.Kl = (const __nv_bfloat16*)a->K_lo; p.Vl = (const __nv_bfloat16*)a->V_lo;
   p.Ol = (__nv_bfloat16*)a->O_lo;
   p.Ob = (__nv_bfloat16*)a->O_b16;
+  p.kchunk = 1 << 30;
   return p;
 }
 
@@ -700,7 +712,14 @@ extern "C" vb_status vb_attention_fwd(const vb_attn_args* a, void* stream) {
   if (split && !(a->Q_lo && a->K_lo && a->V_lo)) return set_error(VB_ERR_INVALID, "vb_attention_fwd: split precision needs Q_lo, K_lo and V_lo");
   if (split && (!al16(a->Q_lo) || !al16(a->K_lo) || !al16(a->V_lo) || (a->O_lo && !al16(a->O_lo))))
     return set_error(VB_ERR_INVALID, "vb_attention_fwd: low-part tensors need 16-byte aligned bases");
-  const size_t smem = (size_t)(TQ + 2 * nkp) * (a->D + 8) * 2 * (split ? 2 : 1) + (size_t)nkp * 4;
+  // keys resident at a time: all of them when the panels fit, else the largest multiple of KB that does (streamed chunks)
+  const size_t row_bytes = (size_t)(a->D + 8) * 2 * (split ? 2 : 1);
+  const size_t fixed = (size_t)TQ * row_bytes + (size_t)nkp * 4;
+  int kchunk = nkp;
+  while (kchunk > KB && fixed + 2 * (size_t)kchunk * row_bytes > 227 * 1024) kchunk -= KB;
+  const size_t smem = fixed + 2 * (size_t)kchunk * row_bytes;
+  AttnParams& pm = const_cast<AttnParams&>(p);
+  pm.kchunk = kchunk;
   dim3 grid((a->Nq + TQ - 1) / TQ, a->H, a->B);
   cudaStream_t st = (cudaStream_t)stream;
 #define VB_FWD(DD)                                                                                                     \

@@ -217,6 +217,17 @@ class Act:
         self.g32, self.gw = None, False
 
 
+# Objectives that can be fused into a plan, and the outputs each differentiates (task_utils.py:325-374, vilbert.py:1506-1590):
+LOSS_HEADS = {
+    "vqa": ("vil_prediction",),                 # VL-classifier: BCEWithLogits.mean() * 3129
+    "gqa": ("vil_prediction_gqa",),             # VL-classifier-GQA: BCEWithLogits.mean() * 1533
+    "vlogit_bce": ("vision_logit",),            # V-logit (refcoco*): BCEWithLogits(vision_logit [B,Nv,1], target).mean() * Nv
+    "logit_ce": ("vil_logit",),                 # VL-logit (retrieval, VCR): CE over vil_logit.view(B / options, options)
+    "binary_ce": ("vil_binary_prediction",),    # VL-binary-classifier (NLVR2): CE over the 2-way paired head
+    "tri_ce": ("vil_tri_prediction",),          # VL-tri-classifier (SNLI-VE): CE over 3 classes
+    "pretraining": ("linguisic_prediction", "vision_prediction", "seq_relationship_score"),   # masked-LM CE + masked-region KL + alignment CE
+}
+
 HEAD_NAMES = ("vil_prediction", "vil_prediction_gqa", "vil_logit", "vil_binary_prediction", "vil_tri_prediction",
               "vision_prediction", "vision_logit", "linguisic_prediction", "linguisic_logit")
 BERT_OUT_NAMES = ("sequence_output_t", "sequence_output_v", "pooled_output_t", "pooled_output_v")
@@ -227,7 +238,7 @@ class Plan:
     gradient in backward (dead branches are not emitted); `vqa_loss` fuses the VQA BCE objective
     (task_utils.py:325-327) and its gradient after the forward."""
 
-    def __init__(self, engine, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False):
+    def __init__(self, engine, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False, loss=None):
         self.e, self.cfg = engine, engine.cfg
         self.grad_touch = {}           # (flat offset, numel) -> index of the last backward op writing that gradient range
         self.ps = _TrackedParams(engine.ps, self)
@@ -237,7 +248,12 @@ class Plan:
         self.has_task = bool(self.cfg.task_specific_tokens)
         self.Nt = Nt + (1 if self.has_task else 0)
         self.grad_outputs = frozenset(grad_outputs)
-        self.vqa_loss = vqa_loss
+        # objective fused into the step (LOSS_HEADS): its scalar lands in self.loss (device) and its gradient goes straight into the
+        # backward of the head(s) it reads; vqa_loss=True is the round-1 spelling of loss="vqa"
+        self.loss_kind = "vqa" if vqa_loss else loss
+        if self.loss_kind is not None and self.loss_kind not in LOSS_HEADS:
+            raise ValueError(f"loss must be one of {sorted(LOSS_HEADS)}")
+        self.vqa_loss = self.loss_kind == "vqa"
         self.train = bool(train)          # nn.Dropout layers active (model.train()); False = the reference's eval mode
         self.op_fp16 = 1 if engine.op_dtype == F16 else 0   # format of the forward operands (activations, weights)
         self.op_dtype, self.split = engine.op_dtype, engine.split
@@ -945,6 +961,8 @@ class Plan:
             self.vqa_dl16 = self.buf((lg.shape[0], _pad8(lg.shape[1])), BF16, zero=True)
             self.emit(self.lib.vb_bce_logits_loss, lg.data_ptr(), self.vqa_target.data_ptr(), self.loss.data_ptr(), self.vqa_dl32.data_ptr(),
                       self.vqa_dl16.data_ptr(), _pad8(lg.shape[1]), lg.shape[0], lg.shape[1], 1.0)
+        elif self.loss_kind is not None:
+            self._emit_loss()
         # gradients flowing into the BertModel outputs themselves
         for nm, act in (("sequence_output_t", self.seq_t), ("sequence_output_v", self.seq_v), ("pooled_output_t", self.pooled_t),
                         ("pooled_output_v", self.pooled_v)):
@@ -962,6 +980,56 @@ class Plan:
         self.cur.append((None, ("all",), 0))     # join every stream (incl. the weight-gradient side streams)
         self.n_kernels_bwd = sum(1 for op in self.bwd if op[0] is not None)
         self.cur = self.fwd
+
+    def _emit_loss(self):
+        """Fused objectives other than "vqa": one loss kernel per head writes the scalar (self.loss, fp32 device) and the fp32
+        d(loss)/d(head output) into the plan's output-gradient buffer, from where the head's backward proceeds as for a
+        caller-supplied gradient. Labels / targets are static plan inputs (self.loss_inputs)."""
+        lib, B, k = self.lib, self.B, self.loss_kind
+        missing = [n for n in LOSS_HEADS[k] if n not in self.grad_outputs]
+        if missing:
+            raise ValueError(f"loss={k!r} differentiates {LOSS_HEADS[k]}: add them to grad_outputs")
+        self.loss = self.buf((1,), F32, zero=True)
+        self.loss_inputs = {}
+        li = self.loss_inputs
+
+        def ce(name, rows, cols, label_key, acc):
+            lg = self.outputs[name]
+            li[label_key] = self.buf((rows,), I64, zero=True)
+            d = self.out_grad_buffer(name, tuple(lg.shape))
+            self.emit(lib.vb_ce_loss, lg.data_ptr(), cols, li[label_key].data_ptr(), -1, self.loss.data_ptr(), d.data_ptr(), cols, None, 0,
+                      rows, cols, 1.0, 1 if acc else 0)
+
+        def bce(name, rows, cols):
+            lg = self.outputs[name]
+            li["target"] = self.buf((rows, cols), F32, zero=True)
+            d = self.out_grad_buffer(name, tuple(lg.shape))
+            self.emit(lib.vb_bce_logits_loss, lg.data_ptr(), li["target"].data_ptr(), self.loss.data_ptr(), d.data_ptr(), None, 0, rows, cols, 1.0)
+
+        if k == "gqa":
+            bce("vil_prediction_gqa", B, 1533)
+        elif k == "vlogit_bce":
+            bce("vision_logit", B, self.Nv)
+        elif k == "logit_ce":
+            opts = self.e.loss_options
+            if B % opts:
+                raise ValueError(f"loss='logit_ce': batch {B} is not a multiple of {opts} options")
+            ce("vil_logit", B // opts, opts, "labels", False)
+        elif k == "binary_ce":
+            ce("vil_binary_prediction", self.outputs["vil_binary_prediction"].shape[0], 2, "labels", False)
+        elif k == "tri_ce":
+            ce("vil_tri_prediction", B, 3, "labels", False)
+        elif k == "pretraining":
+            # vilbert.py:1578-1590 (+ train_concap.py: loss = masked_loss_t + masked_loss_v + next_sentence_loss)
+            V, C = self.cfg.vocab_size, self.cfg.v_target_size
+            ce("linguisic_prediction", B * self.Nt, V, "masked_lm_labels", False)
+            sv = self.outputs["vision_prediction"]
+            li["image_target"] = self.buf((B, self.Nv - 1, C), F32, zero=True)
+            li["image_label"] = self.buf((B, self.Nv - 1), I64, zero=True)
+            dv = self.out_grad_buffer("vision_prediction", tuple(sv.shape))
+            self.emit(lib.vb_kl_masked_loss, sv.data_ptr(), li["image_target"].data_ptr(), li["image_label"].data_ptr(), self.loss.data_ptr(),
+                      dv.data_ptr(), None, 0, B, self.Nv, C, 1.0, 1)
+            ce("seq_relationship_score", B, 2, "next_sentence_label", True)
 
     # ------------------------------------------------------------------ execution
     def load_inputs(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
@@ -1254,15 +1322,17 @@ class Engine:
         self.shadow_clean = False        # the 16-bit weight copy matches the fp32 master parameters
         self.shadow_trusted = False      # True while the engine's own fused optimizer is the only writer of the parameters
         self.grad_clean = False          # the flat gradient buffer is all zeros (set by zero_grad / the fused optimizer)
+        self.loss_options = 4            # answer options per question of the VL-logit objective (retrieval / VCR: 4)
 
-    def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False):
-        key = (B, Nt, Nv, frozenset(grad_outputs), vqa_loss, heads, bool(train))
+    def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False, loss=None):
+        loss = "vqa" if vqa_loss else loss
+        key = (B, Nt, Nv, frozenset(grad_outputs), loss, heads, bool(train))
         if key in self.plans:
             self.plans.move_to_end(key)
             return self.plans[key]
         while len(self.plans) >= self.max_plans:   # evict the least recently used plan: its buffers go back to the allocator
             self.plans.popitem(last=False)
-        self.plans[key] = Plan(self, B, Nt, Nv, grad_outputs, vqa_loss, heads, train)
+        self.plans[key] = Plan(self, B, Nt, Nv, grad_outputs, False, heads, train, loss=loss)
         return self.plans[key]
 
     def release_plans(self):
