@@ -236,6 +236,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of a single-task config")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce after the whole backward instead of overlapping it")
+    ap.add_argument("--ddp-mode", default="graph", choices=["graph", "pieces"],
+                    help="N > 1 overlapped step: 'graph' = ONE CUDA graph per step with the NCCL all-reduces captured on a side stream; "
+                         "'pieces' = one graph per backward piece, collectives issued from the host between them (round-1 scheme)")
     ap.add_argument("--segments", type=int, default=8, help="N > 1: number of backward pieces whose gradient ranges are all-reduced while the rest runs")
     ap.add_argument("--eval-mode", action="store_true", help="disable the dropout layers (reference eval mode); default is train mode")
     ap.add_argument("--legacy-prologue", action="store_true", help="round-1 step body: weight cast + gradient memset inside the step, no fused optimizer")
@@ -345,7 +348,22 @@ def main():
     single = len(T) == 1
     overlapped = world > 1 and single and not a.no_graph and not a.no_overlap
     comm_stream = None
-    if overlapped:
+    ddp_graph = False
+    if overlapped and a.ddp_mode == "graph":
+        plan = T[0]["plan"]
+        try:
+            for _ in range(2):      # warm-up outside capture (lazy module loads, NCCL channel set-up for every range size)
+                plan.run_step(); reducer.allreduce()
+            torch.cuda.synchronize()
+            plan.capture_step_ddp(reducer.allreduce_range_sync, a.segments)
+            ddp_graph = True
+        except Exception as e:   # noqa: BLE001
+            print(f"[bench] rank {rank}: capture_step_ddp failed ({e}); falling back to per-piece graphs", file=sys.stderr)
+            try:
+                torch.cuda.synchronize()
+            except Exception:    # noqa: BLE001
+                pass
+    if overlapped and not ddp_graph:
         plan = T[0]["plan"]
         for tail_cut in (True, False):
             try:
@@ -367,7 +385,9 @@ def main():
     def step(with_opt=False):
         for t in T:
             plan = t["plan"]
-            if overlapped:
+            if ddp_graph:
+                plan.run_step_ddp()
+            elif overlapped:
                 works = plan.run_step_overlapped(reducer.allreduce_range, comm_stream)
                 for w in works:
                     if w is not None:
@@ -461,7 +481,9 @@ def main():
             for k in keys:
                 t["dst"][k].copy_(t["stage"][s][k], non_blocking=True)
             t["ev_free"][s].record(cur)
-            if overlapped:
+            if ddp_graph:
+                plan.run_step_ddp()
+            elif overlapped:
                 for w in plan.run_step_overlapped(reducer.allreduce_range, comm_stream):
                     if w is not None:
                         w.wait()
@@ -547,7 +569,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "global_batch": samples, "parallelism": f"dp{world}", "cuda_graph": not a.no_graph,
                    "tasks": [dict(task=t["name"], batch=t["B"], regions=t["plan"].Nv, tokens=t["plan"].Nt, objective=t["kind"]) for t in T] if len(T) > 1 else None,
-                   "allreduce": ("none (1 GPU)" if world == 1 else (f"NCCL AVG of the flat fp32 gradient buffer, {len(T[0]['plan'].segments)} tail ranges overlapped with backward" if overlapped
+                   "allreduce": ("none (1 GPU)" if world == 1 else (f"NCCL AVG of the flat fp32 gradient buffer, {len(T[0]['plan'].segments)} tail ranges overlapped with backward"
+                                                                         + (" (one CUDA graph per step, collectives captured, never-written ranges skipped)" if ddp_graph else " (one graph per backward piece)") if overlapped
                                  else "NCCL AVG of the flat fp32 gradient buffer after each backward (8 buckets)")),
                    "l2": "working set (activations + weights + grads, GBs per step) exceeds the 126 MB L2; no explicit flush",
                    "streams": "text and vision segments on two CUDA streams (parallel graph branches)" if eng.two_streams else "single stream",

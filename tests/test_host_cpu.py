@@ -175,6 +175,9 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "pairs/s" and d["higher_is_better"] is True
     assert "bert_base_6layer_6conect" in d["metric"] and "bert_base_6layer_6conect" in d["config"]["workload"]
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] >= 1 and d["dtype"] == "f32" and d["data"] == "synthetic"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader
+    # the unmodified reference is timed where it exists (this container), the bit-identical oracle port elsewhere (the GPU box)
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 

@@ -29,15 +29,11 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle span of bf16
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
 constexpr int EPI_WARPS = 8;      // two epilogue warps per TMEM lane quadrant: twice the global-memory requests in flight
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32 + 32;   // + warp 10: TMA producer of the epilogue's fp32 residual tiles
-constexpr int RES_WARP = 2 + EPI_WARPS;
-// fp32 residual of the F32 epilogue (LN(dense(x) + residual), dgrad accumulation): staged by TMA as 128-row x 32-column
-// boxes (16 KB, dense 128-byte rows) into a ring of RES_SLOTS slots by a dedicated warp that runs up to RES_SLOTS chunks
-// ahead of the epilogue warps — the next tile's residual arrives during the current main loop instead of being fetched
-// with 8 dependent 16-byte loads per lane after the accumulator is ready (the epilogue was latency-bound on exactly
-// those loads: 10.8k cycles per 128x128 tile with a residual vs 3-5k without, profiles/r01_gemm_timeline_v6).
-constexpr int RES_SLOTS = 4;
-constexpr int RES_SLOT_BYTES = 128 * 32 * 4;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+// (Round 2 experiment, rejected: staging the fp32 residual of the F32 epilogue through a TMA ring fed by an 11th warp. The
+// epilogue is not latency-bound but bandwidth-bound — all 148 CTAs run their epilogues in lockstep, 64 KB read + 64 KB written
+// per tile = 7.5 TB/s chip-wide during that phase — and giving up two operand stages for the ring slowed the main loop:
+// 34.3 us vs 29.8 us on 6400x1024x1024, profiles/r02_gemm_timeline_residual_tma_ring_rejected.log.)
 // Epilogue staging tile per warp: 32 rows x 32 fp32, dense 128-byte rows whose 16-byte chunks are XOR-swizzled with the
 // row index (chunk ^ (row & 7)): thread-per-row 128-bit stores and row-wise 128-bit loads are both bank-conflict free
 // without padding (4 KB per warp).
@@ -46,18 +42,15 @@ __device__ __forceinline__ int stg_off(int row, int col) { return row * 32 + (((
 
 // CG = 1: one CTA per 128 x BN tile. CG = 2: CTA pairs (tcgen05 cta_group::2) on a 256 x BN tile; each CTA stages its 128
 // rows of A and its BN/2 rows of B, so a stage is smaller and the ring deeper (192 KB of operand stages either way).
-template <int BN, int CG, bool RES = false>
+template <int BN, int CG>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RES_BYTES = RES ? RES_SLOTS * RES_SLOT_BYTES : 0;
-  static constexpr int NUM_STAGES = (192 * 1024 - RES_BYTES) / STAGE_BYTES;   // 6 / 4 (CG 1), 8 / 6 (CG 2); 4 / - , 5 / 4 with the residual ring
+  static constexpr int NUM_STAGES = (192 * 1024) / STAGE_BYTES;   // 6 / 4 (CG 1), 8 / 6 (CG 2)
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + RES_BYTES + EPI_WARPS * STAGING_BYTES_PER_WARP + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES_PER_WARP + 256 /*barriers*/;
 };
-// the residual ring exists in the F32 epilogue specialisation, except for 128x256 single-CTA tiles (only 2 operand stages would be left)
-template <int BN, int EPI, int CG> struct ResOn { static constexpr bool value = (EPI == 0 /*EPI_F32*/) && !(BN == 256 && CG == 1); };
 
 struct GemmKernelParams {
   int M, N, K;
@@ -95,7 +88,6 @@ struct GemmKernelParams {
                              // half of the B tile -> per-SM operand traffic (L2 -> smem and smem -> tensor core) drops by 25-33 %
   int num_m_groups;          // ceil(num_m_blocks / cluster)
   int fast_ok;               // every buffer the specialised epilogue touches allows 128/64-bit accesses
-  int res_tma;               // the fp32 residual is staged through the TMA ring (tmap_res valid)
   unsigned long long* dbg;   // optional per-CTA timeline [grid][10] (8 x clock64 + 2 x globaltimer ns), NULL in production
 };
 
@@ -103,7 +95,7 @@ struct GemmKernelParams {
 // the matrix, 128/64-bit aligned buffers) plus a shared non-inlined generic path for ragged edges / odd layouts.
 // (A single kernel with every variant inlined is ~180 KB of SASS and thrashes the instruction cache: the epilogue
 // of one 128x128 tile then costs ~29k cycles instead of ~2k — measured with the clock64 timeline, profiles/.)
-enum { EPI_F32 = 0,     // v = alpha*acc (+bias) (+fp32 residual) -> out_f32                (out-proj / FFN2 / dgrad-into-residual / logits)
+enum { EPI_F32 = 0,     // v = alpha*acc (+bias) (ReLU) (+fp32 residual) -> out_f32 (+ 16-bit copy)   (out-proj / FFN2 / dgrad-into-residual / logits / poolers)
        EPI_BF16 = 1,    // v = alpha*acc (+bias) -> out_bf16                                 (QKV, plain dgrads)
        EPI_GELU = 2,    // pre = acc + bias; gelu(pre) -> out_bf16 / out_f32; gelu'(pre) -> out_pre (bf16, saved for backward)
        EPI_DGELU = 3,   // v = acc * aux (aux = saved gelu'(pre)) -> out_bf16 (+ column sums)
@@ -176,8 +168,7 @@ __device__ __forceinline__ void store16x4(const GemmKernelParams& p, long long o
 
 template <int EPI>
 __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const float* stg, int m_base, int n, int rr, int cc,
-                                               const float4 (&resv)[8], const uint2 (&auxv)[8], const float4 b4,
-                                               const float* res_smem = nullptr) {
+                                               const float4 (&resv)[8], const uint2 (&auxv)[8], const float4 b4) {
   float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
   const uint32_t dseed = (EPI == EPI_F32 && p.drop.ctr) ? drop_seed(p.drop) : 0u;
 #pragma unroll
@@ -199,21 +190,20 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
       cs0 += v0; cs1 += v1; cs2 += v2; cs3 += v3;
       store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);
     } else if (EPI == EPI_F32) {
+      if (p.act == VB_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }   // poolers
       if (p.drop.ctr) {   // LN(dropout(dense(x)) + residual): mask the dense output, element index m*N + n
         const uint32_t e0 = (uint32_t)(m * p.N + n);
         v0 = drop_apply(v0, dseed, e0, p.drop); v1 = drop_apply(v1, dseed, e0 + 1, p.drop);
         v2 = drop_apply(v2, dseed, e0 + 2, p.drop); v3 = drop_apply(v3, dseed, e0 + 3, p.drop);
       }
-      if (res_smem) {   // residual chunk staged by TMA: this warp's 32 rows x 32 columns, dense 128-byte rows
-        const float4 r4 = *reinterpret_cast<const float4*>(res_smem + row * 32 + cc);
-        v0 += r4.x; v1 += r4.y; v2 += r4.z; v3 += r4.w;
-      } else if (p.residual) { v0 += resv[ps].x; v1 += resv[ps].y; v2 += resv[ps].z; v3 += resv[ps].w; }
+      if (p.residual) { v0 += resv[ps].x; v1 += resv[ps].y; v2 += resv[ps].z; v3 += resv[ps].w; }
       float* dst = p.out_f32 + m * p.ld_of + n;
       if (p.vec_f32) {
         *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
       } else {   // row pitch not a multiple of 4 floats (30522-/1601-/3129-wide logits): same bytes, 32-bit stores
         dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
       }
+      if (p.out_bf16) store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);   // operand copy next to the fp32 value (poolers)
     } else if (EPI == EPI_BF16) {
       store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);
     } else if (EPI == EPI_ATOMIC) {
@@ -237,9 +227,8 @@ template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
-                    const __grid_constant__ CUtensorMap tmap_res, const GemmKernelParams p) {
-  constexpr bool RES = ResOn<BN, EPI, CG>::value;
-  using Cfg = GemmCfg<BN, CG, RES>;
+                    const GemmKernelParams p) {
+  using Cfg = GemmCfg<BN, CG>;
   constexpr bool pair = (CG == 2);
   constexpr int NUM_STAGES = Cfg::NUM_STAGES;
 
@@ -248,16 +237,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smem_tiles = smem;
-  float* res_ring = reinterpret_cast<float*>(smem + NUM_STAGES * Cfg::STAGE_BYTES);   // [RES_SLOTS][128][32] fp32 (RES only)
-  float* staging = reinterpret_cast<float*>(smem + NUM_STAGES * Cfg::STAGE_BYTES + Cfg::RES_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * Cfg::STAGE_BYTES + Cfg::RES_BYTES + EPI_WARPS * STAGING_BYTES_PER_WARP);
+  float* staging = reinterpret_cast<float*>(smem + NUM_STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * Cfg::STAGE_BYTES + EPI_WARPS * STAGING_BYTES_PER_WARP);
   uint64_t* full_bar = bars;                       // [NUM_STAGES]
   uint64_t* empty_bar = bars + NUM_STAGES;         // [NUM_STAGES]
   uint64_t* tmem_full_bar = bars + 2 * NUM_STAGES; // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
-  uint64_t* res_full_bar = tmem_empty_bar + 2;     // [RES_SLOTS]
-  uint64_t* res_empty_bar = res_full_bar + RES_SLOTS;   // [RES_SLOTS]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + RES_SLOTS);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -277,11 +263,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_WARPS * CG);   // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    for (int s = 0; s < RES_SLOTS; ++s) {
-      mbar_init(smem_u32(&res_full_bar[s]), 1);
-      mbar_init(smem_u32(&res_empty_bar[s]), 4);   // the four lane-quadrant warps that consume a 128-row chunk
-    }
-    if (RES && p.res_tma) tma_prefetch_desc(&tmap_res);
     fence_mbar_init();
   }
   __syncwarp();
@@ -415,29 +396,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       __syncwarp();
     }
-  } else if (warp_idx == RES_WARP) {
-    // ================================================================ residual producer (F32 epilogue with an fp32 residual)
-    if constexpr (RES) {
-      if (p.res_tma) {
-        constexpr int NC = BN / 32;
-        uint32_t gchunk = 0;
-        for (int w = group; w < total_work; w += num_groups) {
-          const int t2 = w / p.split_k;
-          const int m_blk = (t2 % p.num_m_groups) * CG + crank;
-          const int n_blk = t2 / p.num_m_groups;
-          for (int c = 0; c < NC; ++c, ++gchunk) {
-            if (elect_one()) {
-              const int slot = gchunk % RES_SLOTS;
-              mbar_wait(smem_u32(&res_empty_bar[slot]), ((gchunk / RES_SLOTS) & 1) ^ 1);
-              const uint32_t fb = smem_u32(&res_full_bar[slot]);
-              mbar_arrive_expect_tx(fb, RES_SLOT_BYTES);
-              tma_load_2d(smem_u32(res_ring + slot * (RES_SLOT_BYTES / 4)), &tmap_res, n_blk * BN + c * 32, m_blk * BM, fb);
-            }
-            __syncwarp();
-          }
-        }
-      }
-    }
   } else {
     // ================================================================ epilogue (warps 2..9)
     // Per 32-column chunk: (1) issue the global reads of this chunk (fp32 residual / bf16 GELU pre-activation) so their
@@ -473,7 +431,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c >= NC || !rows_live || !chunk_fast(c)) return;
         const int n = n_blk * BN + c * 32 + cc;
-        if (EPI == EPI_F32 && p.residual && !(RES && p.res_tma)) {
+        if (EPI == EPI_F32 && p.residual) {
 #pragma unroll
           for (int ps = 0; ps < 8; ++ps) {
             const float* src = p.residual + (long long)(m_base + ps * 4 + rr) * p.ld_res + n;
@@ -491,13 +449,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       auto process = [&](int c, const float4 (&resv)[8], const uint2 (&auxv)[8], const float4 b4) {
         const int n_chunk = n_blk * BN + c * 32;
         const bool chunk_live = (n_chunk < p.N) && rows_live;  // warp-uniform
-        // residual chunk (it * NC + c) of this CTA's sequence: slot / phase as the producer warp counts them
-        const uint32_t gchunk = (uint32_t)it * NC + (uint32_t)c;
-        const int rslot = gchunk % RES_SLOTS;
-        const bool use_res = RES && p.res_tma;
-        auto res_release = [&]() {
-          if (use_res) { __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&res_empty_bar[rslot])); }
-        };
         if (!waited) {
           mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
           tc_fence_after();
@@ -522,14 +473,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             else                mbar_arrive(smem_u32(&tmem_empty_bar[as]));
           }
         }
-        if (use_res) mbar_wait(smem_u32(&res_full_bar[rslot]), (gchunk / RES_SLOTS) & 1);   // every chunk is loaded, live or not
-        if (!chunk_live) { res_release(); return; }
+        if (!chunk_live) return;
         __syncwarp();
         // coalesced row pass
-        if (chunk_fast(c)) epi_fast_chunk<EPI>(p, stg, m_base, n_chunk + cc, rr, cc, resv, auxv, b4,
-                                               use_res ? res_ring + rslot * (RES_SLOT_BYTES / 4) + lane_grp * 32 * 32 : nullptr);
+        if (chunk_fast(c)) epi_fast_chunk<EPI>(p, stg, m_base, n_chunk + cc, rr, cc, resv, auxv, b4);
         else               epi_generic_chunk(p, stg, m_base, n_chunk + cc, rr, cc);
-        res_release();
         __syncwarp();
       };
       prefetch(half, res0, aux0, bia0);
@@ -594,8 +542,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
 template <int BN, int EPI, int CG>
 static int launch_gemm(const CUtensorMap* tm, GemmKernelParams& p, long long total_work, int max_ctas,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, ResOn<BN, EPI, CG>::value>;
-  if (!ResOn<BN, EPI, CG>::value) p.res_tma = 0;
+  using Cfg = GemmCfg<BN, CG>;
   auto kern = gemm_tcgen05_kernel<BN, EPI, CG>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
@@ -624,7 +571,7 @@ static int launch_gemm(const CUtensorMap* tm, GemmKernelParams& p, long long tot
   }
   const int groups = (int)(total_work < groups_cap ? total_work : groups_cap);
   const int grid = groups * CG;
-  cudaError_t e = launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, stream, CG, tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  cudaError_t e = launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, stream, CG, tm[0], tm[1], tm[2], tm[3], p);
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return VB_OK;
 }
@@ -808,7 +755,7 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   p.drop.thresh = (uint32_t)((double)a->dropout.p * 4294967296.0);
   p.drop.scale = a->dropout.p < 1.f ? 1.f / (1.f - a->dropout.p) : 0.f;
 
-  CUtensorMap tm[5];   // A, B, A_lo, B_lo (the lo maps alias the hi ones when a low part is absent), fp32 residual
+  CUtensorMap tm[4];   // A, B, A_lo, B_lo (the lo maps alias the hi ones when a low part is absent)
   int st;
   for (int i = 0; i < 4; ++i) {
     const bool is_a = (i & 1) == 0;
@@ -825,23 +772,6 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   }
 
   const long long total_work = (long long)p.num_m_groups * num_n * split_k;
-  // fp32 residual through TMA: 128-row x 32-column boxes, no swizzle (dense 128-byte rows in shared memory)
-  p.res_tma = 0;
-  tm[4] = tm[0];
-  {
-    static const bool res_tma_off = getenv("VB_GEMM_RES_TMA") && getenv("VB_GEMM_RES_TMA")[0] == '0';   // development switch
-    if (a->residual && !res_tma_off && split_k == 1 && aligned(a->residual, 16) && (a->ld_res % 4 == 0)) {
-      PFN_encodeTiled enc = get_encode_fn();
-      cuuint64_t dims[2] = {(cuuint64_t)a->N, (cuuint64_t)a->M};
-      cuuint64_t strides[1] = {(cuuint64_t)a->ld_res * 4};
-      cuuint32_t box[2] = {32, 128};
-      cuuint32_t estr[2] = {1, 1};
-      if (enc && enc(&tm[4], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->residual), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-        p.res_tma = 1;
-    }
-  }
-
   // pick the epilogue specialisation; anything unusual runs the generic one
   int epi = EPI_GENERIC;
   const bool no_extra = !a->out_colsum;
@@ -854,6 +784,8 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
     }
   } else if (a->act == VB_ACT_DGELU) {
     if (a->out_bf16 && !a->out_f32 && !a->residual && !a->bias && !has_drop) { epi = EPI_DGELU; p.fast_ok = p.vec_bf16 && p.vec_aux; }
+  } else if (a->act == VB_ACT_RELU) {
+    if (a->out_f32 && no_extra && !a->residual && !has_drop) { epi = EPI_F32; p.fast_ok = !a->out_bf16 || p.vec_bf16; }   // poolers: fp32 + operand copy
   } else if (a->act == VB_ACT_NONE) {
     if (a->out_f32 && !a->out_bf16 && no_extra) { epi = EPI_F32; p.fast_ok = 1; }   // unaligned pitches use 32-bit accesses
     else if (a->out_bf16 && !a->out_f32 && !a->residual && no_extra && !has_drop) { epi = EPI_BF16; p.fast_ok = p.vec_bf16; }

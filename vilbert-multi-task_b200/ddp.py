@@ -43,6 +43,17 @@ class FlatGradAllReducer:
         t.div_(self.world)
         return w
 
+    def allreduce_range_sync(self, lo, hi):
+        """flat[lo:hi] averaged over all ranks, enqueued on the CURRENT stream (used under CUDA-graph capture)."""
+        if self.world == 1 or hi <= lo:
+            return
+        t = self.flat[lo:hi]
+        if self.use_avg:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world)
+
     def broadcast_params(self, flat_params, src=0):
         """Rank-`src` parameters to every rank (what apex DDP does at wrap time)."""
         if self.world > 1:

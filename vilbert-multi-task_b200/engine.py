@@ -1248,6 +1248,55 @@ class Plan:
             self.segment_graphs.append(g)
         torch.cuda.synchronize()
 
+    def live_ranges(self, lo, hi):
+        """Sub-ranges of the flat gradient range [lo, hi) that the backward of THIS plan writes (coalesced, 1024-element
+        granularity): parameters whose gradient is identically zero for this plan (heads outside the objective, the never-called
+        q_dense1/2 of BertBiOutput, vilbert.py:834,841) are not exchanged — zeros average to zeros on every rank."""
+        spans = sorted((off, off + n) for (off, n) in self.grad_touch if off + n > lo and off < hi)
+        out = []
+        for a, b in spans:
+            a, b = max(a, lo) // 1024 * 1024, min(-(-min(b, hi) // 1024) * 1024, hi)
+            a = max(a, lo)
+            if out and a <= out[-1][1] + 4096:
+                out[-1][1] = max(out[-1][1], b)
+            else:
+                out.append([a, b])
+        return [(a, b) for a, b in out if b > a]
+
+    def capture_step_ddp(self, allreduce_range, n_segments=8, tail_cut=True, skip_dead=True):
+        """Data-parallel step as ONE CUDA graph: prologue + forward + the backward pieces of ddp_segments, with the all-reduce of
+        each finished gradient range captured on a communication stream inside the same graph (NCCL collectives are capturable),
+        forked after its piece and joined at the end. Compared with capture_segments / run_step_overlapped there is a single
+        graph launch per step and no host-side event bookkeeping between pieces. `allreduce_range(lo, hi)` must enqueue the
+        collective on the current stream (async_op=False semantics)."""
+        self.segments = self.ddp_segments(n_segments, tail_cut=tail_cut)
+        torch.cuda.synchronize()
+        barrier = [(None, ("all",), 0)]
+        g = torch.cuda.CUDAGraph()
+        comm = torch.cuda.Stream(device=self.dev)
+        self._ddp_comm = comm
+        with torch.cuda.graph(g):
+            main = torch.cuda.current_stream()
+            self._run(self.prologue); self._run(self.fwd)
+            for (lo_op, hi_op, lo, hi) in self.segments:
+                self._run(barrier + self.bwd[lo_op:hi_op] + barrier)
+                if hi > lo:
+                    ev = torch.cuda.Event(); ev.record(main)
+                    comm.wait_event(ev)
+                    with torch.cuda.stream(comm):
+                        for (a, b) in (self.live_ranges(lo, hi) if skip_dead else [(lo, hi)]):
+                            allreduce_range(a, b)
+            ev = torch.cuda.Event(); ev.record(comm)
+            main.wait_event(ev)
+            self._run(self.epilogue)
+        self.graph_step_ddp = g
+        torch.cuda.synchronize()
+
+    def run_step_ddp(self):
+        self.fwd_id += 1
+        self.e.grad_clean = False
+        self.graph_step_ddp.replay()
+
     def run_step_overlapped(self, allreduce_range, comm_stream):
         """Replays the segment graphs; after each one the finished tail range of the flat gradient buffer is handed to
         `allreduce_range(lo, hi)` (issued under `comm_stream`, which first waits for that segment) so the collective
