@@ -164,13 +164,20 @@ def attn_case(B, H, Nq, Nk, D, cross, peaked=1.0, iters=0, seed=0, fp16=False, s
     L.check(lib.vb_attention_fwd(C.byref(a), stream()), "vb_attention_fwd")
     L.check(lib.vb_attention_bwd(C.byref(a), stream()), "vb_attention_bwd")
     torch.cuda.synchronize()
-    qf = q.float().view(B, Nq, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
-    kf = k.float().view(B, Nk, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
-    vf = v.float().view(B, Nk, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
-    s = qf @ kf.transpose(-1, -2) / math.sqrt(D) + mask[:, None, None, :]
-    p = torch.softmax(s, -1)
-    o = (p @ vf).permute(0, 2, 1, 3).reshape(B * Nq, Hd)
-    o.backward(dO.float())
+    def ref(qq, kk, vv):
+        qf = qq.float().view(B, Nq, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
+        kf = kk.float().view(B, Nk, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
+        vf = vv.float().view(B, Nk, H, D).permute(0, 2, 1, 3).detach().requires_grad_(True)
+        s = qf @ kf.transpose(-1, -2) / math.sqrt(D) + mask[:, None, None, :]
+        p = torch.softmax(s, -1)
+        o = (p @ vf).permute(0, 2, 1, 3).reshape(B * Nq, Hd)
+        o.backward(dO.float())
+        return qf, kf, vf, s, o.detach()
+    qf, kf, vf, s, o = ref(q, k, v)
+    if fp16:
+        # the backward kernels contract in bf16 (dO / dS are bf16 operands): their Q / K / V panels are the fp16 values rounded to
+        # bf16, so the gradient reference is the attention of those rounded inputs; the forward reference keeps the fp16 values
+        qf, kf, vf, _, _ = ref(q.to(BF), k.to(BF), v.to(BF))
     if split:
         # forward against the fp32 (hi + lo) inputs; the backward of split precision contracts the hi parts only
         qs = q32[:, :Hd].view(B, Nq, H, D).permute(0, 2, 1, 3); ks = k32[:, Hd:2 * Hd].view(B, Nk, H, D).permute(0, 2, 1, 3)

@@ -30,13 +30,14 @@ def test_attention_fwd_bwd(B, H, Nq, Nk, D, cross):
     (4, 8, 100, 36, 128, True), (2, 8, 257, 306, 128, True), (2, 2, 7, 12, 16, True)])
 def test_attention_fp16_operands(B, H, Nq, Nk, D, cross):
     """The engine's default arithmetic: Q/K/V/O fp16 (forward operands), dO/dQ/dK/dV bf16. The forward is checked at fp16
-    accuracy; the backward converts its Q/K/V panels to bf16 (dS and dO are bf16 MMA operands): 4e-2 of max|ref| (measured
-    2.8e-2 worst on dK at 100 x 100 x 128; whole-model gradient parity is bounded in tests/test_model_gpu.py)."""
+    accuracy; the backward converts its Q/K/V panels to bf16 (dS and dO are bf16 MMA operands); whole-model gradient parity is
+    bounded in tests/test_model_gpu.py."""
     from _gpu_util import attn_case
     errs, _ = attn_case(B, H, Nq, Nk, D, cross, fp16=True)
     assert errs["lse"] < 1e-5 and errs["O"] < 2e-3 and errs["O_b16"] < 1e-3, errs
-    # the reference differentiates through the fp16 values; the kernel rounds Q / K / V to bf16 for its backward products
-    assert max(errs.values()) < 4e-2, errs
+    # gradients vs the attention of the bf16-rounded inputs (what the backward kernels contract); the saved row log-sum-exp comes
+    # from the fp16 forward, so the recomputed probabilities differ from the reference's by the bf16 rounding of the scores
+    assert max(errs.values()) < 3e-2, errs
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk,D,cross", [

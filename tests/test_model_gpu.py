@@ -117,7 +117,7 @@ def test_peaked_attention_tiny(golden_dir):
     (error ~ |S| * 2^-11); still inside the 1e-2 contract in the default precision and 1e-3 in split precision."""
     from _gpu_util import model_case
     _check(model_case(_cfg(golden_dir, "tiny_b4"), 2, 37, 21, seed=2, qk_scale=8.0))
-    _check(model_case(_cfg(golden_dir, "tiny_b4"), 2, 37, 21, seed=2, qk_scale=8.0, precision="fp32", grads=False), "fp32")
+    _check(model_case(_cfg(golden_dir, "tiny_b4"), 2, 37, 21, seed=2, qk_scale=8.0, precision="fp32", grads=False, oracle_modes=("fp32",)), "fp32", modes=("fp32",))
 
 
 def test_vqa_only_gradient_set_skips_dead_heads(golden_dir):
@@ -141,8 +141,8 @@ def test_base_2layer_2conect_config1(golden_dir):
     _check(r, modes=("op",), grad_worst=3e-2, grad_median=1.5e-2)
     for n, e in r["out_fp32"].items():
         assert e < 1e-2, ("fp32-oracle output", n, e)
-    r = model_case(_cfg(golden_dir, "base_2layer_2conect_cfg1"), 2, 36, 20, precision="fp32", grads=False)
-    _check(r, "fp32")
+    r = model_case(_cfg(golden_dir, "base_2layer_2conect_cfg1"), 2, 36, 20, precision="fp32", grads=False, oracle_modes=("fp32",))
+    _check(r, "fp32", modes=("fp32",))
 
 
 @pytest.mark.parametrize("precision", ["fp16", "fp32"])
@@ -195,8 +195,10 @@ def test_config3_pretraining_objective_fused_losses(golden_dir):
     ref = lt + lv + ln
     ref.backward()
     assert abs(plan.loss.item() - ref.item()) < 2e-3 * abs(ref.item()), (plan.loss.item(), ref.item())
-    l2 = sorted((rel_l2(eng.ps.g(k), Pg[k].grad), k) for k in eng.ps.entries if Pg[k].grad is not None and Pg[k].grad.abs().max() > 0)
-    assert l2[-1][0] < 3e-2 and l2[len(l2) // 2][0] < 1e-2, l2[-3:]
+    # tensors whose exact gradient is ~0 (key biases: softmax shift invariance) are excluded by a floor of 1e-3 of the largest gradient
+    gmax = max(v.grad.abs().max().item() for v in Pg.values() if v.grad is not None)
+    l2 = sorted((rel_l2(eng.ps.g(k), Pg[k].grad), k) for k in eng.ps.entries if Pg[k].grad is not None and Pg[k].grad.abs().max().item() > 1e-3 * gmax)
+    assert len(l2) > 100 and l2[-1][0] < 3e-2 and l2[len(l2) // 2][0] < 1e-2, l2[-3:]
 
 
 def test_module_surface_autograd_and_state_dict(golden_dir):

@@ -703,9 +703,16 @@ static int launch_att(Kern kern, dim3 grid, size_t smem, const AttnParams& p, cu
 
 }  // namespace vb
 
+namespace vb {
+// tcgen05 / TMEM / TMA forward for Nq, Nk <= 128 and head dim 64 / 128 (vb_attn_tc.cu)
+bool attn_fwd_tc_eligible(const vb_attn_args* a);
+int attn_fwd_tc_launch(const vb_attn_args* a, cudaStream_t st);
+}  // namespace vb
+
 extern "C" vb_status vb_attention_fwd(const vb_attn_args* a, void* stream) {
   using namespace vb;
   if (int s = validate(a, false)) return s;
+  if (attn_fwd_tc_eligible(a)) return attn_fwd_tc_launch(a, (cudaStream_t)stream);
   const AttnParams p = to_params(a);
   const int nkp = (a->Nk + KB - 1) / KB * KB;
   const bool split = a->Q_lo || a->K_lo || a->V_lo;

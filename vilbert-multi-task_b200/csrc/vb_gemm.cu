@@ -153,8 +153,11 @@ __device__ __noinline__ void epi_generic_chunk(const GemmKernelParams& p, const 
   }
 }
 
-// 4 consecutive values -> out_bf16 (bf16 or fp16 per p.out_fp16) and, in split precision, their low parts -> out_lo
-__device__ __forceinline__ void store16x4(const GemmKernelParams& p, long long off, float v0, float v1, float v2, float v3) {
+// 16-bit output variants of the specialised epilogues (template parameter OUT16; kept out of line / out of the kernels that do
+// not need them: the fast paths are 8x unrolled and the epilogue time follows the instruction footprint, see the note above):
+//   0 = bf16 (gradient operands, bf16 precision)   1 = fp16 (forward operands)   2 = fp16 + an always-bf16 copy (forward
+//   operands the backward's weight-gradient GEMM reads).  Split precision (out_lo) takes the shared slow path.
+__device__ __noinline__ void store16x4_slow(const GemmKernelParams& p, long long off, float v0, float v1, float v2, float v3) {
   if (p.out_lo) {
     uint32_t l01, l23;
     const uint32_t h01 = pack16_split(v0, v1, p.out_fp16, l01), h23 = pack16_split(v2, v3, p.out_fp16, l23);
@@ -165,8 +168,32 @@ __device__ __forceinline__ void store16x4(const GemmKernelParams& p, long long o
   }
   if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
 }
+template <int OUT16>
+__device__ __forceinline__ void store16x4(const GemmKernelParams& p, long long off, float v0, float v1, float v2, float v3) {
+  if (OUT16 == 0) {
+    *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+  } else {
+    *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_f16(v0, v1), pack_f16(v2, v3));
+    if (OUT16 == 2) *reinterpret_cast<uint2*>(p.out_b16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+  }
+}
 
-template <int EPI>
+// Poolers (vilbert.py:1116-1122, 1131-1137): relu(acc + bias) -> fp32 and a 16-bit operand copy. Two tiny launches per step: one
+// compact out-of-line routine selected per chunk inside the F32 kernel, so that kernel's unrolled fast path stays as small as it was.
+__device__ __noinline__ void epi_pool_chunk(const GemmKernelParams& p, const float* stg, int m_base, int n, int rr, int cc, const float4 b4) {
+#pragma unroll 1
+  for (int ps = 0; ps < 8; ++ps) {
+    const int row = ps * 4 + rr;
+    const long long m = m_base + row;
+    const float4 a4 = *reinterpret_cast<const float4*>(stg + stg_off(row, cc));
+    const float v0 = fmaxf(fmaf(a4.x, p.alpha, b4.x), 0.f), v1 = fmaxf(fmaf(a4.y, p.alpha, b4.y), 0.f);
+    const float v2 = fmaxf(fmaf(a4.z, p.alpha, b4.z), 0.f), v3 = fmaxf(fmaf(a4.w, p.alpha, b4.w), 0.f);
+    *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_of + n) = make_float4(v0, v1, v2, v3);
+    if (p.out_bf16) store16x4_slow(p, m * p.ld_ob + n, v0, v1, v2, v3);
+  }
+}
+
+template <int EPI, int OUT16>
 __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const float* stg, int m_base, int n, int rr, int cc,
                                                const float4 (&resv)[8], const uint2 (&auxv)[8], const float4 b4) {
   float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
@@ -182,15 +209,14 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
       gelu_erf_and_grad(v0, v0, d0); gelu_erf_and_grad(v1, v1, d1); gelu_erf_and_grad(v2, v2, d2); gelu_erf_and_grad(v3, v3, d3);
       *reinterpret_cast<uint2*>(p.out_pre + m * p.ld_op + n) = make_uint2(pack_bf16(d0, d1), pack_bf16(d2, d3));   // gelu'(pre) for backward
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_of + n) = make_float4(v0, v1, v2, v3);
-      if (p.out_bf16) store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);
+      if (p.out_bf16) store16x4<OUT16>(p, m * p.ld_ob + n, v0, v1, v2, v3);
     } else if (EPI == EPI_DGELU) {
       const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].x));
       const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&auxv[ps].y));
       v0 *= x01.x; v1 *= x01.y; v2 *= x23.x; v3 *= x23.y;   // aux = gelu'(pre) saved by the forward epilogue
       cs0 += v0; cs1 += v1; cs2 += v2; cs3 += v3;
-      store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);
+      store16x4<0>(p, m * p.ld_ob + n, v0, v1, v2, v3);   // a gradient operand: always bf16
     } else if (EPI == EPI_F32) {
-      if (p.act == VB_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }   // poolers
       if (p.drop.ctr) {   // LN(dropout(dense(x)) + residual): mask the dense output, element index m*N + n
         const uint32_t e0 = (uint32_t)(m * p.N + n);
         v0 = drop_apply(v0, dseed, e0, p.drop); v1 = drop_apply(v1, dseed, e0 + 1, p.drop);
@@ -203,9 +229,8 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
       } else {   // row pitch not a multiple of 4 floats (30522-/1601-/3129-wide logits): same bytes, 32-bit stores
         dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
       }
-      if (p.out_bf16) store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);   // operand copy next to the fp32 value (poolers)
     } else if (EPI == EPI_BF16) {
-      store16x4(p, m * p.ld_ob + n, v0, v1, v2, v3);
+      store16x4<OUT16>(p, m * p.ld_ob + n, v0, v1, v2, v3);
     } else if (EPI == EPI_ATOMIC) {
       asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p.out_f32 + m * p.ld_of + n), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
     }
@@ -223,7 +248,7 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmKernelParams& p, const 
   }
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int OUT16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
@@ -301,49 +326,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int n_blk = t2 / p.num_m_groups;
       const int kb0 = split * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+      // loads of one (real) k-block from the given tensor maps. Single-pass launches call it with the kernel's own
+      // __grid_constant__ maps (compile-time parameter addresses, as in round 1); split precision selects hi / lo maps per pass.
+      auto issue_loads = [&](const CUtensorMap* tma_a, const CUtensorMap* tma_b, int kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        if constexpr (!pair) {
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+          if (p.a_mn) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), tma_a, m_blk * BM + j * 64, kb * BK, fb);
+          } else {
+            tma_load_2d(sa, tma_a, kb * BK, m_blk * BM, fb);
+          }
+          if (p.b_mn) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), tma_b, n_blk * BN + j * 64, kb * BK, fb);
+          } else {
+            tma_load_2d(sb, tma_b, kb * BK, n_blk * BN, fb);
+          }
+        } else {
+          // both CTAs complete their bytes on the LEADER's full barrier (the leader issues the MMAs for the pair);
+          // this CTA stages its 128 rows of A and columns [crank * BN/2, +BN/2) of the B tile
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
+          if (p.a_mn) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * (BK * 128), tma_a, m_blk * BM + j * 64, kb * BK, fb);
+          } else {
+            tma_load_2d_pair(sa, tma_a, kb * BK, m_blk * BM, fb);
+          }
+          const int n0 = n_blk * BN + crank * (BN / 2);
+          if (p.b_mn) {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * (BK * 128), tma_b, n0 + j * 64, kb * BK, fb);
+          } else {
+            tma_load_2d_pair(sb, tma_b, kb * BK, n0, fb);   // tensor-map box = BN/2 rows
+          }
+        }
+      };
       for (int kbv = kb0; kbv < kb1; ++kbv) {
         if (elect_one()) {
-          // virtual k-block -> (pass, real k-block): split precision walks K once per pass with the hi / lo tensor maps
-          int kb = kbv, sel = 0;
-          if (p.npass > 1) { const int ps = kbv / p.real_k_blocks; kb = kbv - ps * p.real_k_blocks; sel = p.pass_sel[ps]; }
-          const CUtensorMap* tma_a = (sel & 1) ? &tmap_a_lo : &tmap_a;
-          const CUtensorMap* tma_b = (sel & 2) ? &tmap_b_lo : &tmap_b;
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-          if constexpr (!pair) {
-            const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-            if (p.a_mn) {
-#pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), tma_a, m_blk * BM + j * 64, kb * BK, fb);
-            } else {
-              tma_load_2d(sa, tma_a, kb * BK, m_blk * BM, fb);
-            }
-            if (p.b_mn) {
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), tma_b, n_blk * BN + j * 64, kb * BK, fb);
-            } else {
-              tma_load_2d(sb, tma_b, kb * BK, n_blk * BN, fb);
-            }
+          if (p.npass == 1) {
+            issue_loads(&tmap_a, &tmap_b, kbv);
           } else {
-            // both CTAs complete their bytes on the LEADER's full barrier (the leader issues the MMAs for the pair);
-            // this CTA stages its 128 rows of A and columns [crank * BN/2, +BN/2) of the B tile
-            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
-            if (p.a_mn) {
-#pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * (BK * 128), tma_a, m_blk * BM + j * 64, kb * BK, fb);
-            } else {
-              tma_load_2d_pair(sa, tma_a, kb * BK, m_blk * BM, fb);
-            }
-            const int n0 = n_blk * BN + crank * (BN / 2);
-            if (p.b_mn) {
-#pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * (BK * 128), tma_b, n0 + j * 64, kb * BK, fb);
-            } else {
-              tma_load_2d_pair(sb, tma_b, kb * BK, n0, fb);   // tensor-map box = BN/2 rows
-            }
+            // virtual k-block -> (pass, real k-block): split precision walks K once per pass with the hi / lo tensor maps
+            const int ps = kbv / p.real_k_blocks;
+            const int sel = p.pass_sel[ps];
+            issue_loads((sel & 1) ? &tmap_a_lo : &tmap_a, (sel & 2) ? &tmap_b_lo : &tmap_b, kbv - ps * p.real_k_blocks);
           }
           if (kbv == kb0 && w == group) VB_DBG(2);
         }
@@ -476,7 +508,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (!chunk_live) return;
         __syncwarp();
         // coalesced row pass
-        if (chunk_fast(c)) epi_fast_chunk<EPI>(p, stg, m_base, n_chunk + cc, rr, cc, resv, auxv, b4);
+        if (EPI == EPI_F32 && p.act == VB_ACT_RELU && chunk_fast(c)) epi_pool_chunk(p, stg, m_base, n_chunk + cc, rr, cc, b4);
+        else if (chunk_fast(c)) epi_fast_chunk<EPI, OUT16>(p, stg, m_base, n_chunk + cc, rr, cc, resv, auxv, b4);
         else               epi_generic_chunk(p, stg, m_base, n_chunk + cc, rr, cc);
         __syncwarp();
       };
@@ -539,11 +572,11 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
   return VB_OK;
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int OUT16 = 0>
 static int launch_gemm(const CUtensorMap* tm, GemmKernelParams& p, long long total_work, int max_ctas,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
-  auto kern = gemm_tcgen05_kernel<BN, EPI, CG>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, CG, OUT16>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -577,12 +610,18 @@ static int launch_gemm(const CUtensorMap* tm, GemmKernelParams& p, long long tot
 }
 
 template <int BN, int CG>
-static int launch_gemm_epi(int epi, const CUtensorMap* tm, GemmKernelParams& p, long long work, int max_ctas,
+static int launch_gemm_epi(int epi, int out16, const CUtensorMap* tm, GemmKernelParams& p, long long work, int max_ctas,
                            cudaStream_t stream) {
   switch (epi) {
     case EPI_F32: return launch_gemm<BN, EPI_F32, CG>(tm, p, work, max_ctas, stream);
-    case EPI_BF16: return launch_gemm<BN, EPI_BF16, CG>(tm, p, work, max_ctas, stream);
-    case EPI_GELU: return launch_gemm<BN, EPI_GELU, CG>(tm, p, work, max_ctas, stream);
+    case EPI_BF16:
+      if (out16 == 1) return launch_gemm<BN, EPI_BF16, CG, 1>(tm, p, work, max_ctas, stream);
+      if (out16 == 2) return launch_gemm<BN, EPI_BF16, CG, 2>(tm, p, work, max_ctas, stream);
+      return launch_gemm<BN, EPI_BF16, CG, 0>(tm, p, work, max_ctas, stream);
+    case EPI_GELU:
+      if (out16 == 1) return launch_gemm<BN, EPI_GELU, CG, 1>(tm, p, work, max_ctas, stream);
+      if (out16 == 2) return launch_gemm<BN, EPI_GELU, CG, 2>(tm, p, work, max_ctas, stream);
+      return launch_gemm<BN, EPI_GELU, CG, 0>(tm, p, work, max_ctas, stream);
     case EPI_DGELU: return launch_gemm<BN, EPI_DGELU, CG>(tm, p, work, max_ctas, stream);
     case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC, CG>(tm, p, work, max_ctas, stream);
     default: return launch_gemm<BN, EPI_GENERIC, CG>(tm, p, work, max_ctas, stream);
@@ -785,17 +824,25 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   } else if (a->act == VB_ACT_DGELU) {
     if (a->out_bf16 && !a->out_f32 && !a->residual && !a->bias && !has_drop) { epi = EPI_DGELU; p.fast_ok = p.vec_bf16 && p.vec_aux; }
   } else if (a->act == VB_ACT_RELU) {
-    if (a->out_f32 && no_extra && !a->residual && !has_drop) { epi = EPI_F32; p.fast_ok = !a->out_bf16 || p.vec_bf16; }   // poolers: fp32 + operand copy
+    if (a->out_f32 && no_extra && !a->residual && !has_drop) { epi = EPI_F32; p.fast_ok = p.vec_f32 && (!a->out_bf16 || p.vec_bf16); }   // poolers: fp32 + operand copy
   } else if (a->act == VB_ACT_NONE) {
     if (a->out_f32 && !a->out_bf16 && no_extra) { epi = EPI_F32; p.fast_ok = 1; }   // unaligned pitches use 32-bit accesses
     else if (a->out_bf16 && !a->out_f32 && !a->residual && no_extra && !has_drop) { epi = EPI_BF16; p.fast_ok = p.vec_bf16; }
   }
-  if (cluster == 2) {
-    if (bn == 256) return launch_gemm_epi<256, 2>(epi, tm, p, total_work, max_ctas, stream);
-    return launch_gemm_epi<128, 2>(epi, tm, p, total_work, max_ctas, stream);
+  // 16-bit output variant of the BF16 / GELU specialisations; split precision (out_lo) and other combinations run the generic epilogue
+  int out16 = 0;
+  if (epi == EPI_BF16 || epi == EPI_GELU) {
+    if (a->out_lo || (a->out_b16 && !a->out_fp16)) epi = EPI_GENERIC;
+    else out16 = a->out_fp16 ? (a->out_b16 ? 2 : 1) : 0;
+  } else if (epi == EPI_DGELU && (a->out_fp16 || a->out_lo || a->out_b16)) {
+    epi = EPI_GENERIC;
   }
-  if (bn == 256) return launch_gemm_epi<256, 1>(epi, tm, p, total_work, max_ctas, stream);
-  return launch_gemm_epi<128, 1>(epi, tm, p, total_work, max_ctas, stream);
+  if (cluster == 2) {
+    if (bn == 256) return launch_gemm_epi<256, 2>(epi, out16, tm, p, total_work, max_ctas, stream);
+    return launch_gemm_epi<128, 2>(epi, out16, tm, p, total_work, max_ctas, stream);
+  }
+  if (bn == 256) return launch_gemm_epi<256, 1>(epi, out16, tm, p, total_work, max_ctas, stream);
+  return launch_gemm_epi<128, 1>(epi, out16, tm, p, total_work, max_ctas, stream);
 }
 
 extern "C" vb_status vb_gemm_plan(const vb_gemm_args* a, int32_t sm_count_, int32_t* block_n, int32_t* cluster_m, int32_t* split_k) {

@@ -275,6 +275,7 @@ class Plan:
         self._bwd_emitters = []
         self.n_kernels_fwd = self.n_kernels_bwd = 0
         self.graph_fwd = self.graph_bwd = self.graph_step = None
+        self._eager_runs = [0, 0]      # eager forward / backward executions (maybe_capture_passes)
         self._build()
 
     # ------------------------------------------------------------------ infrastructure
@@ -1096,6 +1097,7 @@ class Plan:
             self.graph_fwd.replay()
         else:
             self._run(self.fwd)
+            self._eager_runs[0] += 1
 
     def run_backward(self):
         self.e.grad_clean = False
@@ -1103,6 +1105,24 @@ class Plan:
             self.graph_bwd.replay()
         else:
             self._run(self.bwd)
+            self._eager_runs[1] += 1
+
+    def maybe_capture_passes(self, after=2):
+        """Module-surface path: once a pass of this plan has run eagerly `after` times (kernels loaded, attributes set), capture
+        it into its own CUDA graph — without a warm-up run, which would accumulate into the gradient buffer — so that the
+        ~600 ctypes launches of a step become two graph replays."""
+        if self.graph_fwd is None and self._eager_runs[0] >= after:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run(self.fwd)
+            self.graph_fwd = g
+        if self.graph_bwd is None and self._eager_runs[1] >= after:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run(self.bwd)
+            self.graph_bwd = g
 
     def enable_training_prologue(self, zero_grad=True, refresh_weights=True):
         """Makes run_step a complete training-step body: bump the dropout step counter (train mode), zero the flat
@@ -1372,6 +1392,7 @@ class Engine:
         self.shadow_trusted = False      # True while the engine's own fused optimizer is the only writer of the parameters
         self.grad_clean = False          # the flat gradient buffer is all zeros (set by zero_grad / the fused optimizer)
         self.loss_options = 4            # answer options per question of the VL-logit objective (retrieval / VCR: 4)
+        self.auto_graph = True           # module surface: capture a plan's passes into CUDA graphs after two eager runs
 
     def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False, loss=None):
         loss = "vqa" if vqa_loss else loss

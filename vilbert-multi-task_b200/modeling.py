@@ -95,6 +95,8 @@ class _EngineFn(torch.autograd.Function):
         if train:
             model.engine.bump_dropout_step()      # fresh nn.Dropout masks for this forward
         plan.load_inputs(**inputs)
+        if model.engine.auto_graph:
+            plan.maybe_capture_passes()
         plan.run_forward()
         ctx.model, ctx.names, ctx.inputs, ctx.plan, ctx.fwd_id, ctx.train = model, names, inputs, plan, plan.fwd_id, train
         ctx.drop_step = int(model.engine.drop_step_host)     # the masks this forward used (needed if it has to be recomputed)
@@ -122,6 +124,8 @@ class _EngineFn(torch.autograd.Function):
                 else:
                     plan.run_forward()
             model._attach_grads()
+            if model.engine.auto_graph:
+                plan.maybe_capture_passes()
             for n, g in zip(names, grads):
                 if g is not None:
                     plan.gout[n].copy_(g.reshape(plan.gout[n].shape))
