@@ -277,6 +277,10 @@ vb_status vb_kl_masked_loss(const float* scores, const float* target, const int6
  * extension, :1331-1334). */
 vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_t B, int32_t N, int32_t prepend_one, void* stream);
 
+/* dst[r] = src for r < repeats (`bytes` each, multiple of 16): BertEncoder's FAST_MODE (vilbert.py:1042-1053) — the text stream
+ * of ONE caption, computed at batch 1 up to the first connection layer, broadcast to the image batch (txt_embedding.expand). */
+vb_status vb_broadcast_rows(const void* src, void* dst, int64_t bytes, int32_t repeats, void* stream);
+
 /* step += 1 on the device (the dropout step counter; one launch per training step, capturable in a CUDA graph). */
 vb_status vb_step_counter_bump(uint32_t* step, void* stream);
 

@@ -165,6 +165,28 @@ def check_all_encoded_layers(ref, cfg_json):
     assert len(r[0]) == len(o[0]) and max(errs) < TOL
 
 
+def check_fast_mode(ref, cfg_json):
+    """fast_mode=True (eval_retrieval.py): text batch 1 broadcast to the image batch at the first connection layer."""
+    cfgj = dict(cfg_json, fast_mode=True)
+    cfg = O.make_config(cfgj)
+    model = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfgj)), num_labels=1, default_gpu=False)
+    P = O.synth_params(cfg, seed=0)
+    model.load_state_dict(P, strict=False); model.tie_weights(); model.eval()
+    inp = O.synth_inputs(cfg, 5, 11, 9, seed=4321)
+    txt = (inp["input_txt"][:1], inp["token_type_ids"][:1], inp["attention_mask"][:1])
+    with torch.no_grad():
+        r = model(txt[0], inp["input_imgs"], inp["image_loc"], txt[1], txt[2], inp["image_attention_mask"], inp["co_attention_mask"][:1])[:9]
+        _, o = O.vilbert_for_vl_tasks(P, cfg, txt[0], inp["input_imgs"], inp["image_loc"], txt[1], txt[2], inp["image_attention_mask"])
+    errs = [rel(a, b) for a, b in zip(o, r)]
+    print(f"{'fast_mode':28s} worst {max(errs):.2e}")
+    assert max(errs) < TOL and tuple(o[0].shape) == (5, 3129)
+    gold = dict(name="tiny_fast_mode", config=cfgj, B=5, Nv=11, Nt=9, seed=0, input_seed=4321,
+                outputs={n: dict(summary(a), shape=list(a.shape)) for n, a in zip(O.HEAD_NAMES, r)},
+                pin=dict(worst_output_rel=max(errs), tolerance=TOL))
+    with open(os.path.join(GOLD, "tiny_fast_mode.json"), "w") as f:
+        json.dump(gold, f)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
@@ -179,6 +201,7 @@ def main():
     run_case(ref, "base_6layer_6conect_tasktok", base66, B=2, Nv=101, Nt=23, task_tokens=True, grads=False, seed=1)
     run_pretraining_case(ref, "tiny_pretraining_losses", TINY, B=4, Nv=9, Nt=8)
     check_all_encoded_layers(ref, TINY)
+    check_fast_mode(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

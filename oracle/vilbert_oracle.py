@@ -188,6 +188,11 @@ def encoder(P, pre, cfg, t, v, mask_t, mask_v, drop=None):
             t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t, drop)
         for i in range(v_start, v_end):
             v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
+        if count == 0 and cfg.get("fast_mode"):
+            # FAST_MODE (vilbert.py:1042-1053): one caption against a batch of images — the text stream, computed once at batch 1
+            # up to the first connection layer, is broadcast to the image batch from there on
+            t = t.expand(v.shape[0], t.shape[1], t.shape[2])
+            mask_t = mask_t.expand(v.shape[0], mask_t.shape[1], mask_t.shape[2], mask_t.shape[3])
         if cfg["with_coattention"]:
             v, t = connection_layer(P, f"{pre}.c_layer.{count}", cfg, v, mask_v, t, mask_t, drop)
         v_start, t_start = v_end, t_end

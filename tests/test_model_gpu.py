@@ -120,6 +120,38 @@ def test_peaked_attention_tiny(golden_dir):
     _check(model_case(_cfg(golden_dir, "tiny_b4"), 2, 37, 21, seed=2, qk_scale=8.0, precision="fp32", grads=False, oracle_modes=("fp32",)), "fp32", modes=("fp32",))
 
 
+@pytest.mark.parametrize("task,Nt", [(False, 12), (True, 9)])
+def test_fast_mode_text_broadcast(golden_dir, task, Nt):
+    """config.fast_mode (BertEncoder FAST_MODE, vilbert.py:1042-1053; eval_retrieval.py): ONE caption (text batch 1) scored against
+    a batch of images — the text stream runs at batch 1 up to the first connection layer and is broadcast from there. All 13
+    outputs vs the oracle (pinned bit-exact against the reference for this path: tests/golden/tiny_fast_mode.json), through the
+    engine and through the module surface; it is an inference path (train mode / gradients are refused)."""
+    import vilbert_b200
+    from _gpu_util import build_engine, rel
+    cfgj = dict(_cfg(golden_dir, "tiny_b4"), fast_mode=True, task_specific_tokens=task)
+    cfg = O.make_config(cfgj)
+    B, Nv = 6, 33
+    P = O.synth_params(cfg, seed=0, device="cuda")
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=4321, device="cuda", task_id=3 if task else None)
+    txt = dict(input_txt=inp["input_txt"][:1], token_type_ids=inp["token_type_ids"][:1], attention_mask=inp["attention_mask"][:1],
+               task_ids=inp["task_ids"][:1] if task else None)
+    bert_o, heads_o = O.vilbert_for_vl_tasks(P, cfg, txt["input_txt"], inp["input_imgs"], inp["image_loc"], txt["token_type_ids"], txt["attention_mask"],
+                                             inp["image_attention_mask"], None, txt["task_ids"])
+    eng = build_engine(cfgj, P, "cuda")
+    plan = eng.plan(B, Nt, Nv)
+    plan.load_inputs(txt["input_txt"], inp["input_imgs"], inp["image_loc"], txt["token_type_ids"], txt["attention_mask"], inp["image_attention_mask"],
+                     task_ids=txt["task_ids"])
+    plan.run_forward(); torch.cuda.synchronize()
+    for n, r in list(zip(O.BERT_OUT_NAMES, bert_o)) + list(zip(O.HEAD_NAMES, heads_o)):
+        assert tuple(plan.outputs[n].shape) == tuple(r.shape) and rel(plan.outputs[n], r) < 1e-2, n
+    with pytest.raises(ValueError):
+        eng.plan(B, Nt, Nv, train=True)
+    model = vilbert_b200.VILBertForVLTasks(vilbert_b200.BertConfig.from_dict(cfgj), num_labels=1)
+    model.load_state_dict(P, strict=True); model.eval()
+    out = model(txt["input_txt"], inp["input_imgs"], inp["image_loc"], txt["token_type_ids"], txt["attention_mask"], inp["image_attention_mask"], None, txt["task_ids"])
+    assert tuple(out[2].shape) == (B, 1) and rel(out[2], heads_o[2]) < 1e-2     # vil_logit: the retrieval score of each image
+
+
 def test_vqa_only_gradient_set_skips_dead_heads(golden_dir):
     from _gpu_util import model_case
     r = model_case(_cfg(golden_dir, "tiny_b4"), 4, 11, 9, names=("vil_prediction",))

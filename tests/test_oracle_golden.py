@@ -94,3 +94,22 @@ def test_param_inventory_matches_reference_names(golden_dir):
         assert list(shapes[k]) == s["shape"], k
     n = sum(int(torch.tensor(v).prod()) for k, v in shapes.items() if k != "cls.predictions.decoder.weight")
     assert abs(n / 1e6 - 268.0) < 0.1   # 268.0 M parameters for base-6-6
+
+
+def test_fast_mode_golden(golden_dir):
+    """config.fast_mode (text batch 1 broadcast to the image batch at the first connection layer, vilbert.py:1042-1053): sampled
+    values and norms of the nine head outputs recorded from the reference (oracle/make_golden.py::check_fast_mode)."""
+    meta = json.load(open(os.path.join(golden_dir, "tiny_fast_mode.json")))
+    cfg = O.make_config(meta["config"])
+    P = O.synth_params(cfg, seed=meta["seed"])
+    inp = O.synth_inputs(cfg, meta["B"], meta["Nv"], meta["Nt"], seed=meta["input_seed"])
+    with torch.no_grad():
+        _, heads = O.vilbert_for_vl_tasks(P, cfg, inp["input_txt"][:1], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"][:1],
+                                          inp["attention_mask"][:1], inp["image_attention_mask"])
+    for k, t in zip(O.HEAD_NAMES, heads):
+        s = meta["outputs"][k]
+        t = t.detach().double().flatten()
+        assert list(heads[O.HEAD_NAMES.index(k)].shape) == s["shape"], k
+        got = t[torch.tensor(s["sample_idx"])]
+        assert (got - torch.tensor(s["samples"], dtype=torch.float64)).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), k
+        assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k

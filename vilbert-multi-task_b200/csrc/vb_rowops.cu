@@ -527,6 +527,13 @@ __global__ void mask_to_additive_kernel(const long long* __restrict__ m, float* 
   }
 }
 
+// dst[r][i] = src[i] for r < repeats (16-byte words): FAST_MODE broadcast of the batch-1 text stream to the image batch
+__global__ void broadcast_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16, int repeats) {
+  pdl_entry();
+  const long long total = n16 * repeats;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i % n16];
+}
+
 __global__ void step_bump_kernel(uint32_t* ctr) {
   pdl_entry();
   if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += 1u;
@@ -718,6 +725,14 @@ extern "C" vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_
   launch_pdl(mask_to_additive_kernel, dim3(ew_grid((long long)B * (N + 1))), dim3(256), (size_t)(0), ST(stream), reinterpret_cast<const long long*>(mask), out, B, N, prepend_one ? 1 : 0);
   return check_launch("vb_mask_to_additive");
 }
+extern "C" vb_status vb_broadcast_rows(const void* src, void* dst, int64_t bytes, int32_t repeats, void* stream) {
+  if (bytes <= 0 || repeats <= 0) return VB_OK;
+  if ((bytes & 15) || !al16(src) || !al16(dst)) return set_error(VB_ERR_INVALID, "vb_broadcast_rows: needs 16-byte aligned buffers and size");
+  launch_pdl(broadcast_rows_kernel, dim3(ew_grid(bytes / 16 * repeats)), dim3(256), (size_t)0, ST(stream), static_cast<const uint4*>(src), static_cast<uint4*>(dst),
+             (long long)(bytes / 16), (int)repeats);
+  return check_launch("vb_broadcast_rows");
+}
+
 extern "C" vb_status vb_step_counter_bump(uint32_t* step, void* stream) {
   if (!step) return set_error(VB_ERR_INVALID, "vb_step_counter_bump: null counter");
   cudaError_t e = launch_pdl(step_bump_kernel, dim3(1), dim3(32), (size_t)0, ST(stream), step);

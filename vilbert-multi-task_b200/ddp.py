@@ -60,6 +60,27 @@ class FlatGradAllReducer:
             dist.broadcast(flat_params, src=src, group=self.group)
 
 
+class DistributedDataParallel:
+    """Drop-in for `apex.parallel.DistributedDataParallel(model, delay_allreduce=True)` as the reference uses it
+    (train_tasks.py:490-497): rank 0's parameters are broadcast at wrap time and every `loss.backward()` ends with ONE all-reduce
+    (average over the world) of the flat fp32 gradient buffer. Not an nn.Module wrapper with hooks: the engine's backward calls
+    the reducer itself. `.module` is the wrapped model, calls are forwarded."""
+
+    def __init__(self, model, delay_allreduce=True, n_buckets=8, group=None):
+        self.module = model
+        eng = model.engine
+        self.reducer = FlatGradAllReducer(eng.ps.grad, n_buckets=n_buckets, group=group)
+        self.reducer.broadcast_params(eng.ps.flat)
+        eng.shadow_clean = False
+        model._ddp_reducer = self.reducer
+
+    def __call__(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def __getattr__(self, name):
+        return getattr(self.module, name)
+
+
 def shard_batch(global_batch, rank, world):
     """Per-rank batch like the reference: batch_size // world_size samples each (task_utils.py:435-437)."""
     per = global_batch // world

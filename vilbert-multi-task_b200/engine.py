@@ -247,6 +247,11 @@ class Plan:
         self.B, self.Nt_in, self.Nv = B, Nt, Nv
         self.has_task = bool(self.cfg.task_specific_tokens)
         self.Nt = Nt + (1 if self.has_task else 0)
+        # FAST_MODE (vilbert.py:1042-1053, eval_retrieval.py): one caption (text batch 1) against B images; inference only
+        self.fast = bool(getattr(self.cfg, "fast_mode", False))
+        self.Bt = 1 if self.fast else B
+        if self.fast and (train or grad_outputs or vqa_loss or loss):
+            raise ValueError("fast_mode is an inference path (text batch 1 broadcast to the image batch): no train mode / gradients")
         self.grad_outputs = frozenset(grad_outputs)
         # objective fused into the step (LOSS_HEADS): its scalar lands in self.loss (device) and its gradient goes straight into the
         # backward of the head(s) it reads; vqa_loss=True is the round-1 spelling of loss="vqa"
@@ -631,10 +636,29 @@ class Plan:
                        drop=self.drop(p + ".t_output.dropout", c.hidden_dropout_prob))
         return v2o, t2o
 
+    def broadcast_text(self, t):
+        """FAST_MODE: t [1*Nt, H] -> [B*Nt, H] (fp32 values and operand copies), and the text mask [1, Nt] -> [B, Nt]."""
+        B, M1, H = self.B, t.M, t.H
+        f32 = self.buf((B * M1, H), F32)
+        b16, lo, _ = self.buf16((B * M1, H), bw=False)
+        self.emit(self.lib.vb_broadcast_rows, t.f32.data_ptr(), f32.data_ptr(), M1 * H * 4, B)
+        self.emit(self.lib.vb_broadcast_rows, t.b16.data_ptr(), b16.data_ptr(), M1 * H * 2, B)
+        if lo is not None:
+            self.emit(self.lib.vb_broadcast_rows, t.lo.data_ptr(), lo.data_ptr(), M1 * H * 2, B)
+        nt4 = (self.Nt * 4 + 15) // 16 * 16           # the mask row is padded to 16 bytes for the broadcast kernel
+        if nt4 == self.Nt * 4:
+            m = self.buf((B, self.Nt), F32)
+            self.emit(self.lib.vb_broadcast_rows, self.mask_t.data_ptr(), m.data_ptr(), self.Nt * 4, B)
+        else:
+            m = self.mask_t.new_empty((B, self.Nt)); self._keep.append(m)
+            self.emit(self.lib.vb_mask_to_additive, self.in_amask_b.data_ptr(), m.data_ptr(), B, self.Nt_in, 1 if self.has_task else 0)
+        self.mask_t = m
+        return Act(f32, b16, B * M1, H, lo=lo)
+
     def text_layer(self, x, i):
         p = f"bert.encoder.layer.{i}"
         c = self.cfg
-        h1 = self.self_attention_block(x, self.B, self.Nt, c.num_attention_heads, self.mask_t, p + ".attention", "t",
+        h1 = self.self_attention_block(x, x.M // self.Nt, self.Nt, c.num_attention_heads, self.mask_t, p + ".attention", "t",
                                        p_attn=c.attention_probs_dropout_prob, p_hidden=c.hidden_dropout_prob)
         return self.ffn(h1, c.intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "t.ffn",
                         drop=self.drop(p + ".output.dropout", c.hidden_dropout_prob))
@@ -651,18 +675,20 @@ class Plan:
     def embeddings(self):
         ps, c, B, lib = self.ps, self.cfg, self.B, self.lib
         Ht, Hv, Nt, Nv, Fv = c.hidden_size, c.v_hidden_size, self.Nt, self.Nv, c.v_feature_size
-        Mt, Mv = B * Nt, B * Nv
-        # static inputs
-        self.in_ids = self.buf((B, self.Nt_in), I64, zero=True)
-        self.in_tt = self.buf((B, self.Nt_in), I64, zero=True)
-        self.in_task = self.buf((B,), I64, zero=True) if self.has_task else None
-        self.in_amask = self.buf((B, self.Nt_in), I64, zero=True)
+        Bt = self.Bt
+        Mt, Mv = Bt * Nt, B * Nv
+        # static inputs (the text side has batch 1 in FAST_MODE)
+        self.in_ids = self.buf((Bt, self.Nt_in), I64, zero=True)
+        self.in_tt = self.buf((Bt, self.Nt_in), I64, zero=True)
+        self.in_task = self.buf((Bt,), I64, zero=True) if self.has_task else None
+        self.in_amask = self.buf((Bt, self.Nt_in), I64, zero=True)
+        self.in_amask_b = self.in_amask.expand(B, self.Nt_in).contiguous() if self.fast else self.in_amask   # refreshed in load_inputs
         self.in_imask = self.buf((B, Nv), I64, zero=True)
         self.in_feat = self.buf((B, Nv, Fv), F32, zero=True)
         self.in_loc = self.buf((B, Nv, 5), F32, zero=True)
-        self.mask_t = self.buf((B, Nt), F32)
+        self.mask_t = self.buf((Bt, Nt), F32)
         self.mask_v = self.buf((B, Nv), F32)
-        self.emit(lib.vb_mask_to_additive, self.in_amask.data_ptr(), self.mask_t.data_ptr(), B, self.Nt_in, 1 if self.has_task else 0)
+        self.emit(lib.vb_mask_to_additive, self.in_amask.data_ptr(), self.mask_t.data_ptr(), Bt, self.Nt_in, 1 if self.has_task else 0)
         self.emit(lib.vb_mask_to_additive, self.in_imask.data_ptr(), self.mask_v.data_ptr(), B, Nv, 0)
         self.sync_streams()
         # text: gather-sum (+ task row) then LayerNorm (vilbert.py:346-367)
@@ -670,7 +696,7 @@ class Plan:
         e = "bert.embeddings"
         self.emit(lib.vb_embed_text_fwd, self.in_ids.data_ptr(), self.in_tt.data_ptr(), self._ptr(self.in_task), ps.p(e + ".word_embeddings.weight").data_ptr(),
                   ps.p(e + ".position_embeddings.weight").data_ptr(), ps.p(e + ".token_type_embeddings.weight").data_ptr(),
-                  ps.p(e + ".task_embeddings.weight").data_ptr() if self.has_task else None, xe.data_ptr(), B, self.Nt_in, Ht)
+                  ps.p(e + ".task_embeddings.weight").data_ptr() if self.has_task else None, xe.data_ptr(), Bt, self.Nt_in, Ht)
         tdrop = self.drop(e + ".dropout", c.hidden_dropout_prob)
         t32, t16, tmean, trstd, tlo, tbw = self.ln_fwd(xe, ps.p(e + ".LayerNorm.weight"), ps.p(e + ".LayerNorm.bias"), Mt, Ht, out_drop=tdrop)
         t = Act(t32, t16, Mt, Ht, lo=tlo, bw=tbw)
@@ -924,6 +950,8 @@ class Plan:
             with self.on(1):
                 for i in range(v_start, v_end):
                     v = self.image_layer(v, i)
+            if count == 0 and self.fast:
+                t = self.broadcast_text(t)
             if c.with_coattention:
                 v, t = self.connection_layer(v, t, count)
             v_start, t_start = v_end, t_end
@@ -1045,6 +1073,8 @@ class Plan:
             self.in_amask.fill_(1)
         else:
             self.in_amask.copy_(attention_mask, non_blocking=non_blocking)
+        if self.fast:
+            self.in_amask_b.copy_(self.in_amask.expand_as(self.in_amask_b))
         if image_attention_mask is None:
             self.in_imask.fill_(1)
         else:

@@ -86,8 +86,8 @@ class _EngineFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, names, anchor, inputs):
-        B, Nt = inputs["input_txt"].shape
-        Nv = inputs["input_imgs"].shape[1]
+        Nt = inputs["input_txt"].shape[1]
+        B, Nv = inputs["input_imgs"].shape[:2]     # FAST_MODE: the text batch is 1, the image batch sets the plan
         train = bool(model.training)
         hint = model._grad_hint.get((B, Nt, Nv, names, train), ())
         plan = model.engine.plan(B, Nt, Nv, grad_outputs=hint, heads=model._heads_for(names), train=train)
@@ -109,8 +109,8 @@ class _EngineFn(torch.autograd.Function):
         model, names, inputs, plan = ctx.model, ctx.names, ctx.inputs, ctx.plan
         live = tuple(n for n, g in zip(names, grads) if g is not None)
         if live:
-            B, Nt = inputs["input_txt"].shape
-            Nv = inputs["input_imgs"].shape[1]
+            Nt = inputs["input_txt"].shape[1]
+            B, Nv = inputs["input_imgs"].shape[:2]
             if frozenset(live) != plan.grad_outputs or plan.fwd_id != ctx.fwd_id:
                 model._grad_hint[(B, Nt, Nv, names, ctx.train)] = live
                 plan = model.engine.plan(B, Nt, Nv, grad_outputs=live, heads=model._heads_for(names), train=ctx.train)
@@ -130,6 +130,8 @@ class _EngineFn(torch.autograd.Function):
                 if g is not None:
                     plan.gout[n].copy_(g.reshape(plan.gout[n].shape))
             plan.run_backward()
+            if model._ddp_reducer is not None:     # data parallel: average the flat gradient buffer over the ranks (apex DDP, delay_allreduce=True)
+                model._ddp_reducer.allreduce()
         return None, None, None, None
 
 
@@ -159,6 +161,7 @@ class BertPreTrainedModel(nn.Module):
         self._anchor = torch.zeros((), device=dev, requires_grad=True)
         self._shadow_version = None
         self._opt_epoch = -1
+        self._ddp_reducer = None
         self.init_weights()
 
     # ---- reference init (vilbert.py:1274-1285): N(0, initializer_range) for Linear/Embedding weights, zero bias, LN 1/0
@@ -229,8 +232,32 @@ class BertPreTrainedModel(nn.Module):
             self._params[name].grad = ps.g(name)
 
     def _apply(self, fn, recurse=True):
-        raise L.VBError("vilbert_b200 models own flat CUDA parameter buffers; .to()/.cuda()/.half() are not supported "
-                        "(construct the model on the target GPU)")
+        raise L.VBError("vilbert_b200 models own flat CUDA parameter buffers that cannot be moved or re-typed in place "
+                        "(construct the model on the target GPU; reduced precision is the `precision=` argument)")
+
+    # The calls the reference's drivers make on a freshly built model (train_tasks.py:486-500: model.to(device), model.cuda(),
+    # model.half() under --fp16) are accepted when they ask for what the model already is: fp32 master parameters on its GPU.
+    def to(self, *args, **kwargs):
+        device, dtype, _, _ = torch._C._nn._parse_to(*args, **kwargs)
+        mine = self.engine.device
+        if device is not None and (device.type != "cuda" or (device.index is not None and device.index != mine.index)):
+            raise L.VBError(f"vilbert_b200 model lives on {mine}; it cannot be moved to {device}")
+        if dtype is not None and dtype != torch.float32:
+            raise L.VBError("parameters stay fp32 (master weights); the tensor-core operand precision is chosen with precision=")
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device) if isinstance(device, int) else (device or "cuda"))
+
+    def float(self):
+        return self
+
+    def half(self):
+        """The reference's --fp16 path (`model.half()` + apex FP16_Optimizer, train_concap.py:504-505): here the default precision
+        already runs fp16 forward operands with fp32 master weights and accumulation, so this is a no-op for precision "fp16"."""
+        if self.engine.precision != "fp16":
+            raise L.VBError('model.half(): construct the model with precision="fp16" (the default)')
+        return self
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, *model_args, config=None, state_dict=None, **kwargs):
