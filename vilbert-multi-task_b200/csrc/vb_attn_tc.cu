@@ -281,8 +281,12 @@ static bool make_tmap3(CUtensorMap* tm, const void* base, int cols, int N, int B
 }
 
 bool attn_fwd_tc_eligible(const vb_attn_args* a) {
-  static const bool off = getenv("VB_ATTN_TC") && getenv("VB_ATTN_TC")[0] == '0';   // development switch: force the mma.sync kernel
-  if (off) return false;
+  // Opt-in (VB_ATTN_TC=1): measured on B200 (profiles/r02_attn_fwd_probe_*.log) the kernel is faster than the mma.sync one only on
+  // the 100 x 100 x 128 image self-attention (24.0 vs 30.0 us) and slower on the short text-query shapes (17.8 vs 8.8 us at
+  // 36 x 36 x 64), where one 128-row tcgen05 tile per problem is mostly padding and the per-problem latency chain (TMA -> MMA ->
+  // softmax -> MMA -> store) is not hidden by the 2.6 - 5 problems an SM gets; inside the training step it costs 0.25 ms.
+  static const bool on = getenv("VB_ATTN_TC") && getenv("VB_ATTN_TC")[0] == '1';
+  if (!on) return false;
   if (a->Q_lo || a->K_lo || a->V_lo || a->O_lo) return false;
   if (a->Nq > 128 || a->Nk > 128 || (a->D != 64 && a->D != 128)) return false;
   return true;
