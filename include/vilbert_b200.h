@@ -167,7 +167,8 @@ typedef struct vb_attn_args {
   int32_t qkv_fp16;
   const void* Q_lo; const void* K_lo; const void* V_lo;
   void* O_lo;
-  void* O_b16;   /* forward: optional always-bf16 copy of O (same ldo): the operand of the out-projection's weight gradient */
+  void* O_b16;   /* forward: optional always-bf16 copy of O (same ldo): the operand of the out-projection's weight gradient.
+                    backward: if given, delta = rowsum(dO o O) reads this copy (consistent with the bf16 products of the backward) */
 } vb_attn_args;
 
 vb_status vb_attention_fwd(const vb_attn_args* args, void* stream);

@@ -336,7 +336,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
   // delta = rowsum(dO o O) for rows g, g+8 of this warp; each quad lane sums a quarter of the columns.
   float dl[2] = {0.f, 0.f};
   {
-    const __nv_bfloat16* Og = p.O + ((long long)b * p.Nq + q0) * p.ldo + h * D;
+    // delta = rowsum(dO o O) must cancel against dP = dO V^T formed from the bf16-rounded V: use the bf16 copy of O when the
+    // forward wrote one (an fp16 O differs from P V_bf16 by the bf16 rounding of V, which peaked rows do not forgive)
+    const int o_fp16 = p.Ob ? 0 : p.qkv_fp16;
+    const __nv_bfloat16* Og = (p.Ob ? p.Ob : p.O) + ((long long)b * p.Nq + q0) * p.ldo + h * D;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       const int r = r0 + g + hh * 8;
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
           const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float2 of = unpack16(o2[i], p.qkv_fp16), df = __bfloat1622float2(d2[i]);
+            const float2 of = unpack16(o2[i], o_fp16), df = __bfloat1622float2(d2[i]);
             acc += of.x * df.x + of.y * df.y;
           }
         }
@@ -561,7 +564,8 @@ __global__ void __launch_bounds__(ATT1_THREADS) attn_bwd_fused_kernel(const Attn
     // ---- phase 1: this warp's 16 query rows
     float dl[2] = {0.f, 0.f};   // delta = rowsum(dO o O)
     {
-      const __nv_bfloat16* Og = p.O + (long long)b * p.Nq * p.ldo + h * D;
+      const int o_fp16 = p.Ob ? 0 : p.qkv_fp16;      // see attn_bwd_dq_kernel: the bf16 copy of O keeps delta consistent with dP
+      const __nv_bfloat16* Og = (p.Ob ? p.Ob : p.O) + (long long)b * p.Nq * p.ldo + h * D;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int r = r0 + g + hh * 8;
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(ATT1_THREADS) attn_bwd_fused_kernel(const Attn
             const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float2 of = unpack16(o2[i], p.qkv_fp16), df = __bfloat1622float2(d2[i]);
+              const float2 of = unpack16(o2[i], o_fp16), df = __bfloat1622float2(d2[i]);
               acc += of.x * df.x + of.y * df.y;
             }
           }

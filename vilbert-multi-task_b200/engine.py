@@ -398,8 +398,7 @@ class Plan:
                   v_lo=None, o_lo=None, o_b16=None):
         a = L.AttnArgs()
         a.qkv_fp16 = self.op_fp16
-        if not bwd:
-            a.O_b16 = self._ptr(o_b16)
+        a.O_b16 = self._ptr(o_b16)     # forward: written; backward: read for delta (consistent with the bf16 backward products)
         if not bwd and self.split:
             a.Q_lo, a.K_lo, a.V_lo, a.O_lo = self._ptr(q_lo), self._ptr(k_lo), self._ptr(v_lo), self._ptr(o_lo)
         a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
@@ -549,7 +548,7 @@ class Plan:
             gb = ps.g(prefix + ".self.qkv.bias")     # bias gradients = column sums of dQ|dK|dV, fused into the attention backward
             self.attention(True, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dO=dctx, lddo=H,
                            dQ=dqkv[:, 0:H], lddq=3 * H, dK=dqkv[:, H:2 * H], lddk=3 * H, dV=dqkv[:, 2 * H:], lddv=3 * H, delta=delta,
-                           dbq=gb[0:H], dbk=gb[H:2 * H], dbv=gb[2 * H:], dropout=adrop)
+                           dbq=gb[0:H], dbk=gb[H:2 * H], dbv=gb[2 * H:], dropout=adrop, o_b16=self._extra(ctxb, ctx))
             self.linear_wgrad(dqkv, 3 * H, None, 0, x.bw, H, M, 3 * H, H, prefix + ".self.qkv")
             self.dgrad_into(x, dqkv, 3 * H, ps.w16b(prefix + ".self.qkv.weight"), M, 3 * H, H, extra32=dy32)
         self.push_bwd(bwd)
@@ -617,10 +616,10 @@ class Plan:
             d2 = self.scratch("c.delta2", (B, nh, Nv), F32)
             self.attention(True, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1, dO=dctx1, lddo=Hb,
                            dQ=dqkv2[:, 0:Hb], lddq=L3, dK=dqkv1[:, Hb:2 * Hb], lddk=L3, dV=dqkv1[:, 2 * Hb:], lddv=L3, delta=d1,
-                           dbq=gb2[0:Hb], dbk=gb1[Hb:2 * Hb], dbv=gb1[2 * Hb:], dropout=adrop1)
+                           dbq=gb2[0:Hb], dbk=gb1[Hb:2 * Hb], dbv=gb1[2 * Hb:], dropout=adrop1, o_b16=self._extra(ctx1b, ctx1))
             self.attention(True, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dO=dctx2, lddo=Hb,
                            dQ=dqkv1[:, 0:Hb], lddq=L3, dK=dqkv2[:, Hb:2 * Hb], lddk=L3, dV=dqkv2[:, 2 * Hb:], lddv=L3, delta=d2,
-                           dbq=gb1[0:Hb], dbk=gb2[Hb:2 * Hb], dbv=gb2[2 * Hb:], dropout=adrop2)
+                           dbq=gb1[0:Hb], dbk=gb2[Hb:2 * Hb], dbv=gb2[2 * Hb:], dropout=adrop2, o_b16=self._extra(ctx2b, ctx2))
             self.linear_wgrad(dqkv1, L3, None, 0, v.bw, Hv, Mv, L3, Hv, p + ".biattention.qkv1")
             self.linear_wgrad(dqkv2, L3, None, 0, t.bw, Ht, Mt, L3, Ht, p + ".biattention.qkv2")
             self.dgrad_into(v, dqkv1, L3, ps.w16b(p + ".biattention.qkv1.weight"), Mv, L3, Hv, extra32=dyv32)
