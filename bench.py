@@ -236,9 +236,12 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of a single-task config")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce after the whole backward instead of overlapping it")
-    ap.add_argument("--ddp-mode", default="graph", choices=["graph", "pieces"],
-                    help="N > 1 overlapped step: 'graph' = ONE CUDA graph per step with the NCCL all-reduces captured on a side stream; "
-                         "'pieces' = one graph per backward piece, collectives issued from the host between them (round-1 scheme)")
+    ap.add_argument("--ddp-mode", default="pieces", choices=["graph", "pieces"],
+                    help="N > 1 overlapped step: 'pieces' (default) = one graph per backward piece, collectives issued from the host between "
+                         "them; 'graph' = ONE CUDA graph per step with the NCCL all-reduces captured on a side stream (measured 0.6 %% faster at "
+                         "N = 2, but ProcessGroupNCCL's watchdog hangs at teardown while captured collectives are alive: opt-in)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: cap NCCL's CTAs per collective (NCCL_MAX_CTAS) so that the all-reduce "
+                                                                  "overlapping the backward takes fewer SMs from the persistent GEMMs; 0 = NCCL default")
     ap.add_argument("--segments", type=int, default=8, help="N > 1: number of backward pieces whose gradient ranges are all-reduced while the rest runs")
     ap.add_argument("--eval-mode", action="store_true", help="disable the dropout layers (reference eval mode); default is train mode")
     ap.add_argument("--legacy-prologue", action="store_true", help="round-1 step body: weight cast + gradient memset inside the step, no fused optimizer")
@@ -287,6 +290,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1 and a.nccl_max_ctas > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(a.nccl_max_ctas))
     if world > 1:
         # NCCL prints its version banner on stdout; keep stdout for the single JSON line
         sys.stdout.flush()
@@ -300,6 +305,11 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
+    if world > 1:
+        # a collective that never completes must not hold the box until the caller's limit: give up loudly after 15 minutes
+        wd = threading.Timer(900.0, lambda: (print(f"[bench] rank {rank}: watchdog: no result after 900 s, aborting", file=sys.stderr), os._exit(3)))
+        wd.daemon = True
+        wd.start()
     W = max(a.warmup, 3)
     cfg_o = O.make_config(cfgj)
     eng = Engine(BertConfig.from_dict(cfgj), dev, heads=C.get("heads", "vl"), precision=a.precision)
@@ -554,6 +564,10 @@ def main():
 
     if rank != 0:
         if world > 1:
+            if ddp_graph:
+                for t in T:
+                    t["plan"].graph_step_ddp = None
+                torch.cuda.synchronize()
             dist.destroy_process_group()
         return
 
@@ -631,7 +645,12 @@ def main():
         r = run_cpu_reference(c2, a.cpu_batch, 100, 36, steps=3, warmup=1, budget_s=45.0)
         out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
+        if ddp_graph:      # captured collectives must be gone before the process group is torn down (else its watchdog hangs)
+            for t in T:
+                t["plan"].graph_step_ddp = None
+            torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

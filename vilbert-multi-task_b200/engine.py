@@ -1346,10 +1346,11 @@ class Plan:
         self.e.grad_clean = False
         self.graph_step_ddp.replay()
 
-    def run_step_overlapped(self, allreduce_range, comm_stream):
+    def run_step_overlapped(self, allreduce_range, comm_stream, skip_dead=True):
         """Replays the segment graphs; after each one the finished tail range of the flat gradient buffer is handed to
         `allreduce_range(lo, hi)` (issued under `comm_stream`, which first waits for that segment) so the collective
-        overlaps the rest of the backward. Returns the list of whatever allreduce_range returned (async work handles)."""
+        overlaps the rest of the backward. Ranges no backward op of this plan writes (live_ranges) are not exchanged.
+        Returns the list of whatever allreduce_range returned (async work handles)."""
         self.fwd_id += 1
         self.e.grad_clean = False
         main = torch.cuda.current_stream()
@@ -1361,8 +1362,15 @@ class Plan:
                 ev.record(main)
                 with torch.cuda.stream(comm_stream):
                     comm_stream.wait_event(ev)
-                    works.append(allreduce_range(lo, hi))
+                    for (a, b) in (self._live_cache(lo, hi) if skip_dead else [(lo, hi)]):
+                        works.append(allreduce_range(a, b))
         return works
+
+    def _live_cache(self, lo, hi):
+        c = self.__dict__.setdefault("_live_ranges_cache", {})
+        if (lo, hi) not in c:
+            c[(lo, hi)] = self.live_ranges(lo, hi)
+        return c[(lo, hi)]
 
     def capture(self, separate=False):
         """Captures the plan into CUDA graphs (one for the whole step, or one per pass)."""
