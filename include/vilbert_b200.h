@@ -282,6 +282,11 @@ vb_status vb_mask_to_additive(const int64_t* mask, float* out, int32_t B, int32_
  * of ONE caption, computed at batch 1 up to the first connection layer, broadcast to the image batch (txt_embedding.expand). */
 vb_status vb_broadcast_rows(const void* src, void* dst, int64_t bytes, int32_t repeats, void* stream);
 
+/* dst[i * repeats + r] = src[i] for `items` items of `bytes` each (multiple of 16): the batch expansion of the reference's
+ * `process: expand / dialog` tasks (task_utils.py:248-274, 198-246): region features / boxes / masks of one image replicated once
+ * per answer option, features.unsqueeze(1).expand(B, options, ...).contiguous().view(-1, ...), done in one pass on the device. */
+vb_status vb_repeat_rows(const void* src, void* dst, int64_t bytes, int64_t items, int32_t repeats, void* stream);
+
 /* step += 1 on the device (the dropout step counter; one launch per training step, capturable in a CUDA graph). */
 vb_status vb_step_counter_bump(uint32_t* step, void* stream);
 

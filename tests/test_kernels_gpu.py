@@ -179,3 +179,27 @@ def test_misc_rowops():
     torch.cuda.synchronize()
     ref0 = (1.0 - m.float()) * -10000.0
     assert torch.equal(o0, ref0) and torch.equal(o1[:, 1:], ref0) and o1[:, 0].abs().max().item() == 0
+
+
+def test_batch_expansion_and_prefetcher():
+    """Input-pipeline edge (task_utils.py:186-310): device-side `expand` / `dialog` replication (vb_repeat_rows), the view-only
+    `retrieval` / `nlvr` reshapes, and the pinned double-buffered host -> device prefetcher."""
+    from vilbert_b200.data import PinnedBatchPrefetcher, expand_batch
+    dev = "cuda"
+    B, R, Nv, Nt = 3, 4, 7, 5
+    feats = torch.randn(B, Nv, 2048, device=dev); sp = torch.rand(B, Nv, 5, device=dev); im = (torch.rand(B, Nv, device=dev) < 0.7).long()
+    q = torch.randint(0, 100, (B, R, Nt), device=dev); am = torch.ones_like(q); seg = torch.zeros_like(q)
+    co = torch.zeros(B, R, Nv, Nt, device=dev)
+    f2, s2, m2, q2, a2, g2, c2, bs, no = expand_batch("expand", feats, sp, im, q, am, seg, co)
+    # the reference's own expressions (task_utils.py:248-274)
+    assert torch.equal(f2, feats.unsqueeze(1).expand(B, R, Nv, 2048).contiguous().view(-1, Nv, 2048))
+    assert torch.equal(s2, sp.unsqueeze(1).expand(B, R, Nv, 5).contiguous().view(-1, Nv, 5))      # 140-byte items: falls back to views
+    assert torch.equal(m2, im.unsqueeze(1).expand(B, R, Nv).contiguous().view(-1, Nv))
+    assert torch.equal(q2, q.view(-1, Nt)) and c2.shape == (B * R, Nv, Nt) and (bs, no) == (B, R)
+    f3, s3, m3, q3, a3, g3, _, bs3, _ = expand_batch("nlvr", torch.randn(B, 2 * Nv, 2048, device=dev), torch.rand(B, 2 * Nv, 5, device=dev),
+                                                   torch.ones(B, 2 * Nv, device=dev).long(), q[:, 0], am[:, 0], seg[:, 0])
+    assert f3.shape == (2 * B, Nv, 2048) and torch.equal(q3[0], q3[1]) and torch.equal(q3[0], q[0, 0])
+    batches = [(torch.randn(4, 3), torch.arange(4) + i) for i in range(5)]
+    got = list(PinnedBatchPrefetcher(batches))
+    torch.cuda.synchronize()
+    assert len(got) == 5 and all(torch.equal(g[1].cpu(), b[1]) and torch.equal(g[0].cpu(), b[0]) for g, b in zip(got, batches))

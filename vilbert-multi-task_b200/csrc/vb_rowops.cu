@@ -534,6 +534,16 @@ __global__ void broadcast_rows_kernel(const uint4* __restrict__ src, uint4* __re
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i % n16];
 }
 
+// dst[i * repeats + r] = src[i] (items of n16 16-byte words): the on-device form of x.unsqueeze(1).expand(B, R, ...).contiguous()
+__global__ void repeat_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16, long long items, int repeats) {
+  pdl_entry();
+  const long long total = n16 * items * repeats;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long w = i % n16, row = i / n16;
+    dst[i] = src[(row / repeats) * n16 + w];
+  }
+}
+
 __global__ void step_bump_kernel(uint32_t* ctr) {
   pdl_entry();
   if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += 1u;
@@ -731,6 +741,14 @@ extern "C" vb_status vb_broadcast_rows(const void* src, void* dst, int64_t bytes
   launch_pdl(broadcast_rows_kernel, dim3(ew_grid(bytes / 16 * repeats)), dim3(256), (size_t)0, ST(stream), static_cast<const uint4*>(src), static_cast<uint4*>(dst),
              (long long)(bytes / 16), (int)repeats);
   return check_launch("vb_broadcast_rows");
+}
+
+extern "C" vb_status vb_repeat_rows(const void* src, void* dst, int64_t bytes, int64_t items, int32_t repeats, void* stream) {
+  if (bytes <= 0 || items <= 0 || repeats <= 0) return VB_OK;
+  if ((bytes & 15) || !al16(src) || !al16(dst)) return set_error(VB_ERR_INVALID, "vb_repeat_rows: needs 16-byte aligned buffers and item size");
+  launch_pdl(repeat_rows_kernel, dim3(ew_grid(bytes / 16 * items * repeats)), dim3(256), (size_t)0, ST(stream), static_cast<const uint4*>(src),
+             static_cast<uint4*>(dst), (long long)(bytes / 16), (long long)items, (int)repeats);
+  return check_launch("vb_repeat_rows");
 }
 
 extern "C" vb_status vb_step_counter_bump(uint32_t* step, void* stream) {
