@@ -187,6 +187,43 @@ def check_fast_mode(ref, cfg_json):
         json.dump(gold, f)
 
 
+def check_fixed_layers(ref, cfg_json):
+    """fixed_t_layer / fixed_v_layer: the first layers of each stream run under no_grad (vilbert.py:968-1003): same outputs,
+    no gradient into those layers or anything before them."""
+    cfgj = dict(cfg_json, fixed_t_layer=1, fixed_v_layer=0, v_biattention_id=[0, 1], t_biattention_id=[1, 2])
+    cfg = O.make_config(cfgj)
+    model = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfgj)), num_labels=1, default_gpu=False)
+    P = O.synth_params(cfg, seed=0)
+    model.load_state_dict(P, strict=False); model.tie_weights(); model.eval()
+    inp = O.synth_inputs(cfg, 4, 11, 9, seed=1234)
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], inp["co_attention_mask"])
+    tgt = O.synth_vqa_target(4, 3129)
+    r = model(*args)[:9]
+    O.vqa_loss(r[0], tgt).backward()
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    _, o = O.vilbert_for_vl_tasks(Pg, cfg, *args)
+    O.vqa_loss(o[0], tgt).backward()
+    named = dict(model.named_parameters())
+    worst = max(rel(a, b) for a, b in zip(o, r))
+    frozen = []
+    for k, v in Pg.items():
+        if k == "cls.predictions.decoder.weight":
+            continue
+        rg = named[k].grad
+        if rg is None or rg.abs().max() == 0:
+            assert v.grad is None or v.grad.abs().max() == 0, k
+            frozen.append(k)
+        else:
+            worst = max(worst, rel(v.grad, rg))
+    print(f"{'fixed_layers':28s} worst {worst:.2e}; {len(frozen)} tensors without gradient")
+    assert worst < TOL and "bert.encoder.layer.0.output.dense.weight" in frozen and "bert.embeddings.word_embeddings.weight" in frozen
+    assert "bert.encoder.layer.1.output.dense.weight" not in frozen
+    with open(os.path.join(GOLD, "tiny_fixed_layers.json"), "w") as f:
+        json.dump(dict(name="tiny_fixed_layers", config=cfgj, B=4, Nv=11, Nt=9, frozen=sorted(frozen), loss=float(O.vqa_loss(r[0], tgt)),
+                       pin=dict(worst=worst, tolerance=TOL)), f)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
@@ -202,6 +239,7 @@ def main():
     run_pretraining_case(ref, "tiny_pretraining_losses", TINY, B=4, Nv=9, Nt=8)
     check_all_encoded_layers(ref, TINY)
     check_fast_mode(ref, TINY)
+    check_fixed_layers(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

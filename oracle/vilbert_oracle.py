@@ -184,10 +184,19 @@ def encoder(P, pre, cfg, t, v, mask_t, mask_v, drop=None):
     all_t, all_v = [], []
     n_t, n_v = cfg["num_hidden_layers"], cfg["v_num_hidden_layers"]
     for count, (v_end, t_end) in enumerate(zip(cfg["v_biattention_id"], cfg["t_biattention_id"])):
+        # fixed_t_layer / fixed_v_layer (vilbert.py:968-1003): the first layers of each stream run under torch.no_grad()
         for i in range(t_start, t_end):
-            t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t, drop)
+            if i < cfg.get("fixed_t_layer", 0):
+                with torch.no_grad():
+                    t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t, drop)
+            else:
+                t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t, drop)
         for i in range(v_start, v_end):
-            v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
+            if i < cfg.get("fixed_v_layer", 0):
+                with torch.no_grad():
+                    v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
+            else:
+                v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
         if count == 0 and cfg.get("fast_mode"):
             # FAST_MODE (vilbert.py:1042-1053): one caption against a batch of images — the text stream, computed once at batch 1
             # up to the first connection layer, is broadcast to the image batch from there on

@@ -152,6 +152,20 @@ def test_fast_mode_text_broadcast(golden_dir, task, Nt):
     assert tuple(out[2].shape) == (B, 1) and rel(out[2], heads_o[2]) < 1e-2     # vil_logit: the retrieval score of each image
 
 
+def test_fixed_layers_stop_the_gradient(golden_dir):
+    """config.fixed_t_layer (vilbert.py:968-1003: the first text layers run under torch.no_grad()): outputs unchanged, the frozen
+    layers, the embeddings before them and nothing else lose their gradient (set of gradient-free tensors recorded from the
+    reference: tests/golden/tiny_fixed_layers.json), every other gradient matches the oracle."""
+    from _gpu_util import model_case
+    meta = json.load(open(os.path.join(golden_dir, "tiny_fixed_layers.json")))
+    r = model_case(meta["config"], meta["B"], meta["Nv"], meta["Nt"], names=("vil_prediction",))
+    _check(r)
+    eng = r["engine"]
+    zero = sorted(k for k in eng.ps.entries if eng.ps.g(k).abs().max().item() == 0)
+    assert zero == sorted(k for k in meta["frozen"] if k in eng.ps.entries), set(zero) ^ set(meta["frozen"])
+    assert "bert.encoder.layer.0.output.dense.weight" in zero and "bert.encoder.layer.1.output.dense.weight" not in zero
+
+
 def test_vqa_only_gradient_set_skips_dead_heads(golden_dir):
     from _gpu_util import model_case
     r = model_case(_cfg(golden_dir, "tiny_b4"), 4, 11, 9, names=("vil_prediction",))

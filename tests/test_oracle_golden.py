@@ -113,3 +113,20 @@ def test_fast_mode_golden(golden_dir):
         got = t[torch.tensor(s["sample_idx"])]
         assert (got - torch.tensor(s["samples"], dtype=torch.float64)).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), k
         assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
+
+
+def test_fixed_layers_golden(golden_dir):
+    """config.fixed_t_layer: the set of parameters without a gradient and the loss recorded from the reference."""
+    meta = json.load(open(os.path.join(golden_dir, "tiny_fixed_layers.json")))
+    cfg = O.make_config(meta["config"])
+    P = O.synth_params(cfg, seed=0)
+    inp = O.synth_inputs(cfg, meta["B"], meta["Nv"], meta["Nt"], seed=1234)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    _, heads = O.vilbert_for_vl_tasks(Pg, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+                                      inp["image_attention_mask"])
+    loss = O.vqa_loss(heads[0], O.synth_vqa_target(meta["B"], 3129))
+    loss.backward()
+    assert abs(loss.item() - meta["loss"]) <= 1e-5 * abs(meta["loss"])
+    frozen = sorted(k for k, v in Pg.items() if k != "cls.predictions.decoder.weight" and (v.grad is None or v.grad.abs().max() == 0))
+    assert frozen == meta["frozen"]

@@ -98,7 +98,7 @@ class BertConfig(object):
         for flag in ("dynamic_attention", "in_batch_pairs", "visualization"):
             if getattr(self, flag, False):
                 unsupported.append(flag)
-        if getattr(self, "fixed_t_layer", 0) or getattr(self, "fixed_v_layer", 0):
-            unsupported.append("fixed_t_layer/fixed_v_layer")
+        if getattr(self, "fixed_t_layer", 0) > min(self.t_biattention_id) or getattr(self, "fixed_v_layer", 0) > min(self.v_biattention_id):
+            unsupported.append("fixed_t_layer / fixed_v_layer beyond the first connection layer (the reference asserts the same, vilbert.py:965-966)")
         if unsupported:
             raise NotImplementedError("vilbert_b200: unsupported config options: " + ", ".join(unsupported))

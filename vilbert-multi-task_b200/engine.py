@@ -208,13 +208,14 @@ class _TrackedParams:
 class Act:
     """A residual-stream activation: fp32 values, 16-bit operand copy (b16; lo = its split-precision low part or None),
     fp32 gradient (lazily allocated)."""
-    __slots__ = ("f32", "b16", "lo", "bw", "g32", "gw", "M", "H")
+    __slots__ = ("f32", "b16", "lo", "bw", "g32", "gw", "M", "H", "frozen")
 
     def __init__(self, f32, b16, M, H, lo=None, bw=None):
         """bw: bf16 copy of the operand for the backward's weight-gradient GEMM (== b16 when the operand format is bf16)."""
         self.f32, self.b16, self.lo, self.M, self.H = f32, b16, lo, M, H
         self.bw = b16 if bw is None else bw
         self.g32, self.gw = None, False
+        self.frozen = False     # produced under the reference's torch.no_grad() (fixed_t_layer / fixed_v_layer): no gradient flows into it
 
 
 # Objectives that can be fused into a plan, and the outputs each differentiates (task_utils.py:325-374, vilbert.py:1506-1590):
@@ -339,7 +340,10 @@ class Plan:
         return Plan._On(self, sid)
 
     def push_bwd(self, fn):
-        """Registers a backward emitter; it will emit on the stream that is current now."""
+        """Registers a backward emitter; it will emit on the stream that is current now. Layers built while `self._no_grad` is set
+        (the reference's `with torch.no_grad()` around the first fixed_t_layer / fixed_v_layer layers) register nothing."""
+        if getattr(self, "_no_grad", False):
+            return
         self._bwd_emitters.append((self.sid, fn))
 
     @staticmethod
@@ -457,6 +461,8 @@ class Plan:
 
     # act.g32 (+)= dy16 @ W (+ extra32)
     def dgrad_into(self, act, dy16, ld_dy, W16, M, N_out, K_in, extra32=None):
+        if act.frozen:      # the producer ran under no_grad: the gradient stops here
+            return
         g = self.grad_of(act)
         if not act.gw:
             self.gemm(M, K_in, N_out, dy16, ld_dy, W16, K_in, b_mn=1, residual=extra32, ld_res=K_in, out_f32=g, ld_of=K_in)
@@ -467,6 +473,8 @@ class Plan:
             self.gemm(M, K_in, N_out, dy16, ld_dy, W16, K_in, b_mn=1, residual=g, ld_res=K_in, out_f32=g, ld_of=K_in)
 
     def add_grad(self, act, src32):
+        if act.frozen:
+            return
         g = self.grad_of(act)
         if not act.gw:
             self.emit(self.lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
@@ -944,11 +952,21 @@ class Plan:
         # BertEncoder.forward interleaving schedule (vilbert.py:960-1096)
         t_start = v_start = 0
         for count, (v_end, t_end) in enumerate(zip(c.v_biattention_id, c.t_biattention_id)):
+            # fixed_t_layer / fixed_v_layer (vilbert.py:968-1003): the first layers of a stream run under no_grad — their backward is
+            # not emitted and their output stops the gradient (embeddings and the frozen layers' parameters receive none)
             for i in range(t_start, t_end):
+                frozen = i < getattr(c, "fixed_t_layer", 0)
+                self._no_grad = frozen
                 t = self.text_layer(t, i)
+                self._no_grad = False
+                t.frozen = frozen
             with self.on(1):
                 for i in range(v_start, v_end):
+                    frozen = i < getattr(c, "fixed_v_layer", 0)
+                    self._no_grad = frozen
                     v = self.image_layer(v, i)
+                    self._no_grad = False
+                    v.frozen = frozen
             if count == 0 and self.fast:
                 t = self.broadcast_text(t)
             if c.with_coattention:
