@@ -156,7 +156,7 @@ __device__ __noinline__ void epi_generic_chunk(const GemmKernelParams& p, const 
 // 16-bit output variants of the specialised epilogues (template parameter OUT16; kept out of line / out of the kernels that do
 // not need them: the fast paths are 8x unrolled and the epilogue time follows the instruction footprint, see the note above):
 //   0 = bf16 (gradient operands, bf16 precision)   1 = fp16 (forward operands)   2 = fp16 + an always-bf16 copy (forward
-//   operands the backward's weight-gradient GEMM reads).  Split precision (out_lo) takes the shared slow path.
+//   operands the backward's weight-gradient GEMM reads)   3 = split precision: fp16 hi + lo (+ bf16 copy at run time).
 __device__ __noinline__ void store16x4_slow(const GemmKernelParams& p, long long off, float v0, float v1, float v2, float v3) {
   if (p.out_lo) {
     uint32_t l01, l23;
@@ -172,6 +172,12 @@ template <int OUT16>
 __device__ __forceinline__ void store16x4(const GemmKernelParams& p, long long off, float v0, float v1, float v2, float v3) {
   if (OUT16 == 0) {
     *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+  } else if (OUT16 == 3) {   // split precision: fp16 hi + lo (+ the bf16 copy when asked for)
+    uint32_t l01, l23;
+    const uint32_t h01 = pack16_split(v0, v1, 1, l01), h23 = pack16_split(v2, v3, 1, l23);
+    *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(p.out_lo + off) = make_uint2(l01, l23);
+    if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
   } else {
     *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_f16(v0, v1), pack_f16(v2, v3));
     if (OUT16 == 2) *reinterpret_cast<uint2*>(p.out_b16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
@@ -617,10 +623,12 @@ static int launch_gemm_epi(int epi, int out16, const CUtensorMap* tm, GemmKernel
     case EPI_BF16:
       if (out16 == 1) return launch_gemm<BN, EPI_BF16, CG, 1>(tm, p, work, max_ctas, stream);
       if (out16 == 2) return launch_gemm<BN, EPI_BF16, CG, 2>(tm, p, work, max_ctas, stream);
+      if (out16 == 3) return launch_gemm<BN, EPI_BF16, CG, 3>(tm, p, work, max_ctas, stream);
       return launch_gemm<BN, EPI_BF16, CG, 0>(tm, p, work, max_ctas, stream);
     case EPI_GELU:
       if (out16 == 1) return launch_gemm<BN, EPI_GELU, CG, 1>(tm, p, work, max_ctas, stream);
       if (out16 == 2) return launch_gemm<BN, EPI_GELU, CG, 2>(tm, p, work, max_ctas, stream);
+      if (out16 == 3) return launch_gemm<BN, EPI_GELU, CG, 3>(tm, p, work, max_ctas, stream);
       return launch_gemm<BN, EPI_GELU, CG, 0>(tm, p, work, max_ctas, stream);
     case EPI_DGELU: return launch_gemm<BN, EPI_DGELU, CG>(tm, p, work, max_ctas, stream);
     case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC, CG>(tm, p, work, max_ctas, stream);
@@ -832,8 +840,8 @@ extern "C" vb_status vb_gemm_bf16(const vb_gemm_args* a, void* stream_) {
   // 16-bit output variant of the BF16 / GELU specialisations; split precision (out_lo) and other combinations run the generic epilogue
   int out16 = 0;
   if (epi == EPI_BF16 || epi == EPI_GELU) {
-    if (a->out_lo || (a->out_b16 && !a->out_fp16)) epi = EPI_GENERIC;
-    else out16 = a->out_fp16 ? (a->out_b16 ? 2 : 1) : 0;
+    if ((a->out_lo || a->out_b16) && !a->out_fp16) epi = EPI_GENERIC;     // bf16 hi + lo: not a combination the engine uses
+    else out16 = a->out_lo ? 3 : (a->out_fp16 ? (a->out_b16 ? 2 : 1) : 0);
   } else if (epi == EPI_DGELU && (a->out_fp16 || a->out_lo || a->out_b16)) {
     epi = EPI_GENERIC;
   }
