@@ -287,6 +287,11 @@ vb_status vb_broadcast_rows(const void* src, void* dst, int64_t bytes, int32_t r
  * per answer option, features.unsqueeze(1).expand(B, options, ...).contiguous().view(-1, ...), done in one pass on the device. */
 vb_status vb_repeat_rows(const void* src, void* dst, int64_t bytes, int64_t items, int32_t repeats, void* stream);
 
+/* dst[k*n + e] (+)= sum_{r < count_r} src[k*stride_k + r*stride_r + e] for k < count_k, e < n (f32; n and the strides multiples of 4):
+ * autograd of BertEncoder's in_batch_pairs expansion (vilbert.py:1008-1040), where every text / image item is expanded to B pairs. */
+vb_status vb_sum_strided(const float* src, float* dst, int64_t n, int32_t count_k, int64_t stride_k, int32_t count_r, int64_t stride_r,
+                         int32_t accumulate, void* stream);
+
 /* step += 1 on the device (the dropout step counter; one launch per training step, capturable in a CUDA graph). */
 vb_status vb_step_counter_bump(uint32_t* step, void* stream);
 

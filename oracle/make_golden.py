@@ -187,6 +187,37 @@ def check_fast_mode(ref, cfg_json):
         json.dump(gold, f)
 
 
+def check_in_batch_pairs(ref, cfg_json):
+    """in_batch_pairs=True (vilbert.py:1008-1040) through BertModel (the reference's VILBertForVLTasks adds the unexpanded image mask
+    to vision_logit and cannot run with it): the four BertModel outputs at batch b^2 and the gradients of a loss on them."""
+    cfgj = dict(cfg_json, in_batch_pairs=True)
+    cfg = O.make_config(cfgj)
+    model = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfgj)), num_labels=1, default_gpu=False)
+    P = O.synth_params(cfg, seed=0)
+    model.load_state_dict(P, strict=False); model.tie_weights(); model.eval()
+    inp = O.synth_inputs(cfg, 3, 11, 9, seed=555)
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], inp["co_attention_mask"])
+    r = model.bert(*args)[:4]
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    o = O.bert_model(Pg, cfg, *args)
+    w = [torch.linspace(0.5, 1.5, x.numel()).view_as(x) for x in r]
+    sum((a * b).sum() for a, b in zip(r, w)).backward()
+    sum((a * b).sum() for a, b in zip(o, w)).backward()
+    named = dict(model.named_parameters())
+    worst = max(rel(a, b) for a, b in zip(o, r))
+    for k, v in Pg.items():
+        rg = named[k].grad if k != "cls.predictions.decoder.weight" else None
+        if rg is not None and rg.abs().max() > 0:
+            worst = max(worst, rel(v.grad, rg))
+    print(f"{'in_batch_pairs':28s} worst {worst:.2e}; output batch {o[0].shape[0]}")
+    assert worst < TOL and o[0].shape[0] == 9
+    with open(os.path.join(GOLD, "tiny_in_batch_pairs.json"), "w") as f:
+        json.dump(dict(name="tiny_in_batch_pairs", config=cfgj, B=3, Nv=11, Nt=9, seed=0, input_seed=555,
+                       outputs={n: dict(summary(a), shape=list(a.shape)) for n, a in zip(O.BERT_OUT_NAMES, r)},
+                       pin=dict(worst=worst, tolerance=TOL)), f)
+
+
 def check_fixed_layers(ref, cfg_json):
     """fixed_t_layer / fixed_v_layer: the first layers of each stream run under no_grad (vilbert.py:968-1003): same outputs,
     no gradient into those layers or anything before them."""
@@ -240,6 +271,7 @@ def main():
     check_all_encoded_layers(ref, TINY)
     check_fast_mode(ref, TINY)
     check_fixed_layers(ref, TINY)
+    check_in_batch_pairs(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

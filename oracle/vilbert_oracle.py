@@ -197,6 +197,13 @@ def encoder(P, pre, cfg, t, v, mask_t, mask_v, drop=None):
                     v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
             else:
                 v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
+        if count == 0 and cfg.get("in_batch_pairs"):
+            # vilbert.py:1008-1040: every (text i, image j) combination of the batch becomes sample i * b + j
+            b = t.shape[0]
+            v = v.unsqueeze(0).expand(b, *v.shape).contiguous().view(b * b, v.shape[1], v.shape[2])
+            mask_v = mask_v.unsqueeze(0).expand(b, *mask_v.shape).contiguous().view(b * b, 1, 1, mask_v.shape[-1])
+            t = t.unsqueeze(1).expand(b, b, t.shape[1], t.shape[2]).contiguous().view(b * b, t.shape[1], t.shape[2])
+            mask_t = mask_t.unsqueeze(1).expand(b, b, 1, 1, mask_t.shape[-1]).contiguous().view(b * b, 1, 1, mask_t.shape[-1])
         if count == 0 and cfg.get("fast_mode"):
             # FAST_MODE (vilbert.py:1042-1053): one caption against a batch of images — the text stream, computed once at batch 1
             # up to the first connection layer, is broadcast to the image batch from there on

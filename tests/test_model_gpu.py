@@ -152,6 +152,39 @@ def test_fast_mode_text_broadcast(golden_dir, task, Nt):
     assert tuple(out[2].shape) == (B, 1) and rel(out[2], heads_o[2]) < 1e-2     # vil_logit: the retrieval score of each image
 
 
+def test_in_batch_pairs_expansion(golden_dir):
+    """config.in_batch_pairs (vilbert.py:1008-1040): at the first connection layer every (text i, image j) combination of the batch
+    becomes a sample (batch b -> b^2). BertModel's four outputs and every parameter gradient (the backward sums each item's
+    gradient over its b copies) vs the oracle, which is pinned bit-exact against the reference for this path
+    (tests/golden/tiny_in_batch_pairs.json)."""
+    from _gpu_util import build_engine, rel, rel_l2
+    meta = json.load(open(os.path.join(golden_dir, "tiny_in_batch_pairs.json")))
+    cfgj = meta["config"]
+    cfg = O.make_config(cfgj)
+    b, Nv, Nt = 4, 11, 9
+    P = O.synth_params(cfg, seed=0, device="cuda")
+    inp = O.synth_inputs(cfg, b, Nv, Nt, seed=555, device="cuda")
+    eng = build_engine(cfgj, P, "cuda")
+    plan = eng.plan(b, Nt, Nv, grad_outputs=O.BERT_OUT_NAMES, heads="none")
+    plan.load_inputs(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+    plan.run_forward(); torch.cuda.synchronize()
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    ref = O.bert_model(Pg, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ws = [torch.randn(r.shape, device="cuda", generator=g) * 0.1 for r in ref]
+    for n, r in zip(O.BERT_OUT_NAMES, ref):
+        assert tuple(plan.outputs[n].shape) == tuple(r.shape) and r.shape[0] == b * b and rel(plan.outputs[n], r) < 1e-2, n
+    sum((r * w).sum() for r, w in zip(ref, ws)).backward()
+    eng.zero_grad(force=True)
+    for n, w in zip(O.BERT_OUT_NAMES, ws):
+        plan.gout[n].copy_(w.reshape(plan.gout[n].shape))
+    plan.run_backward(); torch.cuda.synchronize()
+    gmax = max(v.grad.abs().max().item() for v in Pg.values() if v.grad is not None)
+    l2 = sorted((rel_l2(eng.ps.g(k), Pg[k].grad), k) for k in eng.ps.entries if Pg[k].grad is not None and Pg[k].grad.abs().max().item() > 1e-3 * gmax)
+    assert len(l2) > 40 and l2[-1][0] < 2e-2 and l2[len(l2) // 2][0] < 1e-2, l2[-3:]
+
+
 def test_fixed_layers_stop_the_gradient(golden_dir):
     """config.fixed_t_layer (vilbert.py:968-1003: the first text layers run under torch.no_grad()): outputs unchanged, the frozen
     layers, the embeddings before them and nothing else lose their gradient (set of gradient-free tensors recorded from the

@@ -130,3 +130,19 @@ def test_fixed_layers_golden(golden_dir):
     assert abs(loss.item() - meta["loss"]) <= 1e-5 * abs(meta["loss"])
     frozen = sorted(k for k, v in Pg.items() if k != "cls.predictions.decoder.weight" and (v.grad is None or v.grad.abs().max() == 0))
     assert frozen == meta["frozen"]
+
+
+def test_in_batch_pairs_golden(golden_dir):
+    """config.in_batch_pairs: BertModel outputs at batch b^2 recorded from the reference."""
+    meta = json.load(open(os.path.join(golden_dir, "tiny_in_batch_pairs.json")))
+    cfg = O.make_config(meta["config"])
+    P = O.synth_params(cfg, seed=meta["seed"])
+    inp = O.synth_inputs(cfg, meta["B"], meta["Nv"], meta["Nt"], seed=meta["input_seed"])
+    with torch.no_grad():
+        outs = O.bert_model(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+    for k, t in zip(O.BERT_OUT_NAMES, outs):
+        s = meta["outputs"][k]
+        assert list(t.shape) == s["shape"] and t.shape[0] == meta["B"] ** 2, k
+        t = t.detach().double().flatten()
+        assert (t[torch.tensor(s["sample_idx"])] - torch.tensor(s["samples"], dtype=torch.float64)).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), k
+        assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k

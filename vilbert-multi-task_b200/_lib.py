@@ -94,6 +94,7 @@ _SIGNATURES = {
     "vb_step_counter_bump": [_P, _P],
     "vb_broadcast_rows": [_P, _P, _I64, _I32, _P],
     "vb_repeat_rows": [_P, _P, _I64, _I64, _I32, _P],
+    "vb_sum_strided": [_P, _P, _I64, _I32, _I64, _I32, _I64, _I32, _P],
     "vb_relu_bwd": [_P, _P, _P, _P, _I64, _P],
     "vb_axpy_f32": [_P, _P, _I64, _F, _P],
     "vb_bce_logits_loss": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],

@@ -95,10 +95,12 @@ class BertConfig(object):
             unsupported.append("hidden_act != 'gelu'")
         if getattr(self, "model", "bert") != "bert":
             unsupported.append("model='roberta' (out of scope, SURVEY.md appendix B.12)")
-        for flag in ("dynamic_attention", "in_batch_pairs", "visualization"):
+        for flag in ("dynamic_attention", "visualization"):
             if getattr(self, flag, False):
                 unsupported.append(flag)
         if getattr(self, "fixed_t_layer", 0) > min(self.t_biattention_id) or getattr(self, "fixed_v_layer", 0) > min(self.v_biattention_id):
             unsupported.append("fixed_t_layer / fixed_v_layer beyond the first connection layer (the reference asserts the same, vilbert.py:965-966)")
+        if getattr(self, "in_batch_pairs", False) and getattr(self, "fast_mode", False):
+            unsupported.append("in_batch_pairs together with fast_mode")
         if unsupported:
             raise NotImplementedError("vilbert_b200: unsupported config options: " + ", ".join(unsupported))

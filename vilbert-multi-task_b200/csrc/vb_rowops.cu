@@ -544,6 +544,24 @@ __global__ void repeat_rows_kernel(const uint4* __restrict__ src, uint4* __restr
   }
 }
 
+// dst[k][e] (+)= sum_r src[k * stride_k + r * stride_r + e], e < n (fp32, n % 4 == 0): the backward of the in_batch_pairs expansion
+// (the gradient of an item broadcast to B pairs is the sum over its B copies)
+__global__ void sum_strided_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long n4, int count_k, long long stride_k4,
+                                   int count_r, long long stride_r4, int accumulate) {
+  pdl_entry();
+  const long long total = n4 * count_k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / n4, e = i % n4;
+    float4 acc = accumulate ? dst[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* s = src + k * stride_k4 + e;
+    for (int r = 0; r < count_r; ++r) {
+      const float4 v = s[(long long)r * stride_r4];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    dst[i] = acc;
+  }
+}
+
 __global__ void step_bump_kernel(uint32_t* ctr) {
   pdl_entry();
   if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += 1u;
@@ -749,6 +767,15 @@ extern "C" vb_status vb_repeat_rows(const void* src, void* dst, int64_t bytes, i
   launch_pdl(repeat_rows_kernel, dim3(ew_grid(bytes / 16 * items * repeats)), dim3(256), (size_t)0, ST(stream), static_cast<const uint4*>(src),
              static_cast<uint4*>(dst), (long long)(bytes / 16), (long long)items, (int)repeats);
   return check_launch("vb_repeat_rows");
+}
+
+extern "C" vb_status vb_sum_strided(const float* src, float* dst, int64_t n, int32_t count_k, int64_t stride_k, int32_t count_r, int64_t stride_r,
+                                    int32_t accumulate, void* stream) {
+  if (n <= 0 || count_k <= 0 || count_r <= 0) return VB_OK;
+  if ((n & 3) || (stride_k & 3) || (stride_r & 3) || !al16(src) || !al16(dst)) return set_error(VB_ERR_INVALID, "vb_sum_strided: sizes / strides must be multiples of 4 floats, buffers 16-byte aligned");
+  launch_pdl(sum_strided_kernel, dim3(ew_grid(n / 4 * count_k)), dim3(256), (size_t)0, ST(stream), reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst),
+             (long long)(n / 4), (int)count_k, (long long)(stride_k / 4), (int)count_r, (long long)(stride_r / 4), (int)(accumulate ? 1 : 0));
+  return check_launch("vb_sum_strided");
 }
 
 extern "C" vb_status vb_step_counter_bump(uint32_t* step, void* stream) {

@@ -245,7 +245,11 @@ class Plan:
         self.ps = _TrackedParams(engine.ps, self)
         self.lib = L.lib()
         self.dev = engine.device
-        self.B, self.Nt_in, self.Nv = B, Nt, Nv
+        # in_batch_pairs (vilbert.py:1008-1040): at the first connection layer every (text i, image j) combination of the input
+        # batch becomes one sample: the streams run at the input batch before it and at B^2 from there on
+        self.pairs = bool(getattr(engine.cfg, "in_batch_pairs", False))
+        self.Bin = B
+        self.B, self.Nt_in, self.Nv = (B * B if self.pairs else B), Nt, Nv
         self.has_task = bool(self.cfg.task_specific_tokens)
         self.Nt = Nt + (1 if self.has_task else 0)
         # FAST_MODE (vilbert.py:1042-1053, eval_retrieval.py): one caption (text batch 1) against B images; inference only
@@ -662,6 +666,48 @@ class Plan:
         self.mask_t = m
         return Act(f32, b16, B * M1, H, lo=lo)
 
+    def expand_pairs(self, t, v):
+        """in_batch_pairs (vilbert.py:1008-1040): sample p = i * b + j of the expanded batch pairs text i with image j —
+        txt.unsqueeze(1).expand(b, b, ...) (every text repeated b times) and img.unsqueeze(0).expand(b, b, ...) (the image batch
+        tiled b times). Backward: the gradient of an item is the sum over its b copies (vb_sum_strided)."""
+        b, lib = self.Bin, self.lib
+        outs = []
+        self.sync_streams()      # the image stream's tensors are expanded on the main stream
+        for act, N, is_text in ((t, self.Nt, True), (v, self.Nv, False)):
+            n = N * act.H
+            f32 = self.buf((b * b * N, act.H), F32)
+            b16, lo, bw = self.buf16((b * b * N, act.H))
+            bufs = [(act.f32, f32, 4), (act.b16, b16, 2)] + ([(act.lo, lo, 2)] if lo is not None else []) + ([(act.bw, bw, 2)] if bw is not b16 else [])
+            for src, dst, sz in bufs:
+                if is_text:
+                    self.emit(lib.vb_repeat_rows, src.data_ptr(), dst.data_ptr(), n * sz, b, b)
+                else:
+                    self.emit(lib.vb_broadcast_rows, src.data_ptr(), dst.data_ptr(), b * n * sz, b)
+            out = Act(f32, b16, b * b * N, act.H, lo=lo, bw=bw)
+            outs.append(out)
+
+            def bwd(act=act, out=out, n=n, is_text=is_text):
+                if not out.gw or act.frozen:
+                    return
+                g = self.grad_of(act)
+                acc = 1 if act.gw else 0
+                if is_text:   # g[i] = sum_j out.g32[i * b + j]
+                    self.emit(lib.vb_sum_strided, out.g32.data_ptr(), g.data_ptr(), n, b, b * n, b, n, acc)
+                else:         # g[j] = sum_i out.g32[i * b + j]
+                    self.emit(lib.vb_sum_strided, out.g32.data_ptr(), g.data_ptr(), n, b, n, b, b * n, acc)
+                act.gw = True
+            self._bwd_emitters.append(None)
+            self.push_bwd(bwd)
+            self._bwd_emitters.append(None)
+        # masks: text mask rows repeated, image mask tiled (4-byte rows: plain torch-free kernels need 16-byte items -> host-side views)
+        mt = self.buf((b * b, self.Nt), F32); mv = self.buf((b * b, self.Nv), F32)
+        self._pair_masks = (self.mask_t, self.mask_v, mt, mv)
+        self.emit(lib.vb_mask_to_additive, self.in_amask_pairs.data_ptr(), mt.data_ptr(), b * b, self.Nt_in, 1 if self.has_task else 0)
+        self.emit(lib.vb_mask_to_additive, self.in_imask_pairs.data_ptr(), mv.data_ptr(), b * b, self.Nv, 0)
+        self.mask_t, self.mask_v = mt, mv
+        self.sync_streams()
+        return outs[0], outs[1]
+
     def text_layer(self, x, i):
         p = f"bert.encoder.layer.{i}"
         c = self.cfg
@@ -673,14 +719,14 @@ class Plan:
     def image_layer(self, x, i):
         p = f"bert.encoder.v_layer.{i}"
         c = self.cfg
-        h1 = self.self_attention_block(x, self.B, self.Nv, c.v_num_attention_heads, self.mask_v, p + ".attention", "v",
+        h1 = self.self_attention_block(x, x.M // self.Nv, self.Nv, c.v_num_attention_heads, self.mask_v, p + ".attention", "v",
                                        p_attn=c.v_attention_probs_dropout_prob, p_hidden=c.v_hidden_dropout_prob)
         return self.ffn(h1, c.v_intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "v.ffn",
                         drop=self.drop(p + ".output.dropout", c.v_hidden_dropout_prob))
 
     # ------------------------------------------------------------------ embeddings
     def embeddings(self):
-        ps, c, B, lib = self.ps, self.cfg, self.B, self.lib
+        ps, c, B, lib = self.ps, self.cfg, self.Bin, self.lib     # the embeddings run at the INPUT batch
         Ht, Hv, Nt, Nv, Fv = c.hidden_size, c.v_hidden_size, self.Nt, self.Nv, c.v_feature_size
         Bt = self.Bt
         Mt, Mv = Bt * Nt, B * Nv
@@ -690,6 +736,9 @@ class Plan:
         self.in_task = self.buf((Bt,), I64, zero=True) if self.has_task else None
         self.in_amask = self.buf((Bt, self.Nt_in), I64, zero=True)
         self.in_amask_b = self.in_amask.expand(B, self.Nt_in).contiguous() if self.fast else self.in_amask   # refreshed in load_inputs
+        if self.pairs:   # 0/1 masks of the expanded batch (text rows repeated, image rows tiled); refreshed in load_inputs
+            self.in_amask_pairs = self.buf((B * B, self.Nt_in), I64, zero=True)
+            self.in_imask_pairs = self.buf((B * B, Nv), I64, zero=True)
         self.in_imask = self.buf((B, Nv), I64, zero=True)
         self.in_feat = self.buf((B, Nv, Fv), F32, zero=True)
         self.in_loc = self.buf((B, Nv, 5), F32, zero=True)
@@ -969,6 +1018,8 @@ class Plan:
                     v.frozen = frozen
             if count == 0 and self.fast:
                 t = self.broadcast_text(t)
+            if count == 0 and self.pairs:
+                t, v = self.expand_pairs(t, v)
             if c.with_coattention:
                 v, t = self.connection_layer(v, t, count)
             v_start, t_start = v_end, t_end
@@ -1096,6 +1147,10 @@ class Plan:
             self.in_imask.fill_(1)
         else:
             self.in_imask.copy_(image_attention_mask, non_blocking=non_blocking)
+        if self.pairs:
+            b = self.Bin
+            self.in_amask_pairs.view(b, b, -1).copy_(self.in_amask.unsqueeze(1).expand(b, b, -1))
+            self.in_imask_pairs.view(b, b, -1).copy_(self.in_imask.unsqueeze(0).expand(b, b, -1))
         self.in_feat.copy_(input_imgs, non_blocking=non_blocking)
         self.in_loc.copy_(image_loc, non_blocking=non_blocking)
         if self.has_task:
