@@ -173,6 +173,9 @@ typedef struct vb_attn_args {
 
 vb_status vb_attention_fwd(const vb_attn_args* args, void* stream);
 vb_status vb_attention_bwd(const vb_attn_args* args, void* stream);
+/* Attention-probability export of config.visualization (attn_data["attn"], vilbert.py:451-458, 610-617, 813-821):
+ * probs f32 [B, H, Nq, Nk] = softmax(Q K^T * scale + mask) from the Q / K / mask / scale fields of args (eval mode: no dropout). */
+vb_status vb_attention_probs(const vb_attn_args* args, float* probs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-wise (HBM-bound) kernels. One warp per row, 128-bit accesses.

@@ -218,6 +218,47 @@ def check_in_batch_pairs(ref, cfg_json):
                        pin=dict(worst=worst, tolerance=TOL)), f)
 
 
+def check_visualization(ref, cfg_json):
+    """visualization=True + output_all_attention_masks=True: the attn_data dicts of every layer (vilbert.py:451-458, 610-617,
+    813-821) against the oracle's attention hook (probabilities, queries, keys)."""
+    cfgj = dict(cfg_json, visualization=True)
+    cfg = O.make_config(cfgj)
+    model = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfgj)), num_labels=1, default_gpu=False)
+    P = O.synth_params(cfg, seed=0)
+    model.load_state_dict(P, strict=False); model.tie_weights(); model.eval()
+    inp = O.synth_inputs(cfg, 3, 11, 9, seed=777)
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], inp["co_attention_mask"])
+    with torch.no_grad():
+        out = model(*args, None, False, True)
+    at, av, ac = out[9]
+    got = {}
+    O.ATTN_HOOK = lambda name, p, q, k: got.__setitem__(name, (p, q, k))
+    try:
+        with torch.no_grad():
+            O.vilbert_for_vl_tasks(P, cfg, *args)
+    finally:
+        O.ATTN_HOOK = None
+    worst = 0.0
+    for i, d in enumerate(at):
+        p, q, k = got[f"bert.encoder.layer.{i}.attention.self.dropout"]
+        worst = max(worst, rel(p, d["attn"]), rel(q, d["queries"]), rel(k, d["keys"]))
+    for i, d in enumerate(av):
+        p, q, k = got[f"bert.encoder.v_layer.{i}.attention.self.dropout"]
+        worst = max(worst, rel(p, d["attn"]), rel(q, d["queries"]), rel(k, d["keys"]))
+    for i, d in enumerate(ac):
+        p1, q1, k1 = got[f"bert.encoder.c_layer.{i}.biattention.dropout1"]
+        p2, q2, k2 = got[f"bert.encoder.c_layer.{i}.biattention.dropout2"]
+        worst = max(worst, rel(p1, d["attn1"]), rel(q1, d["queries1"]), rel(k1, d["keys1"]), rel(p2, d["attn2"]), rel(q2, d["querues2"]), rel(k2, d["keys2"]))
+    print(f"{'visualization':28s} worst {worst:.2e}; {len(at)} text, {len(av)} image, {len(ac)} connection layers")
+    assert worst < TOL and len(at) == cfg["num_hidden_layers"] and len(ac) == len(cfg["v_biattention_id"])
+    with open(os.path.join(GOLD, "tiny_visualization.json"), "w") as f:
+        json.dump(dict(name="tiny_visualization", config=cfgj, B=3, Nv=11, Nt=9, seed=0, input_seed=777,
+                       attn_text_last=dict(summary(at[-1]["attn"]), shape=list(at[-1]["attn"].shape)),
+                       attn1_last=dict(summary(ac[-1]["attn1"]), shape=list(ac[-1]["attn1"].shape)),
+                       attn2_last=dict(summary(ac[-1]["attn2"]), shape=list(ac[-1]["attn2"].shape)),
+                       pin=dict(worst=worst, tolerance=TOL)), f)
+
+
 def check_fixed_layers(ref, cfg_json):
     """fixed_t_layer / fixed_v_layer: the first layers of each stream run under no_grad (vilbert.py:968-1003): same outputs,
     no gradient into those layers or anything before them."""
@@ -272,6 +313,7 @@ def main():
     check_fast_mode(ref, TINY)
     check_fixed_layers(ref, TINY)
     check_in_batch_pairs(ref, TINY)
+    check_visualization(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

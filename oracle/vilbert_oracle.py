@@ -103,6 +103,9 @@ def linear(P, name, x):
     return F.linear(x, P[name + ".weight"], P.get(name + ".bias"))
 
 
+ATTN_HOOK = None   # optional callable(layer dropout name, probs [B,H,Nq,Nk], queries [B,H,Nq,D], keys [B,H,Nk,D]) used by the visualization tests
+
+
 def _heads(x, n_heads):
     """transpose_for_scores, vilbert.py:416-422 / :732-739."""
     B, N, H = x.shape
@@ -117,6 +120,8 @@ def attention(q, k, v, add_mask, n_heads, drop=None, drop_name=None, drop_p=0.0)
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
     s = s + add_mask
     p = torch.softmax(s, dim=-1)
+    if ATTN_HOOK is not None:       # config.visualization: attn_data of the reference (probabilities before dropout is identity in eval)
+        ATTN_HOOK(drop_name, p, q, k)
     p = _drop(p, drop, drop_name, drop_p)
     ctx = torch.matmul(p, v).permute(0, 2, 1, 3).contiguous()
     return ctx.view(ctx.shape[0], ctx.shape[1], -1)

@@ -185,6 +185,50 @@ def test_in_batch_pairs_expansion(golden_dir):
     assert len(l2) > 40 and l2[-1][0] < 2e-2 and l2[len(l2) // 2][0] < 1e-2, l2[-3:]
 
 
+def test_visualization_attention_export(golden_dir):
+    """config.visualization + output_all_attention_masks=True: the attn_data dicts of every text / image / connection layer
+    (probabilities, queries, keys; vilbert.py:451-458, 610-617, 813-821) through the module surface vs the oracle's attention hook
+    (pinned against the reference: tests/golden/tiny_visualization.json). Without config.visualization the lists hold one None per
+    layer, like the reference."""
+    import vilbert_b200
+    from _gpu_util import rel
+    meta = json.load(open(os.path.join(golden_dir, "tiny_visualization.json")))
+    cfgj = meta["config"]
+    cfg = O.make_config(cfgj)
+    P = O.synth_params(cfg, seed=0, device="cuda")
+    inp = O.synth_inputs(cfg, 3, 11, 9, seed=777, device="cuda")
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+    model = vilbert_b200.VILBertForVLTasks(vilbert_b200.BertConfig.from_dict(cfgj), num_labels=1)
+    model.load_state_dict(P, strict=True); model.eval()
+    out = model(*args, None, None, False, True)
+    at, av, ac = out[9]
+    got = {}
+    O.ATTN_HOOK = lambda name, p, q, k: got.__setitem__(name, (p, q, k))
+    try:
+        with torch.no_grad():
+            O.vilbert_for_vl_tasks(P, cfg, *args)
+    finally:
+        O.ATTN_HOOK = None
+    assert len(at) == cfg["num_hidden_layers"] and len(av) == cfg["v_num_hidden_layers"] and len(ac) == len(cfg["v_biattention_id"])
+    for i, d in enumerate(at):
+        p, q, k = got[f"bert.encoder.layer.{i}.attention.self.dropout"]
+        assert d["attn"].shape == p.shape and rel(d["attn"], p) < 1e-2 and rel(d["queries"], q) < 1e-2 and rel(d["keys"], k) < 1e-2, ("text", i)
+        assert (d["attn"].sum(-1) - 1).abs().max().item() < 1e-5
+    for i, d in enumerate(av):
+        p, q, k = got[f"bert.encoder.v_layer.{i}.attention.self.dropout"]
+        assert rel(d["attn"], p) < 1e-2 and rel(d["queries"], q) < 1e-2 and rel(d["keys"], k) < 1e-2, ("image", i)
+    for i, d in enumerate(ac):
+        p1, q1, k1 = got[f"bert.encoder.c_layer.{i}.biattention.dropout1"]
+        p2, q2, k2 = got[f"bert.encoder.c_layer.{i}.biattention.dropout2"]
+        assert rel(d["attn1"], p1) < 1e-2 and rel(d["queries1"], q1) < 1e-2 and rel(d["keys1"], k1) < 1e-2, ("conn1", i)
+        assert rel(d["attn2"], p2) < 1e-2 and rel(d["querues2"], q2) < 1e-2 and rel(d["keys2"], k2) < 1e-2, ("conn2", i)
+    plain = vilbert_b200.VILBertForVLTasks(vilbert_b200.BertConfig.from_dict(dict(cfgj, visualization=False)), num_labels=1)
+    plain.eval()
+    m = plain(*args, None, None, False, True)[9]
+    assert m == ([None] * cfg["num_hidden_layers"], [None] * cfg["v_num_hidden_layers"], [None] * len(cfg["v_biattention_id"]))
+    assert plain(*args)[9] == ([], [], [])
+
+
 def test_fixed_layers_stop_the_gradient(golden_dir):
     """config.fixed_t_layer (vilbert.py:968-1003: the first text layers run under torch.no_grad()): outputs unchanged, the frozen
     layers, the embeddings before them and nothing else lose their gradient (set of gradient-free tensors recorded from the

@@ -146,3 +146,25 @@ def test_in_batch_pairs_golden(golden_dir):
         t = t.detach().double().flatten()
         assert (t[torch.tensor(s["sample_idx"])] - torch.tensor(s["samples"], dtype=torch.float64)).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), k
         assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
+
+
+def test_visualization_golden(golden_dir):
+    """config.visualization: attention probabilities of the last text layer and last connection layer recorded from the reference."""
+    meta = json.load(open(os.path.join(golden_dir, "tiny_visualization.json")))
+    cfg = O.make_config(meta["config"])
+    P = O.synth_params(cfg, seed=meta["seed"])
+    inp = O.synth_inputs(cfg, meta["B"], meta["Nv"], meta["Nt"], seed=meta["input_seed"])
+    got = {}
+    O.ATTN_HOOK = lambda name, p, q, k: got.__setitem__(name, p)
+    try:
+        with torch.no_grad():
+            O.vilbert_for_vl_tasks(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+    finally:
+        O.ATTN_HOOK = None
+    nl, nc = cfg["num_hidden_layers"] - 1, len(cfg["v_biattention_id"]) - 1
+    for key, name in (("attn_text_last", f"bert.encoder.layer.{nl}.attention.self.dropout"), ("attn1_last", f"bert.encoder.c_layer.{nc}.biattention.dropout1"),
+                      ("attn2_last", f"bert.encoder.c_layer.{nc}.biattention.dropout2")):
+        s, t = meta[key], got[name]
+        assert list(t.shape) == s["shape"], key
+        t = t.double().flatten()
+        assert (t[torch.tensor(s["sample_idx"])] - torch.tensor(s["samples"], dtype=torch.float64)).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), key

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "vb_gemm_plan": [C.POINTER(GemmArgs), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "vb_attention_fwd": [C.POINTER(AttnArgs), _P],
     "vb_attention_bwd": [C.POINTER(AttnArgs), _P],
+    "vb_attention_probs": [C.POINTER(AttnArgs), _P, _P],
     "vb_layernorm_fwd": [_P, _I64, _P, _P, _F, _P, _P, _I64, _P, _P, _I32, _I32, _P, _I32, _P, _P, _P],
     "vb_layernorm_bwd": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I32, _I32, _P, _P, _P],
     "vb_cast_f32_to_bf16": [_P, _P, _I64, _I32, _P, _P, _P],

@@ -95,7 +95,7 @@ class BertConfig(object):
             unsupported.append("hidden_act != 'gelu'")
         if getattr(self, "model", "bert") != "bert":
             unsupported.append("model='roberta' (out of scope, SURVEY.md appendix B.12)")
-        for flag in ("dynamic_attention", "visualization"):
+        for flag in ("dynamic_attention",):
             if getattr(self, flag, False):
                 unsupported.append(flag)
         if getattr(self, "fixed_t_layer", 0) > min(self.t_biattention_id) or getattr(self, "fixed_v_layer", 0) > min(self.v_biattention_id):

@@ -649,6 +649,50 @@ __global__ void __launch_bounds__(ATT1_THREADS) attn_bwd_fused_kernel(const Attn
   }
 }
 
+// ------------------------------------------------------------------------------------------ probability export (visualization)
+// P[b, h, q, :] = softmax(Q K^T * scale + mask) as fp32 — the tensor the reference returns as attn_data["attn"] when
+// config.visualization is set (vilbert.py:451-458, 610-617, 813-821). Inspection path: one warp per (b, h, q) row, fp32 SIMT.
+__global__ void __launch_bounds__(256) attn_probs_kernel(const AttnParams p, float* __restrict__ P, int D) {
+  pdl_entry();
+  extern __shared__ float sq[];            // [8 warps][D] query rows
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rows = (long long)p.B * p.H * p.Nq;
+  float* myq = sq + warp * D;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+    const int q = (int)(r % p.Nq), h = (int)((r / p.Nq) % p.H), b = (int)(r / ((long long)p.Nq * p.H));
+    const uint16_t* qrow = reinterpret_cast<const uint16_t*>(p.Q) + ((long long)b * p.Nq + q) * p.ldq + h * D;
+    for (int d = lane; d < D; d += 32) myq[d] = cvt16_to_f32(qrow[d], p.qkv_fp16);
+    __syncwarp();
+    float* prow = P + r * p.Nk;
+    float mx = -CUDART_INF_F;
+    for (int k = lane; k < p.Nk; k += 32) {
+      const uint16_t* krow = reinterpret_cast<const uint16_t*>(p.K) + ((long long)b * p.Nk + k) * p.ldk + h * D;
+      float acc = 0.f;
+      for (int d = 0; d < D; d += 8) {
+        const uint4 kv = *reinterpret_cast<const uint4*>(krow + d);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&kv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack16(w[i], p.qkv_fp16);
+          acc += myq[d + 2 * i] * f.x + myq[d + 2 * i + 1] * f.y;
+        }
+      }
+      const float s = acc * p.scale + (p.mask ? p.mask[(long long)b * p.Nk + k] : 0.f);
+      prow[k] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int k = lane; k < p.Nk; k += 32) { const float e = __expf(prow[k] - mx); prow[k] = e; sum += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int k = lane; k < p.Nk; k += 32) prow[k] *= inv;
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -785,4 +829,19 @@ extern "C" vb_status vb_attention_bwd(const vb_attn_args* a, void* stream) {
       if ((s = launch_att(attn_bwd_dq_kernel<128>, gq, smem_q, p, st, "vb_attention_bwd(dq)"))) return s;
       return launch_att(attn_bwd_dkv_kernel<128>, gk, smem_k, p, st, "vb_attention_bwd(dkv)");
   }
+}
+
+extern "C" vb_status vb_attention_probs(const vb_attn_args* a, float* probs, void* stream) {
+  using namespace vb;
+  if (!a || !probs || !a->Q || !a->K) return set_error(VB_ERR_INVALID, "vb_attention_probs: null argument");
+  if (a->B <= 0 || a->H <= 0 || a->Nq <= 0 || a->Nk <= 0 || (a->D % 8) || a->D > 512) return set_error(VB_ERR_INVALID, "vb_attention_probs: bad shape");
+  if ((a->ldq % 8) || (a->ldk % 8) || !al16(a->Q) || !al16(a->K)) return set_error(VB_ERR_INVALID, "vb_attention_probs: Q / K need ld %% 8 == 0 and 16-byte aligned bases");
+  AttnParams p = to_params(a);
+  const long long rows = (long long)a->B * a->H * a->Nq;
+  long long blocks = (rows + 7) / 8;
+  int cap = sm_count() * 8; if (cap <= 0) cap = 148 * 8;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  cudaError_t e = launch_pdl(attn_probs_kernel, dim3(grid), dim3(256), (size_t)(8 * a->D * sizeof(float)), (cudaStream_t)stream, p, probs, (int)a->D);
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_attention_probs: %s", cudaGetErrorString(e));
+  return VB_OK;
 }

@@ -253,6 +253,11 @@ class Plan:
         self.has_task = bool(self.cfg.task_specific_tokens)
         self.Nt = Nt + (1 if self.has_task else 0)
         # FAST_MODE (vilbert.py:1042-1053, eval_retrieval.py): one caption (text batch 1) against B images; inference only
+        # config.visualization (vilbert.py:451-458, 610-617, 813-821): export attention probabilities, queries and keys per layer
+        self.viz = bool(getattr(self.cfg, "visualization", False))
+        self.attn_t, self.attn_v, self.attn_c = [], [], []
+        if self.viz and train:
+            raise ValueError("visualization exports the undropped attention probabilities: eval mode only")
         self.fast = bool(getattr(self.cfg, "fast_mode", False))
         self.Bt = 1 if self.fast else B
         if self.fast and (train or grad_outputs or vqa_loss or loss):
@@ -420,6 +425,11 @@ class Plan:
             a.dropout = dropout
         self._keep.append(a)
         self.emit(self.lib.vb_attention_bwd if bwd else self.lib.vb_attention_fwd, C.byref(a))
+        if not bwd and self.viz:
+            # config.visualization: the probabilities (fp32 [B, heads, Nq, Nk]) and views of the queries / keys the reference returns
+            probs = self.buf((B, H, Nq, Nk), F32)
+            self.emit(self.lib.vb_attention_probs, C.byref(a), probs.data_ptr())
+            self._last_attn = dict(attn=probs, q=Q, k=K, B=B, H=H, Nq=Nq, Nk=Nk, D=D)
 
     def ln_fwd(self, x, gamma, beta, M, H, want_f32=True, out_drop=None):
         y32 = self.buf((M, H), F32) if want_f32 else None
@@ -545,6 +555,8 @@ class Plan:
         adrop = self.drop(prefix + ".self.dropout", p_attn)
         self.attention(False, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dropout=adrop, q_lo=ql, k_lo=kl, v_lo=vl, o_lo=ctxl,
                        o_b16=self._extra(ctxb, ctx))
+        if self.viz:
+            (self.attn_t if tag == "t" else self.attn_v).append(self._last_attn)
         out, out_bwd = self.dense_res_ln(ctx, H, x, prefix + ".output.dense", prefix + ".output.LayerNorm", tag + ".ao",
                                          drop=self.drop(prefix + ".output.dropout", p_hidden), a_lo=ctxl, a_bw=ctxb)
 
@@ -596,9 +608,13 @@ class Plan:
         adrop2 = self.drop(p + ".biattention.dropout2", c.attention_probs_dropout_prob)
         self.attention(False, B, nh, Nt, Nv, D, q2, L3, k1, L3, v1, L3, self.mask_v, ctx1, Hb, lse1, dropout=adrop1,
                        q_lo=q2l, k_lo=k1l, v_lo=v1l, o_lo=ctx1l, o_b16=self._extra(ctx1b, ctx1))
+        a1 = self._last_attn if self.viz else None
         with self.on(1):
             self.attention(False, B, nh, Nv, Nt, D, q1, L3, k2, L3, v2, L3, self.mask_t, ctx2, Hb, lse2, dropout=adrop2,
                            q_lo=q1l, k_lo=k2l, v_lo=v2l, o_lo=ctx2l, o_b16=self._extra(ctx2b, ctx2))
+            a2 = self._last_attn if self.viz else None
+        if self.viz:
+            self.attn_c.append((a1, a2))
         # biOutput: ctx2 -> vision stream (dense1 / LayerNorm1), ctx1 -> text stream (dense2 / LayerNorm2) (:890-892)
         with self.on(1):
             v1o, v1_bwd = self.dense_res_ln(ctx2, Hb, v, p + ".biOutput.dense1", p + ".biOutput.LayerNorm1", "c.v.bo",
@@ -1077,6 +1093,20 @@ class Plan:
         self.cur.append((None, ("all",), 0))     # join every stream (incl. the weight-gradient side streams)
         self.n_kernels_bwd = sum(1 for op in self.bwd if op[0] is not None)
         self.cur = self.fwd
+
+    def attention_export(self):
+        """The reference's all_attention_mask triple (BertEncoder.forward, vilbert.py:1098-1107) for config.visualization: lists of
+        attn_data dicts in layer order — text / image: {"attn", "queries", "keys"}; connection layers: {"attn1", "queries1",
+        "keys1", "attn2", "querues2" (the reference's spelling), "keys2"}. Tensors are fp32 [B, heads, N, ...] copies."""
+        def qk(d, which, N):
+            x = d[which]
+            return x.float().reshape(d["B"], N, d["H"], d["D"]).permute(0, 2, 1, 3).contiguous()
+        def one(d):
+            return {"attn": d["attn"].clone(), "queries": qk(d, "q", d["Nq"]), "keys": qk(d, "k", d["Nk"])}
+        ts, vs = [one(d) for d in self.attn_t], [one(d) for d in self.attn_v]
+        cs = [{"attn1": a1["attn"].clone(), "queries1": qk(a1, "q", a1["Nq"]), "keys1": qk(a1, "k", a1["Nk"]),
+               "attn2": a2["attn"].clone(), "querues2": qk(a2, "q", a2["Nq"]), "keys2": qk(a2, "k", a2["Nk"])} for a1, a2 in self.attn_c]
+        return ts, vs, cs
 
     def _emit_loss(self):
         """Fused objectives other than "vqa": one loss kernel per head writes the scalar (self.loss, fp32 device) and the fp32

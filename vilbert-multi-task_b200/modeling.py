@@ -40,11 +40,9 @@ class _BertNode(_Node):
 
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
-        if output_all_attention_masks:
-            raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
         owner = self.__dict__["_owner_ref"]()
         return owner._bert_forward(input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids,
-                                   output_all_encoded_layers)
+                                   output_all_encoded_layers, output_all_attention_masks)
 
 
 def _register_tree(root, store):
@@ -295,8 +293,19 @@ class BertPreTrainedModel(nn.Module):
         model.eval()
         return model
 
+    def _attention_masks(self, output_all_attention_masks):
+        """all_attention_mask of the reference's outputs: empty lists unless asked for; with config.visualization the attn_data
+        dicts of every layer, without it one None per layer (BertEncoder appends whatever the layer returned, vilbert.py:974-1061)."""
+        if not output_all_attention_masks:
+            return ([], [], [])
+        plan = self._last_plan
+        if plan.viz:
+            return plan.attention_export()
+        c = self.config
+        return ([None] * c.num_hidden_layers, [None] * c.v_num_hidden_layers, [None] * len(c.v_biattention_id))
+
     def _bert_forward(self, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids,
-                      output_all_encoded_layers):
+                      output_all_encoded_layers, output_all_attention_masks=False):
         """BertModel.forward outputs (vilbert.py:1388-1406). With output_all_encoded_layers the encoded-layer entries are lists with
         one tensor per connection layer (:1075-1077); only the last entry is connected to autograd here."""
         o = self._run(BERT_OUT_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
@@ -311,8 +320,8 @@ class BertPreTrainedModel(nn.Module):
             # inspection path (not the hot path) reproduces that with two tiny fp32 ops on the pooler parameters.
             pt = F.relu(F.linear(enc_t[-1][:, 0], self._params["bert.t_pooler.dense.weight"], self._params["bert.t_pooler.dense.bias"]))
             pv = F.relu(F.linear(enc_v[-1][:, 0], self._params["bert.v_pooler.dense.weight"], self._params["bert.v_pooler.dense.bias"]))
-            return (enc_t, enc_v, pt, pv, ([], [], []))
-        return (seq_t, seq_v, o["pooled_output_t"], o["pooled_output_v"], ([], [], []))
+            return (enc_t, enc_v, pt, pv, self._attention_masks(output_all_attention_masks))
+        return (seq_t, seq_v, o["pooled_output_t"], o["pooled_output_v"], self._attention_masks(output_all_attention_masks))
 
     # ---- shared forward machinery
     def _run(self, names, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids):
@@ -335,10 +344,8 @@ class BertModel(BertPreTrainedModel):
 
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
-        if output_all_attention_masks:
-            raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
         return self._bert_forward(input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids,
-                                  output_all_encoded_layers)
+                                  output_all_encoded_layers, output_all_attention_masks)
 
 
 class VILBertForVLTasks(BertPreTrainedModel):
@@ -355,14 +362,12 @@ class VILBertForVLTasks(BertPreTrainedModel):
 
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 co_attention_mask=None, task_ids=None, output_all_encoded_layers=False, output_all_attention_masks=False):
-        if output_all_attention_masks:
-            raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
         if output_all_encoded_layers:
             raise NotImplementedError("VILBertForVLTasks(output_all_encoded_layers=True) is not supported; use model.bert(..., output_all_encoded_layers=True)")
         if image_attention_mask is None:
             raise TypeError("image_attention_mask is required by VILBertForVLTasks.forward (vilbert.py:1693)")
         o = self._run(HEAD_NAMES, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, task_ids)
-        return tuple(o[n] for n in HEAD_NAMES) + (([], [], []),)
+        return tuple(o[n] for n in HEAD_NAMES) + (self._attention_masks(output_all_attention_masks),)
 
 
 class BertForMultiModalPreTraining(BertPreTrainedModel):
@@ -379,8 +384,6 @@ class BertForMultiModalPreTraining(BertPreTrainedModel):
 
     def forward(self, input_ids, image_feat, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 masked_lm_labels=None, image_label=None, image_target=None, next_sentence_label=None, output_all_attention_masks=False):
-        if output_all_attention_masks:
-            raise NotImplementedError("attention-probability export (visualization) is out of scope (SURVEY.md §8f.4)")
         names = ("linguisic_prediction", "vision_prediction", "seq_relationship_score")
         o = self._run(names, input_ids, image_feat, image_loc, token_type_ids, attention_mask, image_attention_mask, None)
         prediction_scores_t, prediction_scores_v, seq_relationship_score = (o[n] for n in names)
@@ -391,4 +394,4 @@ class BertForMultiModalPreTraining(BertPreTrainedModel):
             masked_lm_loss = F.cross_entropy(prediction_scores_t.view(-1, self.config.vocab_size), masked_lm_labels.view(-1), ignore_index=-1)
             next_sentence_loss = F.cross_entropy(seq_relationship_score.view(-1, 2), next_sentence_label.view(-1), ignore_index=-1)
             return masked_lm_loss.unsqueeze(0), masked_img_loss.unsqueeze(0), next_sentence_loss.unsqueeze(0)
-        return prediction_scores_t, prediction_scores_v, seq_relationship_score, ([], [], [])
+        return prediction_scores_t, prediction_scores_v, seq_relationship_score, self._attention_masks(output_all_attention_masks)
