@@ -200,6 +200,8 @@ def test_batch_expansion_and_prefetcher():
                                                    torch.ones(B, 2 * Nv, device=dev).long(), q[:, 0], am[:, 0], seg[:, 0])
     assert f3.shape == (2 * B, Nv, 2048) and torch.equal(q3[0], q3[1]) and torch.equal(q3[0], q[0, 0])
     batches = [(torch.randn(4, 3), torch.arange(4) + i) for i in range(5)]
-    got = list(PinnedBatchPrefetcher(batches))
-    torch.cuda.synchronize()
-    assert len(got) == 5 and all(torch.equal(g[1].cpu(), b[1]) and torch.equal(g[0].cpu(), b[0]) for g, b in zip(got, batches))
+    n = 0
+    for g, bt in zip(PinnedBatchPrefetcher(batches), batches):      # a yielded batch is valid until `depth` more are requested: consume it now
+        assert g[0].is_cuda and torch.equal(g[1].cpu(), bt[1]) and torch.equal(g[0].cpu(), bt[0])
+        n += 1
+    assert n == 5

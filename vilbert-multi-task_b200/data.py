@@ -76,7 +76,8 @@ def expand_batch(process, features, spatials, image_mask, question, input_mask, 
 class PinnedBatchPrefetcher:
     """Iterates over `batches` (an iterable of tuples / dicts of CPU tensors, e.g. a DataLoader) and yields them on the GPU one
     batch ahead: each batch is staged in pinned host buffers (allocated once per shape) and copied on a dedicated copy stream while
-    the previous batch computes; the consumer's stream waits on the copy's event only."""
+    the previous batch computes; the consumer's stream waits on the copy's event only. A yielded batch lives in one of
+    `depth + 1` rotating device buffers: it stays valid until `depth` further batches have been requested (consume it, or clone)."""
 
     def __init__(self, batches, device=None, depth=2):
         self.it = iter(batches)
@@ -84,6 +85,7 @@ class PinnedBatchPrefetcher:
         self.stream = torch.cuda.Stream(device=self.device)
         self.depth = depth
         self._pinned = {}
+        self._slot_event = {}
         self._queue = []
         for _ in range(depth):
             self._enqueue()
@@ -104,6 +106,8 @@ class PinnedBatchPrefetcher:
             return
         slot = getattr(self, "_n", 0) % (self.depth + 1)
         self._n = getattr(self, "_n", 0) + 1
+        if slot in self._slot_event:
+            self._slot_event[slot].synchronize()     # the previous H2D out of this slot's pinned buffers has finished
         with torch.cuda.stream(self.stream):
             if isinstance(batch, dict):
                 out = {k: (self._stage(slot, k, v) if torch.is_tensor(v) else v) for k, v in batch.items()}
@@ -111,6 +115,7 @@ class PinnedBatchPrefetcher:
                 out = tuple(self._stage(slot, i, v) if torch.is_tensor(v) else v for i, v in enumerate(batch))
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self._slot_event[slot] = ev
         self._queue.append((out, ev))
 
     def __iter__(self):
