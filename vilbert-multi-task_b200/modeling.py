@@ -371,7 +371,8 @@ class VILBertForVLTasks(BertPreTrainedModel):
 
 
 class BertForMultiModalPreTraining(BertPreTrainedModel):
-    """Reference: vilbert/vilbert.py:1435-1597 (visual_target == 0: KL-divergence region objective). The encoder
+    """Reference: vilbert/vilbert.py:1435-1597; the masked-region objective follows config.visual_target (0: KL divergence to the
+    detector's class distribution, 1: feature regression, 2: noise-contrastive against sampled regions). The encoder
     and the three heads run on the engine; the three scalar losses are formed with torch on the head outputs
     exactly as the reference does (:1506-1590) and their gradients re-enter the engine through autograd."""
     _heads = "pretraining"
@@ -379,8 +380,29 @@ class BertForMultiModalPreTraining(BertPreTrainedModel):
     def __init__(self, config, device=None, precision=None):
         super().__init__(config, device, precision)
         self.visual_target = config.visual_target
-        if self.visual_target != 0:
-            raise NotImplementedError("only visual_target == 0 (KLDiv) is supported")
+        self.num_negative = config.num_negative
+        if self.visual_target not in (0, 1, 2):
+            raise ValueError("visual_target must be 0, 1 or 2")
+
+    def _nce_region_loss(self, pred, target, masked):
+        """visual_target == 2: for every masked region, CE over [its own target feature, 70 % negatives drawn from other samples'
+        regions, 30 % from other regions of the same sample] scored by the dot product with the prediction."""
+        B, R, _ = pred.shape
+        n_across, n_inside = int(self.num_negative * 0.7), int(self.num_negative * 0.3)
+        dev = pred.device
+        rows = torch.randint(0, max(B - 1, 1), (B, R, n_across), device=dev)
+        own = torch.arange(B, device=dev).view(B, 1, 1)
+        rows = torch.where((rows == own) & (own < B - 1), torch.full_like(rows, B - 1), rows)     # never the sample itself
+        across = rows * R + torch.randint(0, R, (B, R, n_across), device=dev)
+        cols = torch.randint(0, max(R - 1, 1), (B, R, n_inside), device=dev)
+        reg = torch.arange(R, device=dev).view(1, R, 1)
+        cols = torch.where((cols == reg) & (reg < R - 1), torch.full_like(cols, R - 1), cols)     # never the region itself
+        inside = own * R + cols
+        index = torch.cat((across, inside), dim=2)[masked]
+        flat = target.reshape(B * R, -1)
+        samples = torch.cat((target[masked].unsqueeze(1), flat[index]), dim=1)
+        score = torch.bmm(samples, pred[masked].unsqueeze(2)).squeeze(2)
+        return F.cross_entropy(score, torch.zeros(score.size(0), dtype=torch.long, device=dev))
 
     def forward(self, input_ids, image_feat, image_loc, token_type_ids=None, attention_mask=None, image_attention_mask=None,
                 masked_lm_labels=None, image_label=None, image_target=None, next_sentence_label=None, output_all_attention_masks=False):
@@ -389,8 +411,15 @@ class BertForMultiModalPreTraining(BertPreTrainedModel):
         prediction_scores_t, prediction_scores_v, seq_relationship_score = (o[n] for n in names)
         if masked_lm_labels is not None and next_sentence_label is not None and image_target is not None:
             prediction_scores_v = prediction_scores_v[:, 1:]
-            img_loss = F.kl_div(F.log_softmax(prediction_scores_v, dim=2), image_target, reduction="none")
-            masked_img_loss = torch.sum(img_loss * (image_label == 1).unsqueeze(2).float()) / max(torch.sum((image_label == 1)), 0)
+            masked = image_label == 1
+            if self.visual_target == 0:      # KL to the soft class target (vilbert.py:1515-1521)
+                img_loss = F.kl_div(F.log_softmax(prediction_scores_v, dim=2), image_target, reduction="none")
+                masked_img_loss = torch.sum(img_loss * masked.unsqueeze(2).float()) / max(torch.sum(masked), 0)
+            elif self.visual_target == 1:    # regression of the 2048-d region feature, mean over the masked elements (:1507-1513)
+                img_loss = F.mse_loss(prediction_scores_v, image_target, reduction="none")
+                masked_img_loss = torch.sum(img_loss * masked.unsqueeze(2).float()) / max(torch.sum(masked.unsqueeze(2).expand_as(img_loss)), 1)
+            else:                            # contrastive: the true feature against num_negative sampled regions (:1523-1575)
+                masked_img_loss = self._nce_region_loss(prediction_scores_v, image_target, masked)
             masked_lm_loss = F.cross_entropy(prediction_scores_t.view(-1, self.config.vocab_size), masked_lm_labels.view(-1), ignore_index=-1)
             next_sentence_loss = F.cross_entropy(seq_relationship_score.view(-1, 2), next_sentence_label.view(-1), ignore_index=-1)
             return masked_lm_loss.unsqueeze(0), masked_img_loss.unsqueeze(0), next_sentence_loss.unsqueeze(0)
