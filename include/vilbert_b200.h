@@ -276,6 +276,19 @@ vb_status vb_kl_masked_loss(const float* scores, const float* target, const int6
                             void* dscores_bf16, int64_t ld_d16, int32_t B, int32_t Nv, int32_t C, float grad_scale,
                             int32_t accumulate_loss, void* stream);
 
+/* Masked-LM head without materialising the [tokens, 30522] logits when only the loss is wanted: only rows with label != ignore_index
+ * enter the cross-entropy (vilbert.py:1578-1583), so the tied decoder GEMM, its CE and its backward run on those rows alone.
+ *   vb_compact_rows      idx[r] = r-th row with labels[row] != ignore_index (-1 beyond the count), labels_compact[r] its label
+ *                        (ignore_index beyond), *count = number of such rows (compare with cap on the host: rows past cap are dropped)
+ *   vb_gather_rows16     dst[r,:] = src[idx[r],:] (zeros where idx[r] < 0), 16-bit rows, optionally a second (src2, dst2) pair
+ *   vb_scatter_rows_f32  dst[idx[r],:] = src[r,:] for idx[r] >= 0 (the caller zeroes dst): gradient of the gather. With count and
+ *                        poison given, *poison = NaN when *count > cap (rows were dropped: the loss must not look valid) */
+vb_status vb_compact_rows(const int64_t* labels, int64_t ignore_index, int32_t rows, int32_t cap, int32_t* idx, int32_t* count,
+                          int64_t* labels_compact, void* stream);
+vb_status vb_gather_rows16(const void* src, void* dst, const void* src2, void* dst2, const int32_t* idx, int32_t cap, int32_t cols, void* stream);
+vb_status vb_scatter_rows_f32(const float* src, float* dst, const int32_t* idx, int32_t cap, int32_t cols, const int32_t* count, float* poison,
+                              void* stream);
+
 /* Additive attention masks of BertModel.forward (vilbert.py:1341-1362): out[b,j] = (1 - mask[b,j]) * -10000,
  * mask int64 0/1 [B,N]; prepend_one != 0 emits N+1 entries per row with a leading 0 (task-token mask
  * extension, :1331-1334). */

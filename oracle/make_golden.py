@@ -296,6 +296,40 @@ def check_fixed_layers(ref, cfg_json):
                        pin=dict(worst=worst, tolerance=TOL)), f)
 
 
+def check_roberta(ref, cfg_json):
+    """model="roberta" (vilbert.py:370-393, 1295-1296): RobertaEmbeddings builds position ids starting at padding_idx + 1 and hands
+    them to BertEmbeddings.forward, which overwrites them with arange(seq_length) (vilbert.py:347-351) — so the embeddings are the
+    BERT ones, and the task-token variant cannot run (RobertaEmbeddings.forward has no task_ids argument: BertModel passes them as
+    position_ids and BertEmbeddings then indexes task_embeddings with None)."""
+    cfgj = dict(cfg_json, model="roberta")
+    cfg = O.make_config(cfgj)
+    model = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfgj)), num_labels=1, default_gpu=False)
+    assert type(model.bert.embeddings).__name__ == "RobertaEmbeddings"
+    P = O.synth_params(cfg, seed=0)
+    model.load_state_dict(P, strict=False); model.tie_weights(); model.eval()
+    inp = O.synth_inputs(cfg, 4, 11, 9, seed=1234)
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], inp["co_attention_mask"])
+    with torch.no_grad():
+        r = model(*args)[:9]
+        _, o = O.vilbert_for_vl_tasks(P, cfg, *args[:6])
+    worst = max(rel(a, b) for a, b in zip(o, r))
+    cfgt = dict(cfgj, task_specific_tokens=True)
+    mt = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfgt)), num_labels=1, default_gpu=False).eval()
+    try:
+        with torch.no_grad():
+            mt(*args, task_ids=torch.zeros(4, 1, dtype=torch.long))
+        task_tokens_run = True
+    except Exception as e:  # noqa: BLE001 - any failure documents that the combination does not run in the reference
+        task_tokens_run = False
+        print(f"{'roberta + task tokens':28s} reference raises {type(e).__name__}")
+    print(f"{'roberta':28s} worst {worst:.2e}")
+    assert worst < TOL and not task_tokens_run
+    with open(os.path.join(GOLD, "tiny_roberta.json"), "w") as f:
+        json.dump(dict(name="tiny_roberta", config=cfgj, B=4, Nv=11, Nt=9, seed=0, input_seed=1234,
+                       outputs={n: dict(summary(a), shape=list(a.shape)) for n, a in zip(O.HEAD_NAMES, r)},
+                       pin=dict(worst_output_rel=worst, tolerance=TOL, task_tokens_run_in_reference=task_tokens_run)), f)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
@@ -314,6 +348,7 @@ def main():
     check_fixed_layers(ref, TINY)
     check_in_batch_pairs(ref, TINY)
     check_visualization(ref, TINY)
+    check_roberta(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

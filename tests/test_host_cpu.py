@@ -53,6 +53,9 @@ def test_config_semantics(tmp_path, golden_dir):
     bad = BertConfig.from_dict(dict(cfgj, dynamic_attention=True))
     with pytest.raises(NotImplementedError):
         bad.check_supported()
+    BertConfig.from_dict(dict(cfgj, model="roberta")).check_supported()      # same embeddings as BERT in the reference (tiny_roberta.json)
+    with pytest.raises(NotImplementedError):
+        BertConfig.from_dict(dict(cfgj, model="roberta", task_specific_tokens=True)).check_supported()
 
 
 def test_param_store_layout(golden_dir):

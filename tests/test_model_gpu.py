@@ -11,6 +11,7 @@ median over all parameter tensors) with the measured values (median 5e-3, worst 
 bert_large) plus margin, and against the oracle run under the engine's operand rounding ("op" mode).
 """
 import json
+import math
 import os
 
 import pytest
@@ -150,6 +151,17 @@ def test_fast_mode_text_broadcast(golden_dir, task, Nt):
     model.load_state_dict(P, strict=True); model.eval()
     out = model(txt["input_txt"], inp["input_imgs"], inp["image_loc"], txt["token_type_ids"], txt["attention_mask"], inp["image_attention_mask"], None, txt["task_ids"])
     assert tuple(out[2].shape) == (B, 1) and rel(out[2], heads_o[2]) < 1e-2     # vil_logit: the retrieval score of each image
+
+
+def test_roberta_config(golden_dir):
+    """config.model == "roberta" (config/bert_base_6layer_6conect roberta variant): the reference's embeddings for it are the
+    BERT ones (tests/golden/tiny_roberta.json pins this against the reference), so all outputs match the oracle; with task tokens
+    the reference cannot run and the config is refused."""
+    _check(model_case(dict(_cfg(golden_dir, "tiny_b4"), model="roberta"), 4, 11, 9, seed=1234))
+    import vilbert_b200
+    with pytest.raises(NotImplementedError):
+        vilbert_b200.VILBertForVLTasks(vilbert_b200.BertConfig.from_dict(dict(_cfg(golden_dir, "tiny_b4"), model="roberta", task_specific_tokens=True)),
+                                       num_labels=1)
 
 
 def test_in_batch_pairs_expansion(golden_dir):
@@ -322,6 +334,48 @@ def test_config3_pretraining_objective_fused_losses(golden_dir):
     gmax = max(v.grad.abs().max().item() for v in Pg.values() if v.grad is not None)
     l2 = sorted((rel_l2(eng.ps.g(k), Pg[k].grad), k) for k in eng.ps.entries if Pg[k].grad is not None and Pg[k].grad.abs().max().item() > 1e-3 * gmax)
     assert len(l2) > 100 and l2[-1][0] < 5e-2 and l2[len(l2) // 2][0] < 1.5e-2, l2[-3:]   # measured 1.5e-2 worst, 1.06e-2 median at B=64
+
+
+def test_pretraining_objective_compacted_lm_head(golden_dir):
+    """The fused pre-training objective runs the tied 30522-way decoder on the labelled rows only (Plan.lm_head_compact):
+    same loss and gradients as the full-logits plan; more labelled rows than the capacity poison the loss with NaN."""
+    from _gpu_util import rel_l2
+    from vilbert_b200.config import BertConfig
+    from vilbert_b200.engine import Engine, LOSS_HEADS
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import synth_loss_inputs
+    cfgj = _cfg(golden_dir, "tiny_b4")
+    cfg = O.make_config(cfgj)
+    B, Nv, Nt = 16, 11, 20
+    P = O.synth_params(cfg, seed=0, device="cuda", with_task_heads=False)
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=3, device="cuda")
+    res = {}
+    for compact in (True, False):
+        eng = Engine(BertConfig.from_dict(cfgj), "cuda", heads="pretraining")
+        eng.lm_compact = compact
+        for k in eng.ps.entries:
+            eng.ps.p(k).copy_(P[k])
+        eng.refresh_weights()
+        plan = eng.plan(B, Nt, Nv, grad_outputs=LOSS_HEADS["pretraining"], loss="pretraining")
+        assert ("linguisic_prediction" in plan.outputs) == (not compact)
+        plan.load_inputs(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+        li = synth_loss_inputs(plan, "pretraining", 5, torch)
+        for k, v in li.items():
+            plan.loss_inputs[k].copy_(v.reshape(plan.loss_inputs[k].shape))
+        eng.zero_grad(); plan.run_step(); torch.cuda.synchronize()
+        res[compact] = (plan.loss.item(), eng.ps.grad.clone())
+        if compact:
+            n, cap = plan.lm_rows()
+            assert n == int((li["masked_lm_labels"] != -1).sum()) and n <= cap < B * Nt
+            idx = plan.lm_c["idx"].cpu()
+            assert idx[:n].tolist() == torch.nonzero(li["masked_lm_labels"] != -1).flatten().tolist() and (idx[n:] == -1).all()
+            # every row labelled: 320 rows > capacity 80 -> the loss must not look valid
+            plan.loss_inputs["masked_lm_labels"].fill_(7)
+            eng.zero_grad(); plan.run_step(); torch.cuda.synchronize()
+            assert plan.lm_rows()[0] == B * Nt and math.isnan(plan.loss.item())
+    assert abs(res[True][0] - res[False][0]) < 1e-5 * abs(res[False][0]), (res[True][0], res[False][0])
+    assert rel_l2(res[True][1], res[False][1]) < 1e-4
 
 
 def test_module_surface_autograd_and_state_dict(golden_dir):

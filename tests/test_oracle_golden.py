@@ -115,6 +115,26 @@ def test_fast_mode_golden(golden_dir):
         assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
 
 
+def test_roberta_golden(golden_dir):
+    """config.model == "roberta": the reference's RobertaEmbeddings position-id shift is overwritten inside BertEmbeddings.forward
+    (vilbert.py:347-351), so the outputs recorded from the reference with model="roberta" are the ones the oracle computes with
+    BERT embeddings (oracle/make_golden.py::check_roberta)."""
+    meta = json.load(open(os.path.join(golden_dir, "tiny_roberta.json")))
+    assert meta["config"]["model"] == "roberta" and meta["pin"]["task_tokens_run_in_reference"] is False
+    cfg = O.make_config(meta["config"])
+    P = O.synth_params(cfg, seed=meta["seed"])
+    inp = O.synth_inputs(cfg, meta["B"], meta["Nv"], meta["Nt"], seed=meta["input_seed"])
+    with torch.no_grad():
+        _, heads = O.vilbert_for_vl_tasks(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"],
+                                          inp["attention_mask"], inp["image_attention_mask"])
+    for k, t in zip(O.HEAD_NAMES, heads):
+        s = meta["outputs"][k]
+        t = t.detach().double().flatten()
+        got = t[torch.tensor(s["sample_idx"])]
+        assert (got - torch.tensor(s["samples"], dtype=torch.float64)).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), k
+        assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
+
+
 def test_fixed_layers_golden(golden_dir):
     """config.fixed_t_layer: the set of parameters without a gradient and the loss recorded from the reference."""
     meta = json.load(open(os.path.join(golden_dir, "tiny_fixed_layers.json")))

@@ -103,6 +103,9 @@ _SIGNATURES = {
     "vb_memset_zero": [_P, _I64, _P],
     "vb_ce_loss": [_P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _F, _I32, _P],
     "vb_kl_masked_loss": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _I32, _P],
+    "vb_compact_rows": [_P, _I64, _I32, _I32, _P, _P, _P, _P],
+    "vb_gather_rows16": [_P, _P, _P, _P, _P, _I32, _I32, _P],
+    "vb_scatter_rows_f32": [_P, _P, _P, _I32, _I32, _P, _P, _P],
     "vb_adamw_step": [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _I32, _P, _P, _F, _I32, _P],
 }
 

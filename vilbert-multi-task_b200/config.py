@@ -93,8 +93,13 @@ class BertConfig(object):
         unsupported = []
         if self.hidden_act != "gelu" or self.v_hidden_act != "gelu":
             unsupported.append("hidden_act != 'gelu'")
-        if getattr(self, "model", "bert") != "bert":
-            unsupported.append("model='roberta' (out of scope, SURVEY.md appendix B.12)")
+        # model="roberta": RobertaEmbeddings' shifted position ids are overwritten by BertEmbeddings.forward (vilbert.py:347-351,
+        # 380-393), so its embeddings ARE the BERT ones (pinned: tests/golden/tiny_roberta.json); with task tokens the reference
+        # raises a TypeError (task_ids land in position_ids), mirrored here
+        if getattr(self, "model", "bert") not in ("bert", "roberta"):
+            unsupported.append("model=%r" % (self.model,))
+        if getattr(self, "model", "bert") == "roberta" and getattr(self, "task_specific_tokens", False):
+            unsupported.append("model='roberta' with task_specific_tokens (the reference cannot run it either: RobertaEmbeddings.forward takes no task_ids)")
         for flag in ("dynamic_attention",):
             if getattr(self, flag, False):
                 unsupported.append(flag)

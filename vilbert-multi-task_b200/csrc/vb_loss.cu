@@ -141,6 +141,69 @@ kl_masked_loss_kernel(const float* __restrict__ scores, const float* __restrict_
   if (threadIdx.x == 0 && blockIdx.x == 0 && n_pos == 0.f) atomicAdd(loss, CUDART_NAN_F);   // 0 / max(0, 0) in the reference
 }
 
+// ------------------------------------------------------------------------------------------ masked-row compaction (masked-LM head)
+// Only the rows whose label != ignore_index contribute to the masked-LM cross-entropy (15 % of the tokens, vilbert.py:1578-1583),
+// so when only the loss is wanted the 30522-way tied decoder runs on those rows alone: idx[r] = r-th selected row (ascending),
+// -1 beyond the count; *count = number of selected rows (may exceed cap: the caller checks).
+__global__ void __launch_bounds__(1024) compact_rows_kernel(const long long* __restrict__ labels, long long ignore_index, int rows, int cap,
+                                                             int* __restrict__ idx, int* __restrict__ count, long long* __restrict__ labels_c) {
+  pdl_entry();
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  for (int i = threadIdx.x; i < cap; i += 1024) { idx[i] = -1; labels_c[i] = ignore_index; }
+  __syncthreads();
+  for (int base = 0; base < rows; base += 1024) {
+    const int r = base + threadIdx.x;
+    const int sel = (r < rows && labels[r] != ignore_index) ? 1 : 0;
+    int v = sel;                                   // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v += n; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = wsum[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += n; }
+      wsum[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int before = carry + (threadIdx.x >= 32 ? wsum[(threadIdx.x >> 5) - 1] : 0) + v - sel;
+    if (sel && before < cap) { idx[before] = r; labels_c[before] = labels[r]; }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry;
+}
+
+// dst[r, :] = idx[r] >= 0 ? src[idx[r], :] : 0 (16-bit rows of `cols` elements, cols % 8 == 0), for up to two sources at once
+__global__ void gather_rows16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const uint4* __restrict__ src2, uint4* __restrict__ dst2,
+                                     const int* __restrict__ idx, int cap, int c8) {
+  pdl_entry();
+  const long long total = (long long)cap * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c8), c = (int)(i % c8);
+    const int s = idx[r];
+    dst[i] = s >= 0 ? src[(long long)s * c8 + c] : make_uint4(0, 0, 0, 0);
+    if (src2) dst2[i] = s >= 0 ? src2[(long long)s * c8 + c] : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// dst[idx[r], :] = src[r, :] for idx[r] >= 0 (fp32 rows, cols % 4 == 0); dst is zeroed by the caller. If more rows were selected
+// than the capacity holds (*count > cap) the result would silently miss rows: the loss scalar is poisoned with NaN instead.
+__global__ void scatter_rows_f32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, const int* __restrict__ idx, int cap, int c4,
+                                        const int* __restrict__ count, float* __restrict__ poison) {
+  pdl_entry();
+  if (count && poison && blockIdx.x == 0 && threadIdx.x == 0 && *count > cap) *poison = CUDART_NAN_F;
+  const long long total = (long long)cap * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4), c = (int)(i % c4);
+    const int d = idx[r];
+    if (d >= 0) dst[(long long)d * c4 + c] = src[i];
+  }
+}
+
 static inline int loss_grid(int rows) {
   int cap = sm_count() * 8;
   if (cap <= 0) cap = 148 * 8;
@@ -179,4 +242,30 @@ extern "C" vb_status vb_kl_masked_loss(const float* scores, const float* target,
              reinterpret_cast<const long long*>(label), loss, dscores_f32, static_cast<__nv_bfloat16*>(dscores_bf16), (long long)ld_d16,
              (int)B, (int)Nv, (int)C, grad_scale);
   return check_launch("vb_kl_masked_loss");
+}
+
+extern "C" vb_status vb_compact_rows(const int64_t* labels, int64_t ignore_index, int32_t rows, int32_t cap, int32_t* idx, int32_t* count,
+                                     int64_t* labels_compact, void* stream) {
+  if (rows <= 0 || cap <= 0 || !labels || !idx || !count || !labels_compact) return set_error(VB_ERR_INVALID, "vb_compact_rows: bad arguments");
+  launch_pdl(compact_rows_kernel, dim3(1), dim3(1024), (size_t)0, static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(labels),
+             (long long)ignore_index, (int)rows, (int)cap, idx, count, reinterpret_cast<long long*>(labels_compact));
+  return check_launch("vb_compact_rows");
+}
+
+extern "C" vb_status vb_gather_rows16(const void* src, void* dst, const void* src2, void* dst2, const int32_t* idx, int32_t cap, int32_t cols,
+                                      void* stream) {
+  if (cap <= 0 || cols <= 0 || (cols & 7) || !src || !dst || !idx) return set_error(VB_ERR_INVALID, "vb_gather_rows16: bad arguments (cols % 8 == 0)");
+  int grid = sm_count() * 8; if (grid <= 0) grid = 148 * 8;
+  launch_pdl(gather_rows16_kernel, dim3(grid), dim3(256), (size_t)0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(src),
+             static_cast<uint4*>(dst), static_cast<const uint4*>(src2), static_cast<uint4*>(dst2), idx, (int)cap, (int)(cols / 8));
+  return check_launch("vb_gather_rows16");
+}
+
+extern "C" vb_status vb_scatter_rows_f32(const float* src, float* dst, const int32_t* idx, int32_t cap, int32_t cols, const int32_t* count,
+                                         float* poison, void* stream) {
+  if (cap <= 0 || cols <= 0 || (cols & 3) || !src || !dst || !idx) return set_error(VB_ERR_INVALID, "vb_scatter_rows_f32: bad arguments (cols % 4 == 0)");
+  int grid = sm_count() * 8; if (grid <= 0) grid = 148 * 8;
+  launch_pdl(scatter_rows_f32_kernel, dim3(grid), dim3(256), (size_t)0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(src),
+             reinterpret_cast<float4*>(dst), idx, (int)cap, (int)(cols / 4), count, poison);
+  return check_launch("vb_scatter_rows_f32");
 }

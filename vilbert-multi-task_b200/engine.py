@@ -869,6 +869,50 @@ class Plan:
             return dl16, ldp, W16b
         return bwd
 
+    def lm_head_compact(self, ht, ht_bwd):
+        """Masked-LM head of the fused pre-training objective without the [tokens, vocab] logits: the rows with a label
+        (masked_lm_labels != -1, 15 % of the tokens; vilbert.py:1578-1583) are compacted on the device into a fixed-capacity
+        operand (engine.lm_capacity of the rows), the tied decoder GEMM, the cross-entropy and both backward GEMMs run on those
+        rows, and the gradient is scattered back to the token rows. More labelled rows than the capacity poison the loss (NaN)."""
+        ps, c, lib = self.ps, self.cfg, self.lib
+        M, Ht, V = ht.M, ht.H, c.vocab_size
+        cap = min(_pad8(M), _pad8(max(64, int(math.ceil(self.e.lm_capacity * M)))))
+        labels = self.buf((M,), I64)
+        labels.fill_(-1)
+        self.loss_inputs["masked_lm_labels"] = labels
+        idx, cnt, lab_c = self.buf((cap,), torch.int32), self.buf((1,), torch.int32, zero=True), self.buf((cap,), I64)
+        self.emit(lib.vb_compact_rows, labels.data_ptr(), -1, M, cap, idx.data_ptr(), cnt.data_ptr(), lab_c.data_ptr())
+        hc, hclo, hcbw = self.buf16((cap, Ht))
+        self.emit(lib.vb_gather_rows16, ht.b16.data_ptr(), hc.data_ptr(), self._ptr(self._extra(ht.bw, ht.b16)), self._ptr(self._extra(hcbw, hc)),
+                  idx.data_ptr(), cap, Ht)
+        if hclo is not None:
+            self.emit(lib.vb_gather_rows16, ht.lo.data_ptr(), hclo.data_ptr(), None, None, idx.data_ptr(), cap, Ht)
+        wn = "bert.embeddings.word_embeddings.weight"
+        logits = self.buf((cap, V), F32)
+        self.gemm(cap, V, Ht, hc, Ht, ps.w16(wn), Ht, bias=ps.p("cls.predictions.bias"), out_f32=logits, ld_of=V, a_lo=hclo, b_lo=ps.w16lo(wn))
+        ldp = _pad8(V)
+        self.lm_c = dict(cap=cap, idx=idx, count=cnt, labels=lab_c, logits=logits, dl32=self.buf((cap, V), F32),
+                         dl16=self.buf((cap, ldp), BF16, zero=True), ldp=ldp)
+
+        def bwd():
+            lc = self.lm_c
+            self.colsum(lc["dl32"], V, ps.g("cls.predictions.bias"), cap, V)
+            self.linear_wgrad(lc["dl16"], ldp, None, 0, hcbw, Ht, cap, V, Ht, None, gw=ps.g(wn))
+            if ht.frozen:
+                return
+            gc = self.scratch("lm.gc", (cap, Ht), F32)
+            self.gemm(cap, Ht, V, lc["dl16"], ldp, ps.w16b(wn), Ht, b_mn=1, out_f32=gc, ld_of=Ht)
+            g = self.grad_of(ht)
+            self.emit(lib.vb_memset_zero, g.data_ptr(), g.numel() * 4)
+            self.emit(lib.vb_scatter_rows_f32, gc.data_ptr(), g.data_ptr(), idx.data_ptr(), cap, Ht, cnt.data_ptr(), self.loss.data_ptr())
+            ht.gw = True
+            ht_bwd()
+        return bwd
+
+    def lm_rows(self):
+        """(labelled rows of the last step, capacity) of the compacted masked-LM head (device sync)."""
+        return int(self.lm_c["count"].item()), self.lm_c["cap"]
+
     def transform(self, x, wdense, lnname, tag):
         """Linear -> GELU -> LayerNorm (BertPredictionHeadTransform / BertImgPredictionHeadTransform / the first three
         stages of SimpleClassifier; vilbert.py:1152-1156, 1172-1176, 1714-1718). x: Act or (b16, M, K) for a plain operand."""
@@ -950,9 +994,15 @@ class Plan:
 
         # --- cls: masked-LM head (decoder tied to the word embeddings), image-region head, alignment head
         ht, ht_bwd = self.transform(seq_t, "cls.predictions.transform.dense", "cls.predictions.transform.LayerNorm", "lm.tr")
-        lm_bwd = self.big_head("linguisic_prediction", ht.b16, Ht, ht, B * Nt, Ht, c.vocab_size, None, "cls.predictions.bias",
-                               w16=ps.w16("bert.embeddings.word_embeddings.weight"), gw=ps.g("bert.embeddings.word_embeddings.weight"),
-                               w16lo=ps.w16lo("bert.embeddings.word_embeddings.weight"), w16b=ps.w16b("bert.embeddings.word_embeddings.weight"))
+        # fused pre-training objective: only the masked rows enter the LM cross-entropy, so the tied decoder runs on those alone
+        self.lm_c = None
+        if self.loss_kind == "pretraining" and self.e.lm_compact:
+            lm_bwd = None
+            lm_compact_bwd = self.lm_head_compact(ht, ht_bwd)
+        else:
+            lm_bwd = self.big_head("linguisic_prediction", ht.b16, Ht, ht, B * Nt, Ht, c.vocab_size, None, "cls.predictions.bias",
+                                   w16=ps.w16("bert.embeddings.word_embeddings.weight"), gw=ps.g("bert.embeddings.word_embeddings.weight"),
+                                   w16lo=ps.w16lo("bert.embeddings.word_embeddings.weight"), w16b=ps.w16b("bert.embeddings.word_embeddings.weight"))
         hv, hv_bwd = self.transform(seq_v, "cls.imagePredictions.transform.dense", "cls.imagePredictions.transform.LayerNorm", "im.tr")
         im_bwd = self.big_head("vision_prediction", hv.b16, Hv, hv, B * Nv, Hv, c.v_target_size, "cls.imagePredictions.decoder",
                                "cls.imagePredictions.decoder.bias")
@@ -968,7 +1018,7 @@ class Plan:
                 hn.gw = True
                 tr_bwd()
             return f
-        self.push_bwd(wide_bwd(lm_bwd, ht, ht_bwd, Ht, c.vocab_size))
+        self.push_bwd(wide_bwd(lm_bwd, ht, ht_bwd, Ht, c.vocab_size) if lm_bwd is not None else lm_compact_bwd)
         self.push_bwd(wide_bwd(im_bwd, hv, hv_bwd, Hv, c.v_target_size))
 
         if self.heads == "pretraining":
@@ -1012,6 +1062,8 @@ class Plan:
     def _build(self):
         c, B = self.cfg, self.B
         self.outputs, self.gout = OrderedDict(), {}
+        self.loss_inputs = {}
+        self.loss = self.buf((1,), F32, zero=True) if (self.loss_kind is not None and not self.vqa_loss) else None
         self.enc_t, self.enc_v = [], []
         t, v = self.embeddings()
         # BertEncoder.forward interleaving schedule (vilbert.py:960-1096)
@@ -1116,8 +1168,6 @@ class Plan:
         missing = [n for n in LOSS_HEADS[k] if n not in self.grad_outputs]
         if missing:
             raise ValueError(f"loss={k!r} differentiates {LOSS_HEADS[k]}: add them to grad_outputs")
-        self.loss = self.buf((1,), F32, zero=True)
-        self.loss_inputs = {}
         li = self.loss_inputs
 
         def ce(name, rows, cols, label_key, acc):
@@ -1149,7 +1199,12 @@ class Plan:
         elif k == "pretraining":
             # vilbert.py:1578-1590 (+ train_concap.py: loss = masked_loss_t + masked_loss_v + next_sentence_loss)
             V, C = self.cfg.vocab_size, self.cfg.v_target_size
-            ce("linguisic_prediction", B * self.Nt, V, "masked_lm_labels", False)
+            if self.lm_c is not None:
+                lc = self.lm_c
+                self.emit(lib.vb_ce_loss, lc["logits"].data_ptr(), V, lc["labels"].data_ptr(), -1, self.loss.data_ptr(), lc["dl32"].data_ptr(), V,
+                          lc["dl16"].data_ptr(), lc["ldp"], lc["cap"], V, 1.0, 0)
+            else:
+                ce("linguisic_prediction", B * self.Nt, V, "masked_lm_labels", False)
             sv = self.outputs["vision_prediction"]
             li["image_target"] = self.buf((B, self.Nv - 1, C), F32, zero=True)
             li["image_label"] = self.buf((B, self.Nv - 1), I64, zero=True)
@@ -1533,10 +1588,12 @@ class Engine:
         self.grad_clean = False          # the flat gradient buffer is all zeros (set by zero_grad / the fused optimizer)
         self.loss_options = 4            # answer options per question of the VL-logit objective (retrieval / VCR: 4)
         self.auto_graph = True           # module surface: capture a plan's passes into CUDA graphs after two eager runs
+        self.lm_compact = True           # fused pre-training objective: masked-LM decoder + CE on the labelled rows only (Plan.lm_head_compact)
+        self.lm_capacity = 0.25          # ... with room for this fraction of the token rows (15 % are masked; more poisons the loss with NaN)
 
     def plan(self, B, Nt, Nv, grad_outputs=(), vqa_loss=False, heads=None, train=False, loss=None):
         loss = "vqa" if vqa_loss else loss
-        key = (B, Nt, Nv, frozenset(grad_outputs), loss, heads, bool(train))
+        key = (B, Nt, Nv, frozenset(grad_outputs), loss, heads, bool(train), (self.lm_compact, self.lm_capacity) if loss == "pretraining" else None)
         if key in self.plans:
             self.plans.move_to_end(key)
             return self.plans[key]
