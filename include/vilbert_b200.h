@@ -276,6 +276,23 @@ vb_status vb_kl_masked_loss(const float* scores, const float* target, const int6
                             void* dscores_bf16, int64_t ld_d16, int32_t B, int32_t Nv, int32_t C, float grad_scale,
                             int32_t accumulate_loss, void* stream);
 
+/* config.dynamic_attention (BertImageSelfAttention, vilbert.py:557-586): the image self-attention's queries and keys are scaled per
+ * (sample, channel) by gate = 1 + sigmoid(dyLinear(pool)), pool = mean of the current text states over the unmasked tokens.
+ *   vb_masked_mean_fwd  pool[b,:] = sum_n m[b,n] x[b,n,:] / sum_n m[b,n]; x f32 [B,N,H]; add_mask f32 [B,N] is the additive text mask
+ *                       ((1-m) * -10000, what vb_mask_to_additive writes); outputs pool f32 [B,H] + its GEMM operand copies
+ *                       (pool16 in the forward format, optional low part and bf16 copy)
+ *   vb_masked_mean_bwd  dx[b,n,:] (+)= m[b,n] / sum_n m[b,n] * dpool[b,:]
+ *   vb_gate_scale_fwd   qk[b*N+n, c] *= 1 + sigmoid(z[b,c]) for c < cols, in place on the Q|K sections of the 16-bit projection
+ *                       buffer (row pitch ld elements, hi (+ lo) parts, fp16 or bf16); z f32 [B, cols] = dyLinear_q | dyLinear_k outputs
+ *   vb_gate_scale_bwd   dqk (bf16, in place) <- gate * dqk;  dz[b,c] = s(1-s) * sum_n dqk[b,n,c] qk[b,n,c] / gate, s = sigmoid(z);
+ *                       qk is the GATED forward buffer; dz f32 [B, cols] and its bf16 operand copy dz16 */
+vb_status vb_masked_mean_fwd(const float* x, const float* add_mask, float* pool, void* pool16, void* pool16_lo, void* pool16_b, int32_t out_fp16,
+                             int32_t B, int32_t N, int32_t H, void* stream);
+vb_status vb_masked_mean_bwd(const float* dpool, const float* add_mask, float* dx, int32_t accumulate, int32_t B, int32_t N, int32_t H, void* stream);
+vb_status vb_gate_scale_fwd(void* qk, void* qk_lo, int64_t ld, const float* z, int32_t B, int32_t N, int32_t cols, int32_t fp16, void* stream);
+vb_status vb_gate_scale_bwd(void* dqk, int64_t ldd, const void* qk, const void* qk_lo, int64_t ld, const float* z, float* dz, void* dz16, int32_t B,
+                            int32_t N, int32_t cols, int32_t fp16, void* stream);
+
 /* Masked-LM head without materialising the [tokens, 30522] logits when only the loss is wanted: only rows with label != ignore_index
  * enter the cross-entropy (vilbert.py:1578-1583), so the tied decoder GEMM, its CE and its backward run on those rows alone.
  *   vb_compact_rows      idx[r] = r-th row with labels[row] != ignore_index (-1 beyond the count), labels_compact[r] its label

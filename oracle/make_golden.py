@@ -330,6 +330,43 @@ def check_roberta(ref, cfg_json):
                        pin=dict(worst_output_rel=worst, tolerance=TOL, task_tokens_run_in_reference=task_tokens_run)), f)
 
 
+def check_dynamic_attention(ref, cfg_json):
+    """config.dynamic_attention (BertImageSelfAttention, vilbert.py:557-586; --dynamic_attention of train_tasks.py:357-358): image
+    queries / keys gated by the pooled text states. All head outputs and every parameter gradient of the VQA loss (incl. the
+    dyLinear_q / dyLinear_k gates and the text stream, which now also receives gradient through the pooling)."""
+    cfgj = dict(cfg_json, dynamic_attention=True)
+    cfg = O.make_config(cfgj)
+    model = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfgj)), num_labels=1, default_gpu=False)
+    P = O.synth_params(cfg, seed=0)
+    missing = [k for k in model.state_dict() if k not in P]
+    assert not missing, missing
+    model.load_state_dict(P, strict=False); model.tie_weights(); model.eval()
+    inp = O.synth_inputs(cfg, 4, 11, 9, seed=1234)
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], inp["co_attention_mask"])
+    tgt = O.synth_vqa_target(4, 3129)
+    r = model(*args)[:9]
+    O.vqa_loss(r[0], tgt).backward()
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    _, o = O.vilbert_for_vl_tasks(Pg, cfg, *args[:6])
+    O.vqa_loss(o[0], tgt).backward()
+    named = dict(model.named_parameters())
+    worst = max(rel(a, b) for a, b in zip(o, r))
+    gates = {}
+    for k, v in Pg.items():
+        if k == "cls.predictions.decoder.weight" or named[k].grad is None:
+            continue
+        worst = max(worst, rel(v.grad, named[k].grad))
+        if "dyLinear" in k:
+            gates[k] = summary(named[k].grad)
+    print(f"{'dynamic_attention':28s} worst {worst:.2e}; {len(gates)} gate tensors with gradient")
+    assert worst < TOL and len(gates) == 4 * cfg["v_num_hidden_layers"]
+    with open(os.path.join(GOLD, "tiny_dynamic_attention.json"), "w") as f:
+        json.dump(dict(name="tiny_dynamic_attention", config=cfgj, B=4, Nv=11, Nt=9, seed=0, input_seed=1234,
+                       outputs={n: dict(summary(a), shape=list(a.shape)) for n, a in zip(O.HEAD_NAMES, r)}, gate_grads=gates,
+                       loss=float(O.vqa_loss(r[0], tgt).detach()), pin=dict(worst=worst, tolerance=TOL)), f)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
@@ -349,6 +386,7 @@ def main():
     check_in_batch_pairs(ref, TINY)
     check_visualization(ref, TINY)
     check_roberta(ref, TINY)
+    check_dynamic_attention(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

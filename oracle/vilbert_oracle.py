@@ -142,11 +142,17 @@ def text_layer(P, pre, cfg, h, mask, drop=None):
                       P[pre + ".output.LayerNorm.weight"], P[pre + ".output.LayerNorm.bias"])
 
 
-def image_layer(P, pre, cfg, h, mask, drop=None):
-    """BertImageLayer.forward, vilbert.py:688-694 (self-attn :571-619 with dynamic_attention off,
-    :629-633, :661-664, :674-678). Same block on the visual stream."""
+def image_layer(P, pre, cfg, h, mask, drop=None, txt=None, txt_mask2=None):
+    """BertImageLayer.forward, vilbert.py:688-694 (self-attn :571-619, :629-633, :661-664, :674-678). Same block on the visual
+    stream. config.dynamic_attention (:577-586): queries and keys are scaled per (sample, channel) by 1 + sigmoid(dyLinear(masked
+    mean of the current text states)); txt_mask2 is attention_mask.unsqueeze(2) (:1344)."""
     a = pre + ".attention"
-    ctx = attention(linear(P, a + ".self.query", h), linear(P, a + ".self.key", h), linear(P, a + ".self.value", h),
+    q, k = linear(P, a + ".self.query", h), linear(P, a + ".self.key", h)
+    if cfg.get("dynamic_attention"):
+        pool = (txt * txt_mask2).sum(1) / txt_mask2.sum(1)
+        q = q * (1 + torch.sigmoid(linear(P, a + ".self.dyLinear_q", pool))).unsqueeze(1)
+        k = k * (1 + torch.sigmoid(linear(P, a + ".self.dyLinear_k", pool))).unsqueeze(1)
+    ctx = attention(q, k, linear(P, a + ".self.value", h),
                     mask, cfg["v_num_attention_heads"], drop, a + ".self.dropout", cfg["v_attention_probs_dropout_prob"])
     hp = cfg["v_hidden_dropout_prob"]
     h1 = layer_norm(_drop(linear(P, a + ".output.dense", ctx), drop, a + ".output.dropout", hp) + h,
@@ -181,7 +187,7 @@ def connection_layer(P, pre, cfg, v, mask_v, t, mask_t, drop=None):
     return v2_, t2_
 
 
-def encoder(P, pre, cfg, t, v, mask_t, mask_v, drop=None):
+def encoder(P, pre, cfg, t, v, mask_t, mask_v, drop=None, mask2=None):
     """BertEncoder.forward interleaving schedule, vilbert.py:934-1107 (fixed layers, in_batch_pairs,
     FAST_MODE off; with_coattention honoured). Returns the per-connection-layer outputs too
     (output_all_encoded_layers, :1075-1077)."""
@@ -199,9 +205,9 @@ def encoder(P, pre, cfg, t, v, mask_t, mask_v, drop=None):
         for i in range(v_start, v_end):
             if i < cfg.get("fixed_v_layer", 0):
                 with torch.no_grad():
-                    v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
+                    v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop, t, mask2)
             else:
-                v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
+                v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop, t, mask2)
         if count == 0 and cfg.get("in_batch_pairs"):
             # vilbert.py:1008-1040: every (text i, image j) combination of the batch becomes sample i * b + j
             b = t.shape[0]
@@ -220,7 +226,7 @@ def encoder(P, pre, cfg, t, v, mask_t, mask_v, drop=None):
         all_t.append(t)
         all_v.append(v)
     for i in range(v_start, n_v):
-        v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop)
+        v = image_layer(P, f"{pre}.v_layer.{i}", cfg, v, mask_v, drop, t, mask2)
     for i in range(t_start, n_t):
         t = text_layer(P, f"{pre}.layer.{i}", cfg, t, mask_t, drop)
     return t, v, all_t, all_v
@@ -266,7 +272,8 @@ def bert_model(P, cfg, input_txt, input_imgs, image_loc, token_type_ids=None, at
     mask_v = (1.0 - image_attention_mask[:, None, None, :].to(dt)) * -10000.0
     t = text_embeddings(P, prefix + ".embeddings", cfg, input_txt, token_type_ids, task_ids, drop)
     v = image_embeddings(P, prefix + ".v_embeddings", input_imgs, image_loc, drop, cfg["hidden_dropout_prob"])
-    t, v, all_t, all_v = encoder(P, prefix + ".encoder", cfg, t, v, mask_t, mask_v, drop)
+    mask2 = attention_mask.unsqueeze(2).to(dt)      # extended_attention_mask2 (:1344): the dynamic_attention text pooling weights
+    t, v, all_t, all_v = encoder(P, prefix + ".encoder", cfg, t, v, mask_t, mask_v, drop, mask2)
     if output_all_encoded_layers:
         # :1098-1101 + :1388-1394 — in this mode the encoder returns only the per-connection-layer states and the poolers see
         # encoded_layers[-1], i.e. the output of the LAST CONNECTION LAYER (the tail layers' result is dropped)
@@ -376,6 +383,8 @@ def param_shapes(cfg, with_task_heads=True):
             p = f"bert.encoder.{kind}.{i}"
             for nm in ("query", "key", "value"):
                 lin(f"{p}.attention.self.{nm}", H, H)
+            if kind == "v_layer" and cfg.get("dynamic_attention"):      # BertImageSelfAttention.dyLinear_q / _k (:561-563)
+                lin(f"{p}.attention.self.dyLinear_q", H, Ht); lin(f"{p}.attention.self.dyLinear_k", H, Ht)
             lin(f"{p}.attention.output.dense", H, H); ln(f"{p}.attention.output.LayerNorm", H)
             lin(f"{p}.intermediate.dense", I, H)
             lin(f"{p}.output.dense", H, I); ln(f"{p}.output.LayerNorm", H)

@@ -50,9 +50,10 @@ def test_config_semantics(tmp_path, golden_dir):
     assert c2.vocab_size == 30522 and c2.v_feature_size == 2048
     with pytest.raises(ValueError):
         BertConfig(3.5)
-    bad = BertConfig.from_dict(dict(cfgj, dynamic_attention=True))
-    with pytest.raises(NotImplementedError):
-        bad.check_supported()
+    BertConfig.from_dict(dict(cfgj, dynamic_attention=True)).check_supported()
+    for bad in (dict(cfgj, dynamic_attention=True, in_batch_pairs=True), dict(cfgj, hidden_act="relu")):
+        with pytest.raises(NotImplementedError):
+            BertConfig.from_dict(bad).check_supported()
     BertConfig.from_dict(dict(cfgj, model="roberta")).check_supported()      # same embeddings as BERT in the reference (tiny_roberta.json)
     with pytest.raises(NotImplementedError):
         BertConfig.from_dict(dict(cfgj, model="roberta", task_specific_tokens=True)).check_supported()

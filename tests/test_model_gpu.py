@@ -157,11 +157,39 @@ def test_roberta_config(golden_dir):
     """config.model == "roberta" (config/bert_base_6layer_6conect roberta variant): the reference's embeddings for it are the
     BERT ones (tests/golden/tiny_roberta.json pins this against the reference), so all outputs match the oracle; with task tokens
     the reference cannot run and the config is refused."""
+    from _gpu_util import model_case
     _check(model_case(dict(_cfg(golden_dir, "tiny_b4"), model="roberta"), 4, 11, 9, seed=1234))
     import vilbert_b200
     with pytest.raises(NotImplementedError):
         vilbert_b200.VILBertForVLTasks(vilbert_b200.BertConfig.from_dict(dict(_cfg(golden_dir, "tiny_b4"), model="roberta", task_specific_tokens=True)),
                                        num_labels=1)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_dynamic_attention_gates(golden_dir, precision):
+    """config.dynamic_attention (BertImageSelfAttention, vilbert.py:557-586; --dynamic_attention of train_tasks.py:357-358): the image
+    self-attention's queries / keys gated by 1 + sigmoid(dyLinear(masked mean of the text states)). All 13 outputs and every
+    parameter gradient (the dyLinear gates, and the text stream through the pooling) vs the oracle, which is pinned bit-exact
+    against the reference for this path (tests/golden/tiny_dynamic_attention.json); ragged text masks, with and without task tokens."""
+    from _gpu_util import model_case
+    cfgj = dict(_cfg(golden_dir, "tiny_b4"), dynamic_attention=True)
+    modes = ("fp32", "op") if precision == "fp16" else ("fp32",)
+    r = model_case(cfgj, 4, 11, 9, seed=1234, precision=precision, oracle_modes=modes)
+    _check(r, precision, modes=modes)
+    gates = [k for k in r["grad_fp32"] if "dyLinear" in k]
+    assert len(gates) == 8 and all(r["engine"].ps.g(k).abs().max().item() > 0 for k in gates)
+    r = model_case(dict(cfgj, task_specific_tokens=True), 3, 7, 12, seed=1, precision=precision, oracle_modes=modes)
+    _check(r, precision, modes=modes)
+
+
+def test_dynamic_attention_base_shape(golden_dir):
+    """dynamic_attention at the base 6-layer widths (Hv 1024 gated by Ht 768) and the VQA sequence lengths, small batch."""
+    from _gpu_util import model_case
+    cfgj = dict(_cfg(golden_dir, "base_6layer_6conect_b4"), dynamic_attention=True)
+    _check(model_case(cfgj, 4, 100, 36, seed=0))
+    import vilbert_b200
+    with pytest.raises(NotImplementedError):
+        vilbert_b200.BertConfig.from_dict(dict(cfgj, fast_mode=True)).check_supported()
 
 
 def test_in_batch_pairs_expansion(golden_dir):

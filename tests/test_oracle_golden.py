@@ -115,6 +115,33 @@ def test_fast_mode_golden(golden_dir):
         assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
 
 
+def test_dynamic_attention_golden(golden_dir):
+    """config.dynamic_attention (vilbert.py:557-586): head outputs, the VQA loss and the gradients of the dyLinear gates recorded
+    from the reference (oracle/make_golden.py::check_dynamic_attention, pinned at 0.0 difference)."""
+    meta = json.load(open(os.path.join(golden_dir, "tiny_dynamic_attention.json")))
+    cfg = O.make_config(meta["config"])
+    P = O.synth_params(cfg, seed=meta["seed"])
+    inp = O.synth_inputs(cfg, meta["B"], meta["Nv"], meta["Nt"], seed=meta["input_seed"])
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    _, heads = O.vilbert_for_vl_tasks(Pg, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"],
+                                      inp["attention_mask"], inp["image_attention_mask"])
+    loss = O.vqa_loss(heads[0], O.synth_vqa_target(meta["B"], 3129))
+    loss.backward()
+    assert abs(loss.item() - meta["loss"]) <= 1e-5 * abs(meta["loss"])
+
+    def check(t, s, k):
+        t = t.detach().double().flatten()
+        got = t[torch.tensor(s["sample_idx"])]
+        assert (got - torch.tensor(s["samples"], dtype=torch.float64)).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), k
+        assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
+    for k, t in zip(O.HEAD_NAMES, heads):
+        check(t, meta["outputs"][k], k)
+    assert len(meta["gate_grads"]) == 4 * cfg["v_num_hidden_layers"]
+    for k, s in meta["gate_grads"].items():
+        check(Pg[k].grad, s, k)
+
+
 def test_roberta_golden(golden_dir):
     """config.model == "roberta": the reference's RobertaEmbeddings position-id shift is overwritten inside BertEmbeddings.forward
     (vilbert.py:347-351), so the outputs recorded from the reference with model="roberta" are the ones the oracle computes with

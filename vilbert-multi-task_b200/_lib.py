@@ -103,6 +103,10 @@ _SIGNATURES = {
     "vb_memset_zero": [_P, _I64, _P],
     "vb_ce_loss": [_P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _F, _I32, _P],
     "vb_kl_masked_loss": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _I32, _P],
+    "vb_masked_mean_fwd": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "vb_masked_mean_bwd": [_P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "vb_gate_scale_fwd": [_P, _P, _I64, _P, _I32, _I32, _I32, _I32, _P],
+    "vb_gate_scale_bwd": [_P, _I64, _P, _P, _I64, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "vb_compact_rows": [_P, _I64, _I32, _I32, _P, _P, _P, _P],
     "vb_gather_rows16": [_P, _P, _P, _P, _P, _I32, _I32, _P],
     "vb_scatter_rows_f32": [_P, _P, _P, _I32, _I32, _P, _P, _P],

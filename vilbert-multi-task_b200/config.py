@@ -100,9 +100,9 @@ class BertConfig(object):
             unsupported.append("model=%r" % (self.model,))
         if getattr(self, "model", "bert") == "roberta" and getattr(self, "task_specific_tokens", False):
             unsupported.append("model='roberta' with task_specific_tokens (the reference cannot run it either: RobertaEmbeddings.forward takes no task_ids)")
-        for flag in ("dynamic_attention",):
-            if getattr(self, flag, False):
-                unsupported.append(flag)
+        if getattr(self, "dynamic_attention", False) and (getattr(self, "in_batch_pairs", False) or getattr(self, "fast_mode", False)):
+            # the reference hands the UNEXPANDED text mask to the gate's pooling after the batch expansion (vilbert.py:1008-1053, 1084)
+            unsupported.append("dynamic_attention together with in_batch_pairs / fast_mode")
         if getattr(self, "fixed_t_layer", 0) > min(self.t_biattention_id) or getattr(self, "fixed_v_layer", 0) > min(self.v_biattention_id):
             unsupported.append("fixed_t_layer / fixed_v_layer beyond the first connection layer (the reference asserts the same, vilbert.py:965-966)")
         if getattr(self, "in_batch_pairs", False) and getattr(self, "fast_mode", False):

@@ -527,6 +527,96 @@ __global__ void mask_to_additive_kernel(const long long* __restrict__ m, float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------ dynamic_attention (vilbert.py:577-586)
+// BertImageSelfAttention with config.dynamic_attention: pool = masked mean of the current text states over the tokens,
+// gate = 1 + sigmoid(dyLinear(pool)) per (sample, channel), queries and keys of the image self-attention are multiplied by it.
+__device__ __forceinline__ float mask_weight(float add) { return 1.f + add / 10000.f; }   // (1 - m) * -10000 -> m
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+
+// pool[b, c] = sum_n w[b, n] x[b, n, c] / sum_n w[b, n]   (x fp32 [B, N, H]; also the 16-bit GEMM operand copies of pool)
+__global__ void __launch_bounds__(256)
+masked_mean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ addmask, float* __restrict__ pool, uint16_t* __restrict__ p16,
+                       uint16_t* __restrict__ p16_lo, __nv_bfloat16* __restrict__ p16_b, int fp16, int N, int H) {
+  pdl_entry();
+  const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= H) return;
+  float acc = 0.f, ws = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float w = mask_weight(addmask[(long long)b * N + n]);
+    acc += w * x[((long long)b * N + n) * H + c];
+    ws += w;
+  }
+  const float v = acc / ws;
+  const long long o = (long long)b * H + c;
+  pool[o] = v;
+  const uint16_t hi = cvt16(v, fp16);
+  p16[o] = hi;
+  if (p16_lo) p16_lo[o] = cvt16(v - cvt16_to_f32(hi, fp16), fp16);
+  if (p16_b) p16_b[o] = __float2bfloat16(v);
+}
+
+// dx[b, n, c] (+)= w[b, n] / sum_n w[b, n] * dpool[b, c]
+__global__ void __launch_bounds__(256)
+masked_mean_bwd_kernel(const float* __restrict__ dpool, const float* __restrict__ addmask, float* __restrict__ dx, int accumulate, int N, int H) {
+  pdl_entry();
+  const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= H) return;
+  float ws = 0.f;
+  for (int n = 0; n < N; ++n) ws += mask_weight(addmask[(long long)b * N + n]);
+  const float d = dpool[(long long)b * H + c] / ws;
+  for (int n = 0; n < N; ++n) {
+    const float g = mask_weight(addmask[(long long)b * N + n]) * d;
+    float* o = dx + ((long long)b * N + n) * H + c;
+    *o = accumulate ? *o + g : g;
+  }
+}
+
+// qk[b * N + n, c] *= 1 + sigmoid(z[b, c]) for c < cols (the Q | K sections of a [B * N, ld] 16-bit projection buffer; hi (+ lo)
+// parts in the operand format). Two columns per thread.
+__global__ void gate_scale_fwd_kernel(uint32_t* __restrict__ qk, uint32_t* __restrict__ qk_lo, long long ld2, const float* __restrict__ z, int N,
+                                      int cols, long long total2, int fp16) {
+  pdl_entry();
+  const int c2n = cols >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / c2n;
+    const int c2 = (int)(i % c2n);
+    const float2 zz = *reinterpret_cast<const float2*>(z + (row / N) * cols + 2 * c2);
+    const float g0 = 1.f + sigmoidf_(zz.x), g1 = 1.f + sigmoidf_(zz.y);
+    float2 v = unpack16(qk[row * ld2 + c2], fp16);
+    if (qk_lo) {
+      const float2 l = unpack16(qk_lo[row * ld2 + c2], fp16);
+      uint32_t lo;
+      qk[row * ld2 + c2] = pack16_split((v.x + l.x) * g0, (v.y + l.y) * g1, fp16, lo);
+      qk_lo[row * ld2 + c2] = lo;
+    } else {
+      qk[row * ld2 + c2] = pack16(v.x * g0, v.y * g1, fp16);
+    }
+  }
+}
+
+// Backward of the gate: with q = gate * q_pre,   d q_pre = gate * dq (in place, bf16)   and
+// d z[b, c] = s (1 - s) * sum_n dq[b, n, c] q_pre[b, n, c],   s = sigmoid(z) = gate - 1,   q_pre = q / gate  (gate in (1, 2)).
+__global__ void __launch_bounds__(256)
+gate_scale_bwd_kernel(__nv_bfloat16* __restrict__ dqk, long long ldd, const uint16_t* __restrict__ qk, const uint16_t* __restrict__ qk_lo, long long ld,
+                      const float* __restrict__ z, float* __restrict__ dz, __nv_bfloat16* __restrict__ dz16, int N, int cols, int fp16) {
+  pdl_entry();
+  const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const float s = sigmoidf_(z[(long long)b * cols + c]), g = 1.f + s;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const long long r = (long long)b * N + n;
+    const float d = __bfloat162float(dqk[r * ldd + c]);
+    float q = cvt16_to_f32(qk[r * ld + c], fp16);
+    if (qk_lo) q += cvt16_to_f32(qk_lo[r * ld + c], fp16);
+    acc += d * q;
+    dqk[r * ldd + c] = __float2bfloat16(d * g);
+  }
+  const float v = acc / g * s * (1.f - s);
+  dz[(long long)b * cols + c] = v;
+  dz16[(long long)b * cols + c] = __float2bfloat16(v);
+}
+
 // dst[r][i] = src[i] for r < repeats (16-byte words): FAST_MODE broadcast of the batch-1 text stream to the image batch
 __global__ void broadcast_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16, int repeats) {
   pdl_entry();
@@ -776,6 +866,41 @@ extern "C" vb_status vb_sum_strided(const float* src, float* dst, int64_t n, int
   launch_pdl(sum_strided_kernel, dim3(ew_grid(n / 4 * count_k)), dim3(256), (size_t)0, ST(stream), reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst),
              (long long)(n / 4), (int)count_k, (long long)(stride_k / 4), (int)count_r, (long long)(stride_r / 4), (int)(accumulate ? 1 : 0));
   return check_launch("vb_sum_strided");
+}
+
+extern "C" vb_status vb_masked_mean_fwd(const float* x, const float* add_mask, float* pool, void* pool16, void* pool16_lo, void* pool16_b,
+                                        int32_t out_fp16, int32_t B, int32_t N, int32_t H, void* stream) {
+  if (B <= 0 || N <= 0 || H <= 0 || !x || !add_mask || !pool || !pool16) return set_error(VB_ERR_INVALID, "vb_masked_mean_fwd: bad arguments");
+  launch_pdl(masked_mean_fwd_kernel, dim3((H + 255) / 256, B), dim3(256), (size_t)0, ST(stream), x, add_mask, pool, static_cast<uint16_t*>(pool16),
+             static_cast<uint16_t*>(pool16_lo), static_cast<__nv_bfloat16*>(pool16_b), (int)(out_fp16 ? 1 : 0), (int)N, (int)H);
+  return check_launch("vb_masked_mean_fwd");
+}
+
+extern "C" vb_status vb_masked_mean_bwd(const float* dpool, const float* add_mask, float* dx, int32_t accumulate, int32_t B, int32_t N, int32_t H,
+                                        void* stream) {
+  if (B <= 0 || N <= 0 || H <= 0 || !dpool || !add_mask || !dx) return set_error(VB_ERR_INVALID, "vb_masked_mean_bwd: bad arguments");
+  launch_pdl(masked_mean_bwd_kernel, dim3((H + 255) / 256, B), dim3(256), (size_t)0, ST(stream), dpool, add_mask, dx, (int)(accumulate ? 1 : 0), (int)N, (int)H);
+  return check_launch("vb_masked_mean_bwd");
+}
+
+extern "C" vb_status vb_gate_scale_fwd(void* qk, void* qk_lo, int64_t ld, const float* z, int32_t B, int32_t N, int32_t cols, int32_t fp16,
+                                       void* stream) {
+  if (B <= 0 || N <= 0 || cols <= 0 || (cols & 1) || (ld & 1) || !qk || !z || (reinterpret_cast<uintptr_t>(qk) & 3) ||
+      (reinterpret_cast<uintptr_t>(qk_lo) & 3) || (reinterpret_cast<uintptr_t>(z) & 7))
+    return set_error(VB_ERR_INVALID, "vb_gate_scale_fwd: bad arguments (even cols / ld, 4-byte aligned rows)");
+  const long long total2 = (long long)B * N * (cols / 2);
+  launch_pdl(gate_scale_fwd_kernel, dim3(ew_grid(total2)), dim3(256), (size_t)0, ST(stream), static_cast<uint32_t*>(qk), static_cast<uint32_t*>(qk_lo),
+             (long long)(ld / 2), z, (int)N, (int)cols, total2, (int)(fp16 ? 1 : 0));
+  return check_launch("vb_gate_scale_fwd");
+}
+
+extern "C" vb_status vb_gate_scale_bwd(void* dqk, int64_t ldd, const void* qk, const void* qk_lo, int64_t ld, const float* z, float* dz, void* dz16,
+                                       int32_t B, int32_t N, int32_t cols, int32_t fp16, void* stream) {
+  if (B <= 0 || N <= 0 || cols <= 0 || !dqk || !qk || !z || !dz || !dz16) return set_error(VB_ERR_INVALID, "vb_gate_scale_bwd: bad arguments");
+  launch_pdl(gate_scale_bwd_kernel, dim3((cols + 255) / 256, B), dim3(256), (size_t)0, ST(stream), static_cast<__nv_bfloat16*>(dqk), (long long)ldd,
+             static_cast<const uint16_t*>(qk), static_cast<const uint16_t*>(qk_lo), (long long)ld, z, dz, static_cast<__nv_bfloat16*>(dz16), (int)N,
+             (int)cols, (int)(fp16 ? 1 : 0));
+  return check_launch("vb_gate_scale_bwd");
 }
 
 extern "C" vb_status vb_step_counter_bump(uint32_t* step, void* stream) {

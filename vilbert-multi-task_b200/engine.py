@@ -83,6 +83,9 @@ class ParamStore:
         def block(kind, i, H, I):
             p = f"bert.encoder.{kind}.{i}"
             self._qkv(f"{p}.attention.self", ("query", "key", "value"), H, H)
+            if kind == "v_layer" and getattr(c, "dynamic_attention", False):
+                # BertImageSelfAttention.dyLinear_q / dyLinear_k (vilbert.py:561-563), contiguous so that one [2Hv, Ht] GEMM computes both gates
+                self._qkv(f"{p}.attention.self", ("dyLinear_q", "dyLinear_k"), H, Ht, fused="dy")
             lin(f"{p}.attention.output.dense", H, H); ln(f"{p}.attention.output.LayerNorm", H)
             lin(f"{p}.intermediate.dense", I, H)
             lin(f"{p}.output.dense", H, I); ln(f"{p}.output.LayerNorm", H)
@@ -150,8 +153,8 @@ class ParamStore:
         b0 = self._off
         for nm in names:
             self._add(f"{prefix}.{nm}.bias", (o,))
-        self.fused[f"{prefix}.{fused}.weight"] = (w0, (3 * o, i))
-        self.fused[f"{prefix}.{fused}.bias"] = (b0, (3 * o,))
+        self.fused[f"{prefix}.{fused}.weight"] = (w0, (len(names) * o, i))
+        self.fused[f"{prefix}.{fused}.bias"] = (b0, (len(names) * o,))
 
     def _view(self, flat, name):
         off, shape = self.entries[name] if name in self.entries else self.fused[name]
@@ -258,6 +261,7 @@ class Plan:
         self.attn_t, self.attn_v, self.attn_c = [], [], []
         if self.viz and train:
             raise ValueError("visualization exports the undropped attention probabilities: eval mode only")
+        self.dyn = bool(getattr(self.cfg, "dynamic_attention", False))
         self.fast = bool(getattr(self.cfg, "fast_mode", False))
         self.Bt = 1 if self.fast else B
         if self.fast and (train or grad_outputs or vqa_loss or loss):
@@ -541,13 +545,21 @@ class Plan:
         self.push_bwd(bwd)
         return out
 
-    def self_attention_block(self, x, B, N, nh, mask, prefix, tag, p_attn=0.0, p_hidden=0.0):
-        """BertAttention (self-attention + output), text or image stream (vilbert.py:424-474, 571-633)."""
+    def self_attention_block(self, x, B, N, nh, mask, prefix, tag, p_attn=0.0, p_hidden=0.0, pool=None):
+        """BertAttention (self-attention + output), text or image stream (vilbert.py:424-474, 571-633). pool: the pooled text states
+        (text_pool) when config.dynamic_attention gates this image layer's queries and keys (:577-586)."""
         ps, M, H = self.ps, x.M, x.H
         D = H // nh
         qkv, qkvl, _ = self.buf16((M, 3 * H), bw=False)     # the attention backward converts its Q/K/V panels in shared memory
         self.gemm(M, 3 * H, H, x.b16, H, ps.w16(prefix + ".self.qkv.weight"), H, bias=ps.p(prefix + ".self.qkv.bias"), out_bf16=qkv, ld_ob=3 * H,
                   a_lo=x.lo, b_lo=ps.w16lo(prefix + ".self.qkv.weight"), out_lo=qkvl)
+        if pool is not None:
+            # z = dyLinear_q | dyLinear_k (pool) as one [B, 2H] GEMM; Q and K are scaled in place by 1 + sigmoid(z)
+            Kp = pool.H
+            z = self.buf((B, 2 * H), F32)
+            self.gemm(B, 2 * H, Kp, pool.b16, Kp, ps.w16(prefix + ".self.dy.weight"), Kp, bias=ps.p(prefix + ".self.dy.bias"), out_f32=z, ld_of=2 * H,
+                      a_lo=pool.lo, b_lo=ps.w16lo(prefix + ".self.dy.weight"))
+            self.emit(self.lib.vb_gate_scale_fwd, qkv.data_ptr(), self._ptr(qkvl), 3 * H, z.data_ptr(), B, N, 2 * H, self.op_fp16)
         ctx, ctxl, ctxb = self.buf16((M, H))
         lse = self.buf((B, nh, N), F32)
         q, k, v = qkv[:, 0:H], qkv[:, H:2 * H], qkv[:, 2 * H:]
@@ -570,9 +582,19 @@ class Plan:
             dqkv = self.scratch(tag + ".dqkv", (M, 3 * H), BF16)
             delta = self.scratch(tag + ".delta", (B, nh, N), F32)
             gb = ps.g(prefix + ".self.qkv.bias")     # bias gradients = column sums of dQ|dK|dV, fused into the attention backward
+            gated = pool is not None                 # ... except under the gate, where the biases sit before the scaling
             self.attention(True, B, nh, N, N, D, q, 3 * H, k, 3 * H, v, 3 * H, mask, ctx, H, lse, dO=dctx, lddo=H,
                            dQ=dqkv[:, 0:H], lddq=3 * H, dK=dqkv[:, H:2 * H], lddk=3 * H, dV=dqkv[:, 2 * H:], lddv=3 * H, delta=delta,
-                           dbq=gb[0:H], dbk=gb[H:2 * H], dbv=gb[2 * H:], dropout=adrop, o_b16=self._extra(ctxb, ctx))
+                           dbq=None if gated else gb[0:H], dbk=None if gated else gb[H:2 * H], dbv=gb[2 * H:], dropout=adrop,
+                           o_b16=self._extra(ctxb, ctx))
+            if gated:
+                dz32 = self.scratch(tag + ".dz32", (B, 2 * H), F32)
+                dz16 = self.scratch(tag + ".dz16", (B, 2 * H), BF16)
+                self.emit(self.lib.vb_gate_scale_bwd, dqkv.data_ptr(), 3 * H, qkv.data_ptr(), self._ptr(qkvl), 3 * H, z.data_ptr(), dz32.data_ptr(),
+                          dz16.data_ptr(), B, N, 2 * H, self.op_fp16)
+                self.colsum(dqkv, 3 * H, gb[0:2 * H], M, 2 * H)
+                self.linear_wgrad(dz16, 2 * H, dz32, 2 * H, pool.bw, pool.H, B, 2 * H, pool.H, prefix + ".self.dy")
+                self.dgrad_into(pool, dz16, 2 * H, ps.w16b(prefix + ".self.dy.weight"), B, 2 * H, pool.H)
             self.linear_wgrad(dqkv, 3 * H, None, 0, x.bw, H, M, 3 * H, H, prefix + ".self.qkv")
             self.dgrad_into(x, dqkv, 3 * H, ps.w16b(prefix + ".self.qkv.weight"), M, 3 * H, H, extra32=dy32)
         self.push_bwd(bwd)
@@ -732,11 +754,32 @@ class Plan:
         return self.ffn(h1, c.intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "t.ffn",
                         drop=self.drop(p + ".output.dropout", c.hidden_dropout_prob))
 
-    def image_layer(self, x, i):
+    def text_pool(self, t):
+        """dynamic_attention: masked mean of the text states over the tokens (vilbert.py:578-579) as an Act [B, Ht] with GEMM operand
+        copies; its backward adds d pool to the gradient of the text states. Emitted on the text stream; the caller places a
+        barrier before the image layers that read it (their backward accumulates d pool, mirrored barrier, then this backward)."""
+        B, Ht, lib = self.B, t.H, self.lib
+        p32 = self.buf((B, Ht), F32)
+        p16, plo, pbw = self.buf16((B, Ht))
+        self.emit(lib.vb_masked_mean_fwd, t.f32.data_ptr(), self.mask_t.data_ptr(), p32.data_ptr(), p16.data_ptr(), self._ptr(plo),
+                  self._ptr(self._extra(pbw, p16)), self.op_fp16, B, self.Nt, Ht)
+        pool = Act(p32, p16, B, Ht, lo=plo, bw=pbw)
+        mask = self.mask_t
+
+        def bwd():
+            if not pool.gw or t.frozen:
+                return
+            g = self.grad_of(t)
+            self.emit(lib.vb_masked_mean_bwd, pool.g32.data_ptr(), mask.data_ptr(), g.data_ptr(), 1 if t.gw else 0, B, self.Nt, Ht)
+            t.gw = True
+        self.push_bwd(bwd)
+        return pool
+
+    def image_layer(self, x, i, pool=None):
         p = f"bert.encoder.v_layer.{i}"
         c = self.cfg
         h1 = self.self_attention_block(x, x.M // self.Nv, self.Nv, c.v_num_attention_heads, self.mask_v, p + ".attention", "v",
-                                       p_attn=c.v_attention_probs_dropout_prob, p_hidden=c.v_hidden_dropout_prob)
+                                       p_attn=c.v_attention_probs_dropout_prob, p_hidden=c.v_hidden_dropout_prob, pool=pool)
         return self.ffn(h1, c.v_intermediate_size, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", "v.ffn",
                         drop=self.drop(p + ".output.dropout", c.v_hidden_dropout_prob))
 
@@ -1077,11 +1120,17 @@ class Plan:
                 t = self.text_layer(t, i)
                 self._no_grad = False
                 t.frozen = frozen
+            pool = None
+            if self.dyn and v_end > v_start:
+                # dynamic_attention: this segment's image layers read the pooled text states of the segment's END (the text layers
+                # run first in the reference, vilbert.py:977-1004), so the two streams cannot overlap here
+                pool = self.text_pool(t)
+                self.sync_streams()
             with self.on(1):
                 for i in range(v_start, v_end):
                     frozen = i < getattr(c, "fixed_v_layer", 0)
                     self._no_grad = frozen
-                    v = self.image_layer(v, i)
+                    v = self.image_layer(v, i, pool)
                     self._no_grad = False
                     v.frozen = frozen
             if count == 0 and self.fast:
@@ -1092,9 +1141,13 @@ class Plan:
                 v, t = self.connection_layer(v, t, count)
             v_start, t_start = v_end, t_end
             self.enc_t.append(t); self.enc_v.append(v)     # output_all_encoded_layers: one entry per connection layer (:1075-1077)
+        pool = None
+        if self.dyn and c.v_num_hidden_layers > v_start:
+            pool = self.text_pool(t)      # the trailing image layers see the text states BEFORE the trailing text layers (:1079-1092)
+            self.sync_streams()
         with self.on(1):
             for i in range(v_start, c.v_num_hidden_layers):
-                v = self.image_layer(v, i)
+                v = self.image_layer(v, i, pool)
         for i in range(t_start, c.num_hidden_layers):
             t = self.text_layer(t, i)
         self.sync_streams()      # poolers and heads read both streams; they run on the main stream
