@@ -186,7 +186,8 @@ def test_dynamic_attention_base_shape(golden_dir):
     """dynamic_attention at the base 6-layer widths (Hv 1024 gated by Ht 768) and the VQA sequence lengths, small batch."""
     from _gpu_util import model_case
     cfgj = dict(_cfg(golden_dir, "base_6layer_6conect_b4"), dynamic_attention=True)
-    _check(model_case(cfgj, 4, 100, 36, seed=0))
+    # measured worst gradient rel-L2 3.1e-2 (query / key biases of the first text layers, whose exact gradient is close to zero at B=4)
+    _check(model_case(cfgj, 4, 100, 36, seed=0), grad_worst=5e-2, grad_median=1.5e-2)
     import vilbert_b200
     with pytest.raises(NotImplementedError):
         vilbert_b200.BertConfig.from_dict(dict(cfgj, fast_mode=True)).check_supported()
