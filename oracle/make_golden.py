@@ -367,6 +367,77 @@ def check_dynamic_attention(ref, cfg_json):
                        loss=float(O.vqa_loss(r[0], tgt).detach()), pin=dict(worst=worst, tolerance=TOL)), f)
 
 
+class _MaskDropout(torch.nn.Module):
+    """Stand-in for one nn.Dropout of the reference in train mode: multiplies by the engine's stateless mask for the given site
+    name(s) (one name per call of the module within a forward, in call order) with the module's OWN probability."""
+
+    def __init__(self, names, p, masks):
+        super().__init__()
+        self.names, self.p, self.masks, self.calls = list(names), p, masks, 0
+
+    def forward(self, x):
+        if not self.training:
+            return x
+        name = self.names[self.calls % len(self.names)]
+        self.calls += 1
+        m = self.masks.mask(name, self.p, tuple(x.shape), x.device)
+        return x if m is None else x * m
+
+
+def check_train_mode_dropout_placement(ref, cfg_json):
+    """Train mode: WHERE every nn.Dropout of the reference acts and with WHICH probability. Every nn.Dropout module of the
+    unmodified reference model is replaced, by its module path, with a mask multiplication that draws the engine's stateless mask
+    for the site of that name and the module's own p (VILBertForVLTasks.dropout is called three times per forward: pooled fusion,
+    sequence_output_v, sequence_output_t, vilbert.py:1677-1695). The oracle with oracle.DropMasks must then reproduce outputs and
+    gradients exactly — which pins the placement, the tensor layout the mask indexes and the five distinct probabilities."""
+    cfgj = dict(cfg_json, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.15, v_hidden_dropout_prob=0.2,
+                v_attention_probs_dropout_prob=0.25)
+    cfg = O.make_config(cfgj)
+    step, head_p = 12345, 0.3
+    model = ref.VILBertForVLTasks(ref.BertConfig.from_dict(dict(cfgj)), num_labels=1, dropout_prob=head_p, default_gpu=False)
+    P = O.synth_params(cfg, seed=0)
+    model.load_state_dict(P, strict=False); model.tie_weights(); model.train()
+    masks = O.DropMasks(step, head_p=head_p)
+    sites = {}
+    for name, mod in list(model.named_modules()):
+        if isinstance(mod, torch.nn.Dropout):
+            parent = model
+            parts = name.split(".")
+            for q in parts[:-1]:
+                parent = getattr(parent, q)
+            names = ["dropout.pooled", "dropout.seq_v", "dropout.seq_t"] if name == "dropout" else [name]
+            setattr(parent, parts[-1], _MaskDropout(names, mod.p, masks))
+            sites[name] = mod.p
+    inp = O.synth_inputs(cfg, 4, 11, 9, seed=1234)
+    args = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], inp["co_attention_mask"])
+    tgt = O.synth_vqa_target(4, 3129)
+    r = model(*args)[:9]
+    loss_r = O.vqa_loss(r[0], tgt) + r[2].sum() * 0.1 + r[6].mul(inp["image_attention_mask"].unsqueeze(2).float()).sum() * 0.01 + r[8].sum() * 0.01
+    loss_r.backward()
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+    Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+    _, o = O.vilbert_for_vl_tasks(Pg, cfg, *args[:6], drop=masks)
+    loss_o = O.vqa_loss(o[0], tgt) + o[2].sum() * 0.1 + o[6].mul(inp["image_attention_mask"].unsqueeze(2).float()).sum() * 0.01 + o[8].sum() * 0.01
+    loss_o.backward()
+    named = dict(model.named_parameters())
+    worst = max(rel(a, b) for a, b in zip(o, r))
+    for k, v in Pg.items():
+        if k != "cls.predictions.decoder.weight" and named[k].grad is not None:
+            worst = max(worst, rel(v.grad, named[k].grad))
+    with torch.no_grad():
+        model.eval()
+        r_eval = model(*args)[:9]
+    differs = rel(r_eval[0], r[0])
+    print(f"{'train-mode dropout sites':28s} worst {worst:.2e}; {len(sites)} nn.Dropout modules, probabilities {sorted(set(sites.values()))}; "
+          f"train vs eval output differs by {differs:.2e}")
+    assert worst < TOL and differs > 1e-2 and len(set(sites.values())) == 5
+    with open(os.path.join(GOLD, "tiny_train_mode_dropout.json"), "w") as f:
+        json.dump(dict(name="tiny_train_mode_dropout", config=cfgj, B=4, Nv=11, Nt=9, seed=0, input_seed=1234, step=step, head_p=head_p,
+                       sites=sites, loss=float(loss_r.detach()),
+                       outputs={n: dict(summary(a), shape=list(a.shape)) for n, a in zip(O.HEAD_NAMES, r)},
+                       pin=dict(worst=worst, tolerance=TOL)), f)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
@@ -387,6 +458,7 @@ def main():
     check_visualization(ref, TINY)
     check_roberta(ref, TINY)
     check_dynamic_attention(ref, TINY)
+    check_train_mode_dropout_placement(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

@@ -233,7 +233,7 @@ def probe_loss(heads, names, tgt):
 
 
 def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, device="cuda", train_step=None, precision="fp16",
-               oracle_modes=("fp32", "op")):
+               oracle_modes=("fp32", "op"), head_dropout_prob=None):
     """Engine vs the oracle in fp32 and in the engine's operand-rounding mode ("op": fp16 forward / bf16 gradient operands for
     precision "fp16" and "fp32", all-bf16 for "bf16"). Returns dict(out_fp32, out_op, grad_fp32, grad_op, ...)
     where each is {tensor name: error}; gradient errors are (max-rel with floor, rel-L2).
@@ -245,6 +245,8 @@ def model_case(cfgj, B, Nv, Nt, seed=0, qk_scale=1.0, names=None, grads=True, de
     P = O.synth_params(cfg, seed=seed, device=dev, qk_scale=qk_scale)
     inp = O.synth_inputs(cfg, B, Nv, Nt, seed=1234 + seed, device=dev)
     eng = build_engine(cfgj, P, dev, precision)
+    if head_dropout_prob is not None:
+        eng.head_dropout_prob = head_dropout_prob     # VILBertForVLTasks(dropout_prob=...)
     drop = None
     if train_step is not None:
         eng.drop_step.fill_(int(train_step))

@@ -78,6 +78,19 @@ def test_train_mode_dropout_matches_oracle_masks(golden_dir, B, Nv, Nt, seed, ta
     assert (r["plan"].outputs["sequence_output_t"] - r_eval["plan"].outputs["sequence_output_t"]).abs().max().item() > 1e-2
 
 
+def test_train_mode_distinct_dropout_probabilities(golden_dir):
+    """Five different probabilities (hidden 0.1, attention 0.15, v_hidden 0.2, v_attention 0.25, head 0.3): each fused dropout
+    site must use the probability of ITS reference module. The site / probability / tensor-layout assignment of the oracle's
+    DropMasks is itself pinned bit-exact against the reference with every nn.Dropout replaced by the same masks
+    (tests/golden/tiny_train_mode_dropout.json, oracle/make_golden.py::check_train_mode_dropout_placement)."""
+    from _gpu_util import model_case
+    meta = json.load(open(os.path.join(golden_dir, "tiny_train_mode_dropout.json")))
+    r = model_case(meta["config"], meta["B"], meta["Nv"], meta["Nt"], seed=0, train_step=meta["step"], head_dropout_prob=meta["head_p"])
+    _check(r)
+    r = model_case(dict(meta["config"], task_specific_tokens=True), 3, 7, 12, seed=1, train_step=7, head_dropout_prob=meta["head_p"])
+    _check(r)
+
+
 def test_dropout_statistics_and_step_counter(golden_dir):
     """Keep fraction ~ 1-p, masks change with the step counter, same counter -> bit-identical forward."""
     from _gpu_util import build_engine

@@ -142,6 +142,29 @@ def test_dynamic_attention_golden(golden_dir):
         check(Pg[k].grad, s, k)
 
 
+def test_train_mode_dropout_golden(golden_dir):
+    """Train mode: outputs and loss recorded from the unmodified reference whose nn.Dropout modules were replaced, by module path,
+    with the engine's stateless masks (oracle/make_golden.py::check_train_mode_dropout_placement, pinned at 0.0 difference incl.
+    all gradients). oracle.DropMasks must reproduce them: dropout placement, per-site probability and mask indexing."""
+    meta = json.load(open(os.path.join(golden_dir, "tiny_train_mode_dropout.json")))
+    cfg = O.make_config(meta["config"])
+    assert len(meta["sites"]) == 35 and len(set(meta["sites"].values())) == 5
+    P = O.synth_params(cfg, seed=meta["seed"])
+    inp = O.synth_inputs(cfg, meta["B"], meta["Nv"], meta["Nt"], seed=meta["input_seed"])
+    with torch.no_grad():
+        _, heads = O.vilbert_for_vl_tasks(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"],
+                                          inp["attention_mask"], inp["image_attention_mask"], drop=O.DropMasks(meta["step"], head_p=meta["head_p"]))
+        _, heads_eval = O.vilbert_for_vl_tasks(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"],
+                                               inp["attention_mask"], inp["image_attention_mask"])
+    assert (heads[0] - heads_eval[0]).abs().max().item() > 1e-2 * heads_eval[0].abs().max().item()
+    for k, t in zip(O.HEAD_NAMES, heads):
+        s = meta["outputs"][k]
+        t = t.detach().double().flatten()
+        got = t[torch.tensor(s["sample_idx"])]
+        assert (got - torch.tensor(s["samples"], dtype=torch.float64)).abs().max().item() <= 1e-5 * max(s["absmax"], 1e-12), k
+        assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
+
+
 def test_roberta_golden(golden_dir):
     """config.model == "roberta": the reference's RobertaEmbeddings position-id shift is overwritten inside BertEmbeddings.forward
     (vilbert.py:347-351), so the outputs recorded from the reference with model="roberta" are the ones the oracle computes with
