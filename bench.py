@@ -242,6 +242,9 @@ def main():
                          "N = 2, but ProcessGroupNCCL's watchdog hangs at teardown while captured collectives are alive: opt-in)")
     ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: cap NCCL's CTAs per collective (NCCL_MAX_CTAS) so that the all-reduce "
                                                                   "overlapping the backward takes fewer SMs from the persistent GEMMs; 0 = NCCL default")
+    ap.add_argument("--bwd-gemm-ctas", type=int, default=-1,
+                    help="N > 1: persistent CTAs of the backward-pass GEMMs (they run beside NCCL's all-reduce kernels; a GEMM CTA that finds "
+                         "its SM taken starts after the others and serialises its whole static tile share). -1 = engine default, 0 = one per SM")
     ap.add_argument("--segments", type=int, default=8, help="N > 1: number of backward pieces whose gradient ranges are all-reduced while the rest runs")
     ap.add_argument("--eval-mode", action="store_true", help="disable the dropout layers (reference eval mode); default is train mode")
     ap.add_argument("--legacy-prologue", action="store_true", help="round-1 step body: weight cast + gradient memset inside the step, no fused optimizer")
@@ -313,6 +316,8 @@ def main():
     W = max(a.warmup, 3)
     cfg_o = O.make_config(cfgj)
     eng = Engine(BertConfig.from_dict(cfgj), dev, heads=C.get("heads", "vl"), precision=a.precision)
+    if world > 1 and a.bwd_gemm_ctas >= 0:
+        eng.bwd_gemm_max_ctas = a.bwd_gemm_ctas
     # random-init weights of the named architecture (reference init: N(0, 0.02), zero bias, LN 1/0); same seed on every rank
     g = torch.Generator(device=dev).manual_seed(0)
     eng.ps.flat.normal_(0.0, 0.02, generator=g)
@@ -586,6 +591,7 @@ def main():
                    "allreduce": ("none (1 GPU)" if world == 1 else (f"NCCL AVG of the flat fp32 gradient buffer, {len(T[0]['plan'].segments)} tail ranges overlapped with backward"
                                                                          + (" (one CUDA graph per step, collectives captured, never-written ranges skipped)" if ddp_graph else " (one graph per backward piece)") if overlapped
                                  else "NCCL AVG of the flat fp32 gradient buffer after each backward (8 buckets)")),
+                   "bwd_gemm_ctas": (eng.bwd_gemm_max_ctas or "one per SM"),
                    "l2": "working set (activations + weights + grads, GBs per step) exceeds the 126 MB L2; no explicit flush",
                    "streams": "text and vision segments on two CUDA streams (parallel graph branches)" if eng.two_streams else "single stream",
                    "numerics": {"fp16": "fp16 forward tensor-core operands, bf16 gradient operands, fp32 accumulate/residual/LayerNorm/softmax",

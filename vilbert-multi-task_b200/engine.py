@@ -403,7 +403,7 @@ class Plan:
         g.out_f32, g.ld_out_f32 = self._ptr(out_f32), ld_of
         g.out_bf16, g.ld_out_bf16 = self._ptr(out_bf16), ld_ob
         g.out_pre, g.ld_out_pre = self._ptr(out_pre), ld_op
-        g.atomic_out, g.split_k, g.block_n, g.max_ctas = atomic, split_k, 0, 0
+        g.atomic_out, g.split_k, g.block_n, g.max_ctas = atomic, split_k, 0, (0 if fwd else self.e.bwd_gemm_max_ctas)
         g.out_colsum = self._ptr(out_colsum)
         if dropout is not None:
             g.dropout = dropout
@@ -1641,6 +1641,7 @@ class Engine:
         self.grad_clean = False          # the flat gradient buffer is all zeros (set by zero_grad / the fused optimizer)
         self.loss_options = 4            # answer options per question of the VL-logit objective (retrieval / VCR: 4)
         self.auto_graph = True           # module surface: capture a plan's passes into CUDA graphs after two eager runs
+        self.bwd_gemm_max_ctas = 0       # persistent CTAs of the backward GEMMs (0 = one per SM); data parallel: leave SMs to NCCL
         self.lm_compact = True           # fused pre-training objective: masked-LM decoder + CE on the labelled rows only (Plan.lm_head_compact)
         self.lm_capacity = 0.25          # ... with room for this fraction of the token rows (15 % are masked; more poisons the loss with NaN)
 
