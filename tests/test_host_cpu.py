@@ -97,6 +97,54 @@ def test_plan_builds_on_cpu(golden_dir, task_tokens, B):
     assert set(bert_only.outputs) == set(O.BERT_OUT_NAMES)
 
 
+def _op_names(ops):
+    return [getattr(op[0], "__name__", None) or getattr(op[0], "_name", "") for op in ops if op[0] is not None]
+
+
+def test_special_mode_plans_build_on_cpu(golden_dir):
+    """Structure of the plans of the optional modes, checked without a GPU: dynamic_attention (gate parameters, pooling / gate ops
+    in both passes, data-parallel pieces still tile the gradient buffer) and the compacted masked-LM head of the fused pre-training
+    objective (no [tokens, vocab] logits output, capacity arithmetic, cache key)."""
+    from vilbert_b200.engine import LOSS_HEADS
+    tiny = json.load(open(os.path.join(golden_dir, "tiny_b4.json")))["config"]
+    cfgj = dict(tiny, dynamic_attention=True)
+    eng = Engine(BertConfig.from_dict(cfgj), "cpu", _build_only=True)
+    names = set(eng.ps.entries)
+    assert names == set(O.param_shapes(O.make_config(cfgj))) - {"cls.predictions.decoder.weight"} | {"bert.embeddings.word_embeddings.weight"}
+    p0 = "bert.encoder.v_layer.0.attention.self"
+    (wq, sq), (wk, sk) = eng.ps.entries[p0 + ".dyLinear_q.weight"], eng.ps.entries[p0 + ".dyLinear_k.weight"]
+    assert sq == sk == (cfgj["v_hidden_size"], cfgj["hidden_size"]) and wk == wq + sq[0] * sq[1]       # contiguous: one fused [2Hv, Ht] GEMM
+    assert eng.ps.fused[p0 + ".dy.weight"] == (wq, (2 * sq[0], sq[1]))
+    plan = eng.plan(4, 9, 11, grad_outputs=O.HEAD_NAMES, train=True)
+    base = Engine(BertConfig.from_dict(tiny), "cpu", _build_only=True).plan(4, 9, 11, grad_outputs=O.HEAD_NAMES, train=True)
+    nv = cfgj["v_num_hidden_layers"]
+    f, b = _op_names(plan.fwd), _op_names(plan.bwd)
+    assert f.count("vb_gate_scale_fwd") == nv and b.count("vb_gate_scale_bwd") == nv
+    assert 1 <= f.count("vb_masked_mean_fwd") <= nv and b.count("vb_masked_mean_bwd") == f.count("vb_masked_mean_fwd")
+    assert plan.n_kernels_fwd > base.n_kernels_fwd and plan.n_kernels_bwd > base.n_kernels_bwd
+    segs = plan.ddp_segments(4)
+    assert segs[0][3] == eng.ps.numel and segs[-1][2] == 0 and all(nx[3] == cur[2] for cur, nx in zip(segs, segs[1:]))
+    for (lo, hi, glo, ghi) in segs:
+        for (off, n), touch in plan.grad_touch.items():
+            if glo <= off < ghi:
+                assert touch < hi
+    # compacted masked-LM head
+    engp = Engine(BertConfig.from_dict(tiny), "cpu", heads="pretraining", _build_only=True)
+    B, Nt = 64, 20
+    pc = engp.plan(B, Nt, 11, grad_outputs=LOSS_HEADS["pretraining"], loss="pretraining")
+    assert "linguisic_prediction" not in pc.outputs and pc.lm_c["cap"] == 320 and tuple(pc.lm_c["logits"].shape) == (320, tiny["vocab_size"])
+    assert set(pc.loss_inputs) == {"masked_lm_labels", "image_target", "image_label", "next_sentence_label"}
+    assert (pc.loss_inputs["masked_lm_labels"] == -1).all()                     # nothing labelled until the caller loads labels
+    engp.lm_capacity = 0.5
+    assert engp.plan(B, Nt, 11, grad_outputs=LOSS_HEADS["pretraining"], loss="pretraining").lm_c["cap"] == 640
+    engp.lm_compact = False
+    pf = engp.plan(B, Nt, 11, grad_outputs=LOSS_HEADS["pretraining"], loss="pretraining")
+    assert pf.lm_c is None and tuple(pf.outputs["linguisic_prediction"].shape) == (B, Nt, tiny["vocab_size"])
+    assert pf is not pc and len(engp.plans) == 3
+    small = Engine(BertConfig.from_dict(tiny), "cpu", heads="pretraining", _build_only=True).plan(4, 9, 11, grad_outputs=LOSS_HEADS["pretraining"], loss="pretraining")
+    assert small.lm_c["cap"] == 40                                              # never more rows than there are (8-padded)
+
+
 def test_ddp_segments_partition_the_gradient_buffer(golden_dir):
     """Overlapped data-parallel step: backward pieces (each with at least one kernel, no side-stream event recorded in one
     piece and waited for in a later one) release tail ranges of the flat gradient buffer that (a) tile it exactly and (b)
