@@ -149,6 +149,45 @@ def run_pretraining_case(ref, name, cfg_json, B, Nv, Nt):
                        pin=dict(worst=max(errs), tolerance=TOL)), f)
 
 
+def check_visual_targets(ref, cfg_json):
+    """config.visual_target 1 (feature regression) and 2 (noise-contrastive estimation with sampled negatives, vilbert.py:1507-1575)
+    of BertForMultiModalPreTraining: the three losses and every parameter gradient. For 2 the reference samples its negatives from
+    torch's global generator; the oracle draws in the same order, so under the same manual_seed the sample is identical."""
+    for vt in (1, 2):
+        cfgj = dict(cfg_json, visual_target=vt, v_target_size=48, num_negative=20)
+        cfg = O.make_config(cfgj)
+        model = ref.BertForMultiModalPreTraining(ref.BertConfig.from_dict(dict(cfgj)))
+        P = O.synth_params(cfg, seed=3, with_task_heads=False)
+        model.load_state_dict(P, strict=False); model.tie_weights(); model.eval()
+        B, Nv, Nt = 4, 9, 8
+        inp = O.synth_inputs(cfg, B, Nv, Nt, seed=77)
+        g = torch.Generator().manual_seed(5)
+        lm = torch.full((B, Nt), -1, dtype=torch.long); lm[:, 1] = torch.randint(0, cfg["vocab_size"], (B,), generator=g)
+        il = torch.full((B, Nv - 1), -1, dtype=torch.long); il[:, 0] = 1; il[:, 3] = 1; il[2, 7] = 1
+        it = torch.randn(B, Nv - 1, 48, generator=g)
+        ns = torch.randint(0, 2, (B,), generator=g)
+        a = (inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"], lm, il, it, ns)
+        torch.manual_seed(4242)
+        lr = model(*a)
+        sum(lr).sum().backward()
+        Pg = {k: v.clone().requires_grad_(True) for k, v in P.items() if k != "cls.predictions.decoder.weight"}
+        Pg["cls.predictions.decoder.weight"] = Pg["bert.embeddings.word_embeddings.weight"]
+        torch.manual_seed(4242)
+        neg = O.nce_negative_indices(B, Nv - 1, 20) if vt == 2 else None
+        lo = O.pretraining_losses(Pg, cfg, *a, neg_index=neg)
+        sum(lo).backward()
+        named = dict(model.named_parameters())
+        worst = max(abs(x.item() - y.item()) / abs(y.item()) for x, y in zip(lo, lr))
+        for k, v in Pg.items():
+            if k != "cls.predictions.decoder.weight" and named[k].grad is not None:
+                worst = max(worst, rel(v.grad, named[k].grad))
+        print(f"{'visual_target ' + str(vt):28s} worst {worst:.2e}  ({[round(float(x.detach()), 5) for x in lr]})")
+        assert worst < TOL
+        with open(os.path.join(GOLD, f"tiny_visual_target_{vt}.json"), "w") as f:
+            json.dump(dict(name=f"tiny_visual_target_{vt}", config=cfgj, B=B, Nv=Nv, Nt=Nt, losses=[float(x.detach()) for x in lr],
+                           neg_index=neg.tolist() if neg is not None else None, seed=4242, pin=dict(worst=worst, tolerance=TOL)), f)
+
+
 def check_all_encoded_layers(ref, cfg_json):
     """output_all_encoded_layers=True: per-connection-layer states + poolers on the last connection layer's output."""
     cfg = O.make_config(cfg_json)
@@ -459,6 +498,7 @@ def main():
     check_roberta(ref, TINY)
     check_dynamic_attention(ref, TINY)
     check_train_mode_dropout_placement(ref, TINY)
+    check_visual_targets(ref, TINY)
     print("oracle pinned against the reference on all cases; fixtures written to", GOLD)
 
 

@@ -341,17 +341,50 @@ HEAD_NAMES = ("vil_prediction", "vil_prediction_gqa", "vil_logit", "vil_binary_p
 BERT_OUT_NAMES = ("sequence_output_t", "sequence_output_v", "pooled_output_t", "pooled_output_v")
 
 
+def nce_negative_indices(B, R, num_negative):
+    """visual_target == 2, vilbert.py:1524-1557: per (sample, region) the flat indices (row * R + col into the [B * R] region
+    table) of int(0.7 n) negatives from OTHER samples and int(0.3 n) from OTHER regions of the same sample. Draws from torch's
+    global CPU generator in the reference's order (row_across, col_across, col_inside; Tensor.random_(0, hi) is [0, hi)), so
+    that under the same torch.manual_seed it reproduces the reference's sample exactly."""
+    n_across, n_inside = int(num_negative * 0.7), int(num_negative * 0.3)
+    rows = torch.empty(B, R, n_across, dtype=torch.long).random_(0, B - 1)
+    cols = torch.empty(B, R, n_across, dtype=torch.long).random_(0, R)
+    own = torch.arange(B).view(B, 1, 1)
+    rows = torch.where((rows == own) & (own < B - 1), torch.full_like(rows, B - 1), rows)       # a sample is never its own negative
+    inside = torch.empty(B, R, n_inside, dtype=torch.long).random_(0, R - 1)
+    reg = torch.arange(R).view(1, R, 1)
+    inside = torch.where((inside == reg) & (reg < R - 1), torch.full_like(inside, R - 1), inside)   # nor a region its own
+    return torch.cat((rows * R + cols, own * R + inside), dim=2)
+
+
 def pretraining_losses(P, cfg, input_ids, image_feat, image_loc, token_type_ids, attention_mask, image_attention_mask,
-                       masked_lm_labels, image_label, image_target, next_sentence_label):
-    """BertForMultiModalPreTraining.forward with labels, visual_target == 0, vilbert.py:1471-1590:
-    masked-LM CE (ignore_index -1), masked-region KL-div against the soft target (global region dropped,
-    :1506; normalised by max(sum(image_label == 1), 0) as written at :1521), NSP/alignment CE."""
+                       masked_lm_labels, image_label, image_target, next_sentence_label, neg_index=None):
+    """BertForMultiModalPreTraining.forward with labels, vilbert.py:1471-1590: masked-LM CE (ignore_index -1), NSP/alignment CE
+    and the masked-region loss (global region dropped, :1506) selected by config.visual_target:
+      0  KL-div against the soft class target, normalised by max(sum(image_label == 1), 0) as written at :1521
+      1  MSE regression of the region feature, mean over the masked ELEMENTS (:1507-1513)
+      2  cross-entropy of the true feature (index 0) against sampled negatives scored by the dot product with the prediction
+         (:1523-1575); neg_index [B, R, n] = nce_negative_indices(...) (drawn here, in the reference's order, when None)."""
     seq_t, seq_v, pooled_t, pooled_v = bert_model(P, cfg, input_ids, image_feat, image_loc, token_type_ids, attention_mask,
                                                   image_attention_mask)
     scores_t, scores_v, seq_rel = pretraining_heads(P, cfg, seq_t, seq_v, pooled_t, pooled_v)
     scores_v = scores_v[:, 1:]
-    img_loss = F.kl_div(F.log_softmax(scores_v, dim=2), image_target, reduction="none")
-    masked_img_loss = torch.sum(img_loss * (image_label == 1).unsqueeze(2).float()) / max(torch.sum(image_label == 1), 0)
+    masked = image_label == 1
+    vt = cfg.get("visual_target", 0)
+    if vt == 1:
+        img_loss = F.mse_loss(scores_v, image_target, reduction="none")
+        masked_img_loss = torch.sum(img_loss * masked.unsqueeze(2).float()) / max(torch.sum(masked.unsqueeze(2).expand_as(img_loss)), 1)
+    elif vt == 2:
+        B, R, _ = scores_v.shape
+        if neg_index is None:
+            neg_index = nce_negative_indices(B, R, cfg.get("num_negative", 128))
+        neg_index = neg_index.to(scores_v.device)
+        samples = torch.cat((image_target[masked].unsqueeze(1), image_target.reshape(B * R, -1)[neg_index[masked]]), dim=1)
+        score = torch.bmm(samples, scores_v[masked].unsqueeze(2)).squeeze(2)
+        masked_img_loss = F.cross_entropy(score, torch.zeros(score.shape[0], dtype=torch.long, device=score.device))
+    else:
+        img_loss = F.kl_div(F.log_softmax(scores_v, dim=2), image_target, reduction="none")
+        masked_img_loss = torch.sum(img_loss * masked.unsqueeze(2).float()) / max(torch.sum(masked), 0)
     masked_lm_loss = F.cross_entropy(scores_t.view(-1, scores_t.shape[-1]), masked_lm_labels.view(-1), ignore_index=-1)
     nsp_loss = F.cross_entropy(seq_rel.view(-1, 2), next_sentence_label.view(-1), ignore_index=-1)
     return masked_lm_loss, masked_img_loss, nsp_loss

@@ -165,6 +165,37 @@ def test_train_mode_dropout_golden(golden_dir):
         assert abs(t.norm().item() - s["l2"]) <= 1e-5 * s["l2"] + 1e-12, k
 
 
+@pytest.mark.parametrize("vt", [1, 2])
+def test_visual_target_golden(golden_dir, vt):
+    """config.visual_target 1 / 2: the three pre-training losses recorded from the reference (for 2 with the negatives the
+    reference sampled, recorded in the fixture; oracle/make_golden.py::check_visual_targets pins losses and gradients at 0.0)."""
+    meta = json.load(open(os.path.join(golden_dir, f"tiny_visual_target_{vt}.json")))
+    cfg = O.make_config(meta["config"])
+    B, Nv, Nt = meta["B"], meta["Nv"], meta["Nt"]
+    P = O.synth_params(cfg, seed=3, with_task_heads=False)
+    inp = O.synth_inputs(cfg, B, Nv, Nt, seed=77)
+    g = torch.Generator().manual_seed(5)
+    lm = torch.full((B, Nt), -1, dtype=torch.long); lm[:, 1] = torch.randint(0, cfg["vocab_size"], (B,), generator=g)
+    il = torch.full((B, Nv - 1), -1, dtype=torch.long); il[:, 0] = 1; il[:, 3] = 1; il[2, 7] = 1
+    it = torch.randn(B, Nv - 1, 48, generator=g)
+    ns = torch.randint(0, 2, (B,), generator=g)
+    neg = torch.tensor(meta["neg_index"]) if vt == 2 else None
+    with torch.no_grad():
+        lo = O.pretraining_losses(P, cfg, inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"],
+                                  inp["image_attention_mask"], lm, il, it, ns, neg_index=neg)
+    for a, b in zip(lo, meta["losses"]):
+        assert abs(a.item() - b) <= 1e-5 * abs(b)
+    if vt == 2:
+        # the oracle's sampler reproduces the reference's draw order under the same seed; negatives never include the sample / region itself
+        torch.manual_seed(meta["seed"])
+        again = O.nce_negative_indices(B, Nv - 1, cfg["num_negative"])
+        assert torch.equal(again, neg)
+        R = Nv - 1
+        own = torch.arange(B).view(B, 1, 1)
+        assert (neg[:, :, :14] // R != own).all() and (neg[:, :, 14:] // R == own).all()
+        assert (neg[:, :, 14:] % R != torch.arange(R).view(1, R, 1)).all()
+
+
 def test_roberta_golden(golden_dir):
     """config.model == "roberta": the reference's RobertaEmbeddings position-id shift is overwritten inside BertEmbeddings.forward
     (vilbert.py:347-351), so the outputs recorded from the reference with model="roberta" are the ones the oracle computes with

@@ -384,12 +384,10 @@ class BertForMultiModalPreTraining(BertPreTrainedModel):
         if self.visual_target not in (0, 1, 2):
             raise ValueError("visual_target must be 0, 1 or 2")
 
-    def _nce_region_loss(self, pred, target, masked):
-        """visual_target == 2: for every masked region, CE over [its own target feature, 70 % negatives drawn from other samples'
-        regions, 30 % from other regions of the same sample] scored by the dot product with the prediction."""
-        B, R, _ = pred.shape
+    def _nce_negatives(self, B, R, dev):
+        """Flat region indices [B, R, n] of the negatives of visual_target == 2: 70 % from other samples, 30 % from other regions of
+        the same sample, sampled on the device (`self.nce_sampler`, a callable (B, R, device) -> index, replaces it in tests)."""
         n_across, n_inside = int(self.num_negative * 0.7), int(self.num_negative * 0.3)
-        dev = pred.device
         rows = torch.randint(0, max(B - 1, 1), (B, R, n_across), device=dev)
         own = torch.arange(B, device=dev).view(B, 1, 1)
         rows = torch.where((rows == own) & (own < B - 1), torch.full_like(rows, B - 1), rows)     # never the sample itself
@@ -397,8 +395,15 @@ class BertForMultiModalPreTraining(BertPreTrainedModel):
         cols = torch.randint(0, max(R - 1, 1), (B, R, n_inside), device=dev)
         reg = torch.arange(R, device=dev).view(1, R, 1)
         cols = torch.where((cols == reg) & (reg < R - 1), torch.full_like(cols, R - 1), cols)     # never the region itself
-        inside = own * R + cols
-        index = torch.cat((across, inside), dim=2)[masked]
+        return torch.cat((across, own * R + cols), dim=2)
+
+    def _nce_region_loss(self, pred, target, masked):
+        """visual_target == 2: for every masked region, CE over [its own target feature, sampled negatives] scored by the dot
+        product with the prediction (pinned against the reference with the reference's own sample: tiny_visual_target_2.json)."""
+        B, R, _ = pred.shape
+        dev = pred.device
+        sampler = getattr(self, "nce_sampler", None)
+        index = (sampler(B, R, dev) if sampler is not None else self._nce_negatives(B, R, dev))[masked]
         flat = target.reshape(B * R, -1)
         samples = torch.cat((target[masked].unsqueeze(1), flat[index]), dim=1)
         score = torch.bmm(samples, pred[masked].unsqueeze(2)).squeeze(2)
