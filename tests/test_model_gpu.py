@@ -378,7 +378,8 @@ def test_config3_pretraining_objective_fused_losses(golden_dir):
     assert len(l2) > 100 and l2[-1][0] < 5e-2 and l2[len(l2) // 2][0] < 1.5e-2, l2[-3:]   # measured 1.5e-2 worst, 1.06e-2 median at B=64
 
 
-def test_pretraining_objective_compacted_lm_head(golden_dir):
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_pretraining_objective_compacted_lm_head(golden_dir, precision):
     """The fused pre-training objective runs the tied 30522-way decoder on the labelled rows only (Plan.lm_head_compact):
     same loss and gradients as the full-logits plan; more labelled rows than the capacity poison the loss with NaN."""
     from _gpu_util import rel_l2
@@ -394,7 +395,7 @@ def test_pretraining_objective_compacted_lm_head(golden_dir):
     inp = O.synth_inputs(cfg, B, Nv, Nt, seed=3, device="cuda")
     res = {}
     for compact in (True, False):
-        eng = Engine(BertConfig.from_dict(cfgj), "cuda", heads="pretraining")
+        eng = Engine(BertConfig.from_dict(cfgj), "cuda", heads="pretraining", precision=precision)
         eng.lm_compact = compact
         for k in eng.ps.entries:
             eng.ps.p(k).copy_(P[k])
