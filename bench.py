@@ -246,6 +246,9 @@ def main():
                     help="N > 1: persistent CTAs of the backward-pass GEMMs (they run beside NCCL's all-reduce kernels; a GEMM CTA that finds "
                          "its SM taken starts after the others and serialises its whole static tile share). -1 = 132 (measured at N = 2: 12.39 ms/step vs "
                          "12.49 with one CTA per SM and 12.46 with 116), 0 = one per SM")
+    ap.add_argument("--arena-gb", type=float, default=0.0,
+                    help="share ONE activation arena of this size between the plans (Engine.enable_activation_arena): config 5 keeps 12 plans "
+                         "whose private activations add up to 42.7 GB; 0 = private buffers per plan")
     ap.add_argument("--segments", type=int, default=8, help="N > 1: number of backward pieces whose gradient ranges are all-reduced while the rest runs")
     ap.add_argument("--eval-mode", action="store_true", help="disable the dropout layers (reference eval mode); default is train mode")
     ap.add_argument("--legacy-prologue", action="store_true", help="round-1 step body: weight cast + gradient memset inside the step, no fused optimizer")
@@ -319,6 +322,8 @@ def main():
     eng = Engine(BertConfig.from_dict(cfgj), dev, heads=C.get("heads", "vl"), precision=a.precision)
     if world > 1:
         eng.bwd_gemm_max_ctas = a.bwd_gemm_ctas if a.bwd_gemm_ctas >= 0 else 132
+    if a.arena_gb > 0:
+        eng.enable_activation_arena(int(a.arena_gb * 2 ** 30))
     # random-init weights of the named architecture (reference init: N(0, 0.02), zero bias, LN 1/0); same seed on every rank
     g = torch.Generator(device=dev).manual_seed(0)
     eng.ps.flat.normal_(0.0, 0.02, generator=g)
@@ -593,6 +598,7 @@ def main():
                                                                          + (" (one CUDA graph per step, collectives captured, never-written ranges skipped)" if ddp_graph else " (one graph per backward piece)") if overlapped
                                  else "NCCL AVG of the flat fp32 gradient buffer after each backward (8 buckets)")),
                    "bwd_gemm_ctas": (eng.bwd_gemm_max_ctas or "one per SM"),
+                   "activation_arena_gb": (round(max(t["plan"].arena_bytes for t in T) / 2 ** 30, 2) if eng.arena is not None else None),
                    "l2": "working set (activations + weights + grads, GBs per step) exceeds the 126 MB L2; no explicit flush",
                    "streams": "text and vision segments on two CUDA streams (parallel graph branches)" if eng.two_streams else "single stream",
                    "numerics": {"fp16": "fp16 forward tensor-core operands, bf16 gradient operands, fp32 accumulate/residual/LayerNorm/softmax",

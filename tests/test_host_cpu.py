@@ -145,6 +145,34 @@ def test_special_mode_plans_build_on_cpu(golden_dir):
     assert small.lm_c["cap"] == 40                                              # never more rows than there are (8-padded)
 
 
+def test_shared_activation_arena_layout(golden_dir):
+    """Engine.enable_activation_arena: activation / scratch buffers of every plan are sub-allocated from one arena (plans overlay
+    each other), while everything loaded or initialised outside a run (inputs, targets, output gradients) stays private."""
+    from vilbert_b200._lib import VBError
+    cfgj = json.load(open(os.path.join(golden_dir, "tiny_b4.json")))["config"]
+    plain = Engine(BertConfig.from_dict(cfgj), "cpu", _build_only=True).plan(4, 9, 11, grad_outputs=("vil_prediction",), vqa_loss=True)
+    eng = Engine(BertConfig.from_dict(cfgj), "cpu", _build_only=True)
+    eng.enable_activation_arena(64 << 20)
+    a = eng.plan(4, 9, 11, grad_outputs=("vil_prediction",), vqa_loss=True)
+    b = eng.plan(6, 20, 33, grad_outputs=("vil_prediction",), vqa_loss=True)
+    assert (a.n_kernels_fwd, a.n_kernels_bwd) == (plain.n_kernels_fwd, plain.n_kernels_bwd)
+    lo, hi = eng.arena.data_ptr(), eng.arena.data_ptr() + eng.arena.numel()
+    inside = lambda t: lo <= t.data_ptr() < hi
+    for p in (a, b):
+        assert not any(inside(t) for t in (p.in_ids, p.in_tt, p.in_amask, p.in_imask, p.in_feat, p.in_loc, p.vqa_target, p.loss))
+        assert all(inside(t) for t in (p.outputs["sequence_output_t"], p.outputs["vil_prediction"], p.mask_t, p.mask_v))
+        assert 0 < p.arena_bytes <= eng.arena.numel() and p.arena_bytes % 256 == 0
+    assert a.mask_t.data_ptr() == b.mask_t.data_ptr() and b.arena_bytes > a.arena_bytes       # same offsets: the plans overlay
+    private = lambda p: sum(t.numel() * t.element_size() for t in p._keep if torch.is_tensor(t))
+    assert private(a) < 0.1 * private(plain)
+    with pytest.raises(VBError):
+        eng.enable_activation_arena(1 << 20)          # only before the first plan
+    small = Engine(BertConfig.from_dict(cfgj), "cpu", _build_only=True)
+    small.enable_activation_arena(1 << 20)
+    with pytest.raises(VBError):
+        small.plan(4, 9, 11)
+
+
 def test_ddp_segments_partition_the_gradient_buffer(golden_dir):
     """Overlapped data-parallel step: backward pieces (each with at least one kernel, no side-stream event recorded in one
     piece and waited for in a later one) release tail ranges of the flat gradient buffer that (a) tile it exactly and (b)

@@ -421,6 +421,65 @@ def test_pretraining_objective_compacted_lm_head(golden_dir, precision):
     assert rel_l2(res[True][1], res[False][1]) < 1e-4
 
 
+def test_shared_activation_arena(golden_dir):
+    """Engine.enable_activation_arena (12-in-1 training keeps one plan per task shape but runs them one at a time): two plans of
+    different shapes overlay their activations in one arena. Each still reproduces the all-private engine's loss and gradients,
+    also after the other plan has run in between; a backward on clobbered activations is refused at the engine level and
+    recomputed by the module surface."""
+    import vilbert_b200
+    from _gpu_util import build_engine, rel_l2
+    from vilbert_b200._lib import VBError
+    cfgj = _cfg(golden_dir, "tiny_b4")
+    cfg = O.make_config(cfgj)
+    P = O.synth_params(cfg, seed=0, device="cuda")
+    shapes = [(4, 9, 11), (6, 24, 33)]
+    inps = [O.synth_inputs(cfg, B, Nv, Nt, seed=10 + i, device="cuda") for i, (B, Nt, Nv) in enumerate(shapes)]
+    tgts = [O.synth_vqa_target(B, 3129, seed=3 + i, device="cuda") for i, (B, _, _) in enumerate(shapes)]
+
+    def engine(arena):
+        eng = build_engine(cfgj, P, "cuda")
+        if arena:
+            eng.enable_activation_arena(64 << 20)
+        plans = []
+        for (B, Nt, Nv), inp, tgt in zip(shapes, inps, tgts):
+            p = eng.plan(B, Nt, Nv, grad_outputs=("vil_prediction",), vqa_loss=True)
+            p.load_inputs(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+            p.vqa_target.copy_(tgt)
+            plans.append(p)
+        return eng, plans
+
+    def step(eng, p):
+        eng.zero_grad(); p.run_step(); torch.cuda.synchronize()
+        return p.loss.item(), eng.ps.grad.clone()
+
+    e0, p0 = engine(False)
+    ref = [step(e0, p) for p in p0]
+    e1, p1 = engine(True)
+    assert p1[0].mask_t.data_ptr() == p1[1].mask_t.data_ptr()
+    for order in ((0, 1), (1, 0), (0, 0, 1, 1, 0)):
+        for i in order:
+            loss, g = step(e1, p1[i])
+            assert abs(loss - ref[i][0]) <= 1e-5 * abs(ref[i][0]) and rel_l2(g, ref[i][1]) < 1e-4, (order, i)
+    p1[0].run_forward(); p1[1].run_forward()
+    with pytest.raises(VBError):
+        p1[0].run_backward()
+    torch.cuda.synchronize()
+    # module surface: two forwards of different shapes, ONE backward of the summed loss -> the first forward is recomputed
+    grads = []
+    for arena in (False, True):
+        model = vilbert_b200.VILBertForVLTasks(vilbert_b200.BertConfig.from_dict(cfgj), num_labels=1)
+        model.load_state_dict(P, strict=True); model.eval()
+        if arena:
+            model.engine.enable_activation_arena(64 << 20)
+        total = 0
+        for inp, tgt in zip(inps, tgts):
+            out = model(inp["input_txt"], inp["input_imgs"], inp["image_loc"], inp["token_type_ids"], inp["attention_mask"], inp["image_attention_mask"])
+            total = total + torch.nn.functional.binary_cross_entropy_with_logits(out[0], tgt, reduction="mean") * tgt.size(1)
+        model.zero_grad(); total.backward(); torch.cuda.synchronize()
+        grads.append((total.item(), model.engine.ps.grad.clone()))
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[0][0]) and rel_l2(grads[1][1], grads[0][1]) < 1e-4
+
+
 def test_module_surface_autograd_and_state_dict(golden_dir):
     """Drop-in API: VILBertForVLTasks(config).forward(...) 10-tuple, loss.backward() through the autograd bridge,
     state_dict with the reference key names, load_state_dict round trip."""

@@ -295,13 +295,32 @@ class Plan:
         self.n_kernels_fwd = self.n_kernels_bwd = 0
         self.graph_fwd = self.graph_bwd = self.graph_step = None
         self._eager_runs = [0, 0]      # eager forward / backward executions (maybe_capture_passes)
+        self._arena_off = self.arena_bytes = 0
         self._build()
 
     # ------------------------------------------------------------------ infrastructure
     def buf(self, shape, dtype=F32, zero=False):
-        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
-        self._keep.append(t)
-        return t
+        """A static buffer of the plan. With the engine's shared activation arena enabled (Engine.enable_activation_arena), buffers
+        that hold no state between runs (activations, scratch: everything a run writes before reading) are sub-allocated from the
+        arena at the same offsets in every plan, so the plans of different shapes overlay each other; buffers that are
+        initialised at build time or loaded from outside a run (zero=True: inputs, labels, output gradients, zero-padded
+        operands) stay private."""
+        arena = self.e.arena
+        if arena is None or zero:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
+            self._keep.append(t)
+            return t
+        n = 1
+        for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        off = self._arena_off
+        if off + nbytes > arena.numel():
+            raise L.VBError(f"activation arena of {arena.numel() / 2**30:.2f} GiB is too small for plan B={self.B} Nt={self.Nt} Nv={self.Nv} "
+                            f"(needs more than {(off + nbytes) / 2**30:.2f} GiB): pass a larger size to Engine.enable_activation_arena")
+        self._arena_off = (off + nbytes + 255) // 256 * 256
+        self.arena_bytes = self._arena_off
+        return arena[off:off + nbytes].view(dtype).view(shape)
 
     def buf16(self, shape, bw=True):
         """Forward-operand buffer in the engine's operand format: (hi, lo, bw) with lo = None unless split precision and
@@ -920,7 +939,7 @@ class Plan:
         ps, c, lib = self.ps, self.cfg, self.lib
         M, Ht, V = ht.M, ht.H, c.vocab_size
         cap = min(_pad8(M), _pad8(max(64, int(math.ceil(self.e.lm_capacity * M)))))
-        labels = self.buf((M,), I64)
+        labels = self.buf((M,), I64, zero=True)      # a plan input (loaded from outside a run): private, never in the shared arena
         labels.fill_(-1)
         self.loss_inputs["masked_lm_labels"] = labels
         idx, cnt, lab_c = self.buf((cap,), torch.int32), self.buf((1,), torch.int32, zero=True), self.buf((cap,), I64)
@@ -1333,6 +1352,7 @@ class Plan:
 
     def run_forward(self):
         self.fwd_id += 1
+        self.e.arena_owner = (self, self.fwd_id)
         if self.graph_fwd is not None:
             self.graph_fwd.replay()
         else:
@@ -1340,6 +1360,9 @@ class Plan:
             self._eager_runs[0] += 1
 
     def run_backward(self):
+        if self.e.arena is not None and self.e.arena_owner != (self, self.fwd_id):
+            raise L.VBError("shared activation arena: another plan's forward ran between this plan's forward and backward "
+                            "(its saved activations are gone); run forward + backward per batch, or disable the arena")
         self.e.grad_clean = False
         if self.graph_bwd is not None:
             self.graph_bwd.replay()
@@ -1414,6 +1437,7 @@ class Plan:
     def run_step(self):
         """(prologue) + forward + (loss) + backward (+ epilogue); gradients accumulate into ParamStore.grad."""
         self.fwd_id += 1
+        self.e.arena_owner = (self, self.fwd_id)
         self.e.grad_clean = False
         if self.graph_step is not None:
             self.graph_step.replay()
@@ -1554,6 +1578,7 @@ class Plan:
 
     def run_step_ddp(self):
         self.fwd_id += 1
+        self.e.arena_owner = (self, self.fwd_id)
         self.e.grad_clean = False
         self.graph_step_ddp.replay()
 
@@ -1641,6 +1666,8 @@ class Engine:
         self.grad_clean = False          # the flat gradient buffer is all zeros (set by zero_grad / the fused optimizer)
         self.loss_options = 4            # answer options per question of the VL-logit objective (retrieval / VCR: 4)
         self.auto_graph = True           # module surface: capture a plan's passes into CUDA graphs after two eager runs
+        self.arena = None                # optional shared activation arena (enable_activation_arena)
+        self.arena_owner = None          # (plan, forward id) whose activations the arena currently holds
         self.bwd_gemm_max_ctas = 0       # persistent CTAs of the backward GEMMs (0 = one per SM); data parallel: leave SMs to NCCL
         self.lm_compact = True           # fused pre-training objective: masked-LM decoder + CE on the labelled rows only (Plan.lm_head_compact)
         self.lm_capacity = 0.25          # ... with room for this fraction of the token rows (15 % are masked; more poisons the loss with NaN)
@@ -1655,6 +1682,15 @@ class Engine:
             self.plans.popitem(last=False)
         self.plans[key] = Plan(self, B, Nt, Nv, grad_outputs, False, heads, train, loss=loss)
         return self.plans[key]
+
+    def enable_activation_arena(self, nbytes):
+        """One activation arena shared by all plans built afterwards (12-in-1 training holds a plan per task shape, but runs one
+        forward + backward at a time, vilbert/task_utils.py:313-374 + train_tasks.py:545-551): their activation / scratch buffers
+        overlay each other in `nbytes` of device memory instead of adding up. A plan's outputs must be consumed (the module
+        surface copies the ones it returns) before another plan runs; run_backward refuses to run on clobbered activations."""
+        if self.plans:
+            raise L.VBError("enable_activation_arena must be called before the first plan is built")
+        self.arena = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
 
     def release_plans(self):
         """Drops every cached plan (and its activation / scratch buffers)."""

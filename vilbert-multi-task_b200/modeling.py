@@ -109,7 +109,8 @@ class _EngineFn(torch.autograd.Function):
         if live:
             Nt = inputs["input_txt"].shape[1]
             B, Nv = inputs["input_imgs"].shape[:2]
-            if frozenset(live) != plan.grad_outputs or plan.fwd_id != ctx.fwd_id:
+            clobbered = model.engine.arena is not None and model.engine.arena_owner != (plan, ctx.fwd_id)   # another plan used the shared arena
+            if frozenset(live) != plan.grad_outputs or plan.fwd_id != ctx.fwd_id or clobbered:
                 model._grad_hint[(B, Nt, Nv, names, ctx.train)] = live
                 plan = model.engine.plan(B, Nt, Nv, grad_outputs=live, heads=model._heads_for(names), train=ctx.train)
                 plan.load_inputs(**inputs)     # different plan (or overwritten activations): recompute the forward ...
